@@ -1,0 +1,164 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see o_linalg.h header).
+//
+// CPU restatement of stage B of hyye/lio-mapping (surf / point-to-plane branch; the corner branch
+// is compiled out in the reference: USE_CORNER undefined, include/imu_processor/Estimator.h:55-56):
+//   PointMapping::PointAssociateToMap   src/point_processor/PointMapping.cc:303-314
+//   RotatePoint                         include/utils/geometry_utils.h:288-299
+//   Estimator::CalculateFeatures        src/imu_processor/Estimator.cc:970-1097
+//   Estimator::CalculateLaserOdom       src/imu_processor/Estimator.cc:1242-1359
+// Eigen pieces restated in o_linalg.h (colPivHouseholderQr, SelfAdjointEigenSolver, quaternion).
+#include "o_api.h"
+#include <cmath>
+
+namespace orc {
+
+void PointAssociateToMap(const PointXYZI &pi, PointXYZI &po, const Transform &t) {
+  Vec3<float> v(pi.x, pi.y, pi.z);
+  Vec3<float> o = t.rot * v;  // RotatePoint: vec_out = q * vec
+  po.x = o.x + t.pos.x;
+  po.y = o.y + t.pos.y;
+  po.z = o.z + t.pos.z;
+  po.intensity = pi.intensity;
+}
+
+static inline float SqDiff(const PointXYZI &a, const PointXYZI &b) {  // math_utils.h:84-91
+  float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+void CalculateFeatures(const KdTree &kd, const Cloud &map, const Cloud &surf_stack, const Transform &local_transform,
+                       const StageBConfig &cfg, std::vector<PointPlaneFeature> &features) {
+  if (!cfg.keep_features) features.clear();  // Estimator.cc:978-980
+  const int num_neighbors = 5;
+  int point_search_idx[5];
+  float point_search_sq_dis[5];
+  PointXYZI point_ori, point_sel;
+  const size_t surf_points_size = surf_stack.size();
+  for (size_t i = 0; i < surf_points_size; i++) {
+    point_ori = surf_stack[i];
+    PointAssociateToMap(point_ori, point_sel, local_transform);
+    kd.Knn(point_sel, num_neighbors, point_search_idx, point_search_sq_dis);
+    if (point_search_sq_dis[num_neighbors - 1] < cfg.min_match_sq_dis) {
+      float A[5][3], B[5], X[3];
+      for (int j = 0; j < num_neighbors; j++) {
+        A[j][0] = map[point_search_idx[j]].x;
+        A[j][1] = map[point_search_idx[j]].y;
+        A[j][2] = map[point_search_idx[j]].z;
+        B[j] = -1.f;
+      }
+      colpiv_householder_qr_solve<float, 5, 3>(A, B, X);  // :1027
+      float pa = X[0], pb = X[1], pc = X[2], pd = 1;
+      float ps = std::sqrt(pa * pa + pb * pb + pc * pc);
+      pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+      bool planeValid = true;
+      for (int j = 0; j < num_neighbors; j++) {
+        const PointXYZI &m = map[point_search_idx[j]];
+        if (std::fabs(pa * m.x + pb * m.y + pc * m.z + pd) > cfg.min_plane_dis) { planeValid = false; break; }
+      }
+      if (planeValid) {
+        float pd2 = pa * point_sel.x + pb * point_sel.y + pc * point_sel.z + pd;
+        // s = 1 - 0.9f*fabs(pd2)/sqrt(CalcPointDistance(point_sel))  (:1056, sqrt of the norm)
+        float dist = std::sqrt(point_sel.x * point_sel.x + point_sel.y * point_sel.y + point_sel.z * point_sel.z);
+        float s = 1 - 0.9f * std::fabs(pd2) / std::sqrt(dist);
+        PointXYZI coeff1;
+        coeff1.x = s * pa; coeff1.y = s * pb; coeff1.z = s * pc; coeff1.intensity = s * pd;
+        bool is_in_laser_fov = false;
+        PointXYZI transform_pos, point_on_z_axis;
+        point_on_z_axis.x = 0.0f; point_on_z_axis.y = 0.0f; point_on_z_axis.z = 10.0f; point_on_z_axis.intensity = 0.f;
+        PointAssociateToMap(point_on_z_axis, point_on_z_axis, local_transform);
+        transform_pos.x = local_transform.pos.x; transform_pos.y = local_transform.pos.y; transform_pos.z = local_transform.pos.z;
+        float squared_side1 = SqDiff(transform_pos, point_sel);
+        float squared_side2 = SqDiff(point_on_z_axis, point_sel);
+        float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * std::sqrt(3.0f) * std::sqrt(squared_side1);
+        float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * std::sqrt(3.0f) * std::sqrt(squared_side1);
+        if (check1 < 0 && check2 > 0) is_in_laser_fov = true;
+        if (s > 0.1 && is_in_laser_fov) {
+          PointPlaneFeature f;
+          f.score = s;
+          f.point[0] = point_ori.x; f.point[1] = point_ori.y; f.point[2] = point_ori.z;
+          f.coeffs[0] = coeff1.x; f.coeffs[1] = coeff1.y; f.coeffs[2] = coeff1.z; f.coeffs[3] = coeff1.intensity;
+          f.src_index = (int)i;
+          features.push_back(f);
+        }
+      }
+    }
+  }
+}
+
+void CalculateLaserOdom(const KdTree &kd, const Cloud &map, const Cloud &surf_stack, Transform &local_transform,
+                        const StageBConfig &cfg, std::vector<PointPlaneFeature> &features, int *iters_done) {
+  bool is_degenerate = false;
+  float matP[6][6] = {};
+  int it_done = 0;
+  for (size_t iter_count = 0; iter_count < (size_t)cfg.num_max_iterations; ++iter_count) {
+    it_done = (int)iter_count + 1;
+    CalculateFeatures(kd, map, surf_stack, local_transform, cfg, features);
+    size_t n = features.size();
+    Quat<float> R_SO3 = local_transform.rot;  // SO3 R_SO3(local_transform.rot): Sophus normalises
+    R_SO3.normalize();
+    // mat_A rows [J_r, J_t], mat_B = -d2 (:1276-1300); AtA/AtB accumulated sequentially in float
+    float AtA[6][6] = {}, AtB[6] = {};
+    Mat3<float> Rm = local_transform.rot.toRotationMatrix();
+    for (size_t i = 0; i < n; i++) {
+      const PointPlaneFeature &f = features[i];
+      Vec3<float> p((float)f.point[0], (float)f.point[1], (float)f.point[2]);
+      Vec3<float> w((float)f.coeffs[0], (float)f.coeffs[1], (float)f.coeffs[2]);
+      float b = (float)f.coeffs[3];
+      // J_r = -w^T (R * skew(p)),  J_t = w^T
+      Mat3<float> RS = Rm * Skew(p);
+      float row[6];
+      for (int c = 0; c < 3; ++c) row[c] = -(w.x * RS(0, c) + w.y * RS(1, c) + w.z * RS(2, c));
+      row[3] = w.x; row[4] = w.y; row[5] = w.z;
+      Vec3<float> rp = local_transform.rot * p + local_transform.pos;  // quaternion transform (:1282)
+      float d2 = w.dot(rp) + b;
+      for (int a = 0; a < 6; ++a) {
+        for (int c = 0; c < 6; ++c) AtA[a][c] += row[a] * row[c];
+        AtB[a] += row[a] * (-d2);
+      }
+    }
+    float Aw[6][6], Bw[6], X[6];
+    for (int a = 0; a < 6; ++a) { for (int c = 0; c < 6; ++c) Aw[a][c] = AtA[a][c]; Bw[a] = AtB[a]; }
+    colpiv_householder_qr_solve<float, 6, 6>(Aw, Bw, X);  // :1306
+    if (iter_count == 0) {  // :1308-1339
+      float E[6], V[36];
+      sym_eigen_jacobi<float>(6, &AtA[0][0], E, V);
+      // mat_V = esolver.eigenvectors() (columns); mat_V2 = mat_V with ROW i zeroed for small E[i]
+      float V2[36];
+      for (int k = 0; k < 36; ++k) V2[k] = V[k];
+      is_degenerate = false;
+      const float eignThre[6] = {100, 100, 100, 100, 100, 100};
+      for (int i = 0; i < 6; ++i) {
+        if (E[i] < eignThre[i]) {
+          for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0;
+          is_degenerate = true;
+        } else break;
+      }
+      // matP = mat_V2 * mat_V.inverse(); V orthogonal => inverse = transpose
+      for (int a = 0; a < 6; ++a)
+        for (int c = 0; c < 6; ++c) {
+          float s = 0;
+          for (int k = 0; k < 6; ++k) s += V2[a * 6 + k] * V[c * 6 + k];
+          matP[a][c] = s;
+        }
+    }
+    if (is_degenerate) {
+      float X2[6];
+      for (int a = 0; a < 6; ++a) { float s = 0; for (int c = 0; c < 6; ++c) s += matP[a][c] * X[c]; X2[a] = s; }
+      for (int a = 0; a < 6; ++a) X[a] = X2[a];
+    }
+    local_transform.pos.x += X[3];
+    local_transform.pos.y += X[4];
+    local_transform.pos.z += X[5];
+    local_transform.rot = local_transform.rot * DeltaQ(Vec3<float>(X[0], X[1], X[2]));
+    if (!std::isfinite(local_transform.pos.x)) local_transform.pos.x = 0.0f;
+    if (!std::isfinite(local_transform.pos.y)) local_transform.pos.y = 0.0f;
+    if (!std::isfinite(local_transform.pos.z)) local_transform.pos.z = 0.0f;
+    float ad = R_SO3.angularDistance(local_transform.rot);
+    float delta_r = (float)(ad * 180.0 / M_PI);
+    float delta_t = std::sqrt(std::pow(X[3] * 100, 2) + std::pow(X[4] * 100, 2) + std::pow(X[5] * 100, 2));
+    if (delta_r < cfg.delta_r_abort && delta_t < cfg.delta_t_abort) break;
+  }
+  if (iters_done) *iters_done = it_done;
+}
+
+}  // namespace orc
