@@ -1,0 +1,79 @@
+"""ctypes loader of liblio_b200.so (the C-ABI in include/lio_b200.h).
+
+There is no CPU fallback: if the shared library is missing or no CUDA device is usable, every
+entry point of this package raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblio_b200.so")
+_LIB = None
+
+
+class LioError(RuntimeError):
+    pass
+
+
+STATUS = {0: "LIO_OK", -1: "LIO_ERR_CUDA", -2: "LIO_ERR_INVALID", -3: "LIO_ERR_CAPACITY", -4: "LIO_ERR_NO_DEVICE",
+          -5: "LIO_ERR_NUMERIC"}
+
+f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+f64p = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
+i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+
+
+class PPConfig(C.Structure):
+    """lio_pp_config (include/lio_b200.h) == PointProcessorConfig (PointProcessor.h:104-120)."""
+    _fields_ = [("lower_bound", C.c_float), ("upper_bound", C.c_float), ("num_rings", C.c_int),
+                ("scan_period", C.c_double), ("num_scan_subregions", C.c_int), ("num_curvature_regions", C.c_int),
+                ("surf_curv_th", C.c_float), ("max_corner_sharp", C.c_int), ("max_corner_less_sharp", C.c_int),
+                ("max_surf_flat", C.c_int), ("less_flat_filter_size", C.c_float)]
+
+
+def lib():
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise LioError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    L.lio_last_error.restype = C.c_char_p
+    L.lio_version.restype = C.c_int
+    L.lio_device_count.restype = C.c_int
+    vp, ip = C.c_void_p, C.c_int
+    L.lio_pp_default_config.argtypes = [C.POINTER(PPConfig)]
+    L.lio_pp_create.argtypes = [C.POINTER(PPConfig), ip, ip, vp, C.POINTER(vp)]
+    L.lio_pp_destroy.argtypes = [vp]
+    L.lio_pp_process_host.argtypes = [vp, f32p, ip]
+    L.lio_pp_process_dev.argtypes = [vp, vp, ip]
+    L.lio_pp_cloud_sizes.argtypes = [vp, i32p]
+    L.lio_pp_download_cloud.argtypes = [vp, ip, f32p, ip, C.POINTER(ip)]
+    L.lio_pp_cloud_dev.argtypes = [vp, ip, C.POINTER(vp)]
+    L.lio_pp_download_index.argtypes = [vp, ip, i32p, ip, C.POINTER(ip)]
+    L.lio_pp_download_scan_ranges.argtypes = [vp, i32p]
+    L.lio_pp_download_mask_labels.argtypes = [vp, u8p, i8p, ip]
+    L.lio_pp_start_ori.argtypes = [vp, C.POINTER(C.c_float)]
+    L.lio_pp_last_launches.argtypes = [vp]
+    _LIB = L
+    return L
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().lio_last_error()
+        raise LioError(f"{what}: {STATUS.get(rc, rc)} {msg.decode() if msg else ''}")
+
+
+def require_device():
+    n = lib().lio_device_count()
+    if n <= 0:
+        raise LioError("no CUDA device: lio_mapping_b200 has no CPU fallback")
+    return n

@@ -1,0 +1,72 @@
+"""Oracle pinned against the reference's own known-answer tests."""
+import math
+
+import numpy as np
+
+
+def test_angle_kats(oracle):
+    # test/test_point_processor/test_point_processor.cc:55-63 (AngleTest), EXPECT_DOUBLE_EQ = 4 ulp
+    L = oracle.lib()
+    cases = [(L.orc_normalize_rad(-3.4 - 2 * math.pi), -3.4 + 2 * math.pi),
+             (L.orc_normalize_rad(3.4 + 2 * math.pi), 3.4 - 2 * math.pi),
+             (L.orc_normalize_deg(-190.0 - 360.0), -190.0 + 360.0),
+             (L.orc_normalize_deg(190.0 + 360.0), 190.0 - 360.0)]
+    for got, want in cases:
+        assert abs(got - want) <= 4 * np.spacing(abs(want)), (got, want)
+
+
+def test_stage_a_oracle_invariants(oracle):
+    from lio_mapping_b200 import synth
+    sensor, scene, traj = synth.default_config("vlp16")
+    sw = synth.make_sweep(sensor, scene, traj, 1.0, seed=1)
+    r = oracle.stage_a(sw, sensor.lower_deg, sensor.upper_deg, sensor.rings)
+    n = r["laser_scans"].shape[0]
+    assert n == sw.shape[0]
+    # ring-ordered cloud is a stable partition of the input by ring
+    orig = r["idx_orig_index"]
+    assert np.array_equal(np.sort(orig), np.arange(n))
+    rings = r["laser_scans"][:, 3].astype(np.int32)
+    assert np.all(np.diff(rings) >= 0)
+    for k in range(sensor.rings):
+        seg = orig[rings == k]
+        assert np.all(np.diff(seg) > 0)
+    assert np.array_equal(r["laser_scans"][:, :3], sw[orig, :3])
+    # sharp is a subset of less-sharp; caps R*8*{2,20,4}
+    assert set(r["idx_sharp"]).issubset(set(r["idx_less_sharp"]))
+    assert len(r["idx_sharp"]) <= sensor.rings * 8 * 2
+    assert len(r["idx_less_sharp"]) <= sensor.rings * 8 * 20
+    assert len(r["idx_flat"]) <= sensor.rings * 8 * 4
+    # labels agree with the index sets
+    assert np.all(r["labels"][r["idx_sharp"]] == 2)
+    assert np.all(r["labels"][r["idx_flat"]] == -1)
+    # rel_time in [0, scan_period)
+    frac = r["laser_scans"][:, 3] - rings
+    assert frac.min() >= 0 and frac.max() < 0.1 + 1e-6
+
+
+def test_voxel_grid_oracle_vs_numpy(oracle):
+    rng = np.random.default_rng(0)
+    pts = rng.uniform(-5, 5, size=(5000, 4)).astype(np.float32)
+    out = oracle.voxel_grid(pts, 0.4)
+    inv = np.float32(1.0) / np.float32(0.4)
+    ijk = np.floor(pts[:, :3] * inv).astype(np.int64)
+    ijk -= np.floor(pts[:, :3].min(0) * inv).astype(np.int64)
+    div = ijk.max(0) + 1
+    key = ijk[:, 0] + ijk[:, 1] * div[0] + ijk[:, 2] * div[0] * div[1]
+    uk, inv_idx = np.unique(key, return_inverse=True)
+    assert out.shape[0] == uk.shape[0]
+    ref = np.zeros((uk.shape[0], 4), np.float64)
+    np.add.at(ref, inv_idx, pts.astype(np.float64))
+    ref /= np.bincount(inv_idx)[:, None]
+    assert np.allclose(out, ref, atol=1e-5)
+
+
+def test_knn_oracle_vs_bruteforce(oracle):
+    rng = np.random.default_rng(1)
+    m = rng.uniform(-10, 10, size=(4000, 4)).astype(np.float32)
+    q = rng.uniform(-10, 10, size=(300, 4)).astype(np.float32)
+    idx, d2 = oracle.knn(m, q, 5)
+    d = ((q[:, None, :3].astype(np.float64) - m[None, :, :3].astype(np.float64)) ** 2).sum(-1)
+    ref = np.argsort(d, axis=1, kind="stable")[:, :5]
+    assert np.array_equal(np.sort(idx, 1), np.sort(ref, 1))
+    assert np.all(np.diff(d2, axis=1) >= 0)
