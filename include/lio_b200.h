@@ -101,6 +101,21 @@ int lio_pp_start_ori(lio_pp *pp, float *start_ori);
 /* Number of kernels launched by the last process call (bench bookkeeping). */
 int lio_pp_last_launches(lio_pp *pp);
 
+/* ------------------------------------------------------------------------------------------
+ * Stage B primitives on explicit host arrays (parity entries; the estimator context below keeps
+ * the same kernels device-resident).
+ * ---------------------------------------------------------------------------------------- */
+/* pcl::VoxelGrid<PointXYZI>::filter with setLeafSize(leaf,leaf,leaf)
+ * (call sites Estimator.cc:679-687, :1518-1519; PointProcessor.cc:737-751).  out sized cap points. */
+int lio_voxel_grid_host(const float *cloud, int n, float leaf, float *out, int cap, int *n_out, int device);
+/* Estimator::CalculateFeatures (Estimator.cc:970-1097) with the kd-tree replaced by the voxel-hash
+ * k-NN: map (K x float4) = local_surf_points_filtered_ptr_, surf (M x float4) = surf_stack_[idx],
+ * tf7 = local_transform {qx,qy,qz,qw,px,py,pz}.  Outputs (sized M): pts4 = {point.xyz, score},
+ * coef4 = coeffs, src = index of the originating surf point. */
+int lio_calculate_features_host(const float *map, int K, const float *surf, int M, const float *tf7,
+                                float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
+                                int *n_out, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -62,6 +62,9 @@ def lib():
     L.lio_pp_download_mask_labels.argtypes = [vp, u8p, i8p, ip]
     L.lio_pp_start_ori.argtypes = [vp, C.POINTER(C.c_float)]
     L.lio_pp_last_launches.argtypes = [vp]
+    L.lio_voxel_grid_host.argtypes = [f32p, ip, C.c_float, f32p, ip, C.POINTER(ip), ip]
+    L.lio_calculate_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, f32p, f32p, i32p,
+                                              C.POINTER(ip), ip]
     _LIB = L
     return L
 

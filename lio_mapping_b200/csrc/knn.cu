@@ -1,0 +1,485 @@
+// Stage B on sm_100a — HBM-resident voxel-hash fixed-radius k-NN + plane fit, replacing
+// pcl::KdTreeFLANN::nearestKSearch + the per-point body of Estimator::CalculateFeatures
+// (reference: src/imu_processor/Estimator.cc:970-1097; PointAssociateToMap PointMapping.cc:303-314).
+//
+// Exactness argument: the reference rejects a match whose 5th neighbour has
+// d^2 >= min_match_sq_dis, so an exact top-5 among all map points within sqrt(min_match_sq_dis)
+// equals the unbounded kd-tree answer for every accepted feature.  With cells of edge >= that
+// radius (+2^-10 margin) all such points lie in the 3x3x3 cell block around the query.  Ties are
+// broken by (d^2, map index), the oracle's documented order.  Compiled with -fmad=false; float
+// expressions follow the reference's source order, so accepted feature sets and coefficients are
+// bit-identical to the CPU path.
+//
+//   ch_insert / ch_scan / ch_scatter : open-addressing hash of occupied cells -> contiguous
+//                                      per-cell point ranges (counting sort by hash slot)
+//   knn_plane : one thread per surf point: transform, scan 27 cells keeping the top-5 in
+//               registers, 5x3 column-pivoted Householder QR plane fit, validity / score / FOV
+//               tests, ordered compaction of accepted features by decoupled look-back
+#include "knn.cuh"
+#include <cfloat>
+
+namespace lio {
+
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr int kHashThreads = 256;
+constexpr int kKnnThreads = 128;
+
+__device__ __forceinline__ unsigned long long pack_cell(int cx, int cy, int cz) {
+  const int off = 1 << 20;
+  unsigned long long a = (unsigned)(min(max(cx + off, 0), (1 << 21) - 1));
+  unsigned long long b = (unsigned)(min(max(cy + off, 0), (1 << 21) - 1));
+  unsigned long long c = (unsigned)(min(max(cz + off, 0), (1 << 21) - 1));
+  return a | (b << 21) | (c << 42);
+}
+__device__ __forceinline__ unsigned hash_cell(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+  return (unsigned)k;
+}
+
+__global__ void __launch_bounds__(kHashThreads)
+ch_insert(const float4 *__restrict__ map, const int *__restrict__ n_dev, float inv_cell, unsigned long long *__restrict__ keys,
+          int *__restrict__ count, int mask, int *__restrict__ slot_of, int *__restrict__ rank_of) {
+  const int n = *n_dev;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(map + i);
+  unsigned long long key = pack_cell((int)floorf(p.x * inv_cell), (int)floorf(p.y * inv_cell), (int)floorf(p.z * inv_cell));
+  unsigned s = hash_cell(key) & mask;
+  while (true) {
+    unsigned long long prev = atomicCAS(keys + s, kEmptyKey, key);
+    if (prev == kEmptyKey || prev == key) break;
+    s = (s + 1) & mask;
+  }
+  slot_of[i] = (int)s;
+  rank_of[i] = atomicAdd(count + s, 1);
+}
+
+// exclusive scan of count[0..table_size) -> start[], single pass with decoupled look-back
+constexpr int kScanPer = 4;
+__global__ void __launch_bounds__(kHashThreads)
+ch_scan(const int *__restrict__ count, int *__restrict__ start, int table_size, unsigned long long *__restrict__ status,
+        int *__restrict__ ticket) {
+  __shared__ int sscan[40];
+  __shared__ int stile, sbc;
+  if (threadIdx.x == 0) stile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = stile;
+  const int base = tile * kHashThreads * kScanPer + threadIdx.x * kScanPer;
+  int v[kScanPer], s = 0;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) { v[k] = (base + k < table_size) ? count[base + k] : 0; s += v[k]; }
+  int tot;
+  int lex = block_scan_excl(s, sscan, &tot);
+  int excl = lookback_exclusive(status, tile, tot, &sbc);
+  int run = excl + lex;
+#pragma unroll
+  for (int k = 0; k < kScanPer; ++k) { if (base + k < table_size) start[base + k] = run; run += v[k]; }
+}
+
+__global__ void __launch_bounds__(kHashThreads)
+ch_scatter(const float4 *__restrict__ map, const int *__restrict__ n_dev, const int *__restrict__ start,
+           const int *__restrict__ slot_of, const int *__restrict__ rank_of, float4 *__restrict__ cellpts) {
+  const int n = *n_dev;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = __ldg(map + i);
+  cellpts[start[slot_of[i]] + rank_of[i]] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+}
+
+int CellHash::init(int cap) {
+  cap_points = cap;
+  table_size = 1024;
+  while (table_size < 2 * cap) table_size <<= 1;
+  int ntiles = table_size / (kHashThreads * kScanPer) + 1;
+  if (cudaMalloc(&keys, sizeof(unsigned long long) * table_size) != cudaSuccess) return -1;
+  if (cudaMalloc(&count, sizeof(int) * table_size) != cudaSuccess) return -1;
+  if (cudaMalloc(&start, sizeof(int) * table_size) != cudaSuccess) return -1;
+  if (cudaMalloc(&slot_of, sizeof(int) * cap) != cudaSuccess) return -1;
+  if (cudaMalloc(&rank_of, sizeof(int) * cap) != cudaSuccess) return -1;
+  if (cudaMalloc(&cellpts, sizeof(float4) * cap) != cudaSuccess) return -1;
+  if (cudaMalloc(&status, sizeof(unsigned long long) * ntiles) != cudaSuccess) return -1;
+  if (cudaMalloc(&ticket, sizeof(int)) != cudaSuccess) return -1;
+  return 0;
+}
+void CellHash::destroy() {
+  void *p[] = {keys, count, start, slot_of, rank_of, cellpts, status, ticket};
+  for (void *q : p) if (q) cudaFree(q);
+  keys = nullptr; count = start = slot_of = rank_of = ticket = nullptr; cellpts = nullptr; status = nullptr;
+}
+
+int CellHash::build(const float4 *map, const int *n_dev, int n_max, float cell_size, cudaStream_t st, int *launches) {
+  if (n_max > cap_points) return LIO_ERR_CAPACITY;
+  cell = cell_size;
+  inv_cell = 1.0f / cell_size;
+  int ntiles = (table_size + kHashThreads * kScanPer - 1) / (kHashThreads * kScanPer);
+  cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * table_size, st);
+  cudaMemsetAsync(count, 0, sizeof(int) * table_size, st);
+  cudaMemsetAsync(status, 0, sizeof(unsigned long long) * ntiles, st);
+  cudaMemsetAsync(ticket, 0, sizeof(int), st);
+  int nb = (n_max + kHashThreads - 1) / kHashThreads;
+  if (nb < 1) nb = 1;
+  ch_insert<<<nb, kHashThreads, 0, st>>>(map, n_dev, inv_cell, keys, count, table_size - 1, slot_of, rank_of);
+  ch_scan<<<ntiles, kHashThreads, 0, st>>>(count, start, table_size, status, ticket);
+  ch_scatter<<<nb, kHashThreads, 0, st>>>(map, n_dev, start, slot_of, rank_of, cellpts);
+  if (launches) *launches += 3;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
+  return LIO_OK;
+}
+
+// ---- 5x3 / 6x6 column-pivoted Householder QR least squares (Eigen 3.3 ColPivHouseholderQR
+// restated; same operation order as the CPU path).  Fully unrolled: register resident.
+template <int R, int C>
+__device__ __forceinline__ void colpiv_qr_solve(float (&a)[R][C], float (&b)[R], float (&x)[C]) {
+  constexpr int size = (R < C) ? R : C;
+  float hCoeffs[size];
+  int transp[size];
+  float normsUpdated[C], normsDirect[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < R; ++i) s += a[i][k] * a[i][k];
+    normsDirect[k] = sqrtf(s);
+    normsUpdated[k] = normsDirect[k];
+  }
+  float maxn = normsUpdated[0];
+#pragma unroll
+  for (int k = 1; k < C; ++k) if (normsUpdated[k] > maxn) maxn = normsUpdated[k];
+  const float eps = FLT_EPSILON;
+  float th = maxn * eps;
+  const float threshold_helper = (th * th) / (float)R;
+  const float norm_downdate_threshold = sqrtf(eps);
+  int nonzero_pivots = size;
+#pragma unroll
+  for (int k = 0; k < size; ++k) {
+    int biggest = k;
+    float bn = normsUpdated[k];
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) if (normsUpdated[j] > bn) { bn = normsUpdated[j]; biggest = j; }
+    float biggest_sq = bn * bn;
+    if (nonzero_pivots == size && biggest_sq < threshold_helper * (float)(R - k)) nonzero_pivots = k;
+    transp[k] = biggest;
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) {
+      if (j == biggest) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) { float t = a[i][k]; a[i][k] = a[i][j]; a[i][j] = t; }
+        float t = normsUpdated[k]; normsUpdated[k] = normsUpdated[j]; normsUpdated[j] = t;
+        t = normsDirect[k]; normsDirect[k] = normsDirect[j]; normsDirect[j] = t;
+      }
+    }
+    float tailSqNorm = 0.f;
+#pragma unroll
+    for (int i = k + 1; i < R; ++i) tailSqNorm += a[i][k] * a[i][k];
+    float c0 = a[k][k];
+    float tau, beta;
+    if (R - k == 1 || tailSqNorm <= FLT_MIN) {
+      tau = 0.f; beta = c0;
+#pragma unroll
+      for (int i = k + 1; i < R; ++i) a[i][k] = 0.f;
+    } else {
+      beta = sqrtf(c0 * c0 + tailSqNorm);
+      if (c0 >= 0.f) beta = -beta;
+      float den = c0 - beta;
+#pragma unroll
+      for (int i = k + 1; i < R; ++i) a[i][k] = a[i][k] / den;
+      tau = (beta - c0) / beta;
+    }
+    hCoeffs[k] = tau;
+    a[k][k] = beta;
+    if (R - k == 1) {
+#pragma unroll
+      for (int j = k + 1; j < C; ++j) a[k][j] *= (1.f - tau);
+    } else if (tau != 0.f) {
+#pragma unroll
+      for (int j = k + 1; j < C; ++j) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int i = k + 1; i < R; ++i) tmp += a[i][k] * a[i][j];
+        tmp += a[k][j];
+        a[k][j] -= tau * tmp;
+#pragma unroll
+        for (int i = k + 1; i < R; ++i) a[i][j] -= tau * a[i][k] * tmp;
+      }
+    }
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) {
+      if (normsUpdated[j] != 0.f) {
+        float temp = fabsf(a[k][j]) / normsUpdated[j];
+        temp = (1.f + temp) * (1.f - temp);
+        temp = temp < 0.f ? 0.f : temp;
+        float ratio = normsUpdated[j] / normsDirect[j];
+        float temp2 = temp * (ratio * ratio);
+        if (temp2 <= norm_downdate_threshold) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = k + 1; i < R; ++i) s += a[i][j] * a[i][j];
+          normsDirect[j] = sqrtf(s);
+          normsUpdated[j] = normsDirect[j];
+        } else {
+          normsUpdated[j] *= sqrtf(temp);
+        }
+      }
+    }
+  }
+  int perm[C];
+#pragma unroll
+  for (int k = 0; k < C; ++k) perm[k] = k;
+#pragma unroll
+  for (int k = 0; k < size; ++k) {
+#pragma unroll
+    for (int j = k + 1; j < C; ++j) if (j == transp[k]) { int t = perm[k]; perm[k] = perm[j]; perm[j] = t; }
+  }
+#pragma unroll
+  for (int k = 0; k < size; ++k) {
+    if (k < nonzero_pivots) {
+      float tau = hCoeffs[k];
+      if (R - k == 1) { b[k] *= (1.f - tau); }
+      else if (tau != 0.f) {
+        float tmp = 0.f;
+#pragma unroll
+        for (int i = k + 1; i < R; ++i) tmp += a[i][k] * b[i];
+        tmp += b[k];
+        b[k] -= tau * tmp;
+#pragma unroll
+        for (int i = k + 1; i < R; ++i) b[i] -= tau * a[i][k] * tmp;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = size - 1; i >= 0; --i) {
+    if (i < nonzero_pivots) {
+      float s = b[i];
+#pragma unroll
+      for (int j = i + 1; j < size; ++j) if (j < nonzero_pivots) s -= a[i][j] * b[j];
+      b[i] = s / a[i][i];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < C; ++k) x[k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < size; ++i) {
+    if (i < nonzero_pivots) {
+#pragma unroll
+      for (int j = 0; j < C; ++j) if (perm[i] == j) x[j] = b[i];
+    }
+  }
+}
+
+// Eigen quaternion * vector, then + pos (PointAssociateToMap)
+__device__ __forceinline__ void assoc_to_map(const TransformF &t, float vx, float vy, float vz, float &ox, float &oy, float &oz) {
+  float ux = t.qy * vz - t.qz * vy, uy = t.qz * vx - t.qx * vz, uz = t.qx * vy - t.qy * vx;
+  ux += ux; uy += uy; uz += uz;
+  float cx = t.qy * uz - t.qz * uy, cy = t.qz * ux - t.qx * uz, cz = t.qx * uy - t.qy * ux;
+  float rx = vx + ux * t.qw + cx, ry = vy + uy * t.qw + cy, rz = vz + uz * t.qw + cz;
+  ox = rx + t.px; oy = ry + t.py; oz = rz + t.pz;
+}
+
+__device__ __forceinline__ bool better(float d, int i, float bd, int bi) { return d < bd || (d == bd && i < bi); }
+
+__global__ void __launch_bounds__(kKnnThreads)
+knn_plane(const unsigned long long *__restrict__ hkeys, const int *__restrict__ hcount, const int *__restrict__ hstart, int hmask,
+          float inv_cell, const float4 *__restrict__ cellpts, const float4 *__restrict__ surf, const int *__restrict__ nsurf_dev,
+          const TransformF *__restrict__ tf_dev, float min_match_sq_dis, float min_plane_dis, float4 *__restrict__ out_p,
+          float4 *__restrict__ out_c, int *__restrict__ out_src, int *__restrict__ out_count, int append,
+          const int *__restrict__ done_flag, unsigned long long *__restrict__ status, int *__restrict__ ticket) {
+  __shared__ int sscan[40];
+  __shared__ int stile, sbc;
+  if (done_flag && *done_flag) return;
+  const int n = *nsurf_dev;
+  const int ntiles = (n + kKnnThreads - 1) / kKnnThreads;
+  if (threadIdx.x == 0) stile = atomicAdd(ticket, 1);
+  __syncthreads();
+  const int tile = stile;
+  const int base_count = append ? *out_count : 0;   // read before the last tile rewrites it (see end)
+  if (tile >= ntiles) {
+    if (n == 0 && tile == 0 && threadIdx.x == 0 && !append) *out_count = 0;
+    return;
+  }
+  const TransformF tf = *tf_dev;
+  const int i = tile * kKnnThreads + threadIdx.x;
+  bool valid = false;
+  float4 po = make_float4(0, 0, 0, 0), co = make_float4(0, 0, 0, 0);
+  if (i < n) {
+    float4 p = __ldg(surf + i);
+    float sx, sy, sz;
+    assoc_to_map(tf, p.x, p.y, p.z, sx, sy, sz);
+    int cx = (int)floorf(sx * inv_cell), cy = (int)floorf(sy * inv_cell), cz = (int)floorf(sz * inv_cell);
+    float bd[5];
+    int bi[5], bp[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) { bd[k] = INFINITY; bi[k] = 0x7fffffff; bp[k] = -1; }
+    for (int dz = -1; dz <= 1; ++dz)
+      for (int dy = -1; dy <= 1; ++dy)
+        for (int dx = -1; dx <= 1; ++dx) {
+          unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz);
+          unsigned s = hash_cell(key) & hmask;
+          int slot = -1;
+          while (true) {
+            unsigned long long k = hkeys[s];
+            if (k == key) { slot = (int)s; break; }
+            if (k == kEmptyKey) break;
+            s = (s + 1) & hmask;
+          }
+          if (slot < 0) continue;
+          int st = hstart[slot], cnt = hcount[slot];
+          for (int j = st; j < st + cnt; ++j) {
+            float4 m = __ldg(cellpts + j);
+            // flann::L2_Simple<float>: sequential diff*diff accumulation over x, y, z
+            float d0 = sx - m.x, d1 = sy - m.y, d2 = sz - m.z;
+            float d = 0.f;
+            d += d0 * d0; d += d1 * d1; d += d2 * d2;
+            int mi = __float_as_int(m.w);
+            if (better(d, mi, bd[4], bi[4])) {
+              bd[4] = d; bi[4] = mi; bp[4] = j;
+#pragma unroll
+              for (int t = 4; t > 0; --t) {
+                if (better(bd[t], bi[t], bd[t - 1], bi[t - 1])) {
+                  float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
+                  int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti;
+                  ti = bp[t]; bp[t] = bp[t - 1]; bp[t - 1] = ti;
+                }
+              }
+            }
+          }
+        }
+    if (bd[4] < min_match_sq_dis) {
+      float A[5][3], B[5], X[3];
+      float nx[5], ny[5], nz[5];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float4 m = __ldg(cellpts + bp[j]);
+        nx[j] = m.x; ny[j] = m.y; nz[j] = m.z;
+        A[j][0] = m.x; A[j][1] = m.y; A[j][2] = m.z;
+        B[j] = -1.f;
+      }
+      colpiv_qr_solve<5, 3>(A, B, X);
+      float pa = X[0], pb = X[1], pc = X[2], pd = 1.f;
+      float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+      pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+      bool planeValid = true;
+#pragma unroll
+      for (int j = 0; j < 5; ++j)
+        if (fabsf(pa * nx[j] + pb * ny[j] + pc * nz[j] + pd) > min_plane_dis) planeValid = false;
+      if (planeValid) {
+        float pd2 = pa * sx + pb * sy + pc * sz + pd;
+        float dist = sqrtf(sx * sx + sy * sy + sz * sz);
+        float s = 1.f - 0.9f * fabsf(pd2) / sqrtf(dist);
+        float zx, zy, zz;
+        assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
+        float e0 = tf.px - sx, e1 = tf.py - sy, e2 = tf.pz - sz;
+        float squared_side1 = e0 * e0 + e1 * e1 + e2 * e2;
+        float f0 = zx - sx, f1 = zy - sy, f2 = zz - sz;
+        float squared_side2 = f0 * f0 + f1 * f1 + f2 * f2;
+        float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
+        float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
+        bool in_fov = (check1 < 0.f && check2 > 0.f);
+        if ((double)s > 0.1 && in_fov) {
+          valid = true;
+          po = make_float4(p.x, p.y, p.z, s);
+          co = make_float4(s * pa, s * pb, s * pc, s * pd);
+        }
+      }
+    }
+  }
+  int tot;
+  int lpos = block_scan_excl(valid ? 1 : 0, sscan, &tot);
+  int excl = lookback_exclusive(status, tile, tot, &sbc);
+  if (valid) {
+    int o = base_count + excl + lpos;
+    out_p[o] = po; out_c[o] = co; out_src[o] = i;
+  }
+  if (tile == ntiles - 1 && threadIdx.x == 0) *out_count = base_count + excl + tot;
+}
+
+int KnnWork::init(int max_queries) {
+  ntiles_max = (max_queries + kKnnThreads - 1) / kKnnThreads + 1;
+  if (cudaMalloc(&status, sizeof(unsigned long long) * ntiles_max) != cudaSuccess) return -1;
+  if (cudaMalloc(&ticket, sizeof(int)) != cudaSuccess) return -1;
+  return 0;
+}
+void KnnWork::destroy() {
+  if (status) cudaFree(status);
+  if (ticket) cudaFree(ticket);
+  status = nullptr; ticket = nullptr;
+}
+
+int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
+                           const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches) {
+  (void)map;
+  int ntiles = (nsurf_max + kKnnThreads - 1) / kKnnThreads;
+  if (ntiles < 1) ntiles = 1;
+  if (ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
+  cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * ntiles, st);
+  cudaMemsetAsync(work.ticket, 0, sizeof(int), st);
+  knn_plane<<<ntiles, kKnnThreads, 0, st>>>(h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, surf, nsurf_dev, tf_dev,
+                                            min_match_sq_dis, min_plane_dis, out.pts, out.coef, out.src, out.count, append,
+                                            done_flag, work.status, work.ticket);
+  if (launches) *launches += 1;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
+  return LIO_OK;
+}
+
+}  // namespace lio
+
+// ---- C-ABI: Estimator::CalculateFeatures on explicit host arrays (parity entry) -----------------
+using namespace lio;
+
+extern "C" int lio_calculate_features_host(const float *map, int K, const float *surf, int M, const float *tf7,
+                                           float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
+                                           int *n_out, int device) {
+  if (!map || !surf || !tf7 || !n_out || K < 0 || M < 0) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  *n_out = 0;
+  if (M == 0) return LIO_OK;
+  CellHash h;
+  KnnWork w;
+  float4 *d_map = nullptr, *d_surf = nullptr;
+  FeatureOut fo;
+  int *d_n = nullptr;
+  TransformF *d_tf = nullptr;
+  int rc = LIO_OK;
+  int Kc = K > 0 ? K : 1;
+  if (h.init(Kc) != 0 || w.init(M) != 0) rc = LIO_ERR_CUDA;
+  if (rc == LIO_OK && (cudaMalloc(&d_map, sizeof(float4) * Kc) != cudaSuccess || cudaMalloc(&d_surf, sizeof(float4) * M) != cudaSuccess ||
+                       cudaMalloc(&fo.pts, sizeof(float4) * M) != cudaSuccess || cudaMalloc(&fo.coef, sizeof(float4) * M) != cudaSuccess ||
+                       cudaMalloc(&fo.src, sizeof(int) * M) != cudaSuccess || cudaMalloc(&d_n, sizeof(int) * 4) != cudaSuccess ||
+                       cudaMalloc(&d_tf, sizeof(TransformF)) != cudaSuccess))
+    rc = LIO_ERR_CUDA;
+  if (rc == LIO_OK) {
+    int hn[3] = {K, M, 0};
+    cudaMemcpy(d_map, map, sizeof(float4) * K, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_surf, surf, sizeof(float4) * M, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tf, tf7, sizeof(TransformF), cudaMemcpyHostToDevice);
+    fo.count = d_n + 2; fo.cap = M;
+    // cell edge >= search radius (with margin, see header)
+    float cell = sqrtf(min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
+    rc = h.build(d_map, d_n, Kc, cell, 0, nullptr);
+    if (rc == LIO_OK) rc = calculate_features_dev(h, d_map, d_surf, d_n + 1, M, d_tf, min_match_sq_dis, min_plane_dis, fo, 0, nullptr, w, 0, nullptr);
+    if (rc == LIO_OK) {
+      int m = 0;
+      cudaError_t e = cudaMemcpy(&m, d_n + 2, sizeof(int), cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); rc = LIO_ERR_CUDA; }
+      else {
+        *n_out = m;
+        if (m > 0) {
+          cudaMemcpy(pts4, fo.pts, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+          cudaMemcpy(coef4, fo.coef, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+          if (src) cudaMemcpy(src, fo.src, sizeof(int) * m, cudaMemcpyDeviceToHost);
+        }
+      }
+    }
+  } else {
+    lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+  }
+  void *fr[] = {d_map, d_surf, fo.pts, fo.coef, fo.src, d_n, d_tf};
+  for (void *q : fr) if (q) cudaFree(q);
+  h.destroy();
+  w.destroy();
+  return rc;
+}

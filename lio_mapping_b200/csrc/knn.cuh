@@ -1,0 +1,51 @@
+// HBM-resident voxel-hash k-NN + plane fit (stage B), see knn.cu.
+#pragma once
+#include "primitives.cuh"
+
+namespace lio {
+
+struct TransformF {  // Twist<float>: rot (x,y,z,w) + pos
+  float qx, qy, qz, qw, px, py, pz;
+};
+
+struct CellHash {
+  int table_size = 0;  // power of two
+  int cap_points = 0;
+  float cell = 1.0f, inv_cell = 1.0f;
+  unsigned long long *keys = nullptr;  // [table_size], ~0 = empty
+  int *count = nullptr;                // [table_size]
+  int *start = nullptr;                // [table_size]
+  int *slot_of = nullptr, *rank_of = nullptr;  // [cap_points]
+  float4 *cellpts = nullptr;           // [cap_points] xyz + bitcast(map index)
+  unsigned long long *status = nullptr;
+  int *ticket = nullptr;
+  int init(int cap_points);
+  void destroy();
+  // Builds the hash over map[0..*n_dev): cells of edge `cell` (>= search radius).
+  int build(const float4 *map, const int *n_dev, int n_max, float cell_size, cudaStream_t st, int *launches);
+};
+
+struct FeatureOut {
+  float4 *pts = nullptr;   // xyz = point_ori, w = score s
+  float4 *coef = nullptr;  // s*(pa,pb,pc,pd)
+  int *src = nullptr;      // index of the originating surf point
+  int *count = nullptr;    // device counter (appended to when keep_features)
+  int cap = 0;
+};
+
+struct KnnWork {
+  unsigned long long *status = nullptr;
+  int *ticket = nullptr;
+  int ntiles_max = 0;
+  int init(int max_queries);
+  void destroy();
+};
+
+// Estimator::CalculateFeatures (Estimator.cc:970-1097) for one frame.  Appends to `out` starting at
+// *out.count when `append` is non-zero, else overwrites from 0.  `done_flag` (optional device int):
+// when non-null and *done_flag != 0 the launch is a no-op (used by the LaserOdom iteration chain).
+int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
+                           const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches);
+
+}  // namespace lio

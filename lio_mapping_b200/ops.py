@@ -1,0 +1,35 @@
+"""Thin Python wrappers over the host-array C-ABI entry points (used by the parity tests)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def voxel_grid(cloud: np.ndarray, leaf: float, device: int = 0) -> np.ndarray:
+    """pcl::VoxelGrid<PointXYZI> on the GPU (lio_voxel_grid_host)."""
+    _lib.require_device()
+    cloud = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4)
+    out = np.zeros((max(cloud.shape[0], 1), 4), np.float32)
+    n = C.c_int()
+    _lib.check(_lib.lib().lio_voxel_grid_host(cloud, cloud.shape[0], leaf, out, out.shape[0], C.byref(n), device),
+               "lio_voxel_grid_host")
+    return out[:n.value].copy()
+
+
+def calculate_features(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, device: int = 0):
+    """Estimator::CalculateFeatures on explicit arrays (lio_calculate_features_host)."""
+    _lib.require_device()
+    m = np.ascontiguousarray(map_pts, np.float32).reshape(-1, 4)
+    s = np.ascontiguousarray(surf, np.float32).reshape(-1, 4)
+    cap = max(s.shape[0], 1)
+    pts = np.zeros((cap, 4), np.float32)
+    coef = np.zeros((cap, 4), np.float32)
+    src = np.zeros(cap, np.int32)
+    n = C.c_int()
+    _lib.check(_lib.lib().lio_calculate_features_host(m, m.shape[0], s, s.shape[0], np.ascontiguousarray(tf7, np.float32),
+                                                      min_match_sq_dis, min_plane_dis, pts, coef, src, C.byref(n), device),
+               "lio_calculate_features_host")
+    return pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy()
