@@ -135,3 +135,163 @@ int orc_laser_odom(const float *map, int K, const float *surf, int M, float *tf7
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// fp64 factors / solver / estimator
+#include "o_estimator.h"
+
+extern "C" {
+
+// PivotPointPlaneFactor::Evaluate (src/factor/PivotPointPlaneFactor.cc:43-137); J* are 1x7 row-major
+void orc_ppp_evaluate(const double *point3, const double *coeff4, const double *pose_pivot, const double *pose_i,
+                      const double *pose_ex, double *residual, double *J0, double *J1, double *J2) {
+  PivotPointPlaneFactor f(point3, coeff4);
+  const double *params[3] = {pose_pivot, pose_i, pose_ex};
+  double *jac[3] = {J0, J1, J2};
+  f.Evaluate(params, residual, (J0 || J1 || J2) ? jac : nullptr);
+}
+
+void orc_prior_evaluate(const double *pos3, const double *quat_xyzw, const double *pose, double *res6, double *J6x7) {
+  PriorFactor f(V3(pos3[0], pos3[1], pos3[2]), Qd(quat_xyzw[3], quat_xyzw[0], quat_xyzw[1], quat_xyzw[2]));
+  const double *params[1] = {pose};
+  double *jac[1] = {J6x7};
+  f.Evaluate(params, res6, J6x7 ? jac : nullptr);
+}
+
+void orc_pose_plus(const double *x7, const double *delta6, double *out7) { PosePlus(x7, delta6, out7); }
+
+// IntegrationBase (include/imu_processor/IntegrationBase.h)
+void *orc_pim_create(const double *acc0, const double *gyr0, const double *ba, const double *bg, const double *cfg5) {
+  IntegrationBaseConfig c;
+  c.acc_n = cfg5[0]; c.gyr_n = cfg5[1]; c.acc_w = cfg5[2]; c.gyr_w = cfg5[3]; c.g_norm = cfg5[4];
+  return new std::shared_ptr<IntegrationBase>(new IntegrationBase(V3(acc0[0], acc0[1], acc0[2]), V3(gyr0[0], gyr0[1], gyr0[2]),
+                                                                  V3(ba[0], ba[1], ba[2]), V3(bg[0], bg[1], bg[2]), c));
+}
+void orc_pim_destroy(void *h) { delete (std::shared_ptr<IntegrationBase> *)h; }
+void orc_pim_push_back(void *h, double dt, const double *acc, const double *gyr) {
+  (*(std::shared_ptr<IntegrationBase> *)h)->push_back(dt, V3(acc[0], acc[1], acc[2]), V3(gyr[0], gyr[1], gyr[2]));
+}
+// out: delta_p(3) delta_q(xyzw 4) delta_v(3) sum_dt(1) | jacobian 225 | covariance 225
+void orc_pim_get(void *h, double *state11, double *jac225, double *cov225) {
+  IntegrationBase &p = **(std::shared_ptr<IntegrationBase> *)h;
+  state11[0] = p.delta_p_.x; state11[1] = p.delta_p_.y; state11[2] = p.delta_p_.z;
+  state11[3] = p.delta_q_.x; state11[4] = p.delta_q_.y; state11[5] = p.delta_q_.z; state11[6] = p.delta_q_.w;
+  state11[7] = p.delta_v_.x; state11[8] = p.delta_v_.y; state11[9] = p.delta_v_.z; state11[10] = p.sum_dt_;
+  if (jac225) std::memcpy(jac225, p.jacobian_.d.data(), 225 * sizeof(double));
+  if (cov225) std::memcpy(cov225, p.covariance_.d.data(), 225 * sizeof(double));
+}
+// ImuFactor::Evaluate (include/factor/ImuFactor.h:53-167): params = pose_i(7) sb_i(9) pose_j(7) sb_j(9)
+void orc_imu_factor_evaluate(void *h, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                             double *res15, double *J0, double *J1, double *J2, double *J3) {
+  ImuFactor f(*(std::shared_ptr<IntegrationBase> *)h);
+  const double *params[4] = {pose_i, sb_i, pose_j, sb_j};
+  double *jac[4] = {J0, J1, J2, J3};
+  f.Evaluate(params, res15, (J0 || J1 || J2 || J3) ? jac : nullptr);
+}
+
+void orc_sym_eigen(const double *A, int n, double *evals, double *evecs) {
+  MatX a(n, n);
+  std::memcpy(a.d.data(), A, sizeof(double) * n * n);
+  VecX ev; MatX V;
+  SymEigen(a, ev, V);
+  std::memcpy(evals, ev.data(), sizeof(double) * n);
+  std::memcpy(evecs, V.d.data(), sizeof(double) * n * n);
+}
+
+// ---------------- estimator ----------------
+// cfg (doubles): [0] window_size [1] opt_window_size [2] min_match_sq_dis [3] min_plane_dis [4] surf_filter_size
+// [5] keep_features [6] estimate_extrinsic [7] opt_extrinsic [8] imu_factor [9] point_distance_factor [10] prior_factor
+// [11] marginalization_factor [12] enable_deskew [13] cutoff_deskew [14..18] acc_n gyr_n acc_w gyr_w g_norm
+// [19] max_num_iterations [20] laser-odom max iterations
+void *orc_est_create(const double *c) {
+  EstimatorConfig cfg;
+  cfg.window_size = (int)c[0]; cfg.opt_window_size = (int)c[1];
+  cfg.b.min_match_sq_dis = (float)c[2]; cfg.b.min_plane_dis = (float)c[3]; cfg.b.surf_filter_size = (float)c[4];
+  cfg.b.keep_features = (int)c[5]; cfg.estimate_extrinsic = (int)c[6]; cfg.opt_extrinsic = c[7] != 0;
+  cfg.imu_factor = c[8] != 0; cfg.point_distance_factor = c[9] != 0; cfg.prior_factor = c[10] != 0;
+  cfg.marginalization_factor = c[11] != 0; cfg.enable_deskew = c[12] != 0; cfg.cutoff_deskew = c[13] != 0;
+  cfg.pim.acc_n = c[14]; cfg.pim.gyr_n = c[15]; cfg.pim.acc_w = c[16]; cfg.pim.gyr_w = c[17]; cfg.pim.g_norm = c[18];
+  cfg.solver.max_num_iterations = (int)c[19];
+  cfg.b.num_max_iterations = (int)c[20];
+  return new Estimator(cfg);
+}
+void orc_est_destroy(void *h) { delete (Estimator *)h; }
+void orc_est_set_extrinsic(void *h, const float *tf7 /* qx qy qz qw px py pz */) {
+  ((Estimator *)h)->transform_lb = Transform(Quat<float>(tf7[3], tf7[0], tf7[1], tf7[2]), Vec3<float>(tf7[4], tf7[5], tf7[6]));
+}
+// state16 = P(3) Q(xyzw 4) V(3) Ba(3) Bg(3); pim may be NULL for frame 0
+void orc_est_init_frame(void *h, int k, const double *s, const float *surf_ds, int n, void *pim) {
+  Estimator *e = (Estimator *)h;
+  Cloud c((const PointXYZI *)surf_ds, (const PointXYZI *)surf_ds + n);
+  std::shared_ptr<IntegrationBase> p = pim ? *(std::shared_ptr<IntegrationBase> *)pim : nullptr;
+  e->InitFrame(k, V3(s[0], s[1], s[2]), Qd(s[6], s[3], s[4], s[5]), V3(s[7], s[8], s[9]), V3(s[10], s[11], s[12]), V3(s[13], s[14], s[15]), c, p);
+}
+void orc_est_finish_init(void *h, const double *acc_last, const double *gyr_last) {
+  ((Estimator *)h)->FinishInit(V3(acc_last[0], acc_last[1], acc_last[2]), V3(gyr_last[0], gyr_last[1], gyr_last[2]));
+}
+void orc_est_process_imu(void *h, double dt, const double *acc, const double *gyr, double stamp) {
+  ((Estimator *)h)->ProcessImu(dt, V3(acc[0], acc[1], acc[2]), V3(gyr[0], gyr[1], gyr[2]), stamp);
+}
+void orc_est_process_scan(void *h, const float *surf_last, int n) {
+  Cloud c((const PointXYZI *)surf_last, (const PointXYZI *)surf_last + n);
+  ((Estimator *)h)->ProcessScan(c);
+}
+// window states: (W+1) x 16 doubles, same layout as init_frame
+void orc_est_get_states(void *h, double *out) {
+  Estimator *e = (Estimator *)h;
+  for (int k = 0; k <= e->W; ++k) {
+    double *s = out + 16 * k;
+    Qd q = Qd::fromRotationMatrix(e->Rs[k]);
+    s[0] = e->Ps[k].x; s[1] = e->Ps[k].y; s[2] = e->Ps[k].z; s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+    for (int a = 0; a < 3; ++a) { s[7 + a] = e->Vs[k][a]; s[10 + a] = e->Bas[k][a]; s[13 + a] = e->Bgs[k][a]; }
+  }
+}
+void orc_est_get_extrinsic(void *h, float *tf7) {
+  Estimator *e = (Estimator *)h;
+  tf7[0] = e->transform_lb.rot.x; tf7[1] = e->transform_lb.rot.y; tf7[2] = e->transform_lb.rot.z; tf7[3] = e->transform_lb.rot.w;
+  tf7[4] = e->transform_lb.pos.x; tf7[5] = e->transform_lb.pos.y; tf7[6] = e->transform_lb.pos.z;
+}
+// summary: [0] iterations [1] successful [2] termination [3] initial_cost [4] final_cost [5] cost_pim [6] cost_ppp
+// [7] cost_marg [8] turn_off [9] convergence_flag [10] map size [11] total features [12] laser odom iters
+// [13..17] t_build_map t_features t_solve t_marg t_total [18] has prior [19] linearizations [20] cost evals
+void orc_est_summary(void *h, double *out) {
+  Estimator *e = (Estimator *)h;
+  out[0] = e->summary.num_iterations; out[1] = e->summary.num_successful_steps; out[2] = e->summary.termination;
+  out[3] = e->summary.initial_cost; out[4] = e->summary.final_cost; out[5] = e->cost_pim; out[6] = e->cost_ppp; out[7] = e->cost_marg;
+  out[8] = e->turn_off; out[9] = e->convergence_flag; out[10] = (double)e->local_surf_points_filtered.size();
+  size_t nf = 0;
+  for (auto &f : e->feature_frames) nf += f.size();
+  out[11] = (double)nf; out[12] = e->laser_odom_iters;
+  out[13] = e->t_build_map; out[14] = e->t_features; out[15] = e->t_solve; out[16] = e->t_marg; out[17] = e->t_total;
+  out[18] = e->last_marginalization_info ? 1 : 0; out[19] = e->summary.num_linearizations; out[20] = e->summary.num_cost_evaluations;
+}
+int orc_est_feature_count(void *h, int frame) { return (int)((Estimator *)h)->feature_frames[frame].size(); }
+void orc_est_get_features(void *h, int frame, float *pts4, float *coef4, int *src) {
+  copy_feats(((Estimator *)h)->feature_frames[frame], pts4, coef4, src);
+}
+int orc_est_map_size(void *h) { return (int)((Estimator *)h)->local_surf_points_filtered.size(); }
+void orc_est_get_map(void *h, float *out) {
+  Estimator *e = (Estimator *)h;
+  if (!e->local_surf_points_filtered.empty())
+    std::memcpy(out, e->local_surf_points_filtered.data(), e->local_surf_points_filtered.size() * sizeof(PointXYZI));
+}
+int orc_est_frame_size(void *h, int frame) { return (int)((Estimator *)h)->surf_stack[frame].size(); }
+void orc_est_get_frame(void *h, int frame, float *out) {
+  Estimator *e = (Estimator *)h;
+  if (!e->surf_stack[frame].empty()) std::memcpy(out, e->surf_stack[frame].data(), e->surf_stack[frame].size() * sizeof(PointXYZI));
+}
+void orc_est_get_local_transform(void *h, int frame, float *tf7) {
+  const Transform &t = ((Estimator *)h)->local_transforms[frame];
+  tf7[0] = t.rot.x; tf7[1] = t.rot.y; tf7[2] = t.rot.z; tf7[3] = t.rot.w; tf7[4] = t.pos.x; tf7[5] = t.pos.y; tf7[6] = t.pos.z;
+}
+// marginalisation prior of the last solve: n, then linearized_jacobians (n x n row-major), residuals (n)
+int orc_est_prior_dim(void *h) { Estimator *e = (Estimator *)h; return e->last_marginalization_info ? e->last_marginalization_info->n : 0; }
+void orc_est_get_prior(void *h, double *J, double *r) {
+  Estimator *e = (Estimator *)h;
+  if (!e->last_marginalization_info) return;
+  auto &mi = *e->last_marginalization_info;
+  std::memcpy(J, mi.linearized_jacobians.d.data(), sizeof(double) * mi.n * mi.n);
+  std::memcpy(r, mi.linearized_residuals.data(), sizeof(double) * mi.n);
+}
+
+}  // extern "C"

@@ -154,3 +154,197 @@ def laser_odom(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, keep
     n = L.orc_laser_odom(m, m.shape[0], s, s.shape[0], tf, min_match_sq_dis, min_plane_dis, keep_features, max_iter,
                          pts, coef, src, it)
     return tf, pts[:n].copy(), coef[:n].copy(), src[:n].copy(), int(it[0])
+
+
+# =================================================================================================
+# fp64 factors / solver / estimator bindings
+def _bind_factors(L):
+    if getattr(L, "_factors_bound", False):
+        return
+    vp = C.c_void_p
+    L.orc_ppp_evaluate.argtypes = [f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
+    L.orc_prior_evaluate.argtypes = [f64p, f64p, f64p, f64p, f64p]
+    L.orc_pose_plus.argtypes = [f64p, f64p, f64p]
+    L.orc_pim_create.restype = vp
+    L.orc_pim_create.argtypes = [f64p, f64p, f64p, f64p, f64p]
+    L.orc_pim_destroy.argtypes = [vp]
+    L.orc_pim_push_back.argtypes = [vp, C.c_double, f64p, f64p]
+    L.orc_pim_get.argtypes = [vp, f64p, f64p, f64p]
+    L.orc_imu_factor_evaluate.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
+    L.orc_sym_eigen.argtypes = [f64p, C.c_int, f64p, f64p]
+    L.orc_est_create.restype = vp
+    L.orc_est_create.argtypes = [f64p]
+    L.orc_est_destroy.argtypes = [vp]
+    L.orc_est_set_extrinsic.argtypes = [vp, f32p]
+    L.orc_est_init_frame.argtypes = [vp, C.c_int, f64p, f32p, C.c_int, vp]
+    L.orc_est_finish_init.argtypes = [vp, f64p, f64p]
+    L.orc_est_process_imu.argtypes = [vp, C.c_double, f64p, f64p, C.c_double]
+    L.orc_est_process_scan.argtypes = [vp, f32p, C.c_int]
+    L.orc_est_get_states.argtypes = [vp, f64p]
+    L.orc_est_get_extrinsic.argtypes = [vp, f32p]
+    L.orc_est_summary.argtypes = [vp, f64p]
+    L.orc_est_feature_count.argtypes = [vp, C.c_int]
+    L.orc_est_get_features.argtypes = [vp, C.c_int, f32p, f32p, i32p]
+    L.orc_est_map_size.argtypes = [vp]
+    L.orc_est_get_map.argtypes = [vp, f32p]
+    L.orc_est_frame_size.argtypes = [vp, C.c_int]
+    L.orc_est_get_frame.argtypes = [vp, C.c_int, f32p]
+    L.orc_est_get_local_transform.argtypes = [vp, C.c_int, f32p]
+    L.orc_est_prior_dim.argtypes = [vp]
+    L.orc_est_get_prior.argtypes = [vp, f64p, f64p]
+    L._factors_bound = True
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def ppp_evaluate(point, coeff, pose_pivot, pose_i, pose_ex):
+    L = lib(); _bind_factors(L)
+    r = np.zeros(1); J = [np.zeros(7) for _ in range(3)]
+    L.orc_ppp_evaluate(_d(point), _d(coeff), _d(pose_pivot), _d(pose_i), _d(pose_ex), r, J[0], J[1], J[2])
+    return float(r[0]), J
+
+
+def prior_evaluate(pos, quat_xyzw, pose):
+    L = lib(); _bind_factors(L)
+    r = np.zeros(6); J = np.zeros(42)
+    L.orc_prior_evaluate(_d(pos), _d(quat_xyzw), _d(pose), r, J)
+    return r, J.reshape(6, 7)
+
+
+def pose_plus(x, delta):
+    L = lib(); _bind_factors(L)
+    out = np.zeros(7)
+    L.orc_pose_plus(_d(x), _d(delta), out)
+    return out
+
+
+def sym_eigen(A):
+    L = lib(); _bind_factors(L)
+    A = _d(A); n = A.shape[0]
+    ev = np.zeros(n); V = np.zeros((n, n))
+    L.orc_sym_eigen(A, n, ev, V)
+    return ev, V
+
+
+class Pim:
+    """IntegrationBase (include/imu_processor/IntegrationBase.h)."""
+
+    def __init__(self, acc0, gyr0, ba, bg, acc_n=0.1, gyr_n=0.01, acc_w=2e-4, gyr_w=2e-5, g_norm=9.805):
+        L = lib(); _bind_factors(L)
+        self.L = L
+        self.h = L.orc_pim_create(_d(acc0), _d(gyr0), _d(ba), _d(bg), _d([acc_n, gyr_n, acc_w, gyr_w, g_norm]))
+
+    def push_back(self, dt, acc, gyr):
+        self.L.orc_pim_push_back(self.h, float(dt), _d(acc), _d(gyr))
+
+    def get(self):
+        s = np.zeros(11); J = np.zeros(225); P = np.zeros(225)
+        self.L.orc_pim_get(self.h, s, J, P)
+        return dict(delta_p=s[0:3], delta_q=s[3:7], delta_v=s[7:10], sum_dt=s[10], jacobian=J.reshape(15, 15), covariance=P.reshape(15, 15))
+
+    def imu_factor(self, pose_i, sb_i, pose_j, sb_j, jac=True):
+        r = np.zeros(15)
+        J = [np.zeros(15 * 7), np.zeros(15 * 9), np.zeros(15 * 7), np.zeros(15 * 9)]
+        self.L.orc_imu_factor_evaluate(self.h, _d(pose_i), _d(sb_i), _d(pose_j), _d(sb_j), r, *J)
+        return r, [J[0].reshape(15, 7), J[1].reshape(15, 9), J[2].reshape(15, 7), J[3].reshape(15, 9)]
+
+    def __del__(self):
+        try:
+            self.L.orc_pim_destroy(self.h)
+        except Exception:
+            pass
+
+
+EST_CFG_DEFAULT = dict(window_size=10, opt_window_size=10, min_match_sq_dis=1.0, min_plane_dis=0.2, surf_filter_size=0.4,
+                       keep_features=0, estimate_extrinsic=1, opt_extrinsic=1, imu_factor=1, point_distance_factor=1,
+                       prior_factor=0, marginalization_factor=1, enable_deskew=1, cutoff_deskew=1, acc_n=0.2, gyr_n=0.02,
+                       acc_w=2e-4, gyr_w=2e-5, g_norm=9.805, max_num_iterations=10, odom_max_iterations=10)
+EST_CFG_ORDER = ["window_size", "opt_window_size", "min_match_sq_dis", "min_plane_dis", "surf_filter_size", "keep_features",
+                 "estimate_extrinsic", "opt_extrinsic", "imu_factor", "point_distance_factor", "prior_factor",
+                 "marginalization_factor", "enable_deskew", "cutoff_deskew", "acc_n", "gyr_n", "acc_w", "gyr_w", "g_norm",
+                 "max_num_iterations", "odom_max_iterations"]
+SUMMARY_KEYS = ["iterations", "successful", "termination", "initial_cost", "final_cost", "cost_pim", "cost_ppp", "cost_marg",
+                "turn_off", "convergence_flag", "map_size", "num_features", "odom_iters", "t_build_map", "t_features",
+                "t_solve", "t_marg", "t_total", "has_prior", "linearizations", "cost_evals"]
+
+
+class Estimator:
+    """Steady-state lio::Estimator (oracle)."""
+
+    def __init__(self, **cfg):
+        L = lib(); _bind_factors(L)
+        self.L = L
+        c = dict(EST_CFG_DEFAULT); c.update(cfg)
+        self.cfg = c
+        self.W = int(c["window_size"])
+        self.h = L.orc_est_create(_d([c[k] for k in EST_CFG_ORDER]))
+
+    def set_extrinsic(self, tf7):
+        self.L.orc_est_set_extrinsic(self.h, np.ascontiguousarray(tf7, np.float32))
+
+    def init_frame(self, k, state16, surf_ds, pim: "Pim | None"):
+        s = np.ascontiguousarray(surf_ds, np.float32).reshape(-1, 4)
+        self.L.orc_est_init_frame(self.h, k, _d(state16), s, s.shape[0], pim.h if pim is not None else None)
+
+    def finish_init(self, acc_last, gyr_last):
+        self.L.orc_est_finish_init(self.h, _d(acc_last), _d(gyr_last))
+
+    def process_imu(self, dt, acc, gyr, stamp):
+        self.L.orc_est_process_imu(self.h, float(dt), _d(acc), _d(gyr), float(stamp))
+
+    def process_scan(self, surf_last):
+        s = np.ascontiguousarray(surf_last, np.float32).reshape(-1, 4)
+        self.L.orc_est_process_scan(self.h, s, s.shape[0])
+
+    def states(self):
+        out = np.zeros((self.W + 1, 16))
+        self.L.orc_est_get_states(self.h, out)
+        return out
+
+    def extrinsic(self):
+        t = np.zeros(7, np.float32)
+        self.L.orc_est_get_extrinsic(self.h, t)
+        return t
+
+    def summary(self):
+        s = np.zeros(32)
+        self.L.orc_est_summary(self.h, s)
+        return dict(zip(SUMMARY_KEYS, s.tolist()))
+
+    def features(self, frame):
+        n = self.L.orc_est_feature_count(self.h, frame)
+        p = np.zeros((max(n, 1), 4), np.float32); c = np.zeros((max(n, 1), 4), np.float32); s = np.zeros(max(n, 1), np.int32)
+        self.L.orc_est_get_features(self.h, frame, p, c, s)
+        return p[:n], c[:n], s[:n]
+
+    def local_map(self):
+        n = self.L.orc_est_map_size(self.h)
+        m = np.zeros((max(n, 1), 4), np.float32)
+        self.L.orc_est_get_map(self.h, m)
+        return m[:n]
+
+    def frame(self, k):
+        n = self.L.orc_est_frame_size(self.h, k)
+        m = np.zeros((max(n, 1), 4), np.float32)
+        self.L.orc_est_get_frame(self.h, k, m)
+        return m[:n]
+
+    def local_transform(self, k):
+        t = np.zeros(7, np.float32)
+        self.L.orc_est_get_local_transform(self.h, k, t)
+        return t
+
+    def prior(self):
+        n = self.L.orc_est_prior_dim(self.h)
+        J = np.zeros((max(n, 1), max(n, 1))); r = np.zeros(max(n, 1))
+        if n:
+            self.L.orc_est_get_prior(self.h, J, r)
+        return J[:n, :n], r[:n]
+
+    def __del__(self):
+        try:
+            self.L.orc_est_destroy(self.h)
+        except Exception:
+            pass
