@@ -116,6 +116,107 @@ int lio_calculate_features_host(const float *map, int K, const float *surf, int 
                                 float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
                                 int *n_out, int device);
 
+/* ------------------------------------------------------------------------------------------
+ * fp64 factor operators — the ceres::CostFunction::Evaluate seam.
+ * Same contract as the reference: residuals always written, each jacobian pointer may be NULL,
+ * blocks are row-major num_residuals x global_size (pose = 7 with a zero last column).
+ * ---------------------------------------------------------------------------------------- */
+/* PivotPointPlaneFactor::Evaluate (src/factor/PivotPointPlaneFactor.cc:43-137), one factor, host math. */
+int lio_ppp_evaluate(const double point[3], const double coeff[4], const double pose_pivot[7], const double pose_i[7],
+                     const double pose_ex[7], double *residual, double *J_pivot_1x7, double *J_i_1x7, double *J_ex_1x7);
+/* The same operator for N factors sharing (pose_pivot, pose_i, pose_ex), evaluated on the GPU through
+ * the rank-6 form used by the fused kernel: r_out[N], J_out[N][18] = [pivot(6) | i(6) | ex(6)] tangent columns. */
+int lio_ppp_evaluate_batch_host(const float *pts4, const float *coef4, int n, const double pose_pivot[7],
+                                const double pose_i[7], const double pose_ex[7], double *r_out, double *J_out, int device);
+
+/* IntegrationBase (include/imu_processor/IntegrationBase.h:72-388) */
+typedef struct lio_pim lio_pim;
+int lio_pim_create(const double acc0[3], const double gyr0[3], const double ba[3], const double bg[3],
+                   const double noise5[5] /* acc_n gyr_n acc_w gyr_w g_norm */, lio_pim **out);
+int lio_pim_destroy(lio_pim *p);
+int lio_pim_push_back(lio_pim *p, double dt, const double acc[3], const double gyr[3]);
+/* state11 = delta_p(3) delta_q(xyzw) delta_v(3) sum_dt; jac225 / cov225 row-major 15x15 (may be NULL) */
+int lio_pim_get(lio_pim *p, double *state11, double *jac225, double *cov225);
+/* ImuFactor::Evaluate (include/factor/ImuFactor.h:53-167): J blocks 15x7, 15x9, 15x7, 15x9 row-major or NULL */
+int lio_imu_factor_evaluate(lio_pim *p, const double pose_i[7], const double sb_i[9], const double pose_j[7],
+                            const double sb_j[9], double *res15, double *J0, double *J1, double *J2, double *J3);
+
+/* ------------------------------------------------------------------------------------------
+ * Stages B+C+D — lio::Estimator in steady state (stage_flag_ == INITED)
+ * (include/imu_processor/Estimator.h:110-170, src/imu_processor/Estimator.cc:338-427, 430-774,
+ *  970-1646, 1648-2438, 2440-2666).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct lio_est_config {   /* EstimatorConfig (Estimator.h:77-108), lidar/solver subset */
+  int window_size;
+  int opt_window_size;
+  float min_match_sq_dis;
+  float min_plane_dis;
+  float surf_filter_size;
+  int keep_features;
+  int estimate_extrinsic;
+  int opt_extrinsic;
+  int imu_factor;
+  int point_distance_factor;
+  int prior_factor;
+  int marginalization_factor;
+  int enable_deskew;
+  int cutoff_deskew;
+  double acc_n, gyr_n, acc_w, gyr_w, g_norm;   /* IntegrationBaseConfig */
+  int max_num_iterations;        /* ceres options.max_num_iterations, Estimator.cc:1916 */
+  int odom_max_iterations;       /* PointMapping num_max_iterations_, PointMapping.h:171 */
+  int max_frame_points;          /* capacity of one down-sampled frame cloud (surf_stack_ entry) */
+  int max_scan_points;           /* capacity of the incoming laser_cloud_surf_last_ */
+} lio_est_config;
+
+typedef struct lio_est lio_est;
+
+void lio_est_default_config(lio_est_config *cfg);
+int lio_est_create(const lio_est_config *cfg, int device, void *cuda_stream, lio_est **out);
+int lio_est_destroy(lio_est *est);
+/* transform_lb_ (Estimator.h:89): float {qx,qy,qz,qw,px,py,pz} */
+int lio_est_set_extrinsic(lio_est *est, const float tf7[7]);
+int lio_est_get_extrinsic(lio_est *est, float tf7[7]);
+/* Warm start of window frame k in [0, W): state16 = P(3) Q(xyzw) V(3) Ba(3) Bg(3), the frame's own
+ * down-sampled surf cloud (host), and the pre-integration ending at the frame (NULL for k = 0;
+ * ownership of pim passes to the estimator). */
+int lio_est_init_frame(lio_est *est, int k, const double state16[16], const float *surf_ds, int n, lio_pim *pim);
+int lio_est_finish_init(lio_est *est, const double acc_last[3], const double gyr_last[3]);
+/* Estimator::ProcessImu (Estimator.cc:338-427) */
+int lio_est_process_imu(lio_est *est, double dt, const double acc[3], const double gyr[3], double stamp);
+/* Estimator::ProcessLaserOdom, INITED branch (Estimator.cc:618-774): de-skew + VoxelGrid + SolveOptimization +
+ * SlideWindow.  surf_last = laser_cloud_surf_last_ (surface_points_less_flat of the new sweep), HOST buffer. */
+int lio_est_process_scan_host(lio_est *est, const float *surf_last, int n);
+/* Same with the cloud already on the device (e.g. lio_pp_cloud_dev(LIO_PP_SURF_LESS_FLAT)); n is read
+ * from *n_dev on the device, n_max bounds it. */
+int lio_est_process_scan_dev(lio_est *est, const float *surf_last_dev, const int *n_dev, int n_max);
+/* Device pointer to the point count of one stage-A output cloud, to chain stage A into the estimator. */
+int lio_pp_cloud_count_dev(lio_pp *pp, int which, const int **n_dev);
+/* window states: (W+1) x 16 doubles (layout of state16) */
+int lio_est_get_states(lio_est *est, double *out);
+/* summary[32]: see lio_mapping_b200/estimator.py SUMMARY_KEYS */
+int lio_est_summary(lio_est *est, double *out32);
+int lio_est_feature_count(lio_est *est, int frame, int *n);
+int lio_est_get_features(lio_est *est, int frame, float *pts4, float *coef4, int32_t *src, int cap);
+int lio_est_map_size(lio_est *est, int *n);
+int lio_est_get_map(lio_est *est, float *out, int cap);
+int lio_est_frame_size(lio_est *est, int frame, int *n);
+int lio_est_get_frame(lio_est *est, int frame, float *out, int cap);
+int lio_est_get_local_transform(lio_est *est, int frame, float tf7[7]);
+/* Marginalisation prior kept for the next solve, as normal-equation terms over the kept blocks in
+ * canonical order [pose_0,sb_0,...,pose_{O-1},sb_{O-1},ex] (tangent, 15*O+6): Hp = J^T J, bp = J^T r0. */
+int lio_est_prior_dim(lio_est *est, int *n);
+int lio_est_get_prior(lio_est *est, double *Hp, double *bp);
+/* Normal equations at the INITIAL point of the last solve (after the convergence gates; tangent order
+ * [pose_0,sb_0,...,pose_O,sb_O,ex], n = 15*(O+1)+6): H n x n row-major, g n, cost. */
+int lio_est_last_normal_equations(lio_est *est, double *H, double *g, double *cost, int *n);
+/* Kernels launched by the last process_scan call. */
+int lio_est_last_launches(lio_est *est);
+/* Multi-GPU: frames i with (i-1) % world == rank are matched/assembled locally; the
+ * callback must sum-allreduce `count` doubles in place on the DEVICE buffer `buf` across ranks
+ * (e.g. ncclAllReduce / torch.distributed.all_reduce on the estimator's stream). */
+typedef int (*lio_allreduce_fn)(void *user, double *buf_dev, int count);
+int lio_est_set_shard(lio_est *est, int rank, int world, lio_allreduce_fn fn, void *user);
+
 #ifdef __cplusplus
 }
 #endif

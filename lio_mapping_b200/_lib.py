@@ -29,6 +29,20 @@ u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
 i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
 
 
+class EstConfig(C.Structure):
+    """lio_est_config (include/lio_b200.h) == lidar/solver subset of EstimatorConfig (Estimator.h:77-108)."""
+    _fields_ = [("window_size", C.c_int), ("opt_window_size", C.c_int), ("min_match_sq_dis", C.c_float),
+                ("min_plane_dis", C.c_float), ("surf_filter_size", C.c_float), ("keep_features", C.c_int),
+                ("estimate_extrinsic", C.c_int), ("opt_extrinsic", C.c_int), ("imu_factor", C.c_int),
+                ("point_distance_factor", C.c_int), ("prior_factor", C.c_int), ("marginalization_factor", C.c_int),
+                ("enable_deskew", C.c_int), ("cutoff_deskew", C.c_int), ("acc_n", C.c_double), ("gyr_n", C.c_double),
+                ("acc_w", C.c_double), ("gyr_w", C.c_double), ("g_norm", C.c_double), ("max_num_iterations", C.c_int),
+                ("odom_max_iterations", C.c_int), ("max_frame_points", C.c_int), ("max_scan_points", C.c_int)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int)
+
+
 class PPConfig(C.Structure):
     """lio_pp_config (include/lio_b200.h) == PointProcessorConfig (PointProcessor.h:104-120)."""
     _fields_ = [("lower_bound", C.c_float), ("upper_bound", C.c_float), ("num_rings", C.c_int),
@@ -65,6 +79,38 @@ def lib():
     L.lio_voxel_grid_host.argtypes = [f32p, ip, C.c_float, f32p, ip, C.POINTER(ip), ip]
     L.lio_calculate_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, f32p, f32p, i32p,
                                               C.POINTER(ip), ip]
+    L.lio_pp_cloud_count_dev.argtypes = [vp, ip, C.POINTER(vp)]
+    L.lio_ppp_evaluate.argtypes = [f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
+    L.lio_ppp_evaluate_batch_host.argtypes = [f32p, f32p, ip, f64p, f64p, f64p, f64p, f64p, ip]
+    L.lio_pim_create.argtypes = [f64p, f64p, f64p, f64p, f64p, C.POINTER(vp)]
+    L.lio_pim_destroy.argtypes = [vp]
+    L.lio_pim_push_back.argtypes = [vp, C.c_double, f64p, f64p]
+    L.lio_pim_get.argtypes = [vp, f64p, f64p, f64p]
+    L.lio_imu_factor_evaluate.argtypes = [vp, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
+    L.lio_est_default_config.argtypes = [C.POINTER(EstConfig)]
+    L.lio_est_create.argtypes = [C.POINTER(EstConfig), ip, vp, C.POINTER(vp)]
+    L.lio_est_destroy.argtypes = [vp]
+    L.lio_est_set_extrinsic.argtypes = [vp, f32p]
+    L.lio_est_get_extrinsic.argtypes = [vp, f32p]
+    L.lio_est_init_frame.argtypes = [vp, ip, f64p, f32p, ip, vp]
+    L.lio_est_finish_init.argtypes = [vp, f64p, f64p]
+    L.lio_est_process_imu.argtypes = [vp, C.c_double, f64p, f64p, C.c_double]
+    L.lio_est_process_scan_host.argtypes = [vp, f32p, ip]
+    L.lio_est_process_scan_dev.argtypes = [vp, vp, vp, ip]
+    L.lio_est_get_states.argtypes = [vp, f64p]
+    L.lio_est_summary.argtypes = [vp, f64p]
+    L.lio_est_feature_count.argtypes = [vp, ip, C.POINTER(ip)]
+    L.lio_est_get_features.argtypes = [vp, ip, f32p, f32p, i32p, ip]
+    L.lio_est_map_size.argtypes = [vp, C.POINTER(ip)]
+    L.lio_est_get_map.argtypes = [vp, f32p, ip]
+    L.lio_est_frame_size.argtypes = [vp, ip, C.POINTER(ip)]
+    L.lio_est_get_frame.argtypes = [vp, ip, f32p, ip]
+    L.lio_est_get_local_transform.argtypes = [vp, ip, f32p]
+    L.lio_est_prior_dim.argtypes = [vp, C.POINTER(ip)]
+    L.lio_est_get_prior.argtypes = [vp, f64p, f64p]
+    L.lio_est_last_normal_equations.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(ip)]
+    L.lio_est_last_launches.argtypes = [vp]
+    L.lio_est_set_shard.argtypes = [vp, ip, ip, ALLREDUCE_FN, vp]
     _LIB = L
     return L
 

@@ -1,0 +1,41 @@
+// Stage C — fused PivotPointPlane residual + Jacobian + J^T J / J^T r reduction (see assemble.cu).
+#pragma once
+#include "common.cuh"
+
+namespace lio {
+
+constexpr int kMaxOpt = 16;        // max frames carrying lidar factors (opt_window_size)
+constexpr int kAsmStride = 32;     // doubles per frame in the output: 28 sym(7x7) + cost_sum + pad
+
+struct AsmFrame {
+  const float4 *pts;   // xyz = feature point (lidar frame i), w = score (unused)
+  const float4 *coef;  // (w, b) of the plane in the pivot lidar frame
+  int n;               // features of this frame
+  int tile0;           // first tile index of this frame
+  double R[9];         // R_lpi, row-major
+  double t[3];         // R_lpi^T * P_lpi
+};
+
+struct AsmParams {
+  AsmFrame f[kMaxOpt];
+  int nframes;
+  int tile_feats;  // features per tile (multiple of the block size)
+  int ntiles;
+};
+
+struct AsmWork {
+  double *partial = nullptr;  // [ntiles_max][kAsmStride]
+  double *out = nullptr;      // [kMaxOpt][kAsmStride] device
+  unsigned *counter = nullptr;
+  int ntiles_max = 0;
+  int init(int max_features_total);
+  void destroy();
+};
+
+// Fills tile0 / ntiles / tile_feats of `p` from the per-frame counts (host side).
+void asm_plan(AsmParams &p, int sm_count);
+// Launches the fused kernel; results land in work.out (device), kAsmStride doubles per frame:
+//   [0..27] upper triangle (row-major) of S = sum rho'(r^2) [g;r][g;r]^T,  [28] sum rho(r^2).
+int asm_launch(const AsmParams &p, AsmWork &work, cudaStream_t st, int *launches);
+
+}  // namespace lio

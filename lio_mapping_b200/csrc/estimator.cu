@@ -1,0 +1,1400 @@
+// lio::Estimator (steady state) on sm_100a — the host shell keeps the reference's control flow
+// (window bookkeeping, gates, slide; src/imu_processor/Estimator.cc) while every per-point /
+// per-feature loop runs in the CUDA kernels of this library:
+//   ProcessLaserOdom INITED branch :618-774 -> process_scan   (de-skew kernel, device VoxelGrid)
+//   BuildLocalMap :1361-1646                -> build_local_map (concat+transform kernel, VoxelGrid, cell hash,
+//                                              voxel-hash kNN + plane fit per frame, device LaserOdom chain)
+//   SolveOptimization :1648-2438            -> solve_optimization (fused residual+Jacobian+J^T J kernel per
+//                                              iteration, dogleg controller, marginalisation)
+//   SlideWindow :2570-2666                  -> slide_window
+// There is no CPU path for the per-point work: without a CUDA device create() fails.
+#include "assemble.cuh"
+#include "factors_host.h"
+#include "knn.cuh"
+#include "qr.cuh"
+#include "solver_host.h"
+#include "voxel.cuh"
+#include <chrono>
+#include <memory>
+#include <new>
+#include <vector>
+
+namespace lio {
+using namespace hm;
+
+constexpr int kMaxWindow = 32;
+
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+struct ConcatParams {
+  const float4 *src[kMaxWindow];
+  const int *n[kMaxWindow];
+  float R[kMaxWindow][9];
+  float t[kMaxWindow][3];
+  float tag[kMaxWindow];
+  int identity[kMaxWindow];  // copy as is (pivot frame keeps its intensity)
+  int skip_first[kMaxWindow];  // drop the first k points (SlideWindow ExtractIndices), value read from *skip_n
+  const int *skip_n[kMaxWindow];
+  int nsrc;
+};
+
+// pcl::transformPointCloud (x' = m00 x + m01 y + m02 z + m03, left to right) + intensity tag + concat
+// (Estimator.cc:1498-1507, :2600-2611).  Exact float order: compiled with -fmad=false.
+__global__ void __launch_bounds__(256)
+k_concat(const ConcatParams P, float4 *__restrict__ dst, int *__restrict__ n_out, int cap) {
+  __shared__ int off[kMaxWindow + 1];
+  __shared__ int skip[kMaxWindow];
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int k = 0; k < P.nsrc; ++k) {
+      int sk = P.skip_first[k] ? *P.skip_n[k] : 0;
+      int nk = *P.n[k] - sk;
+      if (nk < 0) nk = 0;
+      skip[k] = sk;
+      off[k] = run;
+      run += nk;
+    }
+    off[P.nsrc] = run;
+    if (blockIdx.x == 0) *n_out = run < cap ? run : cap;
+  }
+  __syncthreads();
+  const int total = min(off[P.nsrc], cap);
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total; g += gridDim.x * blockDim.x) {
+    int k = 0;
+    while (k + 1 < P.nsrc && g >= off[k + 1]) ++k;
+    float4 p = __ldg(P.src[k] + (g - off[k]) + skip[k]);
+    if (!P.identity[k]) {
+      const float *R = P.R[k];
+      const float *t = P.t[k];
+      float x = R[0] * p.x + R[1] * p.y + R[2] * p.z + t[0];
+      float y = R[3] * p.x + R[4] * p.y + R[5] * p.z + t[1];
+      float z = R[6] * p.x + R[7] * p.y + R[8] * p.z + t[2];
+      p = make_float4(x, y, z, P.tag[k] >= 0.f ? P.tag[k] : p.w);
+    }
+    dst[g] = p;
+  }
+}
+
+__device__ __forceinline__ void qmul_vec(float qx, float qy, float qz, float qw, float vx, float vy, float vz, float &ox, float &oy, float &oz) {
+  float ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
+  ux += ux; uy += uy; uz += uz;
+  float cx = qy * uz - qz * uy, cy = qz * ux - qx * uz, cz = qx * uy - qy * ux;
+  ox = vx + ux * qw + cx; oy = vy + uy * qw + cy; oz = vz + uz * qw + cz;
+}
+
+// TransformToEnd (Estimator.cc:62-103), in place
+__global__ void __launch_bounds__(256)
+k_deskew(float4 *__restrict__ cloud, const int *__restrict__ n_dev, TransformF es, float time_factor) {
+  const int n = *n_dev;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = cloud[i];
+  float s = time_factor * (p.w - (float)(int)p.w);
+  p.x -= s * es.px; p.y -= s * es.py; p.z -= s * es.pz;
+  p.w -= (float)(int)p.w;
+  // q_s = identity.slerp(s, q_e)  (Eigen QuaternionBase::slerp)
+  const float one = 1.0f - FLT_EPSILON;
+  float d = es.qw;  // identity . q_e
+  float absD = fabsf(d);
+  float scale0, scale1;
+  if (absD >= one) { scale0 = 1.0f - s; scale1 = s; }
+  else {
+    float theta = acosf(absD);
+    float sinTheta = sinf(theta);
+    scale0 = sinf((1.0f - s) * theta) / sinTheta;
+    scale1 = sinf(s * theta) / sinTheta;
+  }
+  if (d < 0.f) scale1 = -scale1;
+  float sw = scale0 + scale1 * es.qw, sx = scale1 * es.qx, sy = scale1 * es.qy, sz = scale1 * es.qz;
+  // q_s.conjugate().normalized()
+  float nn = sqrtf(sx * sx + sy * sy + sz * sz + sw * sw);
+  float cx = -sx / nn, cy = -sy / nn, cz = -sz / nn, cw = sw / nn;
+  float ax, ay, az;
+  qmul_vec(cx, cy, cz, cw, p.x, p.y, p.z, ax, ay, az);
+  float bx, by, bz;
+  qmul_vec(es.qx, es.qy, es.qz, es.qw, ax, ay, az, bx, by, bz);
+  cloud[i] = make_float4(bx + es.px, by + es.py, bz + es.pz, p.w);
+}
+
+// ---- device LaserOdom (Estimator::CalculateLaserOdom, Estimator.cc:1242-1359) -------------------
+struct OdomState {
+  double AtA[36];
+  double AtB[6];
+  float matP[36];
+  int degenerate;
+  int done;
+  int iter;
+  unsigned counter;
+};
+
+constexpr int kOdomThreads = 256;
+
+__global__ void __launch_bounds__(kOdomThreads)
+k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, const int *__restrict__ n_dev,
+              const TransformF *__restrict__ tf_dev, OdomState *__restrict__ st, double *__restrict__ partial) {
+  __shared__ double sred[kOdomThreads / 32][27];
+  __shared__ bool is_last;
+  if (st->done) return;
+  const int n = *n_dev;
+  const TransformF tf = *tf_dev;
+  // rot.toRotationMatrix() of the (possibly un-normalised) quaternion, float
+  float R[9];
+  {
+    const float tx = 2.f * tf.qx, ty = 2.f * tf.qy, tz = 2.f * tf.qz;
+    const float twx = tx * tf.qw, twy = ty * tf.qw, twz = tz * tf.qw, txx = tx * tf.qx, txy = ty * tf.qx, txz = tz * tf.qx;
+    const float tyy = ty * tf.qy, tyz = tz * tf.qy, tzz = tz * tf.qz;
+    R[0] = 1.f - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
+    R[3] = txy + twz; R[4] = 1.f - (txx + tzz); R[5] = tyz - twx;
+    R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.f - (txx + tyy);
+  }
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float4 p = __ldg(pts + i), c = __ldg(coef + i);
+    // RS = R * skew(p);  J_r = -w^T RS,  J_t = w^T
+    float RS[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      RS[r * 3 + 0] = R[r * 3 + 1] * p.z + R[r * 3 + 2] * (-p.y);
+      RS[r * 3 + 1] = R[r * 3 + 0] * (-p.z) + R[r * 3 + 2] * p.x;
+      RS[r * 3 + 2] = R[r * 3 + 0] * p.y + R[r * 3 + 1] * (-p.x);
+    }
+    float row[6];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) row[q] = -(c.x * RS[q] + c.y * RS[3 + q] + c.z * RS[6 + q]);
+    row[3] = c.x; row[4] = c.y; row[5] = c.z;
+    float rx, ry, rz;
+    qmul_vec(tf.qx, tf.qy, tf.qz, tf.qw, p.x, p.y, p.z, rx, ry, rz);
+    float d2 = c.x * (rx + tf.px) + c.y * (ry + tf.py) + c.z * (rz + tf.pz) + c.w;
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[k++] += (double)(row[a] * row[b]);
+    }
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(row[a] * (-d2));
+  }
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) sred[warp_id()][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < kOdomThreads / 32; ++w) v += sred[w][threadIdx.x];
+    partial[blockIdx.x * 32 + threadIdx.x] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(&st->counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (threadIdx.x < 27) {
+    double v = 0;
+    for (unsigned b = 0; b < gridDim.x; ++b) v += __ldcg(partial + b * 32 + threadIdx.x);
+    if (threadIdx.x < 21) {
+      int k = threadIdx.x, a = 0;
+      while (k >= 6 - a) { k -= 6 - a; ++a; }
+      int b = a + k;
+      st->AtA[a * 6 + b] = v; st->AtA[b * 6 + a] = v;
+    } else {
+      st->AtB[threadIdx.x - 21] = v;
+    }
+  }
+  if (threadIdx.x == 0) st->counter = 0u;
+}
+
+// cyclic Jacobi eigen-decomposition of a symmetric 6x6 (float), ascending eigenvalues, vectors in columns
+__device__ void sym_eigen6(const float *Ain, float *evals, float *V) {
+  float A[36];
+  for (int i = 0; i < 36; ++i) { A[i] = Ain[i]; V[i] = (i % 7 == 0) ? 1.f : 0.f; }
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    float off = 0.f, diag = 0.f;
+    for (int i = 0; i < 6; ++i) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; ++j) off += A[i * 6 + j] * A[i * 6 + j]; }
+    if (off <= FLT_EPSILON * FLT_EPSILON * diag || off == 0.f) break;
+    for (int p = 0; p < 5; ++p)
+      for (int q = p + 1; q < 6; ++q) {
+        float apq = A[p * 6 + q];
+        if (apq == 0.f) continue;
+        float theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.f * apq);
+        float t = (theta >= 0.f ? 1.f : -1.f) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+        float c = 1.f / sqrtf(t * t + 1.f), s = t * c;
+        for (int k = 0; k < 6; ++k) { float a = A[k * 6 + p], b = A[k * 6 + q]; A[k * 6 + p] = c * a - s * b; A[k * 6 + q] = s * a + c * b; }
+        for (int k = 0; k < 6; ++k) { float a = A[p * 6 + k], b = A[q * 6 + k]; A[p * 6 + k] = c * a - s * b; A[q * 6 + k] = s * a + c * b; }
+        for (int k = 0; k < 6; ++k) { float a = V[k * 6 + p], b = V[k * 6 + q]; V[k * 6 + p] = c * a - s * b; V[k * 6 + q] = s * a + c * b; }
+      }
+  }
+  int idx[6] = {0, 1, 2, 3, 4, 5};
+  for (int i = 0; i < 5; ++i) for (int j = i + 1; j < 6; ++j) if (A[idx[j] * 6 + idx[j]] < A[idx[i] * 6 + idx[i]]) { int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+  float Vc[36];
+  for (int i = 0; i < 36; ++i) Vc[i] = V[i];
+  for (int j = 0; j < 6; ++j) { evals[j] = A[idx[j] * 6 + idx[j]]; for (int k = 0; k < 6; ++k) V[k * 6 + j] = Vc[k * 6 + idx[j]]; }
+}
+
+__global__ void k_odom_solve(OdomState *__restrict__ st, TransformF *__restrict__ tf_dev, double delta_r_abort, double delta_t_abort) {
+  if (threadIdx.x != 0 || st->done) return;
+  float A[6][6], B[6], X[6], AtA[36];
+  for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) { A[a][b] = (float)st->AtA[a * 6 + b]; AtA[a * 6 + b] = A[a][b]; } B[a] = (float)st->AtB[a]; }
+  colpiv_qr_solve<6, 6>(A, B, X);
+  if (st->iter == 0) {
+    float E[6], V[36], V2[36];
+    sym_eigen6(AtA, E, V);
+    for (int k = 0; k < 36; ++k) V2[k] = V[k];
+    int degenerate = 0;
+    for (int i = 0; i < 6; ++i) {
+      if (E[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; degenerate = 1; }
+      else break;
+    }
+    for (int a = 0; a < 6; ++a)
+      for (int c = 0; c < 6; ++c) { float s = 0.f; for (int k = 0; k < 6; ++k) s += V2[a * 6 + k] * V[c * 6 + k]; st->matP[a * 6 + c] = s; }
+    st->degenerate = degenerate;
+  }
+  if (st->degenerate) {
+    float X2[6];
+    for (int a = 0; a < 6; ++a) { float s = 0.f; for (int c = 0; c < 6; ++c) s += st->matP[a * 6 + c] * X[c]; X2[a] = s; }
+    for (int a = 0; a < 6; ++a) X[a] = X2[a];
+  }
+  TransformF tf = *tf_dev;
+  // R_SO3(local_transform.rot): normalised copy of the rotation before the update
+  float n0 = sqrtf(tf.qx * tf.qx + tf.qy * tf.qy + tf.qz * tf.qz + tf.qw * tf.qw);
+  float ox = tf.qx / n0, oy = tf.qy / n0, oz = tf.qz / n0, ow = tf.qw / n0;
+  tf.px += X[3]; tf.py += X[4]; tf.pz += X[5];
+  {  // rot = rot * DeltaQ(X[0..2])  (Hamilton product, not normalised)
+    float dx = X[0] / 2.f, dy = X[1] / 2.f, dz = X[2] / 2.f, dw = 1.f;
+    float nw = tf.qw * dw - tf.qx * dx - tf.qy * dy - tf.qz * dz;
+    float nx = tf.qw * dx + tf.qx * dw + tf.qy * dz - tf.qz * dy;
+    float ny = tf.qw * dy + tf.qy * dw + tf.qz * dx - tf.qx * dz;
+    float nz = tf.qw * dz + tf.qz * dw + tf.qx * dy - tf.qy * dx;
+    tf.qx = nx; tf.qy = ny; tf.qz = nz; tf.qw = nw;
+  }
+  if (!isfinite(tf.px)) tf.px = 0.f;
+  if (!isfinite(tf.py)) tf.py = 0.f;
+  if (!isfinite(tf.pz)) tf.pz = 0.f;
+  *tf_dev = tf;
+  // angularDistance: d = a * b.conjugate(); 2*atan2(|d.vec|, |d.w|)
+  float cw = ow * tf.qw + ox * tf.qx + oy * tf.qy + oz * tf.qz;
+  float cx = -ow * tf.qx + ox * tf.qw - oy * tf.qz + oz * tf.qy;
+  float cy = -ow * tf.qy + oy * tf.qw - oz * tf.qx + ox * tf.qz;
+  float cz = -ow * tf.qz + oz * tf.qw - ox * tf.qy + oy * tf.qx;
+  float ad = 2.f * atan2f(sqrtf(cx * cx + cy * cy + cz * cz), fabsf(cw));
+  float delta_r = (float)((double)ad * 180.0 / M_PI);
+  double tx = (double)(X[3] * 100.f), ty = (double)(X[4] * 100.f), tz = (double)(X[5] * 100.f);
+  float delta_t = (float)sqrt(tx * tx + ty * ty + tz * tz);
+  st->iter += 1;
+  if ((double)delta_r < delta_r_abort && (double)delta_t < delta_t_abort) st->done = 1;
+}
+
+}  // namespace lio
+
+// ------------------------------------------------------------------------------------------------
+using namespace lio;
+using namespace lio::hm;
+
+struct lio_pim {
+  std::shared_ptr<Preintegration> p;
+};
+
+struct ImuStampedF {
+  double time;
+  float q[4];  // x y z w
+  float p[3];
+};
+
+struct MargPrior {
+  bool valid = false;
+  int n = 0;      // 15*O + 6
+  Mat Hp;         // J^T J
+  Vec bp;         // J^T r0
+  double c0 = 0;  // r0^T r0
+  std::vector<double> x0_pose, x0_sb;  // O x 7, O x 9
+  double x0_ex[7];
+};
+
+struct lio_est {
+  lio_est_config cfg;
+  int W = 0, O = 0, device = 0;
+  cudaStream_t stream = 0;
+  int sm_count = 148;
+  // ---- host window state
+  std::vector<V3> Ps, Vs, Bas, Bgs;
+  std::vector<M3> Rs;
+  std::vector<std::shared_ptr<Preintegration>> pre;
+  std::shared_ptr<Preintegration> tmp_pre;
+  ImuNoise noise;
+  V3 acc_last, gyr_last, g_vec;
+  bool first_imu = false;
+  float tlb_q[4] = {0, 0, 0, 1}, tlb_p[3] = {0, 0, -0.1f};  // transform_lb_ (Twist<float>)
+  std::vector<ImuStampedF> imu_stamped;
+  std::vector<std::vector<double>> para_pose, para_sb;
+  double para_ex[7];
+  MargPrior prior;
+  bool convergence_flag = false, init_local_map = false;
+  int extrinsic_stage = 1;
+  bool ex_constant = false;
+  // ---- device
+  std::vector<float4 *> slot_ptr;    // physical slots
+  std::vector<int> slot_of;          // logical frame -> physical slot
+  int *d_slot_n = nullptr;           // counts per physical slot
+  std::vector<int> size_surf_stack;  // host mirror of each frame's own size (logical)
+  int *d_own_n = nullptr;            // device: own size per physical slot (for SlideWindow's skip)
+  int slot_cap = 0;
+  float4 *d_scan = nullptr, *d_local = nullptr, *d_map = nullptr, *d_tmp = nullptr;
+  int local_cap = 0;
+  int *d_counts = nullptr;  // [0] scan n [1] local n [2] map n [3] tmp n
+  VoxelGrid vg;
+  CellHash hash;
+  KnnWork knn;
+  std::vector<FeatureOut> feats;  // logical frame index
+  int *d_feat_counts = nullptr;   // W+1
+  TransformF *d_tf = nullptr;     // W+1
+  TransformF *h_tf = nullptr;     // pinned
+  AsmWork asmw;
+  double *h_S = nullptr;    // pinned kMaxOpt*kAsmStride
+  int *h_counts = nullptr;  // pinned
+  OdomState *d_odom = nullptr;
+  double *d_odom_partial = nullptr;
+  // ---- sharding
+  int rank = 0, world = 1;
+  lio_allreduce_fn allreduce = nullptr;
+  void *allreduce_user = nullptr;
+  // ---- results / stats
+  std::vector<int> h_feat_n;
+  int h_map_n = 0;
+  std::vector<TransformF> local_tf;
+  DoglegSummary summary;
+  double cost_pim = 0, cost_ppp = 0, cost_marg = 0;
+  bool turn_off = true;
+  int odom_iters = 0;
+  double t_build = 0, t_feat = 0, t_solve = 0, t_marg = 0, t_total = 0;
+  int launches = 0;
+  Mat H0;
+  Vec g0;
+  double cost0 = 0;
+  bool have_H0 = false;
+  // cached lidar reduction for the current parameter values
+  bool S_valid = false;
+};
+
+static Tw tlb_double(const lio_est *e) {
+  return Tw(Q(e->tlb_q[3], e->tlb_q[0], e->tlb_q[1], e->tlb_q[2]), V3(e->tlb_p[0], e->tlb_p[1], e->tlb_p[2]));
+}
+
+static Tw lidar_pose(const V3 &P, const M3 &R, const Tw &tlb) {  // Estimator.cc:1387-1390
+  Q rot = fromR(R * toR(inverse(tlb.rot)));
+  V3 pos = P - rotate(rot, tlb.pos);
+  return Tw(rot, pos);
+}
+
+// Twist<double> -> cast<float>() -> transform(): float quaternion normalised in float, float matrix
+struct AffineF { float R[9]; float t[3]; TransformF tf; };
+static AffineF to_affine_f(const Tw &t) {
+  AffineF a;
+  float qx = (float)t.rot.x, qy = (float)t.rot.y, qz = (float)t.rot.z, qw = (float)t.rot.w;
+  float n = std::sqrt(qx * qx + qy * qy + qz * qz + qw * qw);
+  qx /= n; qy /= n; qz /= n; qw /= n;
+  const float tx = 2.f * qx, ty = 2.f * qy, tz = 2.f * qz;
+  const float twx = tx * qw, twy = ty * qw, twz = tz * qw, txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const float tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  a.R[0] = 1.f - (tyy + tzz); a.R[1] = txy - twz; a.R[2] = txz + twy;
+  a.R[3] = txy + twz; a.R[4] = 1.f - (txx + tzz); a.R[5] = tyz - twx;
+  a.R[6] = txz - twy; a.R[7] = tyz + twx; a.R[8] = 1.f - (txx + tyy);
+  a.t[0] = (float)t.pos.x; a.t[1] = (float)t.pos.y; a.t[2] = (float)t.pos.z;
+  // Twist<float>(Affine3f): Quaternionf(linear).normalized()
+  float m[3][3] = {{a.R[0], a.R[1], a.R[2]}, {a.R[3], a.R[4], a.R[5]}, {a.R[6], a.R[7], a.R[8]}};
+  float q[4];
+  float tr = m[0][0] + m[1][1] + m[2][2];
+  if (tr > 0.f) {
+    float s = std::sqrt(tr + 1.0f);
+    q[3] = 0.5f * s;
+    s = 0.5f / s;
+    q[0] = (m[2][1] - m[1][2]) * s; q[1] = (m[0][2] - m[2][0]) * s; q[2] = (m[1][0] - m[0][1]) * s;
+  } else {
+    int i = 0;
+    if (m[1][1] > m[0][0]) i = 1;
+    if (m[2][2] > m[i][i]) i = 2;
+    int j = (i + 1) % 3, k = (j + 1) % 3;
+    float s = std::sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0f);
+    q[i] = 0.5f * s;
+    s = 0.5f / s;
+    q[3] = (m[k][j] - m[j][k]) * s;
+    q[j] = (m[j][i] + m[i][j]) * s;
+    q[k] = (m[k][i] + m[i][k]) * s;
+  }
+  float qn = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  a.tf.qx = q[0] / qn; a.tf.qy = q[1] / qn; a.tf.qz = q[2] / qn; a.tf.qw = q[3] / qn;
+  a.tf.px = a.t[0]; a.tf.py = a.t[1]; a.tf.pz = a.t[2];
+  return a;
+}
+
+template <typename T> static void push_shift(std::vector<T> &v, T x) { v.erase(v.begin()); v.push_back(x); }
+
+#define EST_CUDA(expr) LIO_CUDA_OK(expr)
+
+// ---- creation -----------------------------------------------------------------------------------
+extern "C" void lio_est_default_config(lio_est_config *c) {
+  c->window_size = 10; c->opt_window_size = 10;
+  c->min_match_sq_dis = 1.0f; c->min_plane_dis = 0.2f; c->surf_filter_size = 0.4f;
+  c->keep_features = 0; c->estimate_extrinsic = 1; c->opt_extrinsic = 1;
+  c->imu_factor = 1; c->point_distance_factor = 1; c->prior_factor = 0; c->marginalization_factor = 1;
+  c->enable_deskew = 1; c->cutoff_deskew = 1;
+  c->acc_n = 0.2; c->gyr_n = 0.02; c->acc_w = 2e-4; c->gyr_w = 2e-5; c->g_norm = 9.805;
+  c->max_num_iterations = 10; c->odom_max_iterations = 10;
+  c->max_frame_points = 1 << 16; c->max_scan_points = 1 << 18;
+}
+
+extern "C" int lio_est_destroy(lio_est *e) {
+  if (!e) return LIO_OK;
+  cudaSetDevice(e->device);
+  for (float4 *p : e->slot_ptr) if (p) cudaFree(p);
+  for (FeatureOut &f : e->feats) { if (f.pts) cudaFree(f.pts); if (f.coef) cudaFree(f.coef); if (f.src) cudaFree(f.src); }
+  void *ptrs[] = {e->d_slot_n, e->d_own_n, e->d_scan, e->d_local, e->d_map, e->d_tmp, e->d_counts, e->d_feat_counts, e->d_tf, e->d_odom, e->d_odom_partial};
+  for (void *p : ptrs) if (p) cudaFree(p);
+  if (e->h_tf) cudaFreeHost(e->h_tf);
+  if (e->h_S) cudaFreeHost(e->h_S);
+  if (e->h_counts) cudaFreeHost(e->h_counts);
+  e->vg.destroy(); e->hash.destroy(); e->knn.destroy(); e->asmw.destroy();
+  delete e;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_stream, lio_est **out) {
+  if (!cfg || !out) return LIO_ERR_INVALID;
+  const int W = cfg->window_size, O = cfg->opt_window_size;
+  if (W < 1 || W >= kMaxWindow || O < 1 || O > W || O > kMaxOpt || cfg->max_frame_points < 16 || cfg->max_scan_points < 16 ||
+      !(cfg->surf_filter_size > 0) || !(cfg->min_match_sq_dis > 0) || cfg->odom_max_iterations < 1) {
+    lio_set_last_error(__FILE__, __LINE__, "lio_est_create: configuration outside supported limits");
+    return LIO_ERR_INVALID;
+  }
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  lio_est *e = new (std::nothrow) lio_est();
+  if (!e) return LIO_ERR_INVALID;
+  e->cfg = *cfg; e->W = W; e->O = O; e->device = device; e->stream = (cudaStream_t)cuda_stream;
+  cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+  e->noise.acc_n = cfg->acc_n; e->noise.gyr_n = cfg->gyr_n; e->noise.acc_w = cfg->acc_w; e->noise.gyr_w = cfg->gyr_w; e->noise.g_norm = cfg->g_norm;
+  e->g_vec = V3(0, 0, -cfg->g_norm);
+  e->extrinsic_stage = cfg->estimate_extrinsic;
+  e->Ps.assign(W + 1, V3()); e->Vs.assign(W + 1, V3()); e->Bas.assign(W + 1, V3()); e->Bgs.assign(W + 1, V3());
+  e->Rs.assign(W + 1, M3::I());
+  e->pre.assign(W + 1, nullptr);
+  e->para_pose.assign(O + 1, std::vector<double>(7, 0.0));
+  e->para_sb.assign(O + 1, std::vector<double>(9, 0.0));
+  std::memset(e->para_ex, 0, sizeof(e->para_ex));
+  e->size_surf_stack.assign(W + 1, 0);
+  e->h_feat_n.assign(W + 1, 0);
+  e->local_tf.assign(W + 1, TransformF{0, 0, 0, 1, 0, 0, 0});
+  const int pivot = W - O;
+  e->slot_cap = cfg->max_frame_points * (pivot + 1);
+  e->slot_ptr.assign(W + 1, nullptr);
+  e->slot_of.resize(W + 1);
+  bool ok = true;
+  for (int k = 0; k <= W; ++k) {
+    e->slot_of[k] = k;
+    ok = ok && cudaMalloc(&e->slot_ptr[k], sizeof(float4) * e->slot_cap) == cudaSuccess;
+  }
+  e->local_cap = e->slot_cap + cfg->max_frame_points * (O > 1 ? O - 1 : 1);
+  ok = ok && cudaMalloc(&e->d_slot_n, sizeof(int) * (W + 1)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_own_n, sizeof(int) * (W + 1)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_scan, sizeof(float4) * cfg->max_scan_points) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_local, sizeof(float4) * e->local_cap) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_map, sizeof(float4) * e->local_cap) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_tmp, sizeof(float4) * e->slot_cap) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_counts, sizeof(int) * 8) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_feat_counts, sizeof(int) * (W + 1)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_tf, sizeof(TransformF) * (W + 1)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_odom, sizeof(OdomState)) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_odom_partial, sizeof(double) * 32 * 1024) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&e->h_tf, sizeof(TransformF) * (W + 1)) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&e->h_S, sizeof(double) * kMaxOpt * kAsmStride) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&e->h_counts, sizeof(int) * (W + 16)) == cudaSuccess;
+  int vg_cap = std::max(e->local_cap, cfg->max_scan_points);
+  ok = ok && e->vg.init(vg_cap) == 0;
+  ok = ok && e->hash.init(e->local_cap) == 0;
+  ok = ok && e->knn.init(cfg->max_frame_points) == 0;
+  e->feats.assign(W + 1, FeatureOut());
+  long long total_feat = 0;
+  for (int k = pivot + 1; k <= W && ok; ++k) {
+    int cap = cfg->max_frame_points * ((k == W && cfg->keep_features) ? cfg->odom_max_iterations : 1);
+    FeatureOut &f = e->feats[k];
+    f.cap = cap;
+    f.count = e->d_feat_counts + k;
+    ok = ok && cudaMalloc(&f.pts, sizeof(float4) * cap) == cudaSuccess;
+    ok = ok && cudaMalloc(&f.coef, sizeof(float4) * cap) == cudaSuccess;
+    ok = ok && cudaMalloc(&f.src, sizeof(int) * cap) == cudaSuccess;
+    total_feat += cap;
+  }
+  ok = ok && e->asmw.init((int)std::min<long long>(total_feat, 1ll << 30)) == 0;
+  if (ok) {
+    ok = ok && cudaMemset(e->d_slot_n, 0, sizeof(int) * (W + 1)) == cudaSuccess;
+    ok = ok && cudaMemset(e->d_own_n, 0, sizeof(int) * (W + 1)) == cudaSuccess;
+    ok = ok && cudaMemset(e->d_feat_counts, 0, sizeof(int) * (W + 1)) == cudaSuccess;
+    ok = ok && cudaMemset(e->d_counts, 0, sizeof(int) * 8) == cudaSuccess;
+  }
+  if (!ok) {
+    lio_set_last_error(__FILE__, __LINE__, "lio_est_create: device allocation failed");
+    lio_est_destroy(e);
+    return LIO_ERR_CUDA;
+  }
+  *out = e;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_set_extrinsic(lio_est *e, const float tf7[7]) {
+  if (!e || !tf7) return LIO_ERR_INVALID;
+  for (int k = 0; k < 4; ++k) e->tlb_q[k] = tf7[k];
+  for (int k = 0; k < 3; ++k) e->tlb_p[k] = tf7[4 + k];
+  return LIO_OK;
+}
+extern "C" int lio_est_get_extrinsic(lio_est *e, float tf7[7]) {
+  if (!e || !tf7) return LIO_ERR_INVALID;
+  for (int k = 0; k < 4; ++k) tf7[k] = e->tlb_q[k];
+  for (int k = 0; k < 3; ++k) tf7[4 + k] = e->tlb_p[k];
+  return LIO_OK;
+}
+
+extern "C" int lio_est_init_frame(lio_est *e, int k, const double s[16], const float *surf_ds, int n, lio_pim *pim) {
+  if (!e || !s || k < 0 || k >= e->W || n < 0 || (n > 0 && !surf_ds)) return LIO_ERR_INVALID;
+  if (n > e->cfg.max_frame_points) return LIO_ERR_CAPACITY;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  e->Ps[k] = V3(s); e->Rs[k] = toR(normalized(Q(s[6], s[3], s[4], s[5]))); e->Vs[k] = V3(s + 7); e->Bas[k] = V3(s + 10); e->Bgs[k] = V3(s + 13);
+  const int slot = e->slot_of[k + 1];  // one slot to the right: the first process_scan pushes (see oracle InitFrame)
+  if (n > 0) LIO_CUDA_OK(cudaMemcpyAsync(e->slot_ptr[slot], surf_ds, sizeof(float4) * n, cudaMemcpyHostToDevice, e->stream));
+  LIO_CUDA_OK(cudaMemcpyAsync(e->d_slot_n + slot, &n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  LIO_CUDA_OK(cudaMemcpyAsync(e->d_own_n + slot, &n, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  LIO_CUDA_OK(cudaStreamSynchronize(e->stream));
+  e->size_surf_stack[k + 1] = n;
+  e->pre[k + 1] = pim ? pim->p : nullptr;
+  if (pim) delete pim;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_finish_init(lio_est *e, const double a[3], const double g[3]) {
+  if (!e || !a || !g) return LIO_ERR_INVALID;
+  const int W = e->W;
+  e->Ps[W] = e->Ps[W - 1]; e->Rs[W] = e->Rs[W - 1]; e->Vs[W] = e->Vs[W - 1]; e->Bas[W] = e->Bas[W - 1]; e->Bgs[W] = e->Bgs[W - 1];
+  e->acc_last = V3(a); e->gyr_last = V3(g);
+  e->first_imu = true;
+  e->tmp_pre = std::make_shared<Preintegration>(e->acc_last, e->gyr_last, e->Bas[W], e->Bgs[W], e->noise);
+  e->imu_stamped.clear();
+  return LIO_OK;
+}
+
+extern "C" int lio_est_process_imu(lio_est *e, double dt, const double a[3], const double g[3], double stamp) {
+  if (!e || !a || !g) return LIO_ERR_INVALID;
+  const V3 acc(a), gyr(g);
+  if (!e->first_imu) { e->first_imu = true; e->acc_last = acc; e->gyr_last = gyr; }
+  if (!e->tmp_pre) return LIO_ERR_INVALID;
+  const int j = e->W;
+  e->tmp_pre->push_back(dt, acc, gyr);
+  const V3 un_acc_0 = e->Rs[j] * (e->acc_last - e->Bas[j]) + e->g_vec;
+  const V3 un_gyr = 0.5 * (e->gyr_last + gyr) - e->Bgs[j];
+  e->Rs[j] = e->Rs[j] * toR(deltaQ(un_gyr * dt));
+  const V3 un_acc_1 = e->Rs[j] * (acc - e->Bas[j]) + e->g_vec;
+  const V3 un_acc = 0.5 * (un_acc_0 + un_acc_1);
+  e->Ps[j] = e->Ps[j] + dt * e->Vs[j] + 0.5 * dt * dt * un_acc;
+  e->Vs[j] = e->Vs[j] + dt * un_acc;
+  ImuStampedF tt;
+  tt.time = stamp;
+  tt.p[0] = (float)e->Ps[j].x; tt.p[1] = (float)e->Ps[j].y; tt.p[2] = (float)e->Ps[j].z;
+  {  // Quaternionf(Rs.cast<float>())
+    M3 Rf;
+    for (int a2 = 0; a2 < 3; ++a2) for (int b = 0; b < 3; ++b) Rf(a2, b) = (double)(float)e->Rs[j](a2, b);
+    Q q = fromR(Rf);
+    tt.q[0] = (float)q.x; tt.q[1] = (float)q.y; tt.q[2] = (float)q.z; tt.q[3] = (float)q.w;
+  }
+  e->imu_stamped.push_back(tt);
+  if (e->imu_stamped.size() > 100) e->imu_stamped.erase(e->imu_stamped.begin());
+  e->acc_last = acc; e->gyr_last = gyr;
+  return LIO_OK;
+}
+
+// ---- parameter <-> state ---------------------------------------------------------------------------
+static void vector_to_double(lio_est *e) {  // Estimator.cc:2440-2478
+  const int pivot = e->W - e->O;
+  for (int i = 0, oi = pivot; i <= e->O; ++i, ++oi) {
+    double *pp = e->para_pose[i].data(), *sb = e->para_sb[i].data();
+    pp[0] = e->Ps[oi].x; pp[1] = e->Ps[oi].y; pp[2] = e->Ps[oi].z;
+    Q q = fromR(e->Rs[oi]);
+    pp[3] = q.x; pp[4] = q.y; pp[5] = q.z; pp[6] = q.w;
+    for (int k = 0; k < 3; ++k) { sb[k] = e->Vs[oi][k]; sb[3 + k] = e->Bas[oi][k]; sb[6 + k] = e->Bgs[oi][k]; }
+  }
+  e->para_ex[0] = e->tlb_p[0]; e->para_ex[1] = e->tlb_p[1]; e->para_ex[2] = e->tlb_p[2];
+  e->para_ex[3] = e->tlb_q[0]; e->para_ex[4] = e->tlb_q[1]; e->para_ex[5] = e->tlb_q[2]; e->para_ex[6] = e->tlb_q[3];
+  e->S_valid = false;
+}
+
+static void double_to_vector(lio_est *e) {  // Estimator.cc:2479-2568
+  const int pivot = e->W - e->O, O = e->O;
+  const V3 origin_P0 = e->Ps[pivot];
+  const V3 origin_R0 = R2ypr(e->Rs[pivot]);
+  auto qpose = [&](int i) { const double *p = e->para_pose[i].data(); return toR(normalized(Q(p[6], p[3], p[4], p[5]))); };
+  const V3 origin_R00 = R2ypr(qpose(0));
+  const double y_diff = origin_R0.x - origin_R00.x;
+  M3 rot_diff = ypr2R(V3(y_diff, 0, 0));
+  if (std::fabs(std::fabs(origin_R0.y) - 90) < 1.0 || std::fabs(std::fabs(origin_R00.y) - 90) < 1.0) rot_diff = e->Rs[pivot] * T(qpose(0));
+  {
+    Tw trans_pivot(fromR(e->Rs[pivot]), e->Ps[pivot]);
+    Tw trans_opt_pivot(fromR(rot_diff * qpose(0)), origin_P0);
+    for (int idx = 0; idx < pivot; ++idx) {
+      Tw trans_idx(fromR(e->Rs[idx]), e->Ps[idx]);
+      Tw o = tw_mul(tw_mul(trans_opt_pivot, tw_inverse(trans_pivot)), trans_idx);
+      e->Ps[idx] = o.pos;
+      e->Rs[idx] = toR(normalized(o.rot));
+    }
+  }
+  for (int i = 0, oi = pivot; i <= O; ++i, ++oi) {
+    const double *pp = e->para_pose[i].data(), *p0 = e->para_pose[0].data(), *sb = e->para_sb[i].data();
+    e->Rs[oi] = rot_diff * qpose(i);
+    e->Ps[oi] = rot_diff * V3(pp[0] - p0[0], pp[1] - p0[1], pp[2] - p0[2]) + origin_P0;
+    e->Vs[oi] = rot_diff * V3(sb[0], sb[1], sb[2]);
+    e->Bas[oi] = V3(sb[3], sb[4], sb[5]);
+    e->Bgs[oi] = V3(sb[6], sb[7], sb[8]);
+  }
+  e->tlb_p[0] = (float)e->para_ex[0]; e->tlb_p[1] = (float)e->para_ex[1]; e->tlb_p[2] = (float)e->para_ex[2];
+  e->tlb_q[0] = (float)e->para_ex[3]; e->tlb_q[1] = (float)e->para_ex[4]; e->tlb_q[2] = (float)e->para_ex[5]; e->tlb_q[3] = (float)e->para_ex[6];
+}
+
+// ---- stage B orchestration -----------------------------------------------------------------------
+static bool owns_frame(const lio_est *e, int idx) {  // idx: logical frame > pivot
+  const int pivot = e->W - e->O;
+  return ((idx - pivot - 1) % e->world) == e->rank;
+}
+
+static int build_local_map(lio_est *e) {
+  const int W = e->W, O = e->O, pivot = W - O;
+  cudaStream_t st = e->stream;
+  const double t0 = now_s();
+  const Tw tlb = tlb_double(e);
+  const Tw transform_pivot = lidar_pose(e->Ps[pivot], e->Rs[pivot], tlb);
+  const Tw pivot_inv = tw_inverse(transform_pivot);
+  if (!e->init_local_map) {  // :1409-1441 merge frames 0..pivot into the pivot cloud
+    if (pivot > 0) {
+      ConcatParams cp;
+      std::memset(&cp, 0, sizeof(cp));
+      cp.nsrc = pivot + 1;
+      for (int i = 0; i <= pivot; ++i) {
+        AffineF a = to_affine_f(tw_mul(pivot_inv, lidar_pose(e->Ps[i], e->Rs[i], tlb)));
+        cp.src[i] = e->slot_ptr[e->slot_of[i]];
+        cp.n[i] = e->d_slot_n + e->slot_of[i];
+        std::memcpy(cp.R[i], a.R, sizeof(a.R)); std::memcpy(cp.t[i], a.t, sizeof(a.t));
+        cp.tag[i] = -1.f;  // keep intensity
+      }
+      k_concat<<<std::max(1, std::min(e->sm_count * 2, (e->slot_cap + 255) / 256)), 256, 0, st>>>(cp, e->d_tmp, e->d_counts + 3, e->slot_cap);
+      ++e->launches;
+      const int ps = e->slot_of[pivot];
+      EST_CUDA(cudaMemcpyAsync(e->slot_ptr[ps], e->d_tmp, sizeof(float4) * e->slot_cap, cudaMemcpyDeviceToDevice, st));
+      EST_CUDA(cudaMemcpyAsync(e->d_slot_n + ps, e->d_counts + 3, sizeof(int), cudaMemcpyDeviceToDevice, st));
+    }
+    e->init_local_map = true;
+  }
+  ConcatParams cp;
+  std::memset(&cp, 0, sizeof(cp));
+  int ns = 0;
+  for (int i = 0; i <= W; ++i) {
+    AffineF a = to_affine_f(tw_mul(pivot_inv, lidar_pose(e->Ps[i], e->Rs[i], tlb)));
+    e->local_tf[i] = a.tf;
+    e->h_tf[i] = a.tf;
+    if (i < pivot || i == W) continue;
+    cp.src[ns] = e->slot_ptr[e->slot_of[i]];
+    cp.n[ns] = e->d_slot_n + e->slot_of[i];
+    if (i == pivot) cp.identity[ns] = 1;
+    else { std::memcpy(cp.R[ns], a.R, sizeof(a.R)); std::memcpy(cp.t[ns], a.t, sizeof(a.t)); cp.tag[ns] = (float)i; }
+    ++ns;
+  }
+  cp.nsrc = ns;
+  EST_CUDA(cudaMemcpyAsync(e->d_tf, e->h_tf, sizeof(TransformF) * (W + 1), cudaMemcpyHostToDevice, st));
+  k_concat<<<std::max(1, std::min(e->sm_count * 4, (e->local_cap + 255) / 256)), 256, 0, st>>>(cp, e->d_local, e->d_counts + 1, e->local_cap);
+  ++e->launches;
+  int rc = e->vg.run(e->d_local, e->d_counts + 1, e->local_cap, e->cfg.surf_filter_size, e->d_map, e->d_counts + 2, nullptr, st, &e->launches);
+  if (rc != LIO_OK) return rc;
+  const float cell = std::sqrt(e->cfg.min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
+  rc = e->hash.build(e->d_map, e->d_counts + 2, e->local_cap, cell, st, &e->launches);
+  if (rc != LIO_OK) return rc;
+  e->t_build = now_s() - t0;
+  const double t1 = now_s();
+  EST_CUDA(cudaMemsetAsync(e->d_feat_counts, 0, sizeof(int) * (W + 1), st));
+  for (int idx = pivot + 1; idx <= W; ++idx) {
+    if (!owns_frame(e, idx)) continue;
+    const int slot = e->slot_of[idx];
+    if (idx != W || !e->cfg.imu_factor) {
+      rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
+                                  e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], 0, nullptr, e->knn, st, &e->launches);
+      if (rc != LIO_OK) return rc;
+    } else {
+      EST_CUDA(cudaMemsetAsync(e->d_odom, 0, sizeof(OdomState), st));
+      const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
+      for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
+        rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
+                                    e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], e->cfg.keep_features ? 1 : 0,
+                                    &e->d_odom->done, e->knn, st, &e->launches);
+        if (rc != LIO_OK) return rc;
+        k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
+        k_odom_solve<<<1, 32, 0, st>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
+        e->launches += 2;
+      }
+    }
+  }
+  // one synchronisation: feature counts, map size, odom iterations
+  EST_CUDA(cudaMemcpyAsync(e->h_counts, e->d_feat_counts, sizeof(int) * (W + 1), cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 1, e->d_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 5, &e->d_odom->iter, sizeof(int), cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaMemcpyAsync(e->h_tf + W, e->d_tf + W, sizeof(TransformF), cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaStreamSynchronize(st));
+  for (int k = 0; k <= W; ++k) e->h_feat_n[k] = e->h_counts[k];
+  e->h_map_n = e->h_counts[W + 1 + 2];
+  e->odom_iters = e->h_counts[W + 5];
+  e->local_tf[W] = e->h_tf[W];
+  for (int k = pivot + 1; k <= W; ++k)
+    if (e->h_feat_n[k] > e->feats[k].cap) { lio_set_last_error(__FILE__, __LINE__, "feature buffer overflow"); return LIO_ERR_CAPACITY; }
+  if (e->h_counts[W + 1 + 1] >= e->local_cap) { lio_set_last_error(__FILE__, __LINE__, "local map capacity exceeded"); return LIO_ERR_CAPACITY; }
+  e->t_feat = now_s() - t1;
+  return LIO_OK;
+}
+
+// ---- stage C: lidar reduction at the current parameter values ------------------------------------
+struct FrameTerms { double R[9], t[3], M[6 * 18]; };
+
+static int eval_lidar(lio_est *e, std::vector<FrameTerms> &ft) {
+  const int O = e->O, pivot = e->W - O;
+  ft.resize(O + 1);
+  AsmParams ap;
+  std::memset(&ap, 0, sizeof(ap));
+  ap.nframes = O;
+  for (int i = 1; i <= O; ++i) {
+    ppp_frame_terms(e->para_pose[0].data(), e->para_pose[i].data(), e->para_ex, ft[i].R, ft[i].t, ft[i].M);
+    AsmFrame &f = ap.f[i - 1];
+    const FeatureOut &fo = e->feats[pivot + i];
+    f.pts = fo.pts; f.coef = fo.coef;
+    f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
+    std::memcpy(f.R, ft[i].R, sizeof(f.R)); std::memcpy(f.t, ft[i].t, sizeof(f.t));
+  }
+  if (e->S_valid) return LIO_OK;
+  asm_plan(ap, e->sm_count);
+  int rc = asm_launch(ap, e->asmw, e->stream, &e->launches);
+  if (rc != LIO_OK) return rc;
+  if (e->world > 1 && e->allreduce) {
+    rc = e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride);
+    if (rc != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
+  }
+  EST_CUDA(cudaMemcpyAsync(e->h_S, e->asmw.out, sizeof(double) * O * kAsmStride, cudaMemcpyDeviceToHost, e->stream));
+  EST_CUDA(cudaStreamSynchronize(e->stream));
+  e->S_valid = true;
+  return LIO_OK;
+}
+
+// tangent layout: [pose_k(6) sb_k(9)] k=0..O, then ex(6)
+static inline int off_pose(int k) { return 15 * k; }
+static inline int off_sb(int k) { return 15 * k + 6; }
+
+// adds M^T S M into H/g over (pose_0, pose_i, ex) column offsets o0, oi, oe (oe < 0: extrinsic not a variable)
+static void add_lidar_block(const double *S /*kAsmStride*/, const double *M /*6x18*/, Mat *H, Vec *g, int o0, int oi, int oe) {
+  double Sg[6][6], Sr[6];
+  {
+    int k = 0;
+    for (int a = 0; a < 7; ++a) for (int b = a; b < 7; ++b) { double v = S[k++]; if (b < 6) { Sg[a][b] = v; Sg[b][a] = v; } else if (a < 6) Sr[a] = v; }
+  }
+  double SM[6][18];
+  for (int a = 0; a < 6; ++a) for (int c = 0; c < 18; ++c) { double s = 0; for (int b = 0; b < 6; ++b) s += Sg[a][b] * M[b * 18 + c]; SM[a][c] = s; }
+  const int offs[3] = {o0, oi, oe};
+  for (int bi = 0; bi < 3; ++bi) {
+    if (offs[bi] < 0) continue;
+    for (int a = 0; a < 6; ++a) {
+      const int ca = bi * 6 + a;
+      double gs = 0;
+      for (int k = 0; k < 6; ++k) gs += M[k * 18 + ca] * Sr[k];
+      (*g)[offs[bi] + a] += gs;
+      if (!H) continue;
+      for (int bj = 0; bj < 3; ++bj) {
+        if (offs[bj] < 0) continue;
+        for (int b = 0; b < 6; ++b) {
+          const int cb = bj * 6 + b;
+          double s = 0;
+          for (int k = 0; k < 6; ++k) s += M[k * 18 + ca] * SM[k][cb];
+          (*H)(offs[bi] + a, offs[bj] + b) += s;
+        }
+      }
+    }
+  }
+}
+
+static void prior_dx(const lio_est *e, const MargPrior &pr, Vec &dx) {  // MarginalizationFactor::Evaluate :347-372
+  const int O = e->O;
+  dx.assign(pr.n, 0.0);
+  auto pose_dx = [&](const double *x, const double *x0, double *out) {
+    for (int k = 0; k < 3; ++k) out[k] = x[k] - x0[k];
+    Q q0(x0[6], x0[3], x0[4], x0[5]), q(x[6], x[3], x[4], x[5]);
+    Q dq = inverse(q0) * q;
+    Q dn = normalized(dq);
+    double s = dq.w < 0 ? -2.0 : 2.0;
+    out[3] = s * dn.x; out[4] = s * dn.y; out[5] = s * dn.z;
+  };
+  for (int k = 0; k < O; ++k) {
+    pose_dx(e->para_pose[k].data(), &pr.x0_pose[7 * k], &dx[15 * k]);
+    for (int a = 0; a < 9; ++a) dx[15 * k + 6 + a] = e->para_sb[k][a] - pr.x0_sb[9 * k + a];
+  }
+  pose_dx(e->para_ex, pr.x0_ex, &dx[15 * O]);
+}
+
+// Full linearisation at the current parameter values.  n_t = tangent dim (ex block present iff !ex_constant).
+static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, double *c_ppp, double *c_marg) {
+  const int O = e->O, pivot = e->W - O;
+  const bool ex_free = !e->ex_constant;
+  const int n = 15 * (O + 1) + (ex_free ? 6 : 0);
+  const int oe = ex_free ? 15 * (O + 1) : -1;
+  if (H.r != n) H = Mat(n, n); else H.zero();
+  g.assign(n, 0.0);
+  std::vector<FrameTerms> ft;
+  if (eval_lidar(e, ft) != LIO_OK) return false;
+  double cp = 0, ci = 0, cm = 0;
+  if (e->cfg.point_distance_factor) {
+    for (int i = 1; i <= O; ++i) {
+      const double *S = e->h_S + (i - 1) * kAsmStride;
+      cp += 0.5 * S[28];
+      add_lidar_block(S, ft[i].M, &H, &g, off_pose(0), off_pose(i), oe);
+    }
+  }
+  if (e->cfg.imu_factor) {
+    for (int i = 0; i < O; ++i) {
+      const int j = i + 1;
+      Preintegration &pim = *e->pre[pivot + j];
+      if (pim.sum_dt > 10.0) continue;
+      double r[15], Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
+      imu_factor_evaluate(pim, e->para_pose[i].data(), e->para_sb[i].data(), e->para_pose[j].data(), e->para_sb[j].data(), r, Ji, Jsi, Jj, Jsj);
+      double J[15][30];
+      for (int a = 0; a < 15; ++a) {
+        for (int c = 0; c < 6; ++c) { J[a][c] = Ji[a][c]; J[a][15 + c] = Jj[a][c]; }
+        for (int c = 0; c < 9; ++c) { J[a][6 + c] = Jsi[a][c]; J[a][21 + c] = Jsj[a][c]; }
+      }
+      const int base = 15 * i;  // pose_i, sb_i, pose_j, sb_j are contiguous in the tangent layout
+      for (int a = 0; a < 30; ++a) {
+        double gs = 0;
+        for (int k = 0; k < 15; ++k) gs += J[k][a] * r[k];
+        g[base + a] += gs;
+        for (int b = 0; b < 30; ++b) {
+          double s = 0;
+          for (int k = 0; k < 15; ++k) s += J[k][a] * J[k][b];
+          H(base + a, base + b) += s;
+        }
+      }
+      double sq = 0;
+      for (int k = 0; k < 15; ++k) sq += r[k] * r[k];
+      ci += 0.5 * sq;
+    }
+  }
+  if (e->cfg.marginalization_factor && e->prior.valid) {
+    const MargPrior &pr = e->prior;
+    Vec dx;
+    prior_dx(e, pr, dx);
+    Vec Hdx = mul(pr.Hp, dx);
+    cm = 0.5 * (pr.c0 + 2.0 * vdot(pr.bp, dx) + vdot(dx, Hdx));
+    auto tmap = [&](int pi) { return pi < 15 * O ? pi : (ex_free ? 15 * (O + 1) + (pi - 15 * O) : -1); };
+    for (int a = 0; a < pr.n; ++a) {
+      const int ta = tmap(a);
+      if (ta < 0) continue;
+      g[ta] += Hdx[a] + pr.bp[a];
+      const double *row = &pr.Hp.d[(size_t)a * pr.n];
+      for (int b = 0; b < pr.n; ++b) {
+        const int tb = tmap(b);
+        if (tb >= 0) H(ta, tb) += row[b];
+      }
+    }
+  }
+  double cprior = 0;
+  if (e->cfg.prior_factor && ex_free) {  // constant extrinsic: the block is dropped from the reduced program
+    const Tw tt = tlb_double(e);
+    double r[6], J[6][6];
+    prior_factor_evaluate(tt.pos, tt.rot, e->para_ex, r, J);
+    for (int a = 0; a < 6; ++a) {
+      double gs = 0;
+      for (int k = 0; k < 6; ++k) gs += J[k][a] * r[k];
+      g[oe + a] += gs;
+      for (int b = 0; b < 6; ++b) { double s = 0; for (int k = 0; k < 6; ++k) s += J[k][a] * J[k][b]; H(oe + a, oe + b) += s; }
+    }
+    for (int k = 0; k < 6; ++k) cprior += 0.5 * r[k] * r[k];
+  }
+  cost = cp + ci + cm + cprior;
+  if (c_pim) *c_pim = ci;
+  if (c_ppp) *c_ppp = cp;
+  if (c_marg) *c_marg = cm;
+  return std::isfinite(cost);
+}
+
+// ---- marginalisation (MarginalizationInfo::PreMarginalize / Marginalize, MarginalizationFactor.cc:132-311)
+static int marginalize(lio_est *e) {
+  const int O = e->O, pivot = e->W - O;
+  const int m = 15, nr = 15 * O + 6, pos = m + nr;
+  // layout: [pose_0 (6), sb_0 (9) | pose_1, sb_1, ..., pose_O, sb_O, ex]
+  Mat A(pos, pos);
+  Vec b(pos, 0.0);
+  auto idx_pose = [&](int k) { return k == 0 ? 0 : m + 15 * (k - 1); };
+  auto idx_sb = [&](int k) { return k == 0 ? 6 : m + 15 * (k - 1) + 6; };
+  const int idx_ex = m + 15 * O;
+  if (e->prior.valid) {  // previous prior re-wrapped with drop_set {pose_0, sb_0}
+    const MargPrior &pr = e->prior;
+    Vec dx;
+    prior_dx(e, pr, dx);
+    Vec Hdx = mul(pr.Hp, dx);
+    auto map = [&](int pi) {  // prior canonical index -> A index
+      if (pi >= 15 * O) return idx_ex + (pi - 15 * O);
+      int k = pi / 15, a = pi % 15;
+      return (a < 6 ? idx_pose(k) + a : idx_sb(k) + (a - 6));
+    };
+    for (int a = 0; a < pr.n; ++a) {
+      const int ia = map(a);
+      b[ia] += Hdx[a] + pr.bp[a];
+      for (int c = 0; c < pr.n; ++c) A(ia, map(c)) += pr.Hp(a, c);
+    }
+  }
+  if (e->cfg.imu_factor && e->pre[pivot + 1]->sum_dt < 10.0) {
+    double r[15], Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
+    imu_factor_evaluate(*e->pre[pivot + 1], e->para_pose[0].data(), e->para_sb[0].data(), e->para_pose[1].data(), e->para_sb[1].data(), r, Ji, Jsi, Jj, Jsj);
+    double J[15][30];
+    int col[30];
+    for (int c = 0; c < 6; ++c) { col[c] = idx_pose(0) + c; col[15 + c] = idx_pose(1) + c; }
+    for (int c = 0; c < 9; ++c) { col[6 + c] = idx_sb(0) + c; col[21 + c] = idx_sb(1) + c; }
+    for (int a = 0; a < 15; ++a) {
+      for (int c = 0; c < 6; ++c) { J[a][c] = Ji[a][c]; J[a][15 + c] = Jj[a][c]; }
+      for (int c = 0; c < 9; ++c) { J[a][6 + c] = Jsi[a][c]; J[a][21 + c] = Jsj[a][c]; }
+    }
+    for (int a = 0; a < 30; ++a) {
+      double gs = 0;
+      for (int k = 0; k < 15; ++k) gs += J[k][a] * r[k];
+      b[col[a]] += gs;
+      for (int c = 0; c < 30; ++c) { double s = 0; for (int k = 0; k < 15; ++k) s += J[k][a] * J[k][c]; A(col[a], col[c]) += s; }
+    }
+  }
+  if (e->cfg.point_distance_factor) {
+    std::vector<FrameTerms> ft;
+    int rc = eval_lidar(e, ft);
+    if (rc != LIO_OK) return rc;
+    for (int i = 1; i <= O; ++i) add_lidar_block(e->h_S + (i - 1) * kAsmStride, ft[i].M, &A, &b, idx_pose(0), idx_pose(i), idx_ex);
+  }
+  // Schur complement with the eigen pseudo-inverse (eps = 1e-8)
+  const double eps = 1e-8;
+  Mat Amm(m, m);
+  for (int r = 0; r < m; ++r) for (int c = 0; c < m; ++c) Amm(r, c) = 0.5 * (A(r, c) + A(c, r));
+  Vec ev;
+  Mat evec;
+  sym_eigen(Amm, ev, evec);
+  Mat Amm_inv(m, m);
+  for (int r = 0; r < m; ++r)
+    for (int c = 0; c < m; ++c) { double s = 0; for (int k = 0; k < m; ++k) s += evec(r, k) * (ev[k] > eps ? 1.0 / ev[k] : 0.0) * evec(c, k); Amm_inv(r, c) = s; }
+  Mat Tm(nr, m);  // Arm * Amm_inv
+  for (int r = 0; r < nr; ++r) for (int c = 0; c < m; ++c) { double s = 0; for (int k = 0; k < m; ++k) s += A(m + r, k) * Amm_inv(k, c); Tm(r, c) = s; }
+  Mat A2(nr, nr);
+  Vec b2(nr);
+  for (int r = 0; r < nr; ++r) {
+    for (int c = 0; c < nr; ++c) { double s = 0; for (int k = 0; k < m; ++k) s += Tm(r, k) * A(k, m + c); A2(r, c) = A(m + r, m + c) - s; }
+    double s = 0;
+    for (int k = 0; k < m; ++k) s += Tm(r, k) * b[k];
+    b2[r] = b[m + r] - s;
+  }
+  Vec ev2;
+  Mat V2;
+  sym_eigen(A2, ev2, V2);
+  MargPrior np;
+  np.valid = true;
+  np.n = nr;
+  np.Hp = Mat(nr, nr);
+  np.bp.assign(nr, 0.0);
+  np.c0 = 0;
+  // Hp = V S V^T, bp = V_kept V_kept^T b, c0 = sum (v^T b)^2 / lambda over kept eigenpairs
+  std::vector<int> kept;
+  for (int k = 0; k < nr; ++k) if (ev2[k] > eps) kept.push_back(k);
+  Vec vb(nr, 0.0);
+  for (int k : kept) { double s = 0; for (int r = 0; r < nr; ++r) s += V2(r, k) * b2[r]; vb[k] = s; np.c0 += s * s / ev2[k]; }
+  for (int r = 0; r < nr; ++r) {
+    double sb = 0;
+    for (int k : kept) sb += V2(r, k) * vb[k];
+    np.bp[r] = sb;
+    for (int c = r; c < nr; ++c) {
+      double s = 0;
+      for (int k : kept) s += V2(r, k) * ev2[k] * V2(c, k);
+      np.Hp(r, c) = s; np.Hp(c, r) = s;
+    }
+  }
+  np.x0_pose.resize(7 * O); np.x0_sb.resize(9 * O);
+  for (int k = 1; k <= O; ++k) {  // addr_shift: block i -> i-1 in the next window
+    std::memcpy(&np.x0_pose[7 * (k - 1)], e->para_pose[k].data(), 7 * sizeof(double));
+    std::memcpy(&np.x0_sb[9 * (k - 1)], e->para_sb[k].data(), 9 * sizeof(double));
+  }
+  std::memcpy(np.x0_ex, e->para_ex, sizeof(np.x0_ex));
+  e->prior = np;
+  return LIO_OK;
+}
+
+static int solve_optimization(lio_est *e) {
+  const int O = e->O;
+  e->turn_off = true;
+  int rc = build_local_map(e);
+  if (rc != LIO_OK) return rc;
+  const double t0 = now_s();
+  e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
+  vector_to_double(e);
+  // residuals before optimisation + gates (:1924-1985)
+  Mat H;
+  Vec g;
+  double cost;
+  if (!linearize(e, H, g, cost, &e->cost_pim, &e->cost_ppp, &e->cost_marg)) { lio_set_last_error(__FILE__, __LINE__, "non-finite cost at the initial point"); return LIO_ERR_NUMERIC; }
+  if (e->cfg.imu_factor) e->turn_off = e->cost_pim > 1e3;
+  {
+    const double ratio = e->cost_marg / (e->cost_ppp + e->cost_pim);
+    if (!e->convergence_flag && !e->turn_off && ratio <= 2 && ratio != 0) e->convergence_flag = true;
+    if (!e->convergence_flag) {
+      e->ex_constant = true;
+      e->prior.valid = false;
+    }
+  }
+  DoglegProblem P;
+  const bool ex_free = !e->ex_constant;
+  P.n = 15 * (O + 1) + (ex_free ? 6 : 0);
+  bool first = true;
+  P.linearize = [&](Mat &Hh, Vec &gg, double &c) {
+    bool ok = linearize(e, Hh, gg, c, nullptr, nullptr, nullptr);
+    if (ok && first) { e->H0 = Hh; e->g0 = gg; e->cost0 = c; e->have_H0 = true; first = false; }
+    return ok;
+  };
+  P.get_state = [&](Vec &x) {
+    x.clear();
+    for (int k = 0; k <= O; ++k) { x.insert(x.end(), e->para_pose[k].begin(), e->para_pose[k].end()); x.insert(x.end(), e->para_sb[k].begin(), e->para_sb[k].end()); }
+    if (ex_free) x.insert(x.end(), e->para_ex, e->para_ex + 7);
+  };
+  P.set_state = [&](const Vec &x) {
+    for (int k = 0; k <= O; ++k) { std::memcpy(e->para_pose[k].data(), &x[16 * k], 7 * sizeof(double)); std::memcpy(e->para_sb[k].data(), &x[16 * k + 7], 9 * sizeof(double)); }
+    if (ex_free) std::memcpy(e->para_ex, &x[16 * (O + 1)], 7 * sizeof(double));
+    e->S_valid = false;
+  };
+  P.plus = [&](const Vec &x, const Vec &d, Vec &out) {
+    out = x;
+    for (int k = 0; k <= O; ++k) {
+      pose_plus(&x[16 * k], &d[15 * k], &out[16 * k]);
+      for (int a = 0; a < 9; ++a) out[16 * k + 7 + a] = x[16 * k + 7 + a] + d[15 * k + 6 + a];
+    }
+    if (ex_free) pose_plus(&x[16 * (O + 1)], &d[15 * (O + 1)], &out[16 * (O + 1)]);
+  };
+  DoglegOptions opt;
+  opt.max_num_iterations = e->cfg.max_num_iterations;
+  dogleg_solve(opt, P, &e->summary);
+  if (e->summary.termination == 2 && !std::isfinite(e->summary.final_cost)) { lio_set_last_error(__FILE__, __LINE__, "solver breakdown"); return LIO_ERR_NUMERIC; }
+  e->t_solve = now_s() - t0;
+  double_to_vector(e);
+  const double t1 = now_s();
+  if (e->cfg.marginalization_factor && !e->turn_off) {
+    vector_to_double(e);
+    rc = marginalize(e);
+    if (rc != LIO_OK) return rc;
+  }
+  e->t_marg = now_s() - t1;
+  return LIO_OK;
+}
+
+static int slide_window(lio_est *e) {  // Estimator.cc:2570-2666
+  const int W = e->W, O = e->O, pivot = W - O;
+  if (e->init_local_map && pivot > 0) {
+    const Tw tlb = tlb_double(e);
+    const Tw transform_pivot = lidar_pose(e->Ps[pivot], e->Rs[pivot], tlb);
+    const int i = pivot + 1;
+    const Tw transform_li = lidar_pose(e->Ps[i], e->Rs[i], tlb);
+    AffineF a = to_affine_f(tw_mul(tw_inverse(transform_li), transform_pivot));
+    ConcatParams cp;
+    std::memset(&cp, 0, sizeof(cp));
+    cp.nsrc = 2;
+    cp.src[0] = e->slot_ptr[e->slot_of[pivot]]; cp.n[0] = e->d_slot_n + e->slot_of[pivot];
+    std::memcpy(cp.R[0], a.R, sizeof(a.R)); std::memcpy(cp.t[0], a.t, sizeof(a.t));
+    cp.tag[0] = -1.f;
+    cp.skip_first[0] = 1; cp.skip_n[0] = e->d_own_n + e->slot_of[0];  // size_surf_stack_[0]
+    cp.src[1] = e->slot_ptr[e->slot_of[i]]; cp.n[1] = e->d_slot_n + e->slot_of[i];
+    cp.identity[1] = 1;
+    k_concat<<<std::max(1, std::min(e->sm_count * 2, (e->slot_cap + 255) / 256)), 256, 0, e->stream>>>(cp, e->d_tmp, e->d_counts + 3, e->slot_cap);
+    ++e->launches;
+    std::swap(e->slot_ptr[e->slot_of[i]], e->d_tmp);
+    EST_CUDA(cudaMemcpyAsync(e->d_slot_n + e->slot_of[i], e->d_counts + 3, sizeof(int), cudaMemcpyDeviceToDevice, e->stream));
+  }
+  push_shift(e->Ps, e->Ps[W]); push_shift(e->Vs, e->Vs[W]); push_shift(e->Rs, e->Rs[W]); push_shift(e->Bas, e->Bas[W]); push_shift(e->Bgs, e->Bgs[W]);
+  return LIO_OK;
+}
+
+static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max) {
+  const int W = e->W;
+  cudaStream_t st = e->stream;
+  const double t0 = now_s();
+  e->launches = 0;
+  e->have_H0 = false;
+  if (!e->tmp_pre) { lio_set_last_error(__FILE__, __LINE__, "process_scan before finish_init"); return LIO_ERR_INVALID; }
+  push_shift(e->pre, e->tmp_pre);
+  e->tmp_pre = std::make_shared<Preintegration>(e->acc_last, e->gyr_last, e->Bas[W], e->Bgs[W], e->noise);
+  // frame slot rotation (CircularBuffer push): the dropped logical frame 0 becomes the new frame W
+  {
+    const int freed = e->slot_of[0];
+    e->slot_of.erase(e->slot_of.begin());
+    e->slot_of.push_back(freed);
+  }
+  const int slot = e->slot_of[W];
+  const float4 *src = scan_dev;
+  if ((e->cfg.enable_deskew || e->cfg.cutoff_deskew) && !e->cfg.cutoff_deskew && !e->imu_stamped.empty()) {
+    // transform_es_ from the IMU-propagated poses of the last 0.1 s (:632-664), float Twist algebra on the host
+    const ImuStampedF &te = e->imu_stamped.back();
+    ImuStampedF ts = te;
+    for (int i = (int)e->imu_stamped.size() - 1; i >= 0; --i) {
+      ts = e->imu_stamped[i];
+      if (te.time - e->imu_stamped[i].time >= 0.1) break;
+    }
+    auto twf = [](const float *q, const float *p) { return Tw(Q(q[3], q[0], q[1], q[2]), V3(p[0], p[1], p[2])); };
+    // evaluated in double and rounded: the float op order of Eigen::Transform<float> is not reproduced (tolerance-checked)
+    Tw body_es = tw_mul(tw_inverse(twf(te.q, te.p)), twf(ts.q, ts.p));
+    {
+      const float s = (float)(0.1 / (te.time - ts.time));
+      Q qe = body_es.rot;
+      double d = qe.w, absD = std::fabs(d), s0, s1;
+      if (absD >= 1.0 - 1.1920929e-7) { s0 = 1.0 - s; s1 = s; }
+      else { double th = std::acos(absD), sn = std::sin(th); s0 = std::sin((1.0 - s) * th) / sn; s1 = std::sin(s * th) / sn; }
+      if (d < 0) s1 = -s1;
+      body_es.rot = Q(s0 + s1 * qe.w, s1 * qe.x, s1 * qe.y, s1 * qe.z);
+      body_es.pos = body_es.pos * (double)s;
+    }
+    const Tw tlb = tlb_double(e);
+    const Tw es = tw_mul(tw_mul(tlb, body_es), tw_inverse(tlb));
+    TransformF esf{(float)es.rot.x, (float)es.rot.y, (float)es.rot.z, (float)es.rot.w, (float)es.pos.x, (float)es.pos.y, (float)es.pos.z};
+    if (scan_dev != e->d_scan) {
+      EST_CUDA(cudaMemcpyAsync(e->d_scan, scan_dev, sizeof(float4) * n_max, cudaMemcpyDeviceToDevice, st));
+    }
+    k_deskew<<<(n_max + 255) / 256, 256, 0, st>>>(e->d_scan, n_dev, esf, 10.f);
+    ++e->launches;
+    src = e->d_scan;
+  }
+  int rc = e->vg.run(src, n_dev, n_max, e->cfg.surf_filter_size, e->slot_ptr[slot], e->d_slot_n + slot, nullptr, st, &e->launches);
+  if (rc != LIO_OK) return rc;
+  EST_CUDA(cudaMemcpyAsync(e->d_own_n + slot, e->d_slot_n + slot, sizeof(int), cudaMemcpyDeviceToDevice, st));
+  push_shift(e->size_surf_stack, 0);
+  rc = solve_optimization(e);
+  if (rc != LIO_OK) return rc;
+  rc = slide_window(e);
+  if (rc != LIO_OK) return rc;
+  e->t_total = now_s() - t0;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_process_scan_host(lio_est *e, const float *surf_last, int n) {
+  if (!e || n < 0 || (n > 0 && !surf_last)) return LIO_ERR_INVALID;
+  if (n > e->cfg.max_scan_points) return LIO_ERR_CAPACITY;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  if (n > 0) LIO_CUDA_OK(cudaMemcpyAsync(e->d_scan, surf_last, sizeof(float4) * n, cudaMemcpyHostToDevice, e->stream));
+  e->h_counts[e->W + 8] = n;
+  LIO_CUDA_OK(cudaMemcpyAsync(e->d_counts, e->h_counts + e->W + 8, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  return process_scan_common(e, e->d_scan, e->d_counts, n > 0 ? n : 1);
+}
+
+extern "C" int lio_est_process_scan_dev(lio_est *e, const float *surf_last_dev, const int *n_dev, int n_max) {
+  if (!e || !surf_last_dev || !n_dev || n_max <= 0) return LIO_ERR_INVALID;
+  if (n_max > e->cfg.max_scan_points) n_max = e->cfg.max_scan_points;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  return process_scan_common(e, reinterpret_cast<const float4 *>(surf_last_dev), n_dev, n_max);
+}
+
+extern "C" int lio_est_set_shard(lio_est *e, int rank, int world, lio_allreduce_fn fn, void *user) {
+  if (!e || world < 1 || rank < 0 || rank >= world) return LIO_ERR_INVALID;
+  if (world > 1 && !fn) return LIO_ERR_INVALID;
+  e->rank = rank; e->world = world; e->allreduce = fn; e->allreduce_user = user;
+  return LIO_OK;
+}
+
+// ---- getters --------------------------------------------------------------------------------------
+extern "C" int lio_est_get_states(lio_est *e, double *out) {
+  if (!e || !out) return LIO_ERR_INVALID;
+  for (int k = 0; k <= e->W; ++k) {
+    double *s = out + 16 * k;
+    Q q = fromR(e->Rs[k]);
+    s[0] = e->Ps[k].x; s[1] = e->Ps[k].y; s[2] = e->Ps[k].z; s[3] = q.x; s[4] = q.y; s[5] = q.z; s[6] = q.w;
+    for (int a = 0; a < 3; ++a) { s[7 + a] = e->Vs[k][a]; s[10 + a] = e->Bas[k][a]; s[13 + a] = e->Bgs[k][a]; }
+  }
+  return LIO_OK;
+}
+
+extern "C" int lio_est_summary(lio_est *e, double *o) {
+  if (!e || !o) return LIO_ERR_INVALID;
+  for (int k = 0; k < 32; ++k) o[k] = 0;
+  o[0] = e->summary.iterations; o[1] = e->summary.successful_steps; o[2] = e->summary.termination;
+  o[3] = e->summary.initial_cost; o[4] = e->summary.final_cost; o[5] = e->cost_pim; o[6] = e->cost_ppp; o[7] = e->cost_marg;
+  o[8] = e->turn_off; o[9] = e->convergence_flag; o[10] = e->h_map_n;
+  long long nf = 0;
+  for (int v : e->h_feat_n) nf += v;
+  o[11] = (double)nf; o[12] = e->odom_iters;
+  o[13] = e->t_build; o[14] = e->t_feat; o[15] = e->t_solve; o[16] = e->t_marg; o[17] = e->t_total;
+  o[18] = e->prior.valid ? 1 : 0; o[19] = e->summary.evaluations; o[20] = e->summary.evaluations; o[21] = e->launches;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_feature_count(lio_est *e, int frame, int *n) {
+  if (!e || !n || frame < 0 || frame > e->W) return LIO_ERR_INVALID;
+  *n = e->h_feat_n[frame];
+  return LIO_OK;
+}
+
+extern "C" int lio_est_get_features(lio_est *e, int frame, float *pts4, float *coef4, int32_t *src, int cap) {
+  if (!e || frame < 0 || frame > e->W) return LIO_ERR_INVALID;
+  const int n = e->h_feat_n[frame];
+  if (n > cap) return LIO_ERR_CAPACITY;
+  if (n == 0) return LIO_OK;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  const FeatureOut &f = e->feats[frame];
+  if (pts4) LIO_CUDA_OK(cudaMemcpyAsync(pts4, f.pts, sizeof(float4) * n, cudaMemcpyDeviceToHost, e->stream));
+  if (coef4) LIO_CUDA_OK(cudaMemcpyAsync(coef4, f.coef, sizeof(float4) * n, cudaMemcpyDeviceToHost, e->stream));
+  if (src) LIO_CUDA_OK(cudaMemcpyAsync(src, f.src, sizeof(int) * n, cudaMemcpyDeviceToHost, e->stream));
+  LIO_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return LIO_OK;
+}
+
+extern "C" int lio_est_map_size(lio_est *e, int *n) {
+  if (!e || !n) return LIO_ERR_INVALID;
+  *n = e->h_map_n;
+  return LIO_OK;
+}
+extern "C" int lio_est_get_map(lio_est *e, float *out, int cap) {
+  if (!e || !out) return LIO_ERR_INVALID;
+  if (e->h_map_n > cap) return LIO_ERR_CAPACITY;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  if (e->h_map_n > 0) LIO_CUDA_OK(cudaMemcpyAsync(out, e->d_map, sizeof(float4) * e->h_map_n, cudaMemcpyDeviceToHost, e->stream));
+  LIO_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return LIO_OK;
+}
+extern "C" int lio_est_frame_size(lio_est *e, int frame, int *n) {
+  if (!e || !n || frame < 0 || frame > e->W) return LIO_ERR_INVALID;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  LIO_CUDA_OK(cudaMemcpyAsync(n, e->d_slot_n + e->slot_of[frame], sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  LIO_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return LIO_OK;
+}
+extern "C" int lio_est_get_frame(lio_est *e, int frame, float *out, int cap) {
+  int n = 0;
+  int rc = lio_est_frame_size(e, frame, &n);
+  if (rc != LIO_OK) return rc;
+  if (n > cap) return LIO_ERR_CAPACITY;
+  if (n > 0) LIO_CUDA_OK(cudaMemcpyAsync(out, e->slot_ptr[e->slot_of[frame]], sizeof(float4) * n, cudaMemcpyDeviceToHost, e->stream));
+  LIO_CUDA_OK(cudaStreamSynchronize(e->stream));
+  return LIO_OK;
+}
+extern "C" int lio_est_get_local_transform(lio_est *e, int frame, float tf7[7]) {
+  if (!e || !tf7 || frame < 0 || frame > e->W) return LIO_ERR_INVALID;
+  const TransformF &t = e->local_tf[frame];
+  tf7[0] = t.qx; tf7[1] = t.qy; tf7[2] = t.qz; tf7[3] = t.qw; tf7[4] = t.px; tf7[5] = t.py; tf7[6] = t.pz;
+  return LIO_OK;
+}
+extern "C" int lio_est_prior_dim(lio_est *e, int *n) {
+  if (!e || !n) return LIO_ERR_INVALID;
+  *n = e->prior.valid ? e->prior.n : 0;
+  return LIO_OK;
+}
+extern "C" int lio_est_get_prior(lio_est *e, double *Hp, double *bp) {
+  if (!e || !Hp || !bp) return LIO_ERR_INVALID;
+  if (!e->prior.valid) return LIO_ERR_INVALID;
+  std::memcpy(Hp, e->prior.Hp.d.data(), sizeof(double) * e->prior.n * e->prior.n);
+  std::memcpy(bp, e->prior.bp.data(), sizeof(double) * e->prior.n);
+  return LIO_OK;
+}
+extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, double *cost, int *n) {
+  if (!e || !n) return LIO_ERR_INVALID;
+  if (!e->have_H0) { *n = 0; return LIO_OK; }
+  *n = e->H0.r;
+  if (H) std::memcpy(H, e->H0.d.data(), sizeof(double) * e->H0.r * e->H0.r);
+  if (g) std::memcpy(g, e->g0.data(), sizeof(double) * e->H0.r);
+  if (cost) *cost = e->cost0;
+  return LIO_OK;
+}
+extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
+
+// ---- factor-operator seam ---------------------------------------------------------------------------
+extern "C" int lio_ppp_evaluate(const double point[3], const double coeff[4], const double pose_pivot[7], const double pose_i[7],
+                                const double pose_ex[7], double *residual, double *J0, double *J1, double *J2) {
+  if (!point || !coeff || !pose_pivot || !pose_i || !pose_ex || !residual) return LIO_ERR_INVALID;
+  ppp_evaluate_single(point, coeff, pose_pivot, pose_i, pose_ex, residual, J0, J1, J2);
+  return LIO_OK;
+}
+
+namespace lio {
+int ppp_rows_launch(const float4 *pts, const float4 *coef, int n, const double *Rt12_dev, const double *M_dev, double *r_out,
+                    double *J_out, cudaStream_t st);
+}
+
+extern "C" int lio_ppp_evaluate_batch_host(const float *pts4, const float *coef4, int n, const double pose_pivot[7],
+                                           const double pose_i[7], const double pose_ex[7], double *r_out, double *J_out, int device) {
+  if (!pts4 || !coef4 || n < 0 || !pose_pivot || !pose_i || !pose_ex || !r_out || !J_out) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  if (n == 0) return LIO_OK;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  double Rt[12], M[108];
+  ppp_frame_terms(pose_pivot, pose_i, pose_ex, Rt, Rt + 9, M);
+  float4 *dp = nullptr, *dc = nullptr;
+  double *dRt = nullptr, *dM = nullptr, *dr = nullptr, *dJ = nullptr;
+  int rc = LIO_OK;
+  if (cudaMalloc(&dp, sizeof(float4) * n) != cudaSuccess || cudaMalloc(&dc, sizeof(float4) * n) != cudaSuccess ||
+      cudaMalloc(&dRt, sizeof(Rt)) != cudaSuccess || cudaMalloc(&dM, sizeof(M)) != cudaSuccess ||
+      cudaMalloc(&dr, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dJ, sizeof(double) * 18 * (size_t)n) != cudaSuccess) {
+    lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+    rc = LIO_ERR_CUDA;
+  }
+  if (rc == LIO_OK) {
+    cudaMemcpy(dp, pts4, sizeof(float4) * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(dc, coef4, sizeof(float4) * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(dRt, Rt, sizeof(Rt), cudaMemcpyHostToDevice);
+    cudaMemcpy(dM, M, sizeof(M), cudaMemcpyHostToDevice);
+    rc = ppp_rows_launch(dp, dc, n, dRt, dM, dr, dJ, 0);
+    if (rc == LIO_OK) {
+      cudaError_t er = cudaMemcpy(r_out, dr, sizeof(double) * n, cudaMemcpyDeviceToHost);
+      if (er == cudaSuccess) er = cudaMemcpy(J_out, dJ, sizeof(double) * 18 * (size_t)n, cudaMemcpyDeviceToHost);
+      if (er != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(er)); rc = LIO_ERR_CUDA; }
+    }
+  }
+  void *fr[] = {dp, dc, dRt, dM, dr, dJ};
+  for (void *q : fr) if (q) cudaFree(q);
+  return rc;
+}
+
+extern "C" int lio_pim_create(const double a0[3], const double g0[3], const double ba[3], const double bg[3], const double n5[5], lio_pim **out) {
+  if (!a0 || !g0 || !ba || !bg || !n5 || !out) return LIO_ERR_INVALID;
+  ImuNoise nz;
+  nz.acc_n = n5[0]; nz.gyr_n = n5[1]; nz.acc_w = n5[2]; nz.gyr_w = n5[3]; nz.g_norm = n5[4];
+  lio_pim *p = new (std::nothrow) lio_pim();
+  if (!p) return LIO_ERR_INVALID;
+  p->p = std::make_shared<Preintegration>(V3(a0), V3(g0), V3(ba), V3(bg), nz);
+  *out = p;
+  return LIO_OK;
+}
+extern "C" int lio_pim_destroy(lio_pim *p) { delete p; return LIO_OK; }
+extern "C" int lio_pim_push_back(lio_pim *p, double dt, const double a[3], const double g[3]) {
+  if (!p || !a || !g) return LIO_ERR_INVALID;
+  p->p->push_back(dt, V3(a), V3(g));
+  return LIO_OK;
+}
+extern "C" int lio_pim_get(lio_pim *p, double *s, double *jac, double *cov) {
+  if (!p || !s) return LIO_ERR_INVALID;
+  const Preintegration &q = *p->p;
+  s[0] = q.delta_p.x; s[1] = q.delta_p.y; s[2] = q.delta_p.z; s[3] = q.delta_q.x; s[4] = q.delta_q.y; s[5] = q.delta_q.z; s[6] = q.delta_q.w;
+  s[7] = q.delta_v.x; s[8] = q.delta_v.y; s[9] = q.delta_v.z; s[10] = q.sum_dt;
+  if (jac) std::memcpy(jac, q.jac, sizeof(q.jac));
+  if (cov) std::memcpy(cov, q.cov, sizeof(q.cov));
+  return LIO_OK;
+}
+extern "C" int lio_imu_factor_evaluate(lio_pim *p, const double pose_i[7], const double sb_i[9], const double pose_j[7],
+                                       const double sb_j[9], double *res15, double *J0, double *J1, double *J2, double *J3) {
+  if (!p || !pose_i || !sb_i || !pose_j || !sb_j || !res15) return LIO_ERR_INVALID;
+  double Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
+  const bool need = J0 || J1 || J2 || J3;
+  imu_factor_evaluate(*p->p, pose_i, sb_i, pose_j, sb_j, res15, need ? Ji : nullptr, Jsi, Jj, Jsj);
+  if (need) {
+    for (int a = 0; a < 15; ++a) {
+      for (int c = 0; c < 7; ++c) { if (J0) J0[a * 7 + c] = c < 6 ? Ji[a][c] : 0.0; if (J2) J2[a * 7 + c] = c < 6 ? Jj[a][c] : 0.0; }
+      for (int c = 0; c < 9; ++c) { if (J1) J1[a * 9 + c] = Jsi[a][c]; if (J3) J3[a * 9 + c] = Jsj[a][c]; }
+    }
+  }
+  return LIO_OK;
+}
+

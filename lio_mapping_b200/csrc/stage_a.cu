@@ -817,3 +817,16 @@ extern "C" int lio_pp_start_ori(lio_pp *pp, float *start_ori) {
 }
 
 extern "C" int lio_pp_last_launches(lio_pp *pp) { return pp ? pp->launches : 0; }
+
+extern "C" int lio_pp_cloud_count_dev(lio_pp *pp, int which, const int **n_dev) {
+  if (!pp || !n_dev) return LIO_ERR_INVALID;
+  switch (which) {
+    case LIO_PP_LASER_SCANS: case LIO_PP_CLOUD_IN_RINGS: *n_dev = pp->d_counts + 4; break;
+    case LIO_PP_CORNER_SHARP: *n_dev = pp->d_counts + 0; break;
+    case LIO_PP_CORNER_LESS_SHARP: *n_dev = pp->d_counts + 1; break;
+    case LIO_PP_SURF_FLAT: *n_dev = pp->d_counts + 2; break;
+    case LIO_PP_SURF_LESS_FLAT: *n_dev = pp->d_counts + 3; break;
+    default: return LIO_ERR_INVALID;
+  }
+  return LIO_OK;
+}

@@ -1,0 +1,200 @@
+"""Host-side mirror of lio::Estimator (steady state) over the C-ABI (stages B, C, D).
+
+Method names follow the reference (include/imu_processor/Estimator.h:110-170): ProcessImu,
+ProcessLaserOdom (via process_scan), SolveOptimization and SlideWindow run inside the library; the
+Python layer only moves arrays.  IntegrationBase / ImuFactor / PivotPointPlaneFactor operators are
+exposed as Pim / ppp_evaluate.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+SUMMARY_KEYS = ["iterations", "successful", "termination", "initial_cost", "final_cost", "cost_pim", "cost_ppp", "cost_marg",
+                "turn_off", "convergence_flag", "map_size", "num_features", "odom_iters", "t_build_map", "t_features",
+                "t_solve", "t_marg", "t_total", "has_prior", "linearizations", "cost_evals", "launches"]
+
+
+def _d(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def ppp_evaluate(point, coeff, pose_pivot, pose_i, pose_ex):
+    """PivotPointPlaneFactor::Evaluate for one factor (host analytic operator)."""
+    r = np.zeros(1)
+    J = [np.zeros(7) for _ in range(3)]
+    _lib.check(_lib.lib().lio_ppp_evaluate(_d(point), _d(coeff), _d(pose_pivot), _d(pose_i), _d(pose_ex), r, J[0], J[1], J[2]),
+               "lio_ppp_evaluate")
+    return float(r[0]), J
+
+
+def ppp_evaluate_batch(pts4, coef4, pose_pivot, pose_i, pose_ex, device=0):
+    """The same operator for N factors on the GPU: residuals (N,), Jacobian rows (N, 18)."""
+    _lib.require_device()
+    p = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+    c = np.ascontiguousarray(coef4, np.float32).reshape(-1, 4)
+    n = p.shape[0]
+    r = np.zeros(max(n, 1))
+    J = np.zeros((max(n, 1), 18))
+    _lib.check(_lib.lib().lio_ppp_evaluate_batch_host(p, c, n, _d(pose_pivot), _d(pose_i), _d(pose_ex), r, J, device),
+               "lio_ppp_evaluate_batch_host")
+    return r[:n], J[:n]
+
+
+class Pim:
+    """IntegrationBase (include/imu_processor/IntegrationBase.h) + ImuFactor operator."""
+
+    def __init__(self, acc0, gyr0, ba, bg, acc_n=0.1, gyr_n=0.01, acc_w=2e-4, gyr_w=2e-5, g_norm=9.805):
+        self.h = C.c_void_p()
+        _lib.check(_lib.lib().lio_pim_create(_d(acc0), _d(gyr0), _d(ba), _d(bg), _d([acc_n, gyr_n, acc_w, gyr_w, g_norm]),
+                                             C.byref(self.h)), "lio_pim_create")
+        self.owned = True
+
+    def push_back(self, dt, acc, gyr):
+        _lib.check(_lib.lib().lio_pim_push_back(self.h, float(dt), _d(acc), _d(gyr)), "lio_pim_push_back")
+
+    def get(self):
+        s = np.zeros(11); J = np.zeros(225); P = np.zeros(225)
+        _lib.check(_lib.lib().lio_pim_get(self.h, s, J, P), "lio_pim_get")
+        return dict(delta_p=s[0:3], delta_q=s[3:7], delta_v=s[7:10], sum_dt=s[10], jacobian=J.reshape(15, 15),
+                    covariance=P.reshape(15, 15))
+
+    def imu_factor(self, pose_i, sb_i, pose_j, sb_j):
+        r = np.zeros(15)
+        J = [np.zeros(15 * 7), np.zeros(15 * 9), np.zeros(15 * 7), np.zeros(15 * 9)]
+        _lib.check(_lib.lib().lio_imu_factor_evaluate(self.h, _d(pose_i), _d(sb_i), _d(pose_j), _d(sb_j), r, *J),
+                   "lio_imu_factor_evaluate")
+        return r, [J[0].reshape(15, 7), J[1].reshape(15, 9), J[2].reshape(15, 7), J[3].reshape(15, 9)]
+
+    def __del__(self):
+        try:
+            if self.owned and self.h:
+                _lib.lib().lio_pim_destroy(self.h)
+        except Exception:
+            pass
+
+
+class Estimator:
+    def __init__(self, device: int = 0, stream: int = 0, **cfg):
+        L = _lib.lib()
+        _lib.require_device()
+        c = _lib.EstConfig()
+        L.lio_est_default_config(C.byref(c))
+        for k, v in cfg.items():
+            if not hasattr(c, k):
+                raise AttributeError(f"EstimatorConfig has no field {k}")
+            setattr(c, k, v)
+        self.c = c
+        self.cfg = {name: getattr(c, name) for name, _ in c._fields_}
+        self.W = c.window_size
+        self.h = C.c_void_p()
+        _lib.check(L.lio_est_create(C.byref(c), device, C.c_void_p(stream), C.byref(self.h)), "lio_est_create")
+        self._cb = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            _lib.lib().lio_est_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_extrinsic(self, tf7):
+        _lib.check(_lib.lib().lio_est_set_extrinsic(self.h, np.ascontiguousarray(tf7, np.float32)), "set_extrinsic")
+
+    def extrinsic(self):
+        t = np.zeros(7, np.float32)
+        _lib.check(_lib.lib().lio_est_get_extrinsic(self.h, t), "get_extrinsic")
+        return t
+
+    def init_frame(self, k, state16, surf_ds, pim: "Pim | None"):
+        s = np.ascontiguousarray(surf_ds, np.float32).reshape(-1, 4)
+        h = None
+        if pim is not None:
+            h = pim.h
+            pim.owned = False   # ownership passes to the estimator
+        _lib.check(_lib.lib().lio_est_init_frame(self.h, k, _d(state16), s, s.shape[0], h), "lio_est_init_frame")
+
+    def finish_init(self, acc_last, gyr_last):
+        _lib.check(_lib.lib().lio_est_finish_init(self.h, _d(acc_last), _d(gyr_last)), "lio_est_finish_init")
+
+    def process_imu(self, dt, acc, gyr, stamp):
+        _lib.check(_lib.lib().lio_est_process_imu(self.h, float(dt), _d(acc), _d(gyr), float(stamp)), "lio_est_process_imu")
+
+    def process_scan(self, surf_last):
+        s = np.ascontiguousarray(surf_last, np.float32).reshape(-1, 4)
+        _lib.check(_lib.lib().lio_est_process_scan_host(self.h, s, s.shape[0]), "lio_est_process_scan_host")
+
+    def process_scan_dev(self, dev_ptr: int, n_dev_ptr: int, n_max: int):
+        _lib.check(_lib.lib().lio_est_process_scan_dev(self.h, C.c_void_p(dev_ptr), C.c_void_p(n_dev_ptr), n_max),
+                   "lio_est_process_scan_dev")
+
+    def set_shard(self, rank, world, fn):
+        """fn(buf_dev_ptr:int, count:int) -> int must sum-allreduce `count` doubles in place on the device."""
+        if fn is None:
+            cb = _lib.ALLREDUCE_FN()
+        else:
+            cb = _lib.ALLREDUCE_FN(lambda user, buf, count: int(fn(buf, count)))
+        self._cb = cb
+        _lib.check(_lib.lib().lio_est_set_shard(self.h, rank, world, cb, None), "lio_est_set_shard")
+
+    def states(self):
+        out = np.zeros((self.W + 1, 16))
+        _lib.check(_lib.lib().lio_est_get_states(self.h, out), "lio_est_get_states")
+        return out
+
+    def summary(self):
+        s = np.zeros(32)
+        _lib.check(_lib.lib().lio_est_summary(self.h, s), "lio_est_summary")
+        return dict(zip(SUMMARY_KEYS, s.tolist()))
+
+    def features(self, frame):
+        n = C.c_int()
+        _lib.check(_lib.lib().lio_est_feature_count(self.h, frame, C.byref(n)), "feature_count")
+        n = n.value
+        p = np.zeros((max(n, 1), 4), np.float32); c = np.zeros((max(n, 1), 4), np.float32); s = np.zeros(max(n, 1), np.int32)
+        _lib.check(_lib.lib().lio_est_get_features(self.h, frame, p, c, s, max(n, 1)), "get_features")
+        return p[:n], c[:n], s[:n]
+
+    def local_map(self):
+        n = C.c_int()
+        _lib.check(_lib.lib().lio_est_map_size(self.h, C.byref(n)), "map_size")
+        m = np.zeros((max(n.value, 1), 4), np.float32)
+        _lib.check(_lib.lib().lio_est_get_map(self.h, m, m.shape[0]), "get_map")
+        return m[:n.value]
+
+    def frame(self, k):
+        n = C.c_int()
+        _lib.check(_lib.lib().lio_est_frame_size(self.h, k, C.byref(n)), "frame_size")
+        m = np.zeros((max(n.value, 1), 4), np.float32)
+        _lib.check(_lib.lib().lio_est_get_frame(self.h, k, m, m.shape[0]), "get_frame")
+        return m[:n.value]
+
+    def local_transform(self, k):
+        t = np.zeros(7, np.float32)
+        _lib.check(_lib.lib().lio_est_get_local_transform(self.h, k, t), "get_local_transform")
+        return t
+
+    def prior(self):
+        n = C.c_int()
+        _lib.check(_lib.lib().lio_est_prior_dim(self.h, C.byref(n)), "prior_dim")
+        n = n.value
+        H = np.zeros((max(n, 1), max(n, 1))); b = np.zeros(max(n, 1))
+        if n:
+            _lib.check(_lib.lib().lio_est_get_prior(self.h, H, b), "get_prior")
+        return H[:n, :n], b[:n]
+
+    def normal_equations(self):
+        n = C.c_int(); cost = C.c_double()
+        _lib.check(_lib.lib().lio_est_last_normal_equations(self.h, None, None, C.byref(cost), C.byref(n)), "normal_eq")
+        n = n.value
+        H = np.zeros((max(n, 1), max(n, 1))); g = np.zeros(max(n, 1))
+        if n:
+            _lib.check(_lib.lib().lio_est_last_normal_equations(self.h, H, g, C.byref(cost), C.byref(C.c_int())), "normal_eq")
+        return H[:n, :n], g[:n], cost.value

@@ -285,6 +285,13 @@ void orc_est_get_local_transform(void *h, int frame, float *tf7) {
   tf7[0] = t.rot.x; tf7[1] = t.rot.y; tf7[2] = t.rot.z; tf7[3] = t.rot.w; tf7[4] = t.pos.x; tf7[5] = t.pos.y; tf7[6] = t.pos.z;
 }
 // marginalisation prior of the last solve: n, then linearized_jacobians (n x n row-major), residuals (n)
+int orc_est_normal_dim(void *h) { return ((Estimator *)h)->summary.H_initial.r; }
+void orc_est_get_normal(void *h, double *H, double *g) {
+  Estimator *e = (Estimator *)h;
+  int n = e->summary.H_initial.r;
+  std::memcpy(H, e->summary.H_initial.d.data(), sizeof(double) * n * n);
+  std::memcpy(g, e->summary.g_initial.data(), sizeof(double) * n);
+}
 int orc_est_prior_dim(void *h) { Estimator *e = (Estimator *)h; return e->last_marginalization_info ? e->last_marginalization_info->n : 0; }
 void orc_est_get_prior(void *h, double *J, double *r) {
   Estimator *e = (Estimator *)h;

@@ -166,6 +166,8 @@ void Solve(const SolverOptions &opt, Problem *problem, SolverSummary *sum) {
   sum->num_linearizations = 1;
   sum->initial_cost = x_cost;
   sum->cost_trace.push_back(x_cost);
+  sum->H_initial = H;
+  sum->g_initial = g;
   VecX scale(n, 1.0);
   if (opt.jacobi_scaling) for (int i = 0; i < n; ++i) scale[i] = 1.0 / (1.0 + std::sqrt(H(i, i)));
   auto apply_scale = [&]() {

@@ -52,6 +52,8 @@ struct SolverSummary {
   int num_cost_evaluations = 0;
   int termination = 0;               // 0 NO_CONVERGENCE, 1 CONVERGENCE, 2 FAILURE
   std::vector<double> cost_trace;
+  MatX H_initial;   // unscaled J^T J / J^T r at the initial point (parity aid)
+  VecX g_initial;
 };
 
 void Solve(const SolverOptions &opt, Problem *problem, SolverSummary *summary);

@@ -191,6 +191,8 @@ def _bind_factors(L):
     L.orc_est_get_frame.argtypes = [vp, C.c_int, f32p]
     L.orc_est_get_local_transform.argtypes = [vp, C.c_int, f32p]
     L.orc_est_prior_dim.argtypes = [vp]
+    L.orc_est_normal_dim.argtypes = [vp]
+    L.orc_est_get_normal.argtypes = [vp, f64p, f64p]
     L.orc_est_get_prior.argtypes = [vp, f64p, f64p]
     L._factors_bound = True
 
@@ -335,6 +337,13 @@ class Estimator:
         t = np.zeros(7, np.float32)
         self.L.orc_est_get_local_transform(self.h, k, t)
         return t
+
+    def normal_equations(self):
+        n = self.L.orc_est_normal_dim(self.h)
+        H = np.zeros((max(n, 1), max(n, 1))); g = np.zeros(max(n, 1))
+        if n:
+            self.L.orc_est_get_normal(self.h, H, g)
+        return H[:n, :n], g[:n]
 
     def prior(self):
         n = self.L.orc_est_prior_dim(self.h)

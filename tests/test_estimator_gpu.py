@@ -1,0 +1,109 @@
+"""Stages B+C+D parity through the C-ABI: product estimator vs the CPU oracle on the same synthetic
+scans + IMU.  Exact where the data are fp32 / index sets, stated tolerances where fp64 is summed."""
+import numpy as np
+import pytest
+
+from lio_mapping_b200 import synth
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def rand_pose(rng, scale=5.0):
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    return np.concatenate([rng.uniform(-scale, scale, 3), q])
+
+
+def test_ppp_rows_device_vs_oracle(oracle):
+    """a10: per-factor residual + 1x18 Jacobian row from the kernel's rank-6 form vs PivotPointPlaneFactor::Evaluate."""
+    from lio_mapping_b200 import estimator
+    rng = np.random.default_rng(4)
+    x0, xi, xe = rand_pose(rng, 30), rand_pose(rng, 30), rand_pose(rng, 0.5)
+    n = 500
+    pts = np.concatenate([rng.uniform(-50, 50, (n, 3)), rng.uniform(0, 1, (n, 1))], 1).astype(np.float32)
+    w = rng.normal(size=(n, 3)); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    coef = np.concatenate([w * rng.uniform(0.1, 1, (n, 1)), rng.normal(0, 5, (n, 1))], 1).astype(np.float32)
+    r, J = estimator.ppp_evaluate_batch(pts, coef, x0, xi, xe)
+    for k in range(n):
+        ro, Jo = oracle.ppp_evaluate(pts[k, :3].astype(np.float64), coef[k].astype(np.float64), x0, xi, xe)
+        Jo = np.concatenate([j[:6] for j in Jo])
+        assert abs(r[k] - ro) <= 1e-12 * max(1.0, abs(ro), np.abs(pts[k, :3]).max())
+        assert np.abs(J[k] - Jo).max() <= 1e-12 * max(1.0, np.abs(Jo).max())
+
+
+@pytest.fixture(scope="module")
+def vlp_seq(oracle):
+    return helpers.Sequence(oracle, "vlp16", n_total=10, distort=False)
+
+
+def _mk(oracle, seq, W, **cfg):
+    from lio_mapping_b200 import estimator
+    eo = oracle.Estimator(window_size=W, opt_window_size=W, **cfg)
+    eg = estimator.Estimator(window_size=W, opt_window_size=W, max_frame_points=1 << 15, max_scan_points=1 << 17, **cfg)
+    helpers.warm_start(eo, seq, oracle, W, pose_noise=0.01, seed=1,
+                       make_pim=lambda a, g: oracle.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=0.2, gyr_n=0.02))
+    helpers.warm_start(eg, seq, oracle, W, pose_noise=0.01, seed=1,
+                       make_pim=lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=0.2, gyr_n=0.02))
+    return eo, eg
+
+
+def test_window_solve_parity_exact_features(oracle, vlp_seq):
+    """odom_max_iterations = 1 keeps the newest frame's features a pure CalculateFeatures call, so the
+    whole fp32 front of the solve is bit-identical and the fp64 normal equations agree to round-off."""
+    W = 5
+    eo, eg = _mk(oracle, vlp_seq, W, odom_max_iterations=1, prior_factor=1)
+    for k in range(W, 10):
+        helpers.feed_scan(eo, vlp_seq, k)
+        helpers.feed_scan(eg, vlp_seq, k)
+        so, sg = eo.summary(), eg.summary()
+        if k == W:   # first solve: identical inputs by construction
+            assert np.array_equal(eg.local_map(), eo.local_map())
+            for f in range(1, W + 1):
+                # SlideWindow already ran: features are stored per pre-slide frame index
+                po, co, io = eo.features(f)
+                pg, cg, ig = eg.features(f)
+                assert np.array_equal(ig, io) and np.array_equal(cg, co) and np.array_equal(pg, po), f
+            Ho, go = eo.normal_equations()
+            Hg, gg, cg0 = eg.normal_equations()
+            assert Hg.shape == Ho.shape
+            assert np.abs(Hg - Ho).max() <= 1e-9 * np.abs(Ho).max()
+            assert np.abs(gg - go).max() <= 1e-9 * max(1.0, np.abs(go).max())
+            assert abs(sg["initial_cost"] - so["initial_cost"]) <= 1e-9 * so["initial_cost"]
+        assert sg["map_size"] == so["map_size"]
+        assert abs(sg["num_features"] - so["num_features"]) <= 0.001 * so["num_features"]
+        assert sg["iterations"] == so["iterations"]
+        assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-6 * so["final_cost"]
+        xo, xg = eo.states(), eg.states()
+        # pose error <= 1e-4 relative (north_star); in practice ~1e-9 here
+        assert np.abs(xg[:, :3] - xo[:, :3]).max() <= 1e-6
+        assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-7
+        assert np.abs(xg[:, 7:] - xo[:, 7:]).max() <= 1e-5
+        assert sg["has_prior"] == so["has_prior"]
+    # marginalisation prior: same information matrix / vector (in the oracle's own block order they are J^T J, J^T r0)
+    Hp, bp = eg.prior()
+    Jo, ro = eo.prior()
+    assert Hp.shape[0] == 15 * W + 6
+    # compare order-independent invariants: spectrum of the information matrix and b^T H^+ b
+    evg = np.sort(np.linalg.eigvalsh(Hp))[::-1][: Jo.shape[0]]
+    evo = np.sort(np.linalg.eigvalsh(Jo.T @ Jo))[::-1]
+    k = min(len(evg), len(evo))
+    big = evo[:k] > 1e-6 * evo[0]
+    assert np.allclose(evg[:k][big], evo[:k][big], rtol=1e-6)
+    assert abs(bp @ np.linalg.pinv(Hp, rcond=1e-12) @ bp - ro @ ro) <= 1e-6 * max(1.0, ro @ ro)
+
+
+def test_window_solve_parity_full_odom(oracle, vlp_seq):
+    """Default 10 LaserOdom iterations on the newest frame (fp32 reductions differ in order): tolerance parity."""
+    W = 5
+    eo, eg = _mk(oracle, vlp_seq, W, prior_factor=1)
+    for k in range(W, 10):
+        helpers.feed_scan(eo, vlp_seq, k)
+        helpers.feed_scan(eg, vlp_seq, k)
+        so, sg = eo.summary(), eg.summary()
+        assert sg["map_size"] == so["map_size"] or abs(sg["map_size"] - so["map_size"]) <= 2
+        assert abs(sg["num_features"] - so["num_features"]) <= 0.005 * so["num_features"]
+        assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-3 * so["final_cost"]
+        xo, xg = eo.states(), eg.states()
+        scale = max(1.0, np.abs(xo[:, :3]).max())
+        assert np.abs(xg[:, :3] - xo[:, :3]).max() <= 1e-4 * scale      # north_star: pose error <= 1e-4 rel
+        assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-4
