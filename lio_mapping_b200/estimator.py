@@ -191,10 +191,9 @@ class Estimator:
         return H[:n, :n], b[:n]
 
     def normal_equations(self):
+        nmax = 15 * (self.c.opt_window_size + 1) + 6
         n = C.c_int(); cost = C.c_double()
-        _lib.check(_lib.lib().lio_est_last_normal_equations(self.h, None, None, C.byref(cost), C.byref(n)), "normal_eq")
+        H = np.zeros((nmax, nmax)); g = np.zeros(nmax)
+        _lib.check(_lib.lib().lio_est_last_normal_equations(self.h, H, g, C.byref(cost), C.byref(n)), "normal_eq")
         n = n.value
-        H = np.zeros((max(n, 1), max(n, 1))); g = np.zeros(max(n, 1))
-        if n:
-            _lib.check(_lib.lib().lio_est_last_normal_equations(self.h, H, g, C.byref(cost), C.byref(C.c_int())), "normal_eq")
-        return H[:n, :n], g[:n], cost.value
+        return H.reshape(-1)[:n * n].reshape(n, n).copy(), g[:n].copy(), cost.value

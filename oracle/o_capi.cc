@@ -285,6 +285,25 @@ void orc_est_get_local_transform(void *h, int frame, float *tf7) {
   tf7[0] = t.rot.x; tf7[1] = t.rot.y; tf7[2] = t.rot.z; tf7[3] = t.rot.w; tf7[4] = t.pos.x; tf7[5] = t.pos.y; tf7[6] = t.pos.z;
 }
 // marginalisation prior of the last solve: n, then linearized_jacobians (n x n row-major), residuals (n)
+// kept blocks of the prior, in its own order: kind (0 pose, 1 speed-bias, 2 extrinsic), window index (already
+// shifted to the NEXT window's numbering), tangent offset in the prior
+int orc_est_prior_blocks(void *h, int *kind, int *index, int *offset) {
+  Estimator *e = (Estimator *)h;
+  if (!e->last_marginalization_info) return 0;
+  auto &mi = *e->last_marginalization_info;
+  int nb = (int)e->last_marginalization_parameter_blocks.size();
+  for (int b = 0; b < nb; ++b) {
+    double *p = e->last_marginalization_parameter_blocks[b];
+    kind[b] = -1; index[b] = -1;
+    for (int i = 0; i <= e->O; ++i) {
+      if (p == e->para_pose[i]) { kind[b] = 0; index[b] = i; }
+      if (p == e->para_speed_bias[i]) { kind[b] = 1; index[b] = i; }
+    }
+    if (p == e->para_ex_pose) { kind[b] = 2; index[b] = 0; }
+    offset[b] = mi.keep_block_idx[b] - mi.m;
+  }
+  return nb;
+}
 int orc_est_normal_dim(void *h) { return ((Estimator *)h)->summary.H_initial.r; }
 void orc_est_get_normal(void *h, double *H, double *g) {
   Estimator *e = (Estimator *)h;

@@ -57,9 +57,10 @@ Estimator::Estimator(const EstimatorConfig &c) : cfg(c) {
   pre_integrations.assign(W + 1, nullptr);
   surf_stack.assign(W + 1, Cloud());
   size_surf_stack.assign(W + 1, 0);
-  para_pose.assign(O + 1, std::vector<double>(7, 0.0));
-  para_speed_bias.assign(O + 1, std::vector<double>(9, 0.0));
-  for (int k = 0; k < 7; ++k) para_ex_pose[k] = 0;
+  para_storage.assign(16 * (O + 1) + 7, 0.0);
+  para_pose.resize(O + 1); para_speed_bias.resize(O + 1);
+  for (int i = 0; i <= O; ++i) { para_pose[i] = &para_storage[7 * i]; para_speed_bias[i] = &para_storage[7 * (O + 1) + 9 * i]; }
+  para_ex_pose = &para_storage[16 * (O + 1)];
   g_vec = V3(0, 0, -cfg.pim.g_norm);
   extrinsic_stage = cfg.estimate_extrinsic;
   transform_lb = Transform(Quat<float>(1, 0, 0, 0), Vec3<float>(0, 0, -0.1f));  // Estimator.h:89
@@ -258,8 +259,8 @@ void Estimator::SolveOptimization() {
   double t0 = now_s();
   std::vector<double *> para_ids;
   for (int i = 0; i < O + 1; ++i) {
-    problem.AddParameterBlock(para_pose[i].data(), 7, true);
-    problem.AddParameterBlock(para_speed_bias[i].data(), 9, false);
+    problem.AddParameterBlock(para_pose[i], 7, true);
+    problem.AddParameterBlock(para_speed_bias[i], 9, false);
   }
   problem.AddParameterBlock(para_ex_pose, 7, true);
   if (extrinsic_stage == 0 || cfg.opt_extrinsic == false) problem.SetParameterBlockConstant(para_ex_pose);
@@ -279,7 +280,7 @@ void Estimator::SolveOptimization() {
       if (pre_integrations[opt_j]->sum_dt_ > 10.0) continue;
       auto f = std::make_shared<ImuFactor>(pre_integrations[opt_j]);
       res_ids_pim.push_back(problem.AddResidualBlock(
-          f, nullptr, {para_pose[i].data(), para_speed_bias[i].data(), para_pose[j].data(), para_speed_bias[j].data()}));
+          f, nullptr, {para_pose[i], para_speed_bias[i], para_pose[j], para_speed_bias[j]}));
     }
   }
   if (cfg.point_distance_factor) {
@@ -289,7 +290,7 @@ void Estimator::SolveOptimization() {
       if (i == 0) continue;
       for (const PointPlaneFeature &fj : features) {
         auto f = std::make_shared<PivotPointPlaneFactor>(fj.point, fj.coeffs);
-        res_ids_proj.push_back(problem.AddResidualBlock(f, &loss, {para_pose[0].data(), para_pose[i].data(), para_ex_pose}));
+        res_ids_proj.push_back(problem.AddResidualBlock(f, &loss, {para_pose[0], para_pose[i], para_ex_pose}));
       }
     }
   }
@@ -324,7 +325,7 @@ void Estimator::SolveOptimization() {
     if (last_marginalization_info) {
       std::vector<int> drop_set;
       for (int i = 0; i < (int)last_marginalization_parameter_blocks.size(); i++)
-        if (last_marginalization_parameter_blocks[i] == para_pose[0].data() || last_marginalization_parameter_blocks[i] == para_speed_bias[0].data())
+        if (last_marginalization_parameter_blocks[i] == para_pose[0] || last_marginalization_parameter_blocks[i] == para_speed_bias[0])
           drop_set.push_back(i);
       auto mf = std::make_shared<MarginalizationFactor>(last_marginalization_info);
       marginalization_info->AddResidualBlockInfo(std::make_shared<ResidualBlockInfo>(mf, nullptr, last_marginalization_parameter_blocks, drop_set));
@@ -334,7 +335,7 @@ void Estimator::SolveOptimization() {
         auto imu_factor = std::make_shared<ImuFactor>(pre_integrations[pivot_idx + 1]);
         marginalization_info->AddResidualBlockInfo(std::make_shared<ResidualBlockInfo>(
             imu_factor, nullptr,
-            std::vector<double *>{para_pose[0].data(), para_speed_bias[0].data(), para_pose[1].data(), para_speed_bias[1].data()},
+            std::vector<double *>{para_pose[0], para_speed_bias[0], para_pose[1], para_speed_bias[1]},
             std::vector<int>{0, 1}));
       }
     }
@@ -344,7 +345,7 @@ void Estimator::SolveOptimization() {
         for (const PointPlaneFeature &fj : feature_frames[opt_i]) {
           auto f = std::make_shared<PivotPointPlaneFactor>(fj.point, fj.coeffs);
           marginalization_info->AddResidualBlockInfo(std::make_shared<ResidualBlockInfo>(
-              f, &loss, std::vector<double *>{para_pose[0].data(), para_pose[i].data(), para_ex_pose}, std::vector<int>{0}));
+              f, &loss, std::vector<double *>{para_pose[0], para_pose[i], para_ex_pose}, std::vector<int>{0}));
         }
       }
     }
@@ -352,8 +353,8 @@ void Estimator::SolveOptimization() {
     marginalization_info->Marginalize();
     std::map<long, double *> addr_shift;
     for (int i = 1; i < O + 1; ++i) {
-      addr_shift[reinterpret_cast<long>(para_pose[i].data())] = para_pose[i - 1].data();
-      addr_shift[reinterpret_cast<long>(para_speed_bias[i].data())] = para_speed_bias[i - 1].data();
+      addr_shift[reinterpret_cast<long>(para_pose[i])] = para_pose[i - 1];
+      addr_shift[reinterpret_cast<long>(para_speed_bias[i])] = para_speed_bias[i - 1];
     }
     addr_shift[reinterpret_cast<long>(para_ex_pose)] = para_ex_pose;
     std::vector<double *> parameter_blocks = marginalization_info->GetParameterBlocks(addr_shift);

@@ -38,8 +38,11 @@ struct Estimator {
   std::vector<ImuStamped> imu_stampedtransforms;
   Transform transform_es;
   // optimisation parameter arrays (Estimator.h:282-284)
-  std::vector<std::vector<double>> para_pose, para_speed_bias;
-  double para_ex_pose[7];
+  // one contiguous block [pose_0..pose_O | sb_0..sb_O | ex]: the marginalisation orders parameter blocks by
+  // address (std::map), so this fixes the prior's block order to poses, speed-biases, extrinsic
+  std::vector<double> para_storage;
+  std::vector<double *> para_pose, para_speed_bias;
+  double *para_ex_pose = nullptr;
   std::shared_ptr<MarginalizationInfo> last_marginalization_info;
   std::vector<double *> last_marginalization_parameter_blocks;
   bool convergence_flag = false, init_local_map = false;

@@ -191,6 +191,7 @@ def _bind_factors(L):
     L.orc_est_get_frame.argtypes = [vp, C.c_int, f32p]
     L.orc_est_get_local_transform.argtypes = [vp, C.c_int, f32p]
     L.orc_est_prior_dim.argtypes = [vp]
+    L.orc_est_prior_blocks.argtypes = [vp, i32p, i32p, i32p]
     L.orc_est_normal_dim.argtypes = [vp]
     L.orc_est_get_normal.argtypes = [vp, f64p, f64p]
     L.orc_est_get_prior.argtypes = [vp, f64p, f64p]
@@ -337,6 +338,25 @@ class Estimator:
         t = np.zeros(7, np.float32)
         self.L.orc_est_get_local_transform(self.h, k, t)
         return t
+
+    def prior_canonical(self, O):
+        """(Hp, bp) = (J^T J, J^T r0) permuted to the canonical order [pose_0,sb_0,...,pose_{O-1},sb_{O-1},ex]."""
+        J, r = self.prior()
+        kind = np.zeros(64, np.int32); idx = np.zeros(64, np.int32); off = np.zeros(64, np.int32)
+        nb = self.L.orc_est_prior_blocks(self.h, kind, idx, off)
+        n = 15 * O + 6
+        H = np.zeros((n, n)); b = np.zeros(n)
+        A = J.T @ J
+        v = J.T @ r
+        cols = []
+        for k in range(nb):
+            size = 9 if kind[k] == 1 else 6
+            base = {0: 15 * idx[k], 1: 15 * idx[k] + 6, 2: 15 * O}[int(kind[k])]
+            cols += [(off[k] + a, base + a) for a in range(size)]
+        src = np.array([c[0] for c in cols]); dst = np.array([c[1] for c in cols])
+        H[np.ix_(dst, dst)] = A[np.ix_(src, src)]
+        b[dst] = v[src]
+        return H, b
 
     def normal_equations(self):
         n = self.L.orc_est_normal_dim(self.h)
