@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — scans/sec of the steady-state LIO hot path (stage A on the new sweep + stage B for the O
+window frames + <= 10 Gauss-Newton/dogleg iterations of stage C + stage D marginalisation) on synthetic
+HDL-64 sweeps + IMU, window 10/10 (BASELINE.json configs[2], the configuration the metric is quoted on).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload hdl64|vlp16|stress128]
+
+One "step" = one scan through the whole path.  `value` times the path with the raw sweep already resident
+in HBM; `e2e` times the same call chain through the C-ABI with HOST buffers (pageable->device copy of the
+sweep and the result read-back inside the timed region).  `--impl reference` times the CPU restatement of
+the reference path (oracle/, the reference itself cannot be built here: no Eigen/PCL/Ceres/ROS) on the box's
+host cores.  Multi-GPU (torchrun, one rank per GPU): the window's frames are sharded one-per-rank, the
+packed S blocks are sum-allreduced over NCCL once per evaluation (strong scaling of one window solve).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "scans/sec + GN-iter ms, HDL-64 window=10 at 1/2/4/8 B200 vs CPU Ceres ref"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.p = None
+        self.gpu = gpu_index
+        self.path = "/tmp/lio_bench_clocks_%d.csv" % os.getpid()
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        try:
+            self.p.terminate(); self.p.wait(timeout=5); self.f.close()
+            sm, smax, reasons = [], [], set()
+            for line in open(self.path):
+                v = [x.strip() for x in line.split(",")]
+                if len(v) < 9:
+                    continue
+                try:
+                    sm.append(float(v[1])); smax.append(float(v[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], v[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            if sm:
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons)}
+        except Exception:
+            pass
+        return out
+
+
+def load_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args, scn, W, est_cfg):
+    """CPU restatement of the reference path on the host cores (oracle/): the reference arm and cpu_baseline."""
+    from oracle import oracle_py as O
+    from lio_mapping_b200 import scenario
+    O.build()
+    sensor = scn.sensor
+    eo = O.Estimator(window_size=W, opt_window_size=W, **est_cfg)
+    lf = {}
+
+    def stage_a(k):
+        if k not in lf:
+            lf[k] = O.stage_a(scn.raw[k], sensor.lower_deg, sensor.upper_deg, sensor.rings)["less_flat"]
+        return lf[k]
+
+    scenario.warm_start(eo, scn, W, lambda k: O.voxel_grid(stage_a(k), est_cfg["surf_filter_size"]),
+                        lambda a, g: O.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=est_cfg["acc_n"], gyr_n=est_cfg["gyr_n"],
+                                           acc_w=est_cfg["acc_w"], gyr_w=est_cfg["gyr_w"], g_norm=est_cfg["g_norm"]))
+    times, iters, solve_t = [], [], []
+    k0 = W
+    for s in range(args.warmup + args.steps):
+        k = k0 + s
+        t0 = time.perf_counter()
+        r = O.stage_a(scn.raw[k], sensor.lower_deg, sensor.upper_deg, sensor.rings)      # stage A (timed)
+        scenario.feed_imu(eo, scn, k)
+        eo.process_scan(r["less_flat"])
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+            sm = eo.summary()
+            iters.append(sm["iterations"]); solve_t.append(sm["t_solve"])
+    total = float(np.sum(times))
+    return dict(scans_per_s=len(times) / total, ms_per_step=1e3 * total / len(times),
+                gn_iter_ms=1e3 * float(np.sum(solve_t)) / max(1.0, float(np.sum(iters))), steps=len(times))
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="hdl64", choices=["hdl64", "vlp16", "stress128"])
+    ap.add_argument("--cpu-sample", type=int, default=4, help="scans of the cpu_baseline sample (rank 0, N=1 only)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    from lio_mapping_b200 import scenario
+    kind = args.workload
+    W = scenario.WINDOWS[kind]
+    est_cfg = dict(scenario.EST_CFG[kind])
+    workload = {"hdl64": "HDL-64 outdoor_test_config_64 synthetic, 64x2032 sweep, window=10/10, prior_factor=1",
+                "vlp16": "VLP-16 indoor synthetic, 16x1800 sweep, window=10/10",
+                "stress128": "synthetic 128x4096 sweep, window=15/15"}[kind]
+    n_total = W + args.warmup + args.steps + 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scn = scenario.Scenario(kind, n_total=n_total)
+        r = run_reference(args, scn, W, est_cfg)
+        cores = 4
+        line = {"impl": "reference", "metric": METRIC, "value": r["scans_per_s"], "unit": "scans/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 features / f64 solve", "data": "synthetic",
+                "gn_iter_ms": r["gn_iter_ms"],
+                "config": {"workload": workload, "window": W, "opt_window": W, "points_per_scan": int(scn.raw[W].shape[0])},
+                "cpu_baseline": {"value": r["scans_per_s"], "unit": "scans/s", "cores": cores, "kind": "port",
+                                 "sample": "%d scans of the same workload (oracle/: CPU restatement; the reference needs Eigen/PCL/Ceres/ROS, absent here); 1 thread + 4 marginalisation threads" % r["steps"]},
+                "e2e": {"value": r["scans_per_s"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    from lio_mapping_b200 import _lib, estimator, ops
+    from lio_mapping_b200.point_processor import PointProcessor
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (lio_mapping_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    scn = scenario.Scenario(kind, n_total=n_total)
+    sensor = scn.sensor
+    max_pts = max(s.shape[0] for s in scn.raw)
+    pp = PointProcessor(sensor.lower_deg, sensor.upper_deg, sensor.rings, max_points=max_pts, device=local_rank, stream=stream)
+    est = estimator.Estimator(device=local_rank, stream=stream, window_size=W, opt_window_size=W,
+                              max_frame_points=1 << 16 if kind != "stress128" else 1 << 18,
+                              max_scan_points=max_pts, **est_cfg)
+    if world > 1:
+        class _Arr:
+            def __init__(self, ptr, n):
+                self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+        def allreduce(ptr, count):
+            t = torch.as_tensor(_Arr(ptr, count), device=dev)
+            dist.all_reduce(t)
+            return 0
+        est.set_shard(rank, world, allreduce)
+
+    def surf_ds_of(k):
+        pp.SetInputCloud(scn.raw[k]); pp.Process()
+        return ops.voxel_grid(pp.cloud("surface_points_less_flat"), est_cfg["surf_filter_size"], device=local_rank)
+
+    scenario.warm_start(est, scn, W, surf_ds_of,
+                        lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=est_cfg["acc_n"], gyr_n=est_cfg["gyr_n"],
+                                                   acc_w=est_cfg["acc_w"], gyr_w=est_cfg["gyr_w"], g_norm=est_cfg["g_norm"]))
+    L = _lib.lib()
+    lf_ptr = pp.cloud_dev("surface_points_less_flat")
+    nptr = C.c_void_p()
+    _lib.check(L.lio_pp_cloud_count_dev(pp._h, 5, C.byref(nptr)), "lio_pp_cloud_count_dev")
+    # raw sweeps resident in HBM for the device-timed value; pinned host copies for e2e
+    dev_raw = {k: torch.from_numpy(scn.raw[k]).to(dev) for k in range(W, n_total - 1)}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def step_dev(k):
+        t = dev_raw[k]
+        pp.process_device(t.data_ptr(), t.shape[0])
+        scenario.feed_imu(est, scn, k)
+        est.process_scan_dev(lf_ptr, nptr.value, max_pts)
+
+    def step_host(k):
+        pp.SetInputCloud(scn.raw[k]); pp.Process()           # H2D of the sweep inside
+        scenario.feed_imu(est, scn, k)
+        est.process_scan_dev(lf_ptr, nptr.value, max_pts)
+        return est.states()                                  # result read-back (host state after the solve)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # The window is stateful, so the device-timed and e2e passes each consume their own scans:
+    #   warmup scans -> K device-timed scans (value) ; the e2e pass re-runs a fresh estimator on the same scans.
+    k = W
+    for _ in range(args.warmup):
+        step_dev(k); k += 1
+    est.kernel_profile(reset=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches, iters, solve_t, feats = 0, [], [], []
+    brk = {"t_build_map": [], "t_features": [], "t_solve": [], "t_marg": [], "t_total": []}
+    for s in range(args.steps):
+        flush.fill_(1.0)                                      # flush L2 between timed steps (outside the event pair)
+        barrier()
+        ev[s][0].record()
+        step_dev(k)
+        ev[s][1].record()
+        torch.cuda.synchronize()
+        launches += pp.last_launches() + int(L.lio_est_last_launches(est.h))
+        sm = est.summary()
+        iters.append(sm["iterations"]); solve_t.append(sm["t_solve"]); feats.append(sm["num_features"])
+        for kk in brk:
+            brk[kk].append(sm[kk])
+        k += 1
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(ms))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    prof = est.kernel_profile()
+    final_states = est.states()
+
+    # ---- e2e pass (host buffers, fresh estimator, same scans) --------------------------------------
+    est2 = estimator.Estimator(device=local_rank, stream=stream, window_size=W, opt_window_size=W,
+                               max_frame_points=1 << 16 if kind != "stress128" else 1 << 18, max_scan_points=max_pts, **est_cfg)
+    if world > 1:
+        est2.set_shard(rank, world, allreduce)
+    est_saved, est = est, est2
+    scenario.warm_start(est, scn, W, surf_ds_of,
+                        lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=est_cfg["acc_n"], gyr_n=est_cfg["gyr_n"],
+                                                   acc_w=est_cfg["acc_w"], gyr_w=est_cfg["gyr_w"], g_norm=est_cfg["g_norm"]))
+    k = W
+    for _ in range(args.warmup):
+        step_host(k); k += 1
+    e2e_t = 0.0
+    h2d = d2h = 0
+    for s in range(args.steps):
+        flush.fill_(1.0)
+        barrier()
+        t0 = time.perf_counter()
+        st = step_host(k)
+        torch.cuda.synchronize()
+        e2e_t += time.perf_counter() - t0
+        sm = est.summary()
+        h2d += scn.raw[k].shape[0] * 16 + (W + 1) * 28 + 4
+        d2h += int(sm["linearizations"] + 2) * W * 32 * 8 + (W + 8) * 4 + 28
+        k += 1
+    if world > 1:
+        t = torch.tensor([e2e_t], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    # both passes processed the same scans from the same start: their trajectories must agree
+    drift = float(np.abs(st[:, :3] - final_states[:, :3]).max())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = args.steps / (total_ms * 1e-3)
+        asm_launches = max(1, prof["asm_launches"])
+        avg_ms = prof["asm_ms"] / asm_launches
+        bytes_per_launch = prof["bytes_per_feature"] * prof["asm_features"] / asm_launches
+        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+        line = {"metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 features / f64 solve", "data": "synthetic",
+                "gn_iter_ms": 1e3 * float(np.sum(solve_t)) / max(1.0, float(np.sum(iters))),
+                "config": {"workload": workload, "window": W, "opt_window": W, "points_per_scan": int(scn.raw[W].shape[0]),
+                           "features_per_solve": float(np.mean(feats)), "gn_iterations_per_scan": float(np.mean(iters)),
+                           "l2": "flushed between timed steps (256 MB write outside the event pair)",
+                           "parallelism": "frames sharded 1..O over %d rank(s), NCCL allreduce of O x 29 doubles per evaluation" % world,
+                           "e2e_vs_device_pass_max_pos_diff_m": drift,
+                           "host_wall_ms_per_scan": {kk: 1e3 * float(np.mean(v)) for kk, v in brk.items()}},
+                "roofline": {"kernel": "asm_ppp (fused PivotPointPlane residual+Jacobian+JtJ reduction)", "bound": "hbm",
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "avg_launch_us": avg_ms * 1e3, "bytes_per_launch": bytes_per_launch, "launches": prof["asm_launches"],
+                             "peak_source": peak_src,
+                             "note": "32 B/feature x features of the solve; ~4.8 MB per launch on this workload, i.e. launch-latency and L2 bound (SURVEY.md 7.3-4)"},
+                "e2e": {"value": args.steps / e2e_t, "unit": "scans/s", "h2d_bytes_per_step": h2d // args.steps,
+                        "d2h_bytes_per_step": d2h // args.steps},
+                "gpu_launches": launches, "clocks": clocks}
+        if world == 1:
+            try:
+                ra = argparse.Namespace(warmup=1, steps=min(args.cpu_sample, n_total - W - 2))
+                r = run_reference(ra, scn, W, est_cfg)
+                line["cpu_baseline"] = {"value": r["scans_per_s"], "unit": "scans/s", "cores": 4, "kind": "port",
+                                        "gn_iter_ms": r["gn_iter_ms"],
+                                        "sample": "%d scans of the same workload through oracle/ (CPU restatement of the reference; 1 thread + 4 marginalisation threads)" % r["steps"]}
+            except Exception as exc:  # the baseline leg must not take the bench line down
+                line["cpu_baseline"] = {"value": None, "unit": "scans/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -211,6 +211,9 @@ int lio_est_get_prior(lio_est *est, double *Hp, double *bp);
 int lio_est_last_normal_equations(lio_est *est, double *H, double *g, double *cost, int *n);
 /* Kernels launched by the last process_scan call. */
 int lio_est_last_launches(lio_est *est);
+/* CUDA-event timing of the fused residual+Jacobian kernel accumulated since the last reset (events recorded
+ * on the estimator's stream around every launch): out = {sum ms, launches, features processed, bytes/feature}. */
+int lio_est_kernel_profile(lio_est *est, double out[4], int reset);
 /* Multi-GPU: frames i with (i-1) % world == rank are matched/assembled locally; the
  * callback must sum-allreduce `count` doubles in place on the DEVICE buffer `buf` across ranks
  * (e.g. ncclAllReduce / torch.distributed.all_reduce on the estimator's stream). */

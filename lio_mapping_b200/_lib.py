@@ -110,6 +110,7 @@ def lib():
     L.lio_est_get_prior.argtypes = [vp, f64p, f64p]
     L.lio_est_last_normal_equations.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(ip)]
     L.lio_est_last_launches.argtypes = [vp]
+    L.lio_est_kernel_profile.argtypes = [vp, f64p, ip]
     L.lio_est_set_shard.argtypes = [vp, ip, ip, ALLREDUCE_FN, vp]
     _LIB = L
     return L

@@ -382,6 +382,10 @@ struct lio_est {
   bool have_H0 = false;
   // cached lidar reduction for the current parameter values
   bool S_valid = false;
+  // CUDA-event timing of the fused kernel (on the launching stream)
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  double asm_ms_sum = 0;
+  long long asm_launch_count = 0, asm_feat_sum = 0;
 };
 
 static Tw tlb_double(const lio_est *e) {
@@ -458,6 +462,8 @@ extern "C" int lio_est_destroy(lio_est *e) {
   for (FeatureOut &f : e->feats) { if (f.pts) cudaFree(f.pts); if (f.coef) cudaFree(f.coef); if (f.src) cudaFree(f.src); }
   void *ptrs[] = {e->d_slot_n, e->d_own_n, e->d_scan, e->d_local, e->d_map, e->d_tmp, e->d_counts, e->d_feat_counts, e->d_tf, e->d_odom, e->d_odom_partial};
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->h_tf) cudaFreeHost(e->h_tf);
   if (e->h_S) cudaFreeHost(e->h_S);
   if (e->h_counts) cudaFreeHost(e->h_counts);
@@ -539,6 +545,7 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
     ok = ok && cudaMemset(e->d_feat_counts, 0, sizeof(int) * (W + 1)) == cudaSuccess;
     ok = ok && cudaMemset(e->d_counts, 0, sizeof(int) * 8) == cudaSuccess;
   }
+  ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
   if (!ok) {
     lio_set_last_error(__FILE__, __LINE__, "lio_est_create: device allocation failed");
     lio_est_destroy(e);
@@ -779,14 +786,22 @@ static int eval_lidar(lio_est *e, std::vector<FrameTerms> &ft) {
   }
   if (e->S_valid) return LIO_OK;
   asm_plan(ap, e->sm_count);
+  long long nfeat = 0;
+  for (int k = 0; k < ap.nframes; ++k) nfeat += ap.f[k].n;
+  if (e->ev0) cudaEventRecord(e->ev0, e->stream);
   int rc = asm_launch(ap, e->asmw, e->stream, &e->launches);
   if (rc != LIO_OK) return rc;
+  if (e->ev1) cudaEventRecord(e->ev1, e->stream);
   if (e->world > 1 && e->allreduce) {
     rc = e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride);
     if (rc != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
   }
   EST_CUDA(cudaMemcpyAsync(e->h_S, e->asmw.out, sizeof(double) * O * kAsmStride, cudaMemcpyDeviceToHost, e->stream));
   EST_CUDA(cudaStreamSynchronize(e->stream));
+  if (e->ev0 && e->ev1) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
+  }
   e->S_valid = true;
   return LIO_OK;
 }
@@ -1310,6 +1325,13 @@ extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, d
   return LIO_OK;
 }
 extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
+
+extern "C" int lio_est_kernel_profile(lio_est *e, double out[4], int reset) {
+  if (!e || !out) return LIO_ERR_INVALID;
+  out[0] = e->asm_ms_sum; out[1] = (double)e->asm_launch_count; out[2] = (double)e->asm_feat_sum; out[3] = 32.0;
+  if (reset) { e->asm_ms_sum = 0; e->asm_launch_count = 0; e->asm_feat_sum = 0; }
+  return LIO_OK;
+}
 
 // ---- factor-operator seam ---------------------------------------------------------------------------
 extern "C" int lio_ppp_evaluate(const double point[3], const double coeff[4], const double pose_pivot[7], const double pose_i[7],
