@@ -129,6 +129,12 @@ int lio_ppp_evaluate(const double point[3], const double coeff[4], const double 
 int lio_ppp_evaluate_batch_host(const float *pts4, const float *coef4, int n, const double pose_pivot[7],
                                 const double pose_i[7], const double pose_ex[7], double *r_out, double *J_out, int device);
 
+/* The fused stage-C reduction for ONE frame on explicit host arrays: with R9 = R_lpi (row-major), t3 = R_lpi^T P_lpi,
+ * out32[0..27] = upper triangle (row-major) of S = sum_k rho'(r_k^2) [g_k;r_k][g_k;r_k]^T, out32[28] = sum_k rho(r_k^2)
+ * (CauchyLoss(1.0), Estimator.cc:1664).  J^T J / J^T r of the frame's PivotPointPlaneFactors = M^T S M. */
+int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, const double R9[9], const double t3[3],
+                     double out32[32], int device);
+
 /* IntegrationBase (include/imu_processor/IntegrationBase.h:72-388) */
 typedef struct lio_pim lio_pim;
 int lio_pim_create(const double acc0[3], const double gyr0[3], const double ba[3], const double bg[3],
@@ -219,6 +225,8 @@ int lio_est_kernel_profile(lio_est *est, double out[4], int reset);
  * (e.g. ncclAllReduce / torch.distributed.all_reduce on the estimator's stream). */
 typedef int (*lio_allreduce_fn)(void *user, double *buf_dev, int count);
 int lio_est_set_shard(lio_est *est, int rank, int world, lio_allreduce_fn fn, void *user);
+/* Owner rank of window frame pivot+frame_rel (frame_rel = 1..O) under `world` ranks: (frame_rel-1) % world. */
+int lio_est_frame_owner(int frame_rel, int world);
 
 #ifdef __cplusplus
 }

@@ -671,9 +671,10 @@ static void double_to_vector(lio_est *e) {  // Estimator.cc:2479-2568
 }
 
 // ---- stage B orchestration -----------------------------------------------------------------------
+extern "C" int lio_est_frame_owner(int frame_rel, int world);
 static bool owns_frame(const lio_est *e, int idx) {  // idx: logical frame > pivot
   const int pivot = e->W - e->O;
-  return ((idx - pivot - 1) % e->world) == e->rank;
+  return lio_est_frame_owner(idx - pivot, e->world) == e->rank;
 }
 
 static int build_local_map(lio_est *e) {
@@ -1215,6 +1216,11 @@ extern "C" int lio_est_process_scan_dev(lio_est *e, const float *surf_last_dev, 
   return process_scan_common(e, reinterpret_cast<const float4 *>(surf_last_dev), n_dev, n_max);
 }
 
+extern "C" int lio_est_frame_owner(int frame_rel, int world) {  // frame_rel in 1..O (relative to the pivot)
+  if (world < 1 || frame_rel < 1) return -1;
+  return (frame_rel - 1) % world;
+}
+
 extern "C" int lio_est_set_shard(lio_est *e, int rank, int world, lio_allreduce_fn fn, void *user) {
   if (!e || world < 1 || rank < 0 || rank >= world) return LIO_ERR_INVALID;
   if (world > 1 && !fn) return LIO_ERR_INVALID;
@@ -1377,6 +1383,44 @@ extern "C" int lio_ppp_evaluate_batch_host(const float *pts4, const float *coef4
   }
   void *fr[] = {dp, dc, dRt, dM, dr, dJ};
   for (void *q : fr) if (q) cudaFree(q);
+  return rc;
+}
+
+// Stage C reduction of ONE frame on explicit host arrays (parity entry for the fused kernel):
+// out32[0..27] = upper triangle of S = sum rho'(r^2) [g;r][g;r]^T, out32[28] = sum log(1+r^2).
+extern "C" int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, const double R9[9], const double t3[3],
+                                double out32[32], int device) {
+  if (!pts4 || !coef4 || n < 0 || !R9 || !t3 || !out32) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  AsmWork w;
+  float4 *dp = nullptr, *dc = nullptr;
+  int rc = LIO_OK;
+  const int nn = n > 0 ? n : 1;
+  if (w.init(nn) != 0 || cudaMalloc(&dp, sizeof(float4) * nn) != cudaSuccess || cudaMalloc(&dc, sizeof(float4) * nn) != cudaSuccess) {
+    lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+    rc = LIO_ERR_CUDA;
+  }
+  if (rc == LIO_OK) {
+    cudaMemcpy(dp, pts4, sizeof(float4) * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(dc, coef4, sizeof(float4) * n, cudaMemcpyHostToDevice);
+    AsmParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.nframes = 1;
+    ap.f[0].pts = dp; ap.f[0].coef = dc; ap.f[0].n = n;
+    std::memcpy(ap.f[0].R, R9, sizeof(double) * 9); std::memcpy(ap.f[0].t, t3, sizeof(double) * 3);
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    asm_plan(ap, sms);
+    rc = asm_launch(ap, w, 0, nullptr);
+    if (rc == LIO_OK) {
+      cudaError_t er = cudaMemcpy(out32, w.out, sizeof(double) * kAsmStride, cudaMemcpyDeviceToHost);
+      if (er != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(er)); rc = LIO_ERR_CUDA; }
+    }
+  }
+  if (dp) cudaFree(dp);
+  if (dc) cudaFree(dc);
+  w.destroy();
   return rc;
 }
 

@@ -44,6 +44,19 @@ def ppp_evaluate_batch(pts4, coef4, pose_pivot, pose_i, pose_ex, device=0):
     return r[:n], J[:n]
 
 
+def asm_ppp(pts4, coef4, R, t, device=0):
+    """Stage C reduction of one frame on the GPU: (S 7x7, sum rho)."""
+    _lib.require_device()
+    p = np.ascontiguousarray(pts4, np.float32).reshape(-1, 4)
+    c = np.ascontiguousarray(coef4, np.float32).reshape(-1, 4)
+    out = np.zeros(32)
+    _lib.check(_lib.lib().lio_asm_ppp_host(p, c, p.shape[0], _d(R).reshape(9), _d(t), out, device), "lio_asm_ppp_host")
+    S = np.zeros((7, 7))
+    S[np.triu_indices(7)] = out[:28]
+    S = S + S.T - np.diag(np.diag(S))
+    return S, out[28]
+
+
 class Pim:
     """IntegrationBase (include/imu_processor/IntegrationBase.h) + ImuFactor operator."""
 

@@ -31,6 +31,23 @@ def test_ppp_rows_device_vs_oracle(oracle):
         assert np.abs(J[k] - Jo).max() <= 1e-12 * max(1.0, np.abs(Jo).max())
 
 
+@pytest.mark.parametrize("n", [0, 1, 255, 256, 257, 5000, 300001])
+def test_asm_ppp_kernel_vs_numpy(n):
+    """The fused reduction (28 sym entries + cost) vs a float64 numpy statement of the same sums."""
+    from lio_mapping_b200 import estimator
+    from tests.test_shard_gloo import s_blocks
+    rng = np.random.default_rng(n)
+    p = rng.uniform(-60, 60, (n, 4)).astype(np.float32)
+    w = rng.normal(size=(n, 3)); w /= np.maximum(np.linalg.norm(w, axis=1, keepdims=True), 1e-9)
+    c = np.concatenate([w * rng.uniform(0.2, 1, (n, 1)), rng.normal(0, 0.3, (n, 1))], 1).astype(np.float32)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    R = synth.quat_to_rot(q); t = rng.normal(size=3)
+    S, cost = estimator.asm_ppp(p, c, R, t)
+    Sr, cr = s_blocks((p.astype(np.float64), c.astype(np.float64)), R, t)
+    assert np.abs(S - Sr).max() <= 1e-11 * max(1.0, np.abs(Sr).max())
+    assert abs(cost - cr) <= 1e-11 * max(1.0, cr)
+
+
 @pytest.fixture(scope="module")
 def vlp_seq(oracle):
     return helpers.Sequence(oracle, "vlp16", n_total=10, distort=False)
@@ -113,3 +130,59 @@ def test_window_solve_parity_full_odom(oracle, vlp_seq):
         scale = max(1.0, np.abs(xo[:, :3]).max())
         assert np.abs(xg[:, :3] - xo[:, :3]).max() <= 1e-4 * scale      # north_star: pose error <= 1e-4 rel
         assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-4
+
+
+def test_two_rank_shard_equals_single(oracle, vlp_seq):
+    """Frame sharding with an allreduce of the S blocks reproduces the single-rank solve (two estimator instances on
+    one GPU, driven by two threads; the callback sums through the host with a barrier)."""
+    import ctypes as C
+    import threading
+    from lio_mapping_b200 import estimator
+    W = 5
+    cfg = dict(odom_max_iterations=1, prior_factor=1)
+    ref = estimator.Estimator(window_size=W, opt_window_size=W, max_frame_points=1 << 15, max_scan_points=1 << 17, **cfg)
+    ranks = [estimator.Estimator(window_size=W, opt_window_size=W, max_frame_points=1 << 15, max_scan_points=1 << 17, **cfg)
+             for _ in range(2)]
+    mk = lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=0.2, gyr_n=0.02)
+    for e in [ref] + ranks:
+        helpers.warm_start(e, vlp_seq, oracle, W, pose_noise=0.01, seed=1, make_pim=mk)
+    cudart = C.CDLL("libcudart.so.12") if False else None
+    import torch
+    bar = threading.Barrier(2)
+    stage = [None, None]
+
+    def make_cb(r):
+        def cb(ptr, count):
+            class _Arr:
+                __cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+            t = torch.as_tensor(_Arr(), device="cuda")
+            torch.cuda.synchronize()
+            stage[r] = t.cpu().numpy().copy()
+            bar.wait()
+            t.copy_(torch.from_numpy(stage[0] + stage[1]))
+            torch.cuda.synchronize()
+            bar.wait()
+            return 0
+        return cb
+    for r, e in enumerate(ranks):
+        e.set_shard(r, 2, make_cb(r))
+    errs = []
+
+    def run(r):
+        try:
+            for k in range(W, 8):
+                helpers.feed_scan(ranks[r], vlp_seq, k)
+        except Exception as exc:   # pragma: no cover
+            errs.append(exc)
+            bar.abort()
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t_ in th:
+        t_.start()
+    for k in range(W, 8):
+        helpers.feed_scan(ref, vlp_seq, k)
+    for t_ in th:
+        t_.join(timeout=300)
+    assert not errs, errs
+    x = ref.states()
+    for e in ranks:
+        assert np.abs(e.states() - x).max() <= 1e-9 * max(1.0, np.abs(x).max())
