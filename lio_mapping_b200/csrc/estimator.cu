@@ -525,7 +525,7 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   int vg_cap = std::max(e->local_cap, cfg->max_scan_points);
   ok = ok && e->vg.init(vg_cap) == 0;
   ok = ok && e->hash.init(e->local_cap) == 0;
-  ok = ok && e->knn.init(cfg->max_frame_points) == 0;
+  ok = ok && e->knn.init(cfg->max_frame_points * (O + 1)) == 0;
   e->feats.assign(W + 1, FeatureOut());
   long long total_feat = 0;
   for (int k = pivot + 1; k <= W && ok; ++k) {
@@ -730,25 +730,36 @@ static int build_local_map(lio_est *e) {
   e->t_build = now_s() - t0;
   const double t1 = now_s();
   EST_CUDA(cudaMemsetAsync(e->d_feat_counts, 0, sizeof(int) * (W + 1), st));
-  for (int idx = pivot + 1; idx <= W; ++idx) {
-    if (!owns_frame(e, idx)) continue;
-    const int slot = e->slot_of[idx];
-    if (idx != W || !e->cfg.imu_factor) {
+  {
+    // every owned frame except a LaserOdom-driven newest frame: ONE batched kNN + plane-fit launch
+    KnnBatch b;
+    b.nframes = 0;
+    for (int idx = pivot + 1; idx <= W; ++idx) {
+      if (!owns_frame(e, idx)) continue;
+      if (idx == W && e->cfg.imu_factor) continue;
+      const int slot = e->slot_of[idx];
+      KnnFrame &f = b.f[b.nframes++];
+      f.surf = e->slot_ptr[slot]; f.n_dev = e->d_slot_n + slot; f.tf = e->d_tf + idx;
+      const int known = e->size_surf_stack[idx];
+      f.n_bound = (known > 0 && idx < W) ? known : e->cfg.max_frame_points;
+      f.out_p = e->feats[idx].pts; f.out_c = e->feats[idx].coef; f.out_src = e->feats[idx].src; f.out_count = e->feats[idx].count;
+      f.append = 0; f.tile0 = 0;
+    }
+    rc = calculate_features_batch(e->hash, b, e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, nullptr, e->knn, st, &e->launches);
+    if (rc != LIO_OK) return rc;
+  }
+  if (e->cfg.imu_factor && owns_frame(e, W)) {
+    const int idx = W, slot = e->slot_of[W];
+    EST_CUDA(cudaMemsetAsync(e->d_odom, 0, sizeof(OdomState), st));
+    const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
+    for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
       rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
-                                  e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], 0, nullptr, e->knn, st, &e->launches);
+                                  e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], e->cfg.keep_features ? 1 : 0,
+                                  &e->d_odom->done, e->knn, st, &e->launches);
       if (rc != LIO_OK) return rc;
-    } else {
-      EST_CUDA(cudaMemsetAsync(e->d_odom, 0, sizeof(OdomState), st));
-      const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
-      for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
-        rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
-                                    e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], e->cfg.keep_features ? 1 : 0,
-                                    &e->d_odom->done, e->knn, st, &e->launches);
-        if (rc != LIO_OK) return rc;
-        k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
-        k_odom_solve<<<1, 32, 0, st>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
-        e->launches += 2;
-      }
+      k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
+      k_odom_solve<<<1, 32, 0, st>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
+      e->launches += 2;
     }
   }
   // one synchronisation: feature counts, map size, odom iterations
@@ -756,7 +767,9 @@ static int build_local_map(lio_est *e) {
   EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 1, e->d_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 5, &e->d_odom->iter, sizeof(int), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaMemcpyAsync(e->h_tf + W, e->d_tf + W, sizeof(TransformF), cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 6, e->d_slot_n + e->slot_of[W], sizeof(int), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaStreamSynchronize(st));
+  e->size_surf_stack[W] = e->h_counts[W + 6];
   for (int k = 0; k <= W; ++k) e->h_feat_n[k] = e->h_counts[k];
   e->h_map_n = e->h_counts[W + 1 + 2];
   e->odom_iters = e->h_counts[W + 5];
@@ -1028,15 +1041,11 @@ static int marginalize(lio_est *e) {
   for (int k = 0; k < nr; ++k) if (ev2[k] > eps) kept.push_back(k);
   Vec vb(nr, 0.0);
   for (int k : kept) { double s = 0; for (int r = 0; r < nr; ++r) s += V2(r, k) * b2[r]; vb[k] = s; np.c0 += s * s / ev2[k]; }
+  weighted_gram(V2, ev2, kept, np.Hp);
   for (int r = 0; r < nr; ++r) {
     double sb = 0;
     for (int k : kept) sb += V2(r, k) * vb[k];
     np.bp[r] = sb;
-    for (int c = r; c < nr; ++c) {
-      double s = 0;
-      for (int k : kept) s += V2(r, k) * ev2[k] * V2(c, k);
-      np.Hp(r, c) = s; np.Hp(c, r) = s;
-    }
   }
   np.x0_pose.resize(7 * O); np.x0_sb.resize(9 * O);
   for (int k = 1; k <= O; ++k) {  // addr_shift: block i -> i-1 in the next window

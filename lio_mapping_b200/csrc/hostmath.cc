@@ -1,59 +1,80 @@
 // lio_mapping_b200 — dense fp64 kernels of the host shell (n <= 15*(O+1)+6 <= 256).
+// All inner loops are stride-1 (right-looking Cholesky on rows, column-major eigen-solver) and the hot
+// functions are multiversioned (x86-64-v3 = AVX2+FMA when the CPU has it, baseline otherwise).
 #include "hostmath.h"
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#define LIO_MV __attribute__((target_clones("arch=x86-64-v3", "default")))
+#else
+#define LIO_MV
+#endif
 
 namespace lio {
 namespace hm {
 
-bool cholesky(Mat &a) {
+// Right-looking (outer-product) lower Cholesky: after step k the trailing lower triangle has the rank-1
+// update  a[i][j] -= l_ik * l_jk  applied row by row (contiguous axpy, no reduction to reassociate).
+LIO_MV bool cholesky(Mat &a) {
   const int n = a.r;
-  for (int j = 0; j < n; ++j) {
-    double *rj = &a.d[(size_t)j * n];
-    double s = rj[j];
-    for (int k = 0; k < j; ++k) s -= rj[k] * rj[k];
+  std::vector<double> col(n);
+  double *A = a.d.data();
+  for (int k = 0; k < n; ++k) {
+    const double s = A[(size_t)k * n + k];
     if (!(s > 0.0) || !std::isfinite(s)) return false;
     const double l = std::sqrt(s), il = 1.0 / l;
-    rj[j] = l;
-    for (int i = j + 1; i < n; ++i) {
-      double *ri = &a.d[(size_t)i * n];
-      double t = ri[j];
-      for (int k = 0; k < j; ++k) t -= ri[k] * rj[k];
-      ri[j] = t * il;
+    A[(size_t)k * n + k] = l;
+    for (int i = k + 1; i < n; ++i) {
+      const double v = A[(size_t)i * n + k] * il;
+      A[(size_t)i * n + k] = v;
+      col[i] = v;
+    }
+    for (int i = k + 1; i < n; ++i) {
+      double *ri = A + (size_t)i * n;
+      const double lik = col[i];
+      const double *c = col.data();
+      for (int j = k + 1; j <= i; ++j) ri[j] -= lik * c[j];
     }
   }
   return true;
 }
 
-void cholesky_solve(const Mat &L, Vec &b) {
+LIO_MV void cholesky_solve(const Mat &L, Vec &b) {
   const int n = L.r;
+  const double *A = L.d.data();
   for (int i = 0; i < n; ++i) {
-    const double *ri = &L.d[(size_t)i * n];
-    double s = b[i];
-    for (int k = 0; k < i; ++k) s -= ri[k] * b[k];
-    b[i] = s / ri[i];
+    const double *ri = A + (size_t)i * n;
+    double s = 0;
+#pragma omp simd reduction(+ : s)
+    for (int k = 0; k < i; ++k) s += ri[k] * b[k];
+    b[i] = (b[i] - s) / ri[i];
   }
+  // back substitution in axpy form: x_i known -> subtract its column (= row i of L) from the rest
   for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int k = i + 1; k < n; ++k) s -= L.d[(size_t)k * n + i] * b[k];
-    b[i] = s / L.d[(size_t)i * n + i];
+    const double *ri = A + (size_t)i * n;
+    const double xi = b[i] / ri[i];
+    b[i] = xi;
+    for (int k = 0; k < i; ++k) b[k] -= ri[k] * xi;
   }
 }
 
-// Householder reduction to tridiagonal form followed by implicit-shift QL iterations with
-// accumulated transformations (the classical EISPACK tred2/tql2 pair).  Z holds A on entry.
-void sym_eigen(const Mat &A, Vec &d, Mat &Z) {
+// Householder tridiagonalisation + implicit-shift QL with accumulated transformations (EISPACK
+// tred2/tql2), on column-major storage: z(i,j) = Zt[j*n + i], so every inner loop walks a column.
+LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
   const int n = A.r;
-  Z = A;
   d.assign(n, 0.0);
+  Zout = Mat(n, n);
   if (n == 0) return;
+  std::vector<double> Zt((size_t)n * n);
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) Zt[(size_t)j * n + i] = A.d[(size_t)i * n + j];
   Vec e(n, 0.0);
-  auto z = [&](int i, int j) -> double & { return Z.d[(size_t)i * n + j]; };
-  for (int j = 0; j < n; ++j) d[j] = z(n - 1, j);
+  auto col = [&](int j) { return Zt.data() + (size_t)j * n; };
+  for (int j = 0; j < n; ++j) d[j] = col(j)[n - 1];
   for (int i = n - 1; i > 0; --i) {
     double scale = 0.0, h = 0.0;
     for (int k = 0; k < i; ++k) scale += std::fabs(d[k]);
     if (scale == 0.0) {
       e[i] = d[i - 1];
-      for (int j = 0; j < i; ++j) { d[j] = z(i - 1, j); z(i, j) = 0.0; z(j, i) = 0.0; }
+      for (int j = 0; j < i; ++j) { d[j] = col(j)[i - 1]; col(j)[i] = 0.0; col(i)[j] = 0.0; }
     } else {
       const double inv = 1.0 / scale;
       for (int k = 0; k < i; ++k) { d[k] *= inv; h += d[k] * d[k]; }
@@ -63,12 +84,17 @@ void sym_eigen(const Mat &A, Vec &d, Mat &Z) {
       h -= f * g;
       d[i - 1] = f - g;
       for (int j = 0; j < i; ++j) e[j] = 0.0;
+      double *ci = col(i);
       for (int j = 0; j < i; ++j) {
         f = d[j];
-        z(j, i) = f;
-        g = e[j] + z(j, j) * f;
-        for (int k = j + 1; k < i; ++k) { g += z(k, j) * d[k]; e[k] += z(k, j) * f; }
-        e[j] = g;
+        ci[j] = f;
+        double *cj = col(j);
+        double gg = 0.0;
+        const double *dp = d.data();
+        double *ep = e.data();
+#pragma omp simd reduction(+ : gg)
+        for (int k = j + 1; k < i; ++k) { gg += cj[k] * dp[k]; ep[k] += cj[k] * f; }
+        e[j] = e[j] + cj[j] * f + gg;
       }
       f = 0.0;
       for (int j = 0; j < i; ++j) { e[j] /= h; f += e[j] * d[j]; }
@@ -76,29 +102,36 @@ void sym_eigen(const Mat &A, Vec &d, Mat &Z) {
       for (int j = 0; j < i; ++j) e[j] -= hh * d[j];
       for (int j = 0; j < i; ++j) {
         f = d[j]; g = e[j];
-        for (int k = j; k < i; ++k) z(k, j) -= (f * e[k] + g * d[k]);
-        d[j] = z(i - 1, j);
-        z(i, j) = 0.0;
+        double *cj = col(j);
+        const double *dp = d.data(), *ep = e.data();
+        for (int k = j; k < i; ++k) cj[k] -= (f * ep[k] + g * dp[k]);
+        d[j] = cj[i - 1];
+        cj[i] = 0.0;
       }
     }
     d[i] = h;
   }
   for (int i = 0; i < n - 1; ++i) {
-    z(n - 1, i) = z(i, i);
-    z(i, i) = 1.0;
+    col(i)[n - 1] = col(i)[i];
+    col(i)[i] = 1.0;
     const double h = d[i + 1];
     if (h != 0.0) {
-      for (int k = 0; k <= i; ++k) d[k] = z(k, i + 1) / h;
+      const double *c1 = col(i + 1);
+      for (int k = 0; k <= i; ++k) d[k] = c1[k] / h;
       for (int j = 0; j <= i; ++j) {
+        double *cj = col(j);
         double g = 0.0;
-        for (int k = 0; k <= i; ++k) g += z(k, i + 1) * z(k, j);
-        for (int k = 0; k <= i; ++k) z(k, j) -= g * d[k];
+#pragma omp simd reduction(+ : g)
+        for (int k = 0; k <= i; ++k) g += c1[k] * cj[k];
+        const double *dp = d.data();
+        for (int k = 0; k <= i; ++k) cj[k] -= g * dp[k];
       }
     }
-    for (int k = 0; k <= i; ++k) z(k, i + 1) = 0.0;
+    double *c1 = col(i + 1);
+    for (int k = 0; k <= i; ++k) c1[k] = 0.0;
   }
-  for (int j = 0; j < n; ++j) { d[j] = z(n - 1, j); z(n - 1, j) = 0.0; }
-  z(n - 1, n - 1) = 1.0;
+  for (int j = 0; j < n; ++j) { d[j] = col(j)[n - 1]; col(j)[n - 1] = 0.0; }
+  col(n - 1)[n - 1] = 1.0;
   for (int i = 1; i < n; ++i) e[i - 1] = e[i];
   e[n - 1] = 0.0;
   double f = 0.0, tst1 = 0.0;
@@ -132,11 +165,11 @@ void sym_eigen(const Mat &A, Vec &d, Mat &Z) {
           c = p / r;
           p = c * d[i] - s * g;
           d[i + 1] = h + s * (c * g + s * d[i]);
+          double *ca = col(i), *cb = col(i + 1);
           for (int k = 0; k < n; ++k) {
-            double *row = &Z.d[(size_t)k * n];
-            h = row[i + 1];
-            row[i + 1] = s * row[i] + c * h;
-            row[i] = c * row[i] - s * h;
+            const double hb = cb[k], ha = ca[k];
+            cb[k] = s * ha + c * hb;
+            ca[k] = c * ha - s * hb;
           }
         }
         p = -s * s2 * c3 * el1 * e[l] / dl1;
@@ -148,18 +181,36 @@ void sym_eigen(const Mat &A, Vec &d, Mat &Z) {
     d[l] += f;
     e[l] = 0.0;
   }
-  // ascending order
   std::vector<int> idx(n);
   for (int i = 0; i < n; ++i) idx[i] = i;
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return d[a] < d[b]; });
   Vec ds(n);
-  Mat Zs(n, n);
   for (int j = 0; j < n; ++j) {
     ds[j] = d[idx[j]];
-    for (int k = 0; k < n; ++k) Zs.d[(size_t)k * n + j] = Z.d[(size_t)k * n + idx[j]];
+    const double *c = col(idx[j]);
+    for (int k = 0; k < n; ++k) Zout.d[(size_t)k * n + j] = c[k];
   }
   d.swap(ds);
-  Z = Zs;
+}
+
+// C = A * A^T restricted to the first `kc` columns of A scaled by w: C(r,c) = sum_k A(r,k) w[k] A(c,k)
+LIO_MV void weighted_gram(const Mat &A, const Vec &w, const std::vector<int> &cols, Mat &C) {
+  const int n = A.r, kc = (int)cols.size();
+  Mat B(n, kc), Bw(n, kc);  // gathered columns, contiguous per row
+  for (int r = 0; r < n; ++r)
+    for (int k = 0; k < kc; ++k) { double v = A.d[(size_t)r * A.c + cols[k]]; B.d[(size_t)r * kc + k] = v; Bw.d[(size_t)r * kc + k] = v * w[cols[k]]; }
+  C = Mat(n, n);
+  for (int r = 0; r < n; ++r) {
+    const double *br = &Bw.d[(size_t)r * kc];
+    for (int c = r; c < n; ++c) {
+      const double *bc = &B.d[(size_t)c * kc];
+      double s = 0;
+#pragma omp simd reduction(+ : s)
+      for (int k = 0; k < kc; ++k) s += br[k] * bc[k];
+      C.d[(size_t)r * n + c] = s;
+      C.d[(size_t)c * n + r] = s;
+    }
+  }
 }
 
 }  // namespace hm

@@ -148,6 +148,8 @@ bool cholesky(Mat &a);
 void cholesky_solve(const Mat &L, Vec &b);
 // symmetric eigen-decomposition (ascending eigenvalues, eigenvectors in columns)
 void sym_eigen(const Mat &A, Vec &evals, Mat &evecs);
+// C(r,c) = sum_{k in cols} A(r,k) w[k] A(c,k)
+void weighted_gram(const Mat &A, const Vec &w, const std::vector<int> &cols, Mat &C);
 
 }  // namespace hm
 }  // namespace lio

@@ -136,105 +136,146 @@ __device__ __forceinline__ void assoc_to_map(const TransformF &t, float vx, floa
   ox = rx + t.px; oy = ry + t.py; oz = rz + t.pz;
 }
 
-__device__ __forceinline__ bool better(float d, int i, float bd, int bi) { return d < bd || (d == bd && i < bi); }
+// (d^2, map index) packed so that unsigned order == the oracle's total order (d^2 >= 0)
+__device__ __forceinline__ unsigned long long pack_key(float d, int mi) {
+  return ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)mi;
+}
+constexpr unsigned long long kInfKey = 0x7f8000007fffffffull;  // (+inf, INT_MAX)
 
+constexpr int kGroup = 8;                               // lanes cooperating on one query
+constexpr int kQueriesPerBlock = kKnnThreads / kGroup;  // 16
+
+// One 8-lane group per query: lane g scans cells g, g+8, g+16, g+24 of the 3x3x3 block keeping a local
+// sorted top-5; the groups' lists are merged by five rounds of a (d^2, idx) min-reduction (shuffles), which
+// yields exactly the sequence a single sorted scan would; lane 0 of the group then fits the plane.
 __global__ void __launch_bounds__(kKnnThreads)
-knn_plane(const unsigned long long *__restrict__ hkeys, const int *__restrict__ hcount, const int *__restrict__ hstart, int hmask,
-          float inv_cell, const float4 *__restrict__ cellpts, const float4 *__restrict__ surf, const int *__restrict__ nsurf_dev,
-          const TransformF *__restrict__ tf_dev, float min_match_sq_dis, float min_plane_dis, float4 *__restrict__ out_p,
-          float4 *__restrict__ out_c, int *__restrict__ out_src, int *__restrict__ out_count, int append,
-          const int *__restrict__ done_flag, unsigned long long *__restrict__ status, int *__restrict__ ticket) {
+knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const int *__restrict__ hcount,
+          const int *__restrict__ hstart, int hmask, float inv_cell, const float4 *__restrict__ cellpts, float min_match_sq_dis,
+          float min_plane_dis, const int *__restrict__ done_flag, unsigned long long *__restrict__ status, int *__restrict__ ticket) {
   __shared__ int sscan[40];
   __shared__ int stile, sbc;
   if (done_flag && *done_flag) return;
-  const int n = *nsurf_dev;
-  const int ntiles = (n + kKnnThreads - 1) / kKnnThreads;
   if (threadIdx.x == 0) stile = atomicAdd(ticket, 1);
   __syncthreads();
   const int tile = stile;
-  const int base_count = append ? *out_count : 0;   // read before the last tile rewrites it (see end)
-  if (tile >= ntiles) {
-    if (n == 0 && tile == 0 && threadIdx.x == 0 && !append) *out_count = 0;
+  if (tile >= B.ntiles) return;
+  int fi = 0;
+#pragma unroll 1
+  for (int k = 1; k < B.nframes; ++k) if (tile >= B.f[k].tile0) fi = k;
+  const KnnFrame &F = B.f[fi];
+  const int ltile = tile - F.tile0;
+  const int n = *F.n_dev;
+  const int ntiles = (n + kQueriesPerBlock - 1) / kQueriesPerBlock;
+  const int base_count = F.append ? *F.out_count : 0;  // read before the frame's last tile rewrites it
+  if (ltile >= ntiles) {
+    if (n == 0 && ltile == 0 && threadIdx.x == 0 && !F.append) *F.out_count = 0;
     return;
   }
-  const TransformF tf = *tf_dev;
-  const int i = tile * kKnnThreads + threadIdx.x;
+  const TransformF tf = *F.tf;
+  const int g = threadIdx.x & (kGroup - 1);
+  const int q = ltile * kQueriesPerBlock + (threadIdx.x / kGroup);
+  const unsigned gmask = 0xffu << ((lane_id() / kGroup) * kGroup);
   bool valid = false;
   float4 po = make_float4(0, 0, 0, 0), co = make_float4(0, 0, 0, 0);
-  if (i < n) {
-    float4 p = __ldg(surf + i);
-    float sx, sy, sz;
+  const bool active = q < n;
+  float sx = 0.f, sy = 0.f, sz = 0.f;
+  float4 p = make_float4(0, 0, 0, 0);
+  unsigned long long bk[5];
+  int bp[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) { bk[k] = kInfKey; bp[k] = -1; }
+  if (active) {
+    p = __ldg(F.surf + q);
     assoc_to_map(tf, p.x, p.y, p.z, sx, sy, sz);
-    int cx = (int)floorf(sx * inv_cell), cy = (int)floorf(sy * inv_cell), cz = (int)floorf(sz * inv_cell);
-    float bd[5];
-    int bi[5], bp[5];
+    const int cx = (int)floorf(sx * inv_cell), cy = (int)floorf(sy * inv_cell), cz = (int)floorf(sz * inv_cell);
+    for (int c = g; c < 27; c += kGroup) {
+      const int dz = c / 9 - 1, dy = (c / 3) % 3 - 1, dx = c % 3 - 1;
+      const unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz);
+      unsigned s = hash_cell(key) & hmask;
+      int slot = -1;
+      while (true) {
+        unsigned long long k = hkeys[s];
+        if (k == key) { slot = (int)s; break; }
+        if (k == kEmptyKey) break;
+        s = (s + 1) & hmask;
+      }
+      if (slot < 0) continue;
+      const int st = hstart[slot], cnt = hcount[slot];
+      for (int j = st; j < st + cnt; ++j) {
+        const float4 m = __ldg(cellpts + j);
+        // flann::L2_Simple<float>: sequential diff*diff accumulation over x, y, z
+        const float d0 = sx - m.x, d1 = sy - m.y, d2 = sz - m.z;
+        float d = 0.f;
+        d += d0 * d0; d += d1 * d1; d += d2 * d2;
+        const unsigned long long kk = pack_key(d, __float_as_int(m.w));
+        if (kk < bk[4]) {
+          bk[4] = kk; bp[4] = j;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) { bd[k] = INFINITY; bi[k] = 0x7fffffff; bp[k] = -1; }
-    for (int dz = -1; dz <= 1; ++dz)
-      for (int dy = -1; dy <= 1; ++dy)
-        for (int dx = -1; dx <= 1; ++dx) {
-          unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz);
-          unsigned s = hash_cell(key) & hmask;
-          int slot = -1;
-          while (true) {
-            unsigned long long k = hkeys[s];
-            if (k == key) { slot = (int)s; break; }
-            if (k == kEmptyKey) break;
-            s = (s + 1) & hmask;
-          }
-          if (slot < 0) continue;
-          int st = hstart[slot], cnt = hcount[slot];
-          for (int j = st; j < st + cnt; ++j) {
-            float4 m = __ldg(cellpts + j);
-            // flann::L2_Simple<float>: sequential diff*diff accumulation over x, y, z
-            float d0 = sx - m.x, d1 = sy - m.y, d2 = sz - m.z;
-            float d = 0.f;
-            d += d0 * d0; d += d1 * d1; d += d2 * d2;
-            int mi = __float_as_int(m.w);
-            if (better(d, mi, bd[4], bi[4])) {
-              bd[4] = d; bi[4] = mi; bp[4] = j;
-#pragma unroll
-              for (int t = 4; t > 0; --t) {
-                if (better(bd[t], bi[t], bd[t - 1], bi[t - 1])) {
-                  float td = bd[t]; bd[t] = bd[t - 1]; bd[t - 1] = td;
-                  int ti = bi[t]; bi[t] = bi[t - 1]; bi[t - 1] = ti;
-                  ti = bp[t]; bp[t] = bp[t - 1]; bp[t - 1] = ti;
-                }
-              }
+          for (int t = 4; t > 0; --t) {
+            if (bk[t] < bk[t - 1]) {
+              unsigned long long tk = bk[t]; bk[t] = bk[t - 1]; bk[t - 1] = tk;
+              int ti = bp[t]; bp[t] = bp[t - 1]; bp[t - 1] = ti;
             }
           }
         }
-    if (bd[4] < min_match_sq_dis) {
-      float A[5][3], B[5], X[3];
+      }
+    }
+  }
+  // merge the 8 sorted lists: five pops of the group-wide minimum head
+  unsigned long long top_k[5];
+  int top_p[5];
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    unsigned long long m = bk[0];
+#pragma unroll
+    for (int o = kGroup / 2; o > 0; o >>= 1) {
+      unsigned long long other = __shfl_xor_sync(gmask, m, o);
+      m = other < m ? other : m;
+    }
+    const bool mine = (bk[0] == m) && (m != kInfKey);
+    const unsigned wb = __ballot_sync(gmask, mine) & gmask;   // keys are unique per map point: at most one lane
+    const int wl = wb ? (__ffs(wb) - 1) : (int)(lane_id() & ~(kGroup - 1));
+    top_k[r] = m;
+    top_p[r] = __shfl_sync(gmask, bp[0], wl);
+    if (mine) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { bk[t] = bk[t + 1]; bp[t] = bp[t + 1]; }
+      bk[4] = kInfKey; bp[4] = -1;
+    }
+  }
+  if (active && g == 0) {
+    const float d5 = __uint_as_float((unsigned)(top_k[4] >> 32));
+    if (top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+      float A[5][3], Bv[5], X[3];
       float nx[5], ny[5], nz[5];
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
-        float4 m = __ldg(cellpts + bp[j]);
+        const float4 m = __ldg(cellpts + top_p[j]);
         nx[j] = m.x; ny[j] = m.y; nz[j] = m.z;
         A[j][0] = m.x; A[j][1] = m.y; A[j][2] = m.z;
-        B[j] = -1.f;
+        Bv[j] = -1.f;
       }
-      colpiv_qr_solve<5, 3>(A, B, X);
+      colpiv_qr_solve<5, 3>(A, Bv, X);
       float pa = X[0], pb = X[1], pc = X[2], pd = 1.f;
-      float ps = sqrtf(pa * pa + pb * pb + pc * pc);
+      const float ps = sqrtf(pa * pa + pb * pb + pc * pc);
       pa /= ps; pb /= ps; pc /= ps; pd /= ps;
       bool planeValid = true;
 #pragma unroll
       for (int j = 0; j < 5; ++j)
         if (fabsf(pa * nx[j] + pb * ny[j] + pc * nz[j] + pd) > min_plane_dis) planeValid = false;
       if (planeValid) {
-        float pd2 = pa * sx + pb * sy + pc * sz + pd;
-        float dist = sqrtf(sx * sx + sy * sy + sz * sz);
-        float s = 1.f - 0.9f * fabsf(pd2) / sqrtf(dist);
+        const float pd2 = pa * sx + pb * sy + pc * sz + pd;
+        const float dist = sqrtf(sx * sx + sy * sy + sz * sz);
+        const float s = 1.f - 0.9f * fabsf(pd2) / sqrtf(dist);
         float zx, zy, zz;
         assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
-        float e0 = tf.px - sx, e1 = tf.py - sy, e2 = tf.pz - sz;
-        float squared_side1 = e0 * e0 + e1 * e1 + e2 * e2;
-        float f0 = zx - sx, f1 = zy - sy, f2 = zz - sz;
-        float squared_side2 = f0 * f0 + f1 * f1 + f2 * f2;
-        float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
-        float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
-        bool in_fov = (check1 < 0.f && check2 > 0.f);
+        const float e0 = tf.px - sx, e1 = tf.py - sy, e2 = tf.pz - sz;
+        const float squared_side1 = e0 * e0 + e1 * e1 + e2 * e2;
+        const float f0 = zx - sx, f1 = zy - sy, f2 = zz - sz;
+        const float squared_side2 = f0 * f0 + f1 * f1 + f2 * f2;
+        const float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
+        const float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
+        const bool in_fov = (check1 < 0.f && check2 > 0.f);
         if ((double)s > 0.1 && in_fov) {
           valid = true;
           po = make_float4(p.x, p.y, p.z, s);
@@ -244,17 +285,17 @@ knn_plane(const unsigned long long *__restrict__ hkeys, const int *__restrict__ 
     }
   }
   int tot;
-  int lpos = block_scan_excl(valid ? 1 : 0, sscan, &tot);
-  int excl = lookback_exclusive(status, tile, tot, &sbc);
+  const int lpos = block_scan_excl(valid ? 1 : 0, sscan, &tot);   // thread order == query order
+  const int excl = lookback_exclusive(status + F.tile0, ltile, tot, &sbc);
   if (valid) {
-    int o = base_count + excl + lpos;
-    out_p[o] = po; out_c[o] = co; out_src[o] = i;
+    const int o = base_count + excl + lpos;
+    F.out_p[o] = po; F.out_c[o] = co; F.out_src[o] = q;
   }
-  if (tile == ntiles - 1 && threadIdx.x == 0) *out_count = base_count + excl + tot;
+  if (ltile == ntiles - 1 && threadIdx.x == 0) *F.out_count = base_count + excl + tot;
 }
 
-int KnnWork::init(int max_queries) {
-  ntiles_max = (max_queries + kKnnThreads - 1) / kKnnThreads + 1;
+int KnnWork::init(int max_queries_total) {
+  ntiles_max = (max_queries_total + kQueriesPerBlock - 1) / kQueriesPerBlock + kMaxKnnFrames + 1;
   if (cudaMalloc(&status, sizeof(unsigned long long) * ntiles_max) != cudaSuccess) return -1;
   if (cudaMalloc(&ticket, sizeof(int)) != cudaSuccess) return -1;
   return 0;
@@ -265,22 +306,42 @@ void KnnWork::destroy() {
   status = nullptr; ticket = nullptr;
 }
 
-int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
-                           const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
-                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches) {
-  (void)map;
-  int ntiles = (nsurf_max + kKnnThreads - 1) / kKnnThreads;
-  if (ntiles < 1) ntiles = 1;
-  if (ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
-  cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * ntiles, st);
+void knn_plan(KnnBatch &b) {
+  int t = 0;
+  for (int k = 0; k < b.nframes; ++k) {
+    b.f[k].tile0 = t;
+    int nt = (b.f[k].n_bound + kQueriesPerBlock - 1) / kQueriesPerBlock;
+    if (nt < 1) nt = 1;
+    t += nt;
+  }
+  b.ntiles = t;
+}
+
+int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
+                             KnnWork &work, cudaStream_t st, int *launches) {
+  if (b.nframes <= 0) return LIO_OK;
+  knn_plan(b);
+  if (b.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
+  cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * b.ntiles, st);
   cudaMemsetAsync(work.ticket, 0, sizeof(int), st);
-  knn_plane<<<ntiles, kKnnThreads, 0, st>>>(h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, surf, nsurf_dev, tf_dev,
-                                            min_match_sq_dis, min_plane_dis, out.pts, out.coef, out.src, out.count, append,
-                                            done_flag, work.status, work.ticket);
+  knn_plane<<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+                                              min_plane_dis, done_flag, work.status, work.ticket);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
   return LIO_OK;
+}
+
+int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
+                           const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches) {
+  (void)map;
+  KnnBatch b;
+  b.nframes = 1;
+  KnnFrame &f = b.f[0];
+  f.surf = surf; f.n_dev = nsurf_dev; f.n_bound = nsurf_max; f.tf = tf_dev;
+  f.out_p = out.pts; f.out_c = out.coef; f.out_src = out.src; f.out_count = out.count; f.append = append; f.tile0 = 0;
+  return calculate_features_batch(h, b, min_match_sq_dis, min_plane_dis, done_flag, work, st, launches);
 }
 
 }  // namespace lio

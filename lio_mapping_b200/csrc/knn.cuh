@@ -33,13 +33,37 @@ struct FeatureOut {
   int cap = 0;
 };
 
+constexpr int kMaxKnnFrames = 16;
+
+struct KnnFrame {
+  const float4 *surf;
+  const int *n_dev;        // device count of surf points
+  int n_bound;             // host-side upper bound of *n_dev (grid sizing)
+  const TransformF *tf;    // device transform (frame -> pivot frame)
+  float4 *out_p, *out_c;
+  int *out_src, *out_count;
+  int append;
+  int tile0;
+};
+
+struct KnnBatch {
+  KnnFrame f[kMaxKnnFrames];
+  int nframes = 0;
+  int ntiles = 0;
+};
+
 struct KnnWork {
   unsigned long long *status = nullptr;
   int *ticket = nullptr;
   int ntiles_max = 0;
-  int init(int max_queries);
+  int init(int max_queries_total);
   void destroy();
 };
+
+// CalculateFeatures for several frames against the same map in ONE launch (tiles are dealt frame-major so each
+// frame's accepted features are compacted in query order).
+int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
+                             KnnWork &work, cudaStream_t st, int *launches);
 
 // Estimator::CalculateFeatures (Estimator.cc:970-1097) for one frame.  Appends to `out` starting at
 // *out.count when `append` is non-zero, else overwrites from 0.  `done_flag` (optional device int):

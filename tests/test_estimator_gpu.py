@@ -118,7 +118,9 @@ def test_window_solve_parity_exact_features(oracle, vlp_seq):
 def test_window_solve_parity_full_odom(oracle, vlp_seq):
     """Default 10 LaserOdom iterations on the newest frame (fp32 reductions differ in order): tolerance parity."""
     W = 5
-    eo, eg = _mk(oracle, vlp_seq, W, prior_factor=1)
+    # fixed extrinsic: with only 5 frames of a smooth trajectory the lidar-IMU rotation is barely observable and the
+    # free-extrinsic problem amplifies round-off (both sides drift, see test_oracle_factors); the fixed one is well posed
+    eo, eg = _mk(oracle, vlp_seq, W, opt_extrinsic=0)
     for k in range(W, 10):
         helpers.feed_scan(eo, vlp_seq, k)
         helpers.feed_scan(eg, vlp_seq, k)
