@@ -329,6 +329,14 @@ def main():
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": launches, "clocks": clocks}
         if world == 1:
+            try:   # the same kernel on a stream larger than L2 (512 MB): its HBM-resident streaming rate
+                sb = estimator.asm_stream_bench(1 << 24, 10, local_rank)
+                line["roofline_stream"] = {"kernel": "asm_ppp", "features": 1 << 24, "bytes_per_launch": sb["bytes"],
+                                           "avg_launch_ms": sb["avg_ms"], "achieved": sb["gbs"], "peak": peak, "unit": "GB/s",
+                                           "frac": sb["gbs"] / peak,
+                                           "note": "synthetic 16.8 M-feature stream (512 MB > 126 MB L2) split over 8 frames; CUDA events per launch"}
+            except Exception as exc:
+                line["roofline_stream"] = {"error": repr(exc)}
             try:
                 ra = argparse.Namespace(warmup=1, steps=min(args.cpu_sample, n_total - W - 2))
                 r = run_reference(ra, scn, W, est_cfg)

@@ -135,6 +135,10 @@ int lio_ppp_evaluate_batch_host(const float *pts4, const float *coef4, int n, co
 int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, const double R9[9], const double t3[3],
                      double out32[32], int device);
 
+/* Streaming-rate measurement of the fused stage-C kernel on n synthetic features (32 B each) split over 8 frames;
+ * CUDA events around each launch.  out = {avg ms / launch, min ms, algorithmic bytes / launch, launches}. */
+int lio_asm_stream_bench(long long n_features, int iters, int device, double out[4]);
+
 /* IntegrationBase (include/imu_processor/IntegrationBase.h:72-388) */
 typedef struct lio_pim lio_pim;
 int lio_pim_create(const double acc0[3], const double gyr0[3], const double ba[3], const double bg[3],

@@ -1433,6 +1433,71 @@ extern "C" int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, co
   return rc;
 }
 
+__global__ void k_fill_features(float4 *pts, float4 *coef, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned h = (unsigned)(i * 2654435761u);
+  float a = (float)(h & 1023) * (1.0f / 1024.0f), b = (float)((h >> 10) & 1023) * (1.0f / 1024.0f), c = (float)((h >> 20) & 1023) * (1.0f / 1024.0f);
+  pts[i] = make_float4(40.f * (a - 0.5f), 40.f * (b - 0.5f), 4.f * c, 0.9f);
+  float nx = a - 0.5f, ny = b - 0.5f, nz = c + 0.1f, nn = rsqrtf(nx * nx + ny * ny + nz * nz);
+  coef[i] = make_float4(0.8f * nx * nn, 0.8f * ny * nn, 0.8f * nz * nn, 0.05f * (a - b));
+}
+
+// Streaming-rate measurement of the fused stage-C kernel on a synthetic feature stream of n features
+// (choose n*32 B larger than L2 to measure the HBM-resident rate).  CUDA events around each launch on the
+// launching stream.  out = {avg ms per launch, min ms, bytes per launch, launches}.
+extern "C" int lio_asm_stream_bench(long long n_features, int iters, int device, double out[4]) {
+  if (n_features <= 0 || iters <= 0 || !out) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  const int O = 8;  // spread over 8 equal frames like a window
+  const long long per = n_features / O;
+  if (per <= 0 || per > 0x7fffffffLL) return LIO_ERR_INVALID;
+  float4 *dp = nullptr, *dc = nullptr;
+  AsmWork w;
+  int rc = LIO_OK;
+  if (cudaMalloc(&dp, sizeof(float4) * per * O) != cudaSuccess || cudaMalloc(&dc, sizeof(float4) * per * O) != cudaSuccess ||
+      w.init((int)std::min<long long>(per * O, 1ll << 30)) != 0) {
+    lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+    rc = LIO_ERR_CUDA;
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (rc == LIO_OK) {
+    k_fill_features<<<(unsigned)((per * O + 255) / 256), 256>>>(dp, dc, per * O);
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    AsmParams ap;
+    std::memset(&ap, 0, sizeof(ap));
+    ap.nframes = O;
+    for (int k = 0; k < O; ++k) {
+      ap.f[k].pts = dp + per * k; ap.f[k].coef = dc + per * k; ap.f[k].n = (int)per;
+      const double c = std::cos(0.01 * k), s = std::sin(0.01 * k);
+      const double R[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
+      std::memcpy(ap.f[k].R, R, sizeof(R));
+      ap.f[k].t[0] = 0.1 * k; ap.f[k].t[1] = 0.02 * k; ap.f[k].t[2] = 0.0;
+    }
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    asm_plan(ap, sms);
+    double sum = 0, mn = 1e30;
+    for (int it = 0; it < iters + 3 && rc == LIO_OK; ++it) {
+      cudaEventRecord(e0, 0);
+      rc = asm_launch(ap, w, 0, nullptr);
+      cudaEventRecord(e1, 0);
+      if (cudaEventSynchronize(e1) != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, "kernel failed"); rc = LIO_ERR_CUDA; break; }
+      float ms = 0;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (it >= 3) { sum += ms; mn = std::min(mn, (double)ms); }
+    }
+    out[0] = sum / iters; out[1] = mn; out[2] = 32.0 * (double)(per * O); out[3] = iters;
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  if (dp) cudaFree(dp);
+  if (dc) cudaFree(dc);
+  w.destroy();
+  return rc;
+}
+
 extern "C" int lio_pim_create(const double a0[3], const double g0[3], const double ba[3], const double bg[3], const double n5[5], lio_pim **out) {
   if (!a0 || !g0 || !ba || !bg || !n5 || !out) return LIO_ERR_INVALID;
   ImuNoise nz;

@@ -57,6 +57,14 @@ def asm_ppp(pts4, coef4, R, t, device=0):
     return S, out[28]
 
 
+def asm_stream_bench(n_features: int, iters: int = 10, device: int = 0):
+    """Streaming rate of the fused stage-C kernel on a synthetic stream (choose n*32 B > L2 for the HBM rate)."""
+    _lib.require_device()
+    o = np.zeros(4)
+    _lib.check(_lib.lib().lio_asm_stream_bench(int(n_features), int(iters), device, o), "lio_asm_stream_bench")
+    return dict(avg_ms=o[0], min_ms=o[1], bytes=o[2], launches=int(o[3]), gbs=o[2] / (o[0] * 1e-3) / 1e9)
+
+
 class Pim:
     """IntegrationBase (include/imu_processor/IntegrationBase.h) + ImuFactor operator."""
 
