@@ -96,8 +96,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
   }
 }
 
-__global__ void __launch_bounds__(kAsmThreads, 3)
-asm_ppp(const AsmParams P, double *__restrict__ partial, double *__restrict__ out, unsigned *__restrict__ counter) {
+__global__ void __launch_bounds__(kAsmThreads)
+asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ partial, double *__restrict__ out,
+        unsigned *__restrict__ counter) {
   __shared__ __align__(128) float4 s_pts[kAsmStages][kAsmChunk];
   __shared__ __align__(128) float4 s_coef[kAsmStages][kAsmChunk];
   __shared__ __align__(8) unsigned long long full_bar[kAsmStages];
@@ -110,9 +111,9 @@ asm_ppp(const AsmParams P, double *__restrict__ partial, double *__restrict__ ou
   const AsmFrame &F = P.f[fi];
   double R[9], t[3];
 #pragma unroll
-  for (int k = 0; k < 9; ++k) R[k] = F.R[k];
+  for (int k = 0; k < 9; ++k) R[k] = __ldg(Rt + fi * kAsmRtStride + k);
 #pragma unroll
-  for (int k = 0; k < 3; ++k) t[k] = F.t[k];
+  for (int k = 0; k < 3; ++k) t[k] = __ldg(Rt + fi * kAsmRtStride + 9 + k);
   double acc[29];
 #pragma unroll
   for (int k = 0; k < 29; ++k) acc[k] = 0.0;
@@ -236,10 +237,10 @@ void asm_plan(AsmParams &p, int sm_count) {
   p.ntiles = t;
 }
 
-int asm_launch(const AsmParams &p, AsmWork &work, cudaStream_t st, int *launches) {
+int asm_launch(const AsmParams &p, const double *Rt_dev, AsmWork &work, cudaStream_t st, int *launches) {
   if (p.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
   if (p.nframes <= 0) return LIO_OK;
-  asm_ppp<<<p.ntiles, kAsmThreads, 0, st>>>(p, work.partial, work.out, work.counter);
+  asm_ppp<<<p.ntiles, kAsmThreads, 0, st>>>(p, Rt_dev, work.partial, work.out, work.counter);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }

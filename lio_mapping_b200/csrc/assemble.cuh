@@ -12,9 +12,9 @@ struct AsmFrame {
   const float4 *coef;  // (w, b) of the plane in the pivot lidar frame
   int n;               // features of this frame
   int tile0;           // first tile index of this frame
-  double R[9];         // R_lpi, row-major
-  double t[3];         // R_lpi^T * P_lpi
 };
+
+constexpr int kAsmRtStride = 12;  // per frame: R_lpi (9, row-major) then R_lpi^T P_lpi (3), in a DEVICE buffer
 
 struct AsmParams {
   AsmFrame f[kMaxOpt];
@@ -36,6 +36,7 @@ struct AsmWork {
 void asm_plan(AsmParams &p, int sm_count);
 // Launches the fused kernel; results land in work.out (device), kAsmStride doubles per frame:
 //   [0..27] upper triangle (row-major) of S = sum rho'(r^2) [g;r][g;r]^T,  [28] sum rho(r^2).
-int asm_launch(const AsmParams &p, AsmWork &work, cudaStream_t st, int *launches);
+// Rt_dev: device buffer of nframes x kAsmRtStride doubles (written by the host shell or by the device solver).
+int asm_launch(const AsmParams &p, const double *Rt_dev, AsmWork &work, cudaStream_t st, int *launches);
 
 }  // namespace lio

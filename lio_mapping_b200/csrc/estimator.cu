@@ -12,9 +12,11 @@
 #include "factors_host.h"
 #include "knn.cuh"
 #include "qr.cuh"
+#include "solver_dev.cuh"
 #include "solver_host.h"
 #include "voxel.cuh"
 #include <chrono>
+#include <cstddef>
 #include <memory>
 #include <new>
 #include <vector>
@@ -358,6 +360,8 @@ struct lio_est {
   TransformF *d_tf = nullptr;     // W+1
   TransformF *h_tf = nullptr;     // pinned
   AsmWork asmw;
+  double *h_Rt = nullptr;   // pinned kMaxOpt*kAsmRtStride
+  double *d_Rt = nullptr;
   double *h_S = nullptr;    // pinned kMaxOpt*kAsmStride
   int *h_counts = nullptr;  // pinned
   OdomState *d_odom = nullptr;
@@ -380,6 +384,11 @@ struct lio_est {
   Vec g0;
   double cost0 = 0;
   bool have_H0 = false;
+  // device-resident solver
+  DevSolver ds;
+  bool use_dev_solver = false;
+  bool prior_uploaded = false;
+  cudaEvent_t evp[2 * 24] = {};
   // cached lidar reduction for the current parameter values
   bool S_valid = false;
   // CUDA-event timing of the fused kernel (on the launching stream)
@@ -453,6 +462,7 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
   c->acc_n = 0.2; c->gyr_n = 0.02; c->acc_w = 2e-4; c->gyr_w = 2e-5; c->g_norm = 9.805;
   c->max_num_iterations = 10; c->odom_max_iterations = 10;
   c->max_frame_points = 1 << 16; c->max_scan_points = 1 << 18;
+  c->device_solver = 1;
 }
 
 extern "C" int lio_est_destroy(lio_est *e) {
@@ -462,10 +472,14 @@ extern "C" int lio_est_destroy(lio_est *e) {
   for (FeatureOut &f : e->feats) { if (f.pts) cudaFree(f.pts); if (f.coef) cudaFree(f.coef); if (f.src) cudaFree(f.src); }
   void *ptrs[] = {e->d_slot_n, e->d_own_n, e->d_scan, e->d_local, e->d_map, e->d_tmp, e->d_counts, e->d_feat_counts, e->d_tf, e->d_odom, e->d_odom_partial};
   for (void *p : ptrs) if (p) cudaFree(p);
+  for (int k = 0; k < 48; ++k) if (e->evp[k]) cudaEventDestroy(e->evp[k]);
+  e->ds.destroy();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->h_tf) cudaFreeHost(e->h_tf);
   if (e->h_S) cudaFreeHost(e->h_S);
+  if (e->h_Rt) cudaFreeHost(e->h_Rt);
+  if (e->d_Rt) cudaFree(e->d_Rt);
   if (e->h_counts) cudaFreeHost(e->h_counts);
   e->vg.destroy(); e->hash.destroy(); e->knn.destroy(); e->asmw.destroy();
   delete e;
@@ -521,6 +535,8 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   ok = ok && cudaMalloc(&e->d_odom_partial, sizeof(double) * 32 * 1024) == cudaSuccess;
   ok = ok && cudaMallocHost((void **)&e->h_tf, sizeof(TransformF) * (W + 1)) == cudaSuccess;
   ok = ok && cudaMallocHost((void **)&e->h_S, sizeof(double) * kMaxOpt * kAsmStride) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&e->h_Rt, sizeof(double) * kMaxOpt * kAsmRtStride) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->d_Rt, sizeof(double) * kMaxOpt * kAsmRtStride) == cudaSuccess;
   ok = ok && cudaMallocHost((void **)&e->h_counts, sizeof(int) * (W + 16)) == cudaSuccess;
   int vg_cap = std::max(e->local_cap, cfg->max_scan_points);
   ok = ok && e->vg.init(vg_cap) == 0;
@@ -546,6 +562,9 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
     ok = ok && cudaMemset(e->d_counts, 0, sizeof(int) * 8) == cudaSuccess;
   }
   ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
+  for (int k = 0; k < 48 && ok; ++k) ok = ok && cudaEventCreate(&e->evp[k]) == cudaSuccess;
+  e->use_dev_solver = cfg->device_solver != 0 && e->ds.supports(O) && cfg->max_num_iterations <= 22;
+  if (e->use_dev_solver) ok = ok && e->ds.init(O) == 0;
   if (!ok) {
     lio_set_last_error(__FILE__, __LINE__, "lio_est_create: device allocation failed");
     lio_est_destroy(e);
@@ -796,14 +815,16 @@ static int eval_lidar(lio_est *e, std::vector<FrameTerms> &ft) {
     const FeatureOut &fo = e->feats[pivot + i];
     f.pts = fo.pts; f.coef = fo.coef;
     f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
-    std::memcpy(f.R, ft[i].R, sizeof(f.R)); std::memcpy(f.t, ft[i].t, sizeof(f.t));
+    std::memcpy(e->h_Rt + (i - 1) * kAsmRtStride, ft[i].R, sizeof(double) * 9);
+    std::memcpy(e->h_Rt + (i - 1) * kAsmRtStride + 9, ft[i].t, sizeof(double) * 3);
   }
   if (e->S_valid) return LIO_OK;
+  EST_CUDA(cudaMemcpyAsync(e->d_Rt, e->h_Rt, sizeof(double) * O * kAsmRtStride, cudaMemcpyHostToDevice, e->stream));
   asm_plan(ap, e->sm_count);
   long long nfeat = 0;
   for (int k = 0; k < ap.nframes; ++k) nfeat += ap.f[k].n;
   if (e->ev0) cudaEventRecord(e->ev0, e->stream);
-  int rc = asm_launch(ap, e->asmw, e->stream, &e->launches);
+  int rc = asm_launch(ap, e->d_Rt, e->asmw, e->stream, &e->launches);
   if (rc != LIO_OK) return rc;
   if (e->ev1) cudaEventRecord(e->ev1, e->stream);
   if (e->world > 1 && e->allreduce) {
@@ -1122,6 +1143,107 @@ static int solve_optimization(lio_est *e) {
   return LIO_OK;
 }
 
+// ---- SolveOptimization with the device-resident dogleg loop --------------------------------------
+static int solve_optimization_dev(lio_est *e) {
+  const int O = e->O, pivot = e->W - O;
+  cudaStream_t st = e->stream;
+  e->turn_off = true;
+  int rc = build_local_map(e);
+  if (rc != LIO_OK) return rc;
+  const double t0 = now_s();
+  e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
+  vector_to_double(e);
+  DevSolveState &S = *e->ds.h_st;
+  S.O = O; S.n = 15 * (O + 1) + 6; S.max_it = e->cfg.max_num_iterations;
+  S.imu_factor = e->cfg.imu_factor; S.point_distance_factor = e->cfg.point_distance_factor;
+  S.prior_factor = e->cfg.prior_factor; S.marginalization_factor = e->cfg.marginalization_factor;
+  S.ex_free = e->ex_constant ? 0 : 1;
+  S.prior_valid = (e->cfg.marginalization_factor && e->prior.valid) ? 1 : 0;
+  S.convergence_flag = e->convergence_flag ? 1 : 0;
+  S.turn_off = 1; S.done = 0; S.iteration = 0; S.successful = 0; S.evaluations = 0; S.termination = 0; S.reuse = 0; S.invalid = 0;
+  for (int k = 0; k <= O; ++k) { std::memcpy(S.x + 16 * k, e->para_pose[k].data(), 7 * sizeof(double)); std::memcpy(S.x + 16 * k + 7, e->para_sb[k].data(), 9 * sizeof(double)); }
+  std::memcpy(S.x + 16 * (O + 1), e->para_ex, 7 * sizeof(double));
+  {
+    const Tw tt = tlb_double(e);
+    S.ex0_pos[0] = tt.pos.x; S.ex0_pos[1] = tt.pos.y; S.ex0_pos[2] = tt.pos.z;
+    S.ex0_quat[0] = tt.rot.x; S.ex0_quat[1] = tt.rot.y; S.ex0_quat[2] = tt.rot.z; S.ex0_quat[3] = tt.rot.w;
+  }
+  for (int i = 0; i < O; ++i) {
+    Preintegration &pim = *e->pre[pivot + i + 1];
+    S.pim_valid[i] = pim.sum_dt > 10.0 ? 0 : 1;
+    pim.to_data(S.pim[i]);
+  }
+  if (S.prior_valid) {
+    const MargPrior &pr = e->prior;
+    std::memcpy(S.bp, pr.bp.data(), sizeof(double) * pr.n);
+    S.c0 = pr.c0;
+    std::memcpy(S.x0_pose, pr.x0_pose.data(), sizeof(double) * 7 * O);
+    std::memcpy(S.x0_sb, pr.x0_sb.data(), sizeof(double) * 9 * O);
+    std::memcpy(S.x0_ex, pr.x0_ex, sizeof(double) * 7);
+    if (!e->prior_uploaded) {
+      EST_CUDA(cudaMemcpyAsync(e->ds.Hp, pr.Hp.d.data(), sizeof(double) * pr.n * pr.n, cudaMemcpyHostToDevice, st));
+      e->prior_uploaded = true;
+    }
+  }
+  EST_CUDA(cudaMemcpyAsync(e->ds.st, &S, sizeof(DevSolveState), cudaMemcpyHostToDevice, st));
+  AsmParams ap;
+  std::memset(&ap, 0, sizeof(ap));
+  ap.nframes = O;
+  long long nfeat = 0;
+  for (int i = 1; i <= O; ++i) {
+    AsmFrame &f = ap.f[i - 1];
+    const FeatureOut &fo = e->feats[pivot + i];
+    f.pts = fo.pts; f.coef = fo.coef;
+    f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
+    nfeat += f.n;
+  }
+  asm_plan(ap, e->sm_count);
+  rc = dev_solver_terms(e->ds, e->d_Rt, st, &e->launches);
+  if (rc != LIO_OK) return rc;
+  const int nevals = e->cfg.max_num_iterations + 1;
+  for (int ev = 0; ev < nevals; ++ev) {
+    cudaEventRecord(e->evp[2 * ev], st);
+    rc = asm_launch(ap, e->d_Rt, e->asmw, st, &e->launches);
+    if (rc != LIO_OK) return rc;
+    cudaEventRecord(e->evp[2 * ev + 1], st);
+    if (e->world > 1 && e->allreduce) {
+      if (e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride) != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
+    }
+    rc = dev_solver_step(e->ds, e->asmw.out, e->d_Rt, ev, st, &e->launches);
+    if (rc != LIO_OK) return rc;
+  }
+  EST_CUDA(cudaMemcpyAsync(&S, e->ds.st, offsetof(DevSolveState, scale), cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaStreamSynchronize(st));
+  for (int ev = 0; ev < std::min(nevals, S.evaluations); ++ev) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
+  }
+  for (int k = 0; k <= O; ++k) { std::memcpy(e->para_pose[k].data(), S.x + 16 * k, 7 * sizeof(double)); std::memcpy(e->para_sb[k].data(), S.x + 16 * k + 7, 9 * sizeof(double)); }
+  std::memcpy(e->para_ex, S.x + 16 * (O + 1), 7 * sizeof(double));
+  e->S_valid = false;
+  e->summary = DoglegSummary();
+  e->summary.iterations = S.iteration; e->summary.successful_steps = S.successful; e->summary.evaluations = S.evaluations;
+  e->summary.termination = S.termination; e->summary.initial_cost = S.initial_cost; e->summary.final_cost = S.x_cost;
+  e->cost_pim = S.cost_pim; e->cost_ppp = S.cost_ppp; e->cost_marg = S.cost_marg;
+  e->turn_off = S.turn_off != 0;
+  e->convergence_flag = S.convergence_flag != 0;
+  e->ex_constant = S.ex_free == 0;
+  if (!S.prior_valid) e->prior.valid = false;
+  e->have_H0 = true; e->H0 = Mat(); e->cost0 = S.initial_cost;
+  if (S.termination == 2 && !std::isfinite(S.x_cost)) { lio_set_last_error(__FILE__, __LINE__, "solver breakdown"); return LIO_ERR_NUMERIC; }
+  e->t_solve = now_s() - t0;
+  double_to_vector(e);
+  const double t1 = now_s();
+  if (e->cfg.marginalization_factor && !e->turn_off) {
+    vector_to_double(e);
+    rc = marginalize(e);
+    if (rc != LIO_OK) return rc;
+    e->prior_uploaded = false;
+  }
+  e->t_marg = now_s() - t1;
+  return LIO_OK;
+}
+
 static int slide_window(lio_est *e) {  // Estimator.cc:2570-2666
   const int W = e->W, O = e->O, pivot = W - O;
   if (e->init_local_map && pivot > 0) {
@@ -1200,7 +1322,7 @@ static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_
   if (rc != LIO_OK) return rc;
   EST_CUDA(cudaMemcpyAsync(e->d_own_n + slot, e->d_slot_n + slot, sizeof(int), cudaMemcpyDeviceToDevice, st));
   push_shift(e->size_surf_stack, 0);
-  rc = solve_optimization(e);
+  rc = e->use_dev_solver ? solve_optimization_dev(e) : solve_optimization(e);
   if (rc != LIO_OK) return rc;
   rc = slide_window(e);
   if (rc != LIO_OK) return rc;
@@ -1333,6 +1455,19 @@ extern "C" int lio_est_get_prior(lio_est *e, double *Hp, double *bp) {
 extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, double *cost, int *n) {
   if (!e || !n) return LIO_ERR_INVALID;
   if (!e->have_H0) { *n = 0; return LIO_OK; }
+  if (e->use_dev_solver) {
+    // device layout keeps the 6 extrinsic slots; report the reduced system when the extrinsic was constant
+    const int nf = 15 * (e->O + 1) + 6, nr = e->ex_constant ? nf - 6 : nf;
+    *n = nr;
+    LIO_CUDA_OK(cudaSetDevice(e->device));
+    std::vector<double> Hf((size_t)nf * nf), gf(nf);
+    LIO_CUDA_OK(cudaMemcpy(Hf.data(), e->ds.H0, sizeof(double) * nf * nf, cudaMemcpyDeviceToHost));
+    LIO_CUDA_OK(cudaMemcpy(gf.data(), e->ds.g0, sizeof(double) * nf, cudaMemcpyDeviceToHost));
+    if (H) for (int r = 0; r < nr; ++r) std::memcpy(H + (size_t)r * nr, &Hf[(size_t)r * nf], sizeof(double) * nr);
+    if (g) std::memcpy(g, gf.data(), sizeof(double) * nr);
+    if (cost) *cost = e->cost0;
+    return LIO_OK;
+  }
   *n = e->H0.r;
   if (H) std::memcpy(H, e->H0.d.data(), sizeof(double) * e->H0.r * e->H0.r);
   if (g) std::memcpy(g, e->g0.data(), sizeof(double) * e->H0.r);
@@ -1417,11 +1552,17 @@ extern "C" int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, co
     std::memset(&ap, 0, sizeof(ap));
     ap.nframes = 1;
     ap.f[0].pts = dp; ap.f[0].coef = dc; ap.f[0].n = n;
-    std::memcpy(ap.f[0].R, R9, sizeof(double) * 9); std::memcpy(ap.f[0].t, t3, sizeof(double) * 3);
+    double Rt[kAsmRtStride];
+    std::memcpy(Rt, R9, sizeof(double) * 9); std::memcpy(Rt + 9, t3, sizeof(double) * 3);
+    double *dRt = nullptr;
+    cudaMalloc(&dRt, sizeof(Rt));
+    cudaMemcpy(dRt, Rt, sizeof(Rt), cudaMemcpyHostToDevice);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     asm_plan(ap, sms);
-    rc = asm_launch(ap, w, 0, nullptr);
+    rc = asm_launch(ap, dRt, w, 0, nullptr);
+    cudaDeviceSynchronize();
+    cudaFree(dRt);
     if (rc == LIO_OK) {
       cudaError_t er = cudaMemcpy(out32, w.out, sizeof(double) * kAsmStride, cudaMemcpyDeviceToHost);
       if (er != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(er)); rc = LIO_ERR_CUDA; }
@@ -1462,26 +1603,29 @@ extern "C" int lio_asm_stream_bench(long long n_features, int iters, int device,
     rc = LIO_ERR_CUDA;
   }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double *dRt = nullptr;
   if (rc == LIO_OK) {
     k_fill_features<<<(unsigned)((per * O + 255) / 256), 256>>>(dp, dc, per * O);
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     AsmParams ap;
     std::memset(&ap, 0, sizeof(ap));
     ap.nframes = O;
+    double hRt[8 * kAsmRtStride];
     for (int k = 0; k < O; ++k) {
       ap.f[k].pts = dp + per * k; ap.f[k].coef = dc + per * k; ap.f[k].n = (int)per;
       const double c = std::cos(0.01 * k), s = std::sin(0.01 * k);
-      const double R[9] = {c, -s, 0, s, c, 0, 0, 0, 1};
-      std::memcpy(ap.f[k].R, R, sizeof(R));
-      ap.f[k].t[0] = 0.1 * k; ap.f[k].t[1] = 0.02 * k; ap.f[k].t[2] = 0.0;
+      const double Rt[kAsmRtStride] = {c, -s, 0, s, c, 0, 0, 0, 1, 0.1 * k, 0.02 * k, 0.0};
+      std::memcpy(hRt + k * kAsmRtStride, Rt, sizeof(Rt));
     }
+    cudaMalloc(&dRt, sizeof(hRt));
+    cudaMemcpy(dRt, hRt, sizeof(hRt), cudaMemcpyHostToDevice);
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     asm_plan(ap, sms);
     double sum = 0, mn = 1e30;
     for (int it = 0; it < iters + 3 && rc == LIO_OK; ++it) {
       cudaEventRecord(e0, 0);
-      rc = asm_launch(ap, w, 0, nullptr);
+      rc = asm_launch(ap, dRt, w, 0, nullptr);
       cudaEventRecord(e1, 0);
       if (cudaEventSynchronize(e1) != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, "kernel failed"); rc = LIO_ERR_CUDA; break; }
       float ms = 0;
@@ -1492,6 +1636,7 @@ extern "C" int lio_asm_stream_bench(long long n_features, int iters, int device,
   }
   if (e0) cudaEventDestroy(e0);
   if (e1) cudaEventDestroy(e1);
+  if (dRt) cudaFree(dRt);
   if (dp) cudaFree(dp);
   if (dc) cudaFree(dc);
   w.destroy();

@@ -1,20 +1,11 @@
 // lio_mapping_b200 — host fp64 factors (see factors_host.h).
 #include "factors_host.h"
+#include "factors_impl.h"
 
 namespace lio {
 using namespace hm;
 
-enum { O_P = 0, O_R = 3, O_V = 6, O_BA = 9, O_BG = 12 };
-
-static inline void put33(double *dst, int ld, int r0, int c0, const M3 &m) {
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) dst[(r0 + i) * ld + c0 + j] = m(i, j);
-}
-static inline M3 get33(const double *src, int ld, int r0, int c0) {
-  M3 m;
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m(i, j) = src[(r0 + i) * ld + c0 + j];
-  return m;
-}
-static inline Q pose_q(const double *p) { return Q(p[6], p[3], p[4], p[5]); }
+using namespace fi;
 
 // ---- pre-integration (IntegrationBase.h:77-101 ctor, :127-208 MidPointIntegration, :278-307 Propagate)
 Preintegration::Preintegration(const V3 &a0, const V3 &g0, const V3 &ba, const V3 &bg, const ImuNoise &n)
@@ -119,70 +110,24 @@ void Preintegration::ensure_sqrt_info() {
   sqrt_info_valid = true;
 }
 
-static inline M3 left_tl(const Q &q) { return M3::I() * q.w + skew(q.vec()); }    // LeftQuatMatrix top-left 3x3
-static inline M3 right_tl(const Q &p) { return M3::I() * p.w - skew(p.vec()); }   // RightQuatMatrix top-left 3x3
+static void fill_pim(const Preintegration &p, PimData &d) {
+  for (int k = 0; k < 3; ++k) { d.delta_p[k] = p.delta_p[k]; d.delta_v[k] = p.delta_v[k]; d.lin_ba[k] = p.lin_ba[k]; d.lin_bg[k] = p.lin_bg[k]; }
+  d.delta_q[0] = p.delta_q.x; d.delta_q[1] = p.delta_q.y; d.delta_q[2] = p.delta_q.z; d.delta_q[3] = p.delta_q.w;
+  d.sum_dt = p.sum_dt; d.g_norm = p.g_norm;
+  std::memcpy(d.jac, p.jac, sizeof(d.jac));
+  std::memcpy(d.sqrt_info, p.sqrt_info, sizeof(d.sqrt_info));
+}
+
+void Preintegration::to_data(PimData &d) {
+  ensure_sqrt_info();
+  fill_pim(*this, d);
+}
 
 void imu_factor_evaluate(Preintegration &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
                          double r[15], double (*Ji)[6], double (*Jsi)[9], double (*Jj)[6], double (*Jsj)[9]) {
-  pim.ensure_sqrt_info();
-  const V3 Pi(pose_i), Pj(pose_j), Vi(sb_i), Bai(sb_i + 3), Bgi(sb_i + 6), Vj(sb_j), Baj(sb_j + 3), Bgj(sb_j + 6);
-  const Q Qi = pose_q(pose_i), Qj = pose_q(pose_j);
-  const V3 g_vec(0, 0, -pim.g_norm);
-  const double sum_dt = pim.sum_dt;
-  const M3 dp_dba = get33(&pim.jac[0][0], 15, O_P, O_BA), dp_dbg = get33(&pim.jac[0][0], 15, O_P, O_BG);
-  const M3 dq_dbg = get33(&pim.jac[0][0], 15, O_R, O_BG);
-  const M3 dv_dba = get33(&pim.jac[0][0], 15, O_V, O_BA), dv_dbg = get33(&pim.jac[0][0], 15, O_V, O_BG);
-  const V3 dba = Bai - pim.lin_ba, dbg = Bgi - pim.lin_bg;
-  const Q corrected_delta_q = pim.delta_q * deltaQ(dq_dbg * dbg);
-  const V3 corrected_delta_v = pim.delta_v + dv_dba * dba + dv_dbg * dbg;
-  const V3 corrected_delta_p = pim.delta_p + dp_dba * dba + dp_dbg * dbg;
-  const Q Qi_inv = inverse(Qi);
-  const V3 rP = rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt) - corrected_delta_p;
-  const V3 rR = 2.0 * (inverse(corrected_delta_q) * (Qi_inv * Qj)).vec();
-  const V3 rV = rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi) - corrected_delta_v;
-  double raw[15];
-  for (int k = 0; k < 3; ++k) { raw[O_P + k] = rP[k]; raw[O_R + k] = rR[k]; raw[O_V + k] = rV[k]; raw[O_BA + k] = Baj[k] - Bai[k]; raw[O_BG + k] = Bgj[k] - Bgi[k]; }
-  for (int i = 0; i < 15; ++i) { double s = 0; for (int j = i; j < 15; ++j) s += pim.sqrt_info[i][j] * raw[j]; r[i] = s; }
-  if (!Ji) return;
-  const M3 RiT = toR(Qi_inv);
-  double A0[15][6], A1[15][9], A2[15][6], A3[15][9];
-  std::memset(A0, 0, sizeof(A0)); std::memset(A1, 0, sizeof(A1)); std::memset(A2, 0, sizeof(A2)); std::memset(A3, 0, sizeof(A3));
-  put33(&A0[0][0], 6, O_P, 0, -RiT);
-  put33(&A0[0][0], 6, O_P, 3, skew(rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
-  {  // -(L(Qj^-1 Qi) R(corrected_delta_q)) top-left 3x3
-    const Q ql = inverse(Qj) * Qi;
-    M3 m = left_tl(ql) * right_tl(corrected_delta_q);
-    const V3 qv = ql.vec(), pv = corrected_delta_q.vec();
-    for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) m(a, b) -= qv[a] * pv[b];
-    put33(&A0[0][0], 6, O_R, 3, -m);
-  }
-  put33(&A0[0][0], 6, O_V, 3, skew(rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi)));
-  put33(&A1[0][0], 9, O_P, 0, -RiT * sum_dt);
-  put33(&A1[0][0], 9, O_P, 3, -dp_dba);
-  put33(&A1[0][0], 9, O_P, 6, -dp_dbg);
-  put33(&A1[0][0], 9, O_R, 6, -(left_tl(inverse(Qj) * Qi * corrected_delta_q) * dq_dbg));
-  put33(&A1[0][0], 9, O_V, 0, -RiT);
-  put33(&A1[0][0], 9, O_V, 3, -dv_dba);
-  put33(&A1[0][0], 9, O_V, 6, -dv_dbg);
-  put33(&A1[0][0], 9, O_BA, 3, -M3::I());
-  put33(&A1[0][0], 9, O_BG, 6, -M3::I());
-  put33(&A2[0][0], 6, O_P, 0, RiT);
-  put33(&A2[0][0], 6, O_R, 3, left_tl(inverse(corrected_delta_q) * Qi_inv * Qj));
-  put33(&A3[0][0], 9, O_V, 0, RiT);
-  put33(&A3[0][0], 9, O_BA, 3, M3::I());
-  put33(&A3[0][0], 9, O_BG, 6, M3::I());
-  for (int i = 0; i < 15; ++i) {
-    for (int c = 0; c < 6; ++c) {
-      double s0 = 0, s2 = 0;
-      for (int k = i; k < 15; ++k) { s0 += pim.sqrt_info[i][k] * A0[k][c]; s2 += pim.sqrt_info[i][k] * A2[k][c]; }
-      Ji[i][c] = s0; Jj[i][c] = s2;
-    }
-    for (int c = 0; c < 9; ++c) {
-      double s1 = 0, s3 = 0;
-      for (int k = i; k < 15; ++k) { s1 += pim.sqrt_info[i][k] * A1[k][c]; s3 += pim.sqrt_info[i][k] * A3[k][c]; }
-      Jsi[i][c] = s1; Jsj[i][c] = s3;
-    }
-  }
+  PimData d;
+  pim.to_data(d);
+  imu_factor_eval_impl(d, pose_i, sb_i, pose_j, sb_j, r, Ji, Jsi, Jj, Jsj);
 }
 
 // ---- lidar factor -------------------------------------------------------------------------------
@@ -221,54 +166,14 @@ void ppp_evaluate_single(const double point[3], const double coeff[4], const dou
 }
 
 void ppp_frame_terms(const double *pose_pivot, const double *pose_i, const double *pose_ex, double Rout[9], double tout[3], double Mout[6 * 18]) {
-  const V3 P_pivot(pose_pivot), Pi(pose_i), tlb(pose_ex);
-  const M3 Rp = toR(pose_q(pose_pivot)), Ri = toR(pose_q(pose_i)), rlb = toR(pose_q(pose_ex));
-  const M3 Rlpi = rlb * T(Rp) * Ri * T(rlb);
-  // P_lpi = rlb Rp^T (Pi - Pp) - R_lpi tlb + tlb
-  const V3 Plpi = rlb * (T(Rp) * (Pi - P_pivot)) - Rlpi * tlb + tlb;
-  const V3 t = T(Rlpi) * Plpi;
-  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rout[i * 3 + j] = Rlpi(i, j);
-  tout[0] = t.x; tout[1] = t.y; tout[2] = t.z;
-  // closed form of the 6x18 map (derivation in DESIGN.md): rows 0-2 multiply a, rows 3-5 multiply p x a
-  const M3 B = rlb * T(Ri);           // w^T rlb Rp^T = a^T B
-  const M3 C = T(Rp) * Ri * T(rlb);   // rlb^T w = C a
-  const M3 Ct = T(C);
-  const V3 v = T(Rp) * (Pi - P_pivot);
-  const M3 St = skew(tlb), Sv = skew(v);
-  const M3 Z;  // zero
-  const M3 a_blocks[6] = {-B, Ct * Sv - St * Ct, B, St * rlb, T(Rlpi) - M3::I(), St * Ct - St * rlb - Ct * Sv};
-  const M3 x_blocks[6] = {Z, -Ct, Z, rlb, Z, Ct - rlb};
-  for (int blk = 0; blk < 6; ++blk)
-    for (int i = 0; i < 3; ++i)
-      for (int j = 0; j < 3; ++j) {
-        Mout[i * 18 + blk * 3 + j] = a_blocks[blk](i, j);
-        Mout[(3 + i) * 18 + blk * 3 + j] = x_blocks[blk](i, j);
-      }
+  ppp_frame_terms_impl(pose_pivot, pose_i, pose_ex, Rout, tout, Mout);
 }
 
 void prior_factor_evaluate(const V3 &pos0, const Q &rot0, const double *pose_ex, double r[6], double (*J)[6]) {
-  const V3 P(pose_ex);
-  const Q Qx = pose_q(pose_ex);
-  const double wp = 1000.0, wr = 0.1;
-  const V3 rp = P - pos0;
-  const V3 rr = 2.0 * (inverse(rot0) * Qx).vec();
-  for (int k = 0; k < 3; ++k) { r[k] = wp * rp[k]; r[3 + k] = wr * rr[k]; }
-  if (J) {
-    std::memset(J, 0, sizeof(double) * 36);
-    const M3 br = left_tl(inverse(Qx) * rot0);
-    for (int i = 0; i < 3; ++i) {
-      J[i][i] = wp;
-      for (int j = 0; j < 3; ++j) J[3 + i][3 + j] = wr * br(i, j);
-    }
-  }
+  prior_factor_impl(pos0, rot0, pose_ex, r, J);
 }
 
-void pose_plus(const double *x, const double *delta, double *out) {
-  const Q q = pose_q(x);
-  const Q qp = normalized(q * deltaQ(V3(delta[3], delta[4], delta[5])));
-  for (int k = 0; k < 3; ++k) out[k] = x[k] + delta[k];
-  out[3] = qp.x; out[4] = qp.y; out[5] = qp.z; out[6] = qp.w;
-}
+void pose_plus(const double *x, const double *delta, double *out) { pose_plus_impl(x, delta, out); }
 
 V3 R2ypr(const M3 &R) {
   const V3 n(R(0, 0), R(1, 0), R(2, 0)), o(R(0, 1), R(1, 1), R(2, 1)), a(R(0, 2), R(1, 2), R(2, 2));

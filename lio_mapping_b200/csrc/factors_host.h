@@ -5,6 +5,8 @@
 #include "hostmath.h"
 #include <memory>
 
+namespace lio { struct PimData; }
+
 namespace lio {
 
 struct ImuNoise {  // IntegrationBaseConfig (include/imu_processor/IntegrationBase.h:64-70)
@@ -27,6 +29,7 @@ struct Preintegration {
   Preintegration(const hm::V3 &acc0, const hm::V3 &gyr0, const hm::V3 &ba, const hm::V3 &bg, const ImuNoise &n);
   void push_back(double dt, const hm::V3 &acc, const hm::V3 &gyr);
   void ensure_sqrt_info();
+  void to_data(struct PimData &d);
 };
 
 // ImuFactor::Evaluate (include/factor/ImuFactor.h:53-167).  J blocks are 15x6 / 15x9 (tangent

@@ -6,48 +6,54 @@
 #include <cstring>
 #include <vector>
 
+#ifdef __CUDACC__
+#define LIO_HD __host__ __device__
+#else
+#define LIO_HD
+#endif
+
 namespace lio {
 namespace hm {
 
 struct V3 {
   double x = 0, y = 0, z = 0;
-  V3() {}
-  V3(double a, double b, double c) : x(a), y(b), z(c) {}
-  explicit V3(const double *p) : x(p[0]), y(p[1]), z(p[2]) {}
-  double &operator[](int i) { return (&x)[i]; }
-  double operator[](int i) const { return (&x)[i]; }
+  LIO_HD V3() {}
+  LIO_HD V3(double a, double b, double c) : x(a), y(b), z(c) {}
+  LIO_HD explicit V3(const double *p) : x(p[0]), y(p[1]), z(p[2]) {}
+  LIO_HD double &operator[](int i) { return (&x)[i]; }
+  LIO_HD double operator[](int i) const { return (&x)[i]; }
 };
-inline V3 operator+(const V3 &a, const V3 &b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
-inline V3 operator-(const V3 &a, const V3 &b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
-inline V3 operator-(const V3 &a) { return V3(-a.x, -a.y, -a.z); }
-inline V3 operator*(const V3 &a, double s) { return V3(a.x * s, a.y * s, a.z * s); }
-inline V3 operator*(double s, const V3 &a) { return a * s; }
-inline double dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline V3 cross(const V3 &a, const V3 &b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
-inline double norm(const V3 &a) { return std::sqrt(dot(a, a)); }
+LIO_HD inline V3 operator+(const V3 &a, const V3 &b) { return V3(a.x + b.x, a.y + b.y, a.z + b.z); }
+LIO_HD inline V3 operator-(const V3 &a, const V3 &b) { return V3(a.x - b.x, a.y - b.y, a.z - b.z); }
+LIO_HD inline V3 operator-(const V3 &a) { return V3(-a.x, -a.y, -a.z); }
+LIO_HD inline V3 operator*(const V3 &a, double s) { return V3(a.x * s, a.y * s, a.z * s); }
+LIO_HD inline V3 operator*(double s, const V3 &a) { return a * s; }
+LIO_HD inline double dot(const V3 &a, const V3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+LIO_HD inline V3 cross(const V3 &a, const V3 &b) { return V3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+LIO_HD inline double norm(const V3 &a) { return std::sqrt(dot(a, a)); }
 
 struct M3 {
   double m[3][3];
-  M3() { std::memset(m, 0, sizeof(m)); }
-  static M3 I() { M3 r; r.m[0][0] = r.m[1][1] = r.m[2][2] = 1; return r; }
-  double &operator()(int i, int j) { return m[i][j]; }
-  double operator()(int i, int j) const { return m[i][j]; }
+  LIO_HD M3() { for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) m[i][j] = 0.0; }
+  LIO_HD static M3 I() { M3 r; r.m[0][0] = r.m[1][1] = r.m[2][2] = 1; return r; }
+  LIO_HD double &operator()(int i, int j) { return m[i][j]; }
+  LIO_HD double operator()(int i, int j) const { return m[i][j]; }
 };
-inline M3 operator*(const M3 &a, const M3 &b) {
+LIO_HD inline M3 operator*(const M3 &a, const M3 &b) {
   M3 r;
   for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double s = 0; for (int k = 0; k < 3; ++k) s += a.m[i][k] * b.m[k][j]; r.m[i][j] = s; }
   return r;
 }
-inline V3 operator*(const M3 &a, const V3 &v) {
+LIO_HD inline V3 operator*(const M3 &a, const V3 &v) {
   return V3(a.m[0][0] * v.x + a.m[0][1] * v.y + a.m[0][2] * v.z, a.m[1][0] * v.x + a.m[1][1] * v.y + a.m[1][2] * v.z,
             a.m[2][0] * v.x + a.m[2][1] * v.y + a.m[2][2] * v.z);
 }
-inline M3 operator*(const M3 &a, double s) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][j] * s; return r; }
-inline M3 operator+(const M3 &a, const M3 &b) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][j] + b.m[i][j]; return r; }
-inline M3 operator-(const M3 &a, const M3 &b) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][j] - b.m[i][j]; return r; }
-inline M3 operator-(const M3 &a) { return a * -1.0; }
-inline M3 T(const M3 &a) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i]; return r; }
-inline M3 skew(const V3 &v) {
+LIO_HD inline M3 operator*(const M3 &a, double s) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][j] * s; return r; }
+LIO_HD inline M3 operator+(const M3 &a, const M3 &b) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][j] + b.m[i][j]; return r; }
+LIO_HD inline M3 operator-(const M3 &a, const M3 &b) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[i][j] - b.m[i][j]; return r; }
+LIO_HD inline M3 operator-(const M3 &a) { return a * -1.0; }
+LIO_HD inline M3 T(const M3 &a) { M3 r; for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) r.m[i][j] = a.m[j][i]; return r; }
+LIO_HD inline M3 skew(const V3 &v) {
   M3 r;
   r(0, 1) = -v.z; r(0, 2) = v.y; r(1, 0) = v.z; r(1, 2) = -v.x; r(2, 0) = -v.y; r(2, 1) = v.x;
   return r;
@@ -55,24 +61,24 @@ inline M3 skew(const V3 &v) {
 
 struct Q {  // Hamilton quaternion, (x,y,z,w) storage
   double x = 0, y = 0, z = 0, w = 1;
-  Q() {}
-  Q(double w_, double x_, double y_, double z_) : x(x_), y(y_), z(z_), w(w_) {}
-  V3 vec() const { return V3(x, y, z); }
+  LIO_HD Q() {}
+  LIO_HD Q(double w_, double x_, double y_, double z_) : x(x_), y(y_), z(z_), w(w_) {}
+  LIO_HD V3 vec() const { return V3(x, y, z); }
 };
-inline Q conj(const Q &q) { return Q(q.w, -q.x, -q.y, -q.z); }
-inline double norm(const Q &q) { return std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w); }
-inline Q normalized(const Q &q) { double n = norm(q); return Q(q.w / n, q.x / n, q.y / n, q.z / n); }
-inline Q inverse(const Q &q) { double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w; return Q(q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2); }
-inline Q operator*(const Q &a, const Q &b) {
+LIO_HD inline Q conj(const Q &q) { return Q(q.w, -q.x, -q.y, -q.z); }
+LIO_HD inline double norm(const Q &q) { return std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w); }
+LIO_HD inline Q normalized(const Q &q) { double n = norm(q); return Q(q.w / n, q.x / n, q.y / n, q.z / n); }
+LIO_HD inline Q inverse(const Q &q) { double n2 = q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w; return Q(q.w / n2, -q.x / n2, -q.y / n2, -q.z / n2); }
+LIO_HD inline Q operator*(const Q &a, const Q &b) {
   return Q(a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z, a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y,
            a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z, a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x);
 }
-inline V3 rotate(const Q &q, const V3 &v) {
+LIO_HD inline V3 rotate(const Q &q, const V3 &v) {
   V3 u = cross(q.vec(), v);
   u = u + u;
   return v + u * q.w + cross(q.vec(), u);
 }
-inline M3 toR(const Q &q) {
+LIO_HD inline M3 toR(const Q &q) {
   M3 r;
   const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
   const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w, txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
@@ -82,7 +88,7 @@ inline M3 toR(const Q &q) {
   r(2, 0) = txz - twy; r(2, 1) = tyz + twx; r(2, 2) = 1 - (txx + tyy);
   return r;
 }
-inline Q fromR(const M3 &m) {
+LIO_HD inline Q fromR(const M3 &m) {
   Q q;
   double t = m(0, 0) + m(1, 1) + m(2, 2);
   if (t > 0) {
@@ -106,22 +112,22 @@ inline Q fromR(const M3 &m) {
   }
   return q;
 }
-inline Q deltaQ(const V3 &th) { return Q(1.0, th.x / 2, th.y / 2, th.z / 2); }  // mathutils::DeltaQ (not normalised)
+LIO_HD inline Q deltaQ(const V3 &th) { return Q(1.0, th.x / 2, th.y / 2, th.z / 2); }  // mathutils::DeltaQ (not normalised)
 
 // rigid transform with the reference's Twist<T> composition rules (include/utils/Twist.h:40-97)
 struct Tw {
   Q rot;
   V3 pos;
-  Tw() {}
-  Tw(const Q &r, const V3 &p) : rot(r), pos(p) {}
+  LIO_HD Tw() {}
+  LIO_HD Tw(const Q &r, const V3 &p) : rot(r), pos(p) {}
 };
-inline M3 linear(const Tw &t) { return toR(normalized(t.rot)); }
-inline Tw tw_from_affine(const M3 &R, const V3 &t) { return Tw(normalized(fromR(R)), t); }
-inline Tw tw_inverse(const Tw &t) {
+LIO_HD inline M3 linear(const Tw &t) { return toR(normalized(t.rot)); }
+LIO_HD inline Tw tw_from_affine(const M3 &R, const V3 &t) { return Tw(normalized(fromR(R)), t); }
+LIO_HD inline Tw tw_inverse(const Tw &t) {
   M3 Rt = T(linear(t));
   return Tw(fromR(Rt), -(Rt * t.pos));
 }
-inline Tw tw_mul(const Tw &a, const Tw &b) { return tw_from_affine(linear(a) * linear(b), linear(a) * b.pos + a.pos); }
+LIO_HD inline Tw tw_mul(const Tw &a, const Tw &b) { return tw_from_affine(linear(a) * linear(b), linear(a) * b.pos + a.pos); }
 
 // ---- dense row-major matrix ------------------------------------------------------------------
 struct Mat {
