@@ -176,7 +176,8 @@ typedef struct lio_est_config {   /* EstimatorConfig (Estimator.h:77-108), lidar
   int odom_max_iterations;       /* PointMapping num_max_iterations_, PointMapping.h:171 */
   int max_frame_points;          /* capacity of one down-sampled frame cloud (surf_stack_ entry) */
   int max_scan_points;           /* capacity of the incoming laser_cloud_surf_last_ */
-  int device_solver;             /* 1: dogleg loop + dense Cholesky resident on the GPU (default); 0: host controller */
+  int device_solver;             /* 1: dogleg loop + dense Cholesky resident on the GPU (no host sync inside a solve);
+                                    0 (default, faster at n <= 171 in round 1): host controller around the fused kernel */
 } lio_est_config;
 
 typedef struct lio_est lio_est;

@@ -462,7 +462,7 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
   c->acc_n = 0.2; c->gyr_n = 0.02; c->acc_w = 2e-4; c->gyr_w = 2e-5; c->g_norm = 9.805;
   c->max_num_iterations = 10; c->odom_max_iterations = 10;
   c->max_frame_points = 1 << 16; c->max_scan_points = 1 << 18;
-  c->device_solver = 1;
+  c->device_solver = 0;
 }
 
 extern "C" int lio_est_destroy(lio_est *e) {

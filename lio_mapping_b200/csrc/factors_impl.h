@@ -28,8 +28,9 @@ LIO_HD inline M3 left_tl(const Q &q) { return M3::I() * q.w + skew(q.vec()); }
 LIO_HD inline M3 right_tl(const Q &p) { return M3::I() * p.w - skew(p.vec()); }
 }  // namespace fi
 
+// whiten = false returns the raw residual and raw Jacobian blocks (the caller applies sqrt_info, e.g. in parallel)
 LIO_HD inline void imu_factor_eval_impl(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
-                         double r[15], double (*Ji)[6], double (*Jsi)[9], double (*Jj)[6], double (*Jsj)[9]) {
+                         double r[15], double (*Ji)[6], double (*Jsi)[9], double (*Jj)[6], double (*Jsj)[9], bool whiten = true) {
   using namespace hm;
   using namespace fi;
   const V3 Pi(pose_i), Pj(pose_j), Vi(sb_i), Bai(sb_i + 3), Bgi(sb_i + 6), Vj(sb_j), Baj(sb_j + 3), Bgj(sb_j + 6);
@@ -50,7 +51,8 @@ LIO_HD inline void imu_factor_eval_impl(const PimData &pim, const double *pose_i
   const V3 rV = rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi) - corrected_delta_v;
   double raw[15];
   for (int k = 0; k < 3; ++k) { raw[O_P + k] = rP[k]; raw[O_R + k] = rR[k]; raw[O_V + k] = rV[k]; raw[O_BA + k] = Baj[k] - Bai[k]; raw[O_BG + k] = Bgj[k] - Bgi[k]; }
-  for (int i = 0; i < 15; ++i) { double s = 0; for (int j = i; j < 15; ++j) s += pim.sqrt_info[i][j] * raw[j]; r[i] = s; }
+  if (whiten) { for (int i = 0; i < 15; ++i) { double s = 0; for (int j = i; j < 15; ++j) s += pim.sqrt_info[i][j] * raw[j]; r[i] = s; } }
+  else { for (int i = 0; i < 15; ++i) r[i] = raw[i]; }
   if (!Ji) return;
   const M3 RiT = toR(Qi_inv);
   double A0[15][6], A1[15][9], A2[15][6], A3[15][9];
@@ -79,6 +81,13 @@ LIO_HD inline void imu_factor_eval_impl(const PimData &pim, const double *pose_i
   put33(&A3[0][0], 9, O_V, 0, RiT);
   put33(&A3[0][0], 9, O_BA, 3, M3::I());
   put33(&A3[0][0], 9, O_BG, 6, M3::I());
+  if (!whiten) {
+    for (int i = 0; i < 15; ++i) {
+      for (int c = 0; c < 6; ++c) { Ji[i][c] = A0[i][c]; Jj[i][c] = A2[i][c]; }
+      for (int c = 0; c < 9; ++c) { Jsi[i][c] = A1[i][c]; Jsj[i][c] = A3[i][c]; }
+    }
+    return;
+  }
   for (int i = 0; i < 15; ++i) {
     for (int c = 0; c < 6; ++c) {
       double s0 = 0, s2 = 0;

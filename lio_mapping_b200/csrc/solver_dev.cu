@@ -8,6 +8,7 @@
 // [asm_ppp, k_solver_step] pairs; there is no host synchronisation inside a solve.  A frozen extrinsic keeps its
 // 6 tangent slots with an identity block and zero gradient (its step is exactly zero), so n is fixed.
 #include "solver_dev.cuh"
+#include <algorithm>
 
 namespace lio {
 using namespace hm;
@@ -94,7 +95,10 @@ __device__ int chol_solve_smem(const double *__restrict__ H, int n, double mu, c
 #pragma unroll
     for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) { int i = l + 32 * q; b[q] = i < n ? rhs[i] : 0.0; }
     for (int k = 0; k < n; ++k) {  // L y = b
-      double yk = b[k >> 5] / LP(L, k, k);
+      double bk = 0.0;
+#pragma unroll
+      for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) if (q == (k >> 5)) bk = b[q];
+      double yk = bk / LP(L, k, k);
       yk = __shfl_sync(0xffffffffu, yk, k & 31);
 #pragma unroll
       for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) {
@@ -104,7 +108,10 @@ __device__ int chol_solve_smem(const double *__restrict__ H, int n, double mu, c
       }
     }
     for (int k = n - 1; k >= 0; --k) {  // L^T x = y
-      double xk = b[k >> 5] / LP(L, k, k);
+      double bk = 0.0;
+#pragma unroll
+      for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) if (q == (k >> 5)) bk = b[q];
+      double xk = bk / LP(L, k, k);
       xk = __shfl_sync(0xffffffffu, xk, k & 31);
 #pragma unroll
       for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) {
@@ -135,7 +142,8 @@ __device__ void pose_dx_dev(const double *x, const double *x0, double *out) {  /
 
 // Normal equations at state xe into (Hd, gd); cost components into s_cost[0..3] (ppp, pim, marg, ex prior).
 __device__ void build_normal(DevSolveState *S, const double *__restrict__ xe, const double *__restrict__ Sblk, const double *__restrict__ Hp,
-                             double *__restrict__ Hd, double *__restrict__ gd, double *sM, double *sSM, double *s_cost, double *sred) {
+                             double *__restrict__ Hd, double *__restrict__ gd, double *sM, double *sSM, double *scratch, double *s_cost,
+                             double *sred) {
   const int tid = threadIdx.x, T = blockDim.x;
   const int O = S->O, n = S->n;
   const int oe = 15 * (O + 1);
@@ -212,32 +220,48 @@ __device__ void build_normal(DevSolveState *S, const double *__restrict__ xe, co
     if (tid == 0) { double c = 0; for (int i = 0; i < O; ++i) c += 0.5 * Sblk[i * kAsmStride + 28]; s_cost[0] = c; }
   }
   __syncthreads();
-  // ---- ImuFactors
+  // ---- ImuFactors: one thread per factor builds the raw (sparse) Jacobian blocks and residual into shared scratch,
+  // all threads whiten with the upper-triangular sqrt_info in parallel, then J^T J / J^T r are accumulated in two
+  // phases (consecutive factors overlap on one pose/speed-bias block).
   if (S->imu_factor) {
+    double *sA = scratch;                 // O x 15 x 31 raw [J | r]
+    double *sJ = scratch + O * 465;       // O x 15 x 31 whitened
     if (tid < O && S->pim_valid[tid]) {
       double r[15], Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
-      imu_factor_eval_impl(S->pim[tid], x_pose(xe, tid), x_sb(xe, tid), x_pose(xe, tid + 1), x_sb(xe, tid + 1), r, Ji, Jsi, Jj, Jsj);
+      imu_factor_eval_impl(S->pim[tid], x_pose(xe, tid), x_sb(xe, tid), x_pose(xe, tid + 1), x_sb(xe, tid + 1), r, Ji, Jsi, Jj, Jsj, false);
+      double *A = sA + tid * 465;
       for (int a = 0; a < 15; ++a) {
-        for (int c = 0; c < 6; ++c) { S->imu_J[tid][a][c] = Ji[a][c]; S->imu_J[tid][a][15 + c] = Jj[a][c]; }
-        for (int c = 0; c < 9; ++c) { S->imu_J[tid][a][6 + c] = Jsi[a][c]; S->imu_J[tid][a][21 + c] = Jsj[a][c]; }
-        S->imu_r[tid][a] = r[a];
+        for (int c = 0; c < 6; ++c) { A[a * 31 + c] = Ji[a][c]; A[a * 31 + 15 + c] = Jj[a][c]; }
+        for (int c = 0; c < 9; ++c) { A[a * 31 + 6 + c] = Jsi[a][c]; A[a * 31 + 21 + c] = Jsj[a][c]; }
+        A[a * 31 + 30] = r[a];
       }
     }
     __syncthreads();
-    for (int parity = 0; parity < 2; ++parity) {  // consecutive factors overlap on one pose/sb block: two phases
+    for (int p = tid; p < O * 465; p += T) {
+      const int i = p / 465, q = p - i * 465, a = q / 31, c = q - a * 31;
+      if (!S->pim_valid[i]) continue;
+      double s = 0;
+      for (int k = a; k < 15; ++k) s += S->pim[i].sqrt_info[a][k] * sA[i * 465 + k * 31 + c];
+      sJ[p] = s;
+    }
+    __syncthreads();
+    for (int parity = 0; parity < 2; ++parity) {
       for (int p = tid; p < O * 930; p += T) {
         const int i = p / 930, q = p - i * 930;
         if ((i & 1) != parity || !S->pim_valid[i]) continue;
         const int base = 15 * i;
+        const double *J = sJ + i * 465;
         if (q < 900) {
           const int a = q / 30, b = q - a * 30;
           double s = 0;
-          for (int k = 0; k < 15; ++k) s += S->imu_J[i][k][a] * S->imu_J[i][k][b];
+#pragma unroll
+          for (int k = 0; k < 15; ++k) s += J[k * 31 + a] * J[k * 31 + b];
           Hd[(size_t)(base + a) * n + base + b] += s;
         } else {
           const int a = q - 900;
           double s = 0;
-          for (int k = 0; k < 15; ++k) s += S->imu_J[i][k][a] * S->imu_r[i][k];
+#pragma unroll
+          for (int k = 0; k < 15; ++k) s += J[k * 31 + a] * J[k * 31 + 30];
           gd[base + a] += s;
         }
       }
@@ -245,7 +269,7 @@ __device__ void build_normal(DevSolveState *S, const double *__restrict__ xe, co
     }
     if (tid == 0) {
       double c = 0;
-      for (int i = 0; i < O; ++i) if (S->pim_valid[i]) { double sq = 0; for (int k = 0; k < 15; ++k) sq += S->imu_r[i][k] * S->imu_r[i][k]; c += 0.5 * sq; }
+      for (int i = 0; i < O; ++i) if (S->pim_valid[i]) { double sq = 0; for (int k = 0; k < 15; ++k) sq += sJ[i * 465 + k * 31 + 30] * sJ[i * 465 + k * 31 + 30]; c += 0.5 * sq; }
       s_cost[1] = c;
     }
   }
@@ -325,7 +349,7 @@ __global__ void k_solver_terms(DevSolveState *S, double *Rt) { write_terms(S, S-
 
 __global__ void __launch_bounds__(kDsThreads, 1)
 k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict__ Hp, double *H0, double *g0,
-              const double *__restrict__ Sblk, double *Rt, int eval_index) {
+              const double *__restrict__ Sblk, double *Rt, int eval_index, size_t lsize) {
   extern __shared__ double dsm[];
   __shared__ double s_cost[4], sred[33];
   __shared__ int s_flag[4];
@@ -333,7 +357,7 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
   const int tid = threadIdx.x, T = blockDim.x;
   const int O = S->O, n = S->n;
   double *L = dsm;                                   // packed lower triangle, n(n+1)/2
-  double *sM = dsm + (size_t)n * (n + 1) / 2;        // O x 108
+  double *sM = dsm + lsize;                          // O x 108
   double *sSM = sM + O * 108;                        // O x 108
   const double min_diagonal = 1e-6, max_diagonal = 1e32, min_mu = 1e-8, max_mu = 1.0, mu_factor = 10.0;
   const double initial_radius = 1e4, max_radius = 1e16, min_radius = 1e-32, min_relative_decrease = 1e-3;
@@ -342,7 +366,7 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
 
   // ---------------- evaluate ----------------
   const double *xe = eval_index == 0 ? S->x : S->cand;
-  build_normal(S, xe, Sblk, Hp, Hc, S->gc, sM, sSM, s_cost, sred);
+  build_normal(S, xe, Sblk, Hp, Hc, S->gc, sM, sSM, L, s_cost, sred);
   if (eval_index == 0) {
     // residuals before optimisation + gates (Estimator.cc:1924-1985)
     if (tid == 0) {
@@ -360,7 +384,7 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
       s_flag[1] = changed;
     }
     __syncthreads();
-    if (s_flag[1]) build_normal(S, xe, Sblk, Hp, Hc, S->gc, sM, sSM, s_cost, sred);
+    if (s_flag[1]) build_normal(S, xe, Sblk, Hp, Hc, S->gc, sM, sSM, L, s_cost, sred);
     // iteration zero
     for (int p = tid; p < n * n; p += T) { const double v = Hc[p]; H[p] = v; H0[p] = v; }
     for (int p = tid; p < n; p += T) { S->g[p] = S->gc[p]; g0[p] = S->gc[p]; }
@@ -545,13 +569,15 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
 
 bool DevSolver::supports(int O) const {
   const int n = 15 * (O + 1) + 6;
-  const size_t need = sizeof(double) * ((size_t)n * (n + 1) / 2 + (size_t)O * 216);
+  const size_t lsz = std::max((size_t)n * (n + 1) / 2, (size_t)O * 930);
+  const size_t need = sizeof(double) * (lsz + (size_t)O * 216);
   return O <= kMaxOpt && need <= 200 * 1024;
 }
 
 int DevSolver::init(int O) {
   const int n = 15 * (O + 1) + 6, np = 15 * O + 6;
-  smem_bytes = sizeof(double) * ((size_t)n * (n + 1) / 2 + (size_t)O * 216);
+  lsize = std::max((size_t)n * (n + 1) / 2, (size_t)O * 930);  // Cholesky area, also the IMU scratch
+  smem_bytes = sizeof(double) * (lsize + (size_t)O * 216);
   if (cudaMalloc(&st, sizeof(DevSolveState)) != cudaSuccess) return -1;
   if (cudaMalloc(&H, sizeof(double) * n * n) != cudaSuccess) return -1;
   if (cudaMalloc(&Hc, sizeof(double) * n * n) != cudaSuccess) return -1;
@@ -580,7 +606,7 @@ int dev_solver_terms(DevSolver &ds, double *Rt_dev, cudaStream_t st, int *launch
 }
 
 int dev_solver_step(DevSolver &ds, const double *S_dev, double *Rt_dev, int eval_index, cudaStream_t st, int *launches) {
-  k_solver_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.H, ds.Hc, ds.Hp, ds.H0, ds.g0, S_dev, Rt_dev, eval_index);
+  k_solver_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.H, ds.Hc, ds.Hp, ds.H0, ds.g0, S_dev, Rt_dev, eval_index, ds.lsize);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }

@@ -39,7 +39,7 @@ struct DevSolver {
   double *H = nullptr, *Hc = nullptr, *Hp = nullptr, *H0 = nullptr;  // device n x n (row-major), prior np x np
   double *g0 = nullptr;
   DevSolveState *h_st = nullptr;   // pinned staging copy (only the scalar / vector part is moved each scan)
-  size_t smem_bytes = 0;
+  size_t smem_bytes = 0, lsize = 0;
   int init(int O);
   void destroy();
   bool supports(int O) const;
