@@ -115,6 +115,17 @@ int lio_voxel_grid_host(const float *cloud, int n, float leaf, float *out, int c
 int lio_calculate_features_host(const float *map, int K, const float *surf, int M, const float *tf7,
                                 float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
                                 int *n_out, int device);
+/* TransformToEnd (Estimator.cc:62-103): in-place motion compensation of a sweep whose intensity carries
+ * ring + relative time; tf7_es = transform_es {qx,qy,qz,qw,px,py,pz}; time_factor = 10 at the call site
+ * (Estimator.cc:560).  float32, device sinf/acosf: parity tolerance 2e-6 relative to the range. */
+int lio_transform_to_end_host(float *cloud, int n, const float *tf7_es, float time_factor, int device);
+/* Estimator::CalculateLaserOdom (Estimator.cc:1099-1360): up to max_iter rounds of CalculateFeatures +
+ * 6-DoF point-to-plane Gauss-Newton (float features, double normal equations, degeneracy projection at
+ * the first round) refining tf7 in place.  Outputs are sized M * (keep_features ? max_iter : 1); *iters =
+ * rounds executed before the delta_r / delta_t < 0.05 exit. */
+int lio_laser_odom_host(const float *map, int K, const float *surf, int M, float *tf7, float min_match_sq_dis,
+                        float min_plane_dis, int keep_features, int max_iter, float *pts4, float *coef4, int32_t *src,
+                        int *n_out, int *iters, int device);
 
 /* ------------------------------------------------------------------------------------------
  * fp64 factor operators — the ceres::CostFunction::Evaluate seam.

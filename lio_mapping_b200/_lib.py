@@ -80,6 +80,9 @@ def lib():
     L.lio_voxel_grid_host.argtypes = [f32p, ip, C.c_float, f32p, ip, C.POINTER(ip), ip]
     L.lio_calculate_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, f32p, f32p, i32p,
                                               C.POINTER(ip), ip]
+    L.lio_transform_to_end_host.argtypes = [f32p, ip, f32p, C.c_float, ip]
+    L.lio_laser_odom_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, ip, f32p, f32p, i32p,
+                                      C.POINTER(ip), C.POINTER(ip), ip]
     L.lio_pp_cloud_count_dev.argtypes = [vp, ip, C.POINTER(vp)]
     L.lio_ppp_evaluate.argtypes = [f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
     L.lio_ppp_evaluate_batch_host.argtypes = [f32p, f32p, ip, f64p, f64p, f64p, f64p, f64p, ip]

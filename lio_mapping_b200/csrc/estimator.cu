@@ -10,6 +10,7 @@
 // There is no CPU path for the per-point work: without a CUDA device create() fails.
 #include "assemble.cuh"
 #include "factors_host.h"
+#include "factors_impl.h"
 #include "knn.cuh"
 #include "qr.cuh"
 #include "solver_dev.cuh"
@@ -917,24 +918,11 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
       const int j = i + 1;
       Preintegration &pim = *e->pre[pivot + j];
       if (pim.sum_dt > 10.0) continue;
-      double r[15], Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
-      imu_factor_evaluate(pim, e->para_pose[i].data(), e->para_sb[i].data(), e->para_pose[j].data(), e->para_sb[j].data(), r, Ji, Jsi, Jj, Jsj);
-      double J[15][30];
-      for (int a = 0; a < 15; ++a) {
-        for (int c = 0; c < 6; ++c) { J[a][c] = Ji[a][c]; J[a][15 + c] = Jj[a][c]; }
-        for (int c = 0; c < 9; ++c) { J[a][6 + c] = Jsi[a][c]; J[a][21 + c] = Jsj[a][c]; }
-      }
-      const int base = 15 * i;  // pose_i, sb_i, pose_j, sb_j are contiguous in the tangent layout
-      for (int a = 0; a < 30; ++a) {
-        double gs = 0;
-        for (int k = 0; k < 15; ++k) gs += J[k][a] * r[k];
-        g[base + a] += gs;
-        for (int b = 0; b < 30; ++b) {
-          double s = 0;
-          for (int k = 0; k < 15; ++k) s += J[k][a] * J[k][b];
-          H(base + a, base + b) += s;
-        }
-      }
+      double r[15], J[15][30];
+      imu_factor_evaluate30(pim, e->para_pose[i].data(), e->para_sb[i].data(), e->para_pose[j].data(), e->para_sb[j].data(), r, J);
+      int cmap[30];
+      for (int a = 0; a < 30; ++a) cmap[a] = 15 * i + a;  // pose_i, sb_i, pose_j, sb_j are contiguous in the tangent layout
+      add_JtJ_mapped(&J[0][0], r, 15, 30, cmap, H, g);
       double sq = 0;
       for (int k = 0; k < 15; ++k) sq += r[k] * r[k];
       ci += 0.5 * sq;
@@ -944,7 +932,8 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
     const MargPrior &pr = e->prior;
     Vec dx;
     prior_dx(e, pr, dx);
-    Vec Hdx = mul(pr.Hp, dx);
+    Vec Hdx;
+    matvec(pr.Hp, dx, Hdx);
     cm = 0.5 * (pr.c0 + 2.0 * vdot(pr.bp, dx) + vdot(dx, Hdx));
     auto tmap = [&](int pi) { return pi < 15 * O ? pi : (ex_free ? 15 * (O + 1) + (pi - 15 * O) : -1); };
     for (int a = 0; a < pr.n; ++a) {
@@ -952,10 +941,10 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
       if (ta < 0) continue;
       g[ta] += Hdx[a] + pr.bp[a];
       const double *row = &pr.Hp.d[(size_t)a * pr.n];
-      for (int b = 0; b < pr.n; ++b) {
-        const int tb = tmap(b);
-        if (tb >= 0) H(ta, tb) += row[b];
-      }
+      double *hrow = &H.d[(size_t)ta * n];
+      const int nw = 15 * O;  // window part maps one to one
+      for (int b = 0; b < nw; ++b) hrow[b] += row[b];
+      if (ex_free) for (int b = nw; b < pr.n; ++b) hrow[15 * (O + 1) + (b - nw)] += row[b];
     }
   }
   double cprior = 0;
@@ -992,7 +981,8 @@ static int marginalize(lio_est *e) {
     const MargPrior &pr = e->prior;
     Vec dx;
     prior_dx(e, pr, dx);
-    Vec Hdx = mul(pr.Hp, dx);
+    Vec Hdx;
+    matvec(pr.Hp, dx, Hdx);
     auto map = [&](int pi) {  // prior canonical index -> A index
       if (pi >= 15 * O) return idx_ex + (pi - 15 * O);
       int k = pi / 15, a = pi % 15;
@@ -1005,22 +995,12 @@ static int marginalize(lio_est *e) {
     }
   }
   if (e->cfg.imu_factor && e->pre[pivot + 1]->sum_dt < 10.0) {
-    double r[15], Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
-    imu_factor_evaluate(*e->pre[pivot + 1], e->para_pose[0].data(), e->para_sb[0].data(), e->para_pose[1].data(), e->para_sb[1].data(), r, Ji, Jsi, Jj, Jsj);
-    double J[15][30];
+    double r[15], J[15][30];
+    imu_factor_evaluate30(*e->pre[pivot + 1], e->para_pose[0].data(), e->para_sb[0].data(), e->para_pose[1].data(), e->para_sb[1].data(), r, J);
     int col[30];
     for (int c = 0; c < 6; ++c) { col[c] = idx_pose(0) + c; col[15 + c] = idx_pose(1) + c; }
     for (int c = 0; c < 9; ++c) { col[6 + c] = idx_sb(0) + c; col[21 + c] = idx_sb(1) + c; }
-    for (int a = 0; a < 15; ++a) {
-      for (int c = 0; c < 6; ++c) { J[a][c] = Ji[a][c]; J[a][15 + c] = Jj[a][c]; }
-      for (int c = 0; c < 9; ++c) { J[a][6 + c] = Jsi[a][c]; J[a][21 + c] = Jsj[a][c]; }
-    }
-    for (int a = 0; a < 30; ++a) {
-      double gs = 0;
-      for (int k = 0; k < 15; ++k) gs += J[k][a] * r[k];
-      b[col[a]] += gs;
-      for (int c = 0; c < 30; ++c) { double s = 0; for (int k = 0; k < 15; ++k) s += J[k][a] * J[k][c]; A(col[a], col[c]) += s; }
-    }
+    add_JtJ_mapped(&J[0][0], r, 15, 30, col, A, b);
   }
   if (e->cfg.point_distance_factor) {
     std::vector<FrameTerms> ft;
@@ -1171,7 +1151,7 @@ static int solve_optimization_dev(lio_est *e) {
   for (int i = 0; i < O; ++i) {
     Preintegration &pim = *e->pre[pivot + i + 1];
     S.pim_valid[i] = pim.sum_dt > 10.0 ? 0 : 1;
-    pim.to_data(S.pim[i]);
+    S.pim[i] = pim.data();
   }
   if (S.prior_valid) {
     const MargPrior &pr = e->prior;
@@ -1587,6 +1567,104 @@ __global__ void k_fill_features(float4 *pts, float4 *coef, long long n) {
 // Streaming-rate measurement of the fused stage-C kernel on a synthetic feature stream of n features
 // (choose n*32 B larger than L2 to measure the HBM-resident rate).  CUDA events around each launch on the
 // launching stream.  out = {avg ms per launch, min ms, bytes per launch, launches}.
+// ---- C-ABI: TransformToEnd on an explicit host array (parity entry) ----------------------------------------------
+extern "C" int lio_transform_to_end_host(float *cloud, int n, const float *tf7_es, float time_factor, int device) {
+  if (!cloud || !tf7_es || n < 0) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  if (n == 0) return LIO_OK;
+  float4 *d = nullptr;
+  int *dn = nullptr;
+  LIO_CUDA_OK(cudaMalloc(&d, sizeof(float4) * n));
+  cudaError_t ce = cudaMalloc(&dn, sizeof(int));
+  if (ce == cudaSuccess) ce = cudaMemcpy(d, cloud, sizeof(float4) * n, cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) ce = cudaMemcpy(dn, &n, sizeof(int), cudaMemcpyHostToDevice);
+  if (ce == cudaSuccess) {
+    TransformF es;
+    std::memcpy(&es, tf7_es, sizeof(es));
+    k_deskew<<<(n + 255) / 256, 256>>>(d, dn, es, time_factor);
+    ce = cudaMemcpy(cloud, d, sizeof(float4) * n, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d);
+  if (dn) cudaFree(dn);
+  if (ce != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); return LIO_ERR_CUDA; }
+  return LIO_OK;
+}
+
+// ---- C-ABI: Estimator::CalculateLaserOdom on explicit host arrays (parity entry) ---------------------------------
+extern "C" int lio_laser_odom_host(const float *map, int K, const float *surf, int M, float *tf7, float min_match_sq_dis,
+                                   float min_plane_dis, int keep_features, int max_iter, float *pts4, float *coef4, int32_t *src,
+                                   int *n_out, int *iters, int device) {
+  if (!map || !surf || !tf7 || !n_out || K < 0 || M < 0 || max_iter < 0) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  *n_out = 0;
+  if (iters) *iters = 0;
+  if (M == 0 || max_iter == 0) return LIO_OK;
+  const int cap = M * (keep_features ? max_iter : 1);
+  CellHash h;
+  KnnWork w;
+  float4 *d_map = nullptr, *d_surf = nullptr;
+  FeatureOut fo;
+  int *d_n = nullptr;
+  TransformF *d_tf = nullptr;
+  OdomState *d_odom = nullptr;
+  double *d_partial = nullptr;
+  int rc = LIO_OK, sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+  const int Kc = K > 0 ? K : 1;
+  if (h.init(Kc) != 0 || w.init(M) != 0) rc = LIO_ERR_CUDA;
+  if (rc == LIO_OK && (cudaMalloc(&d_map, sizeof(float4) * Kc) != cudaSuccess || cudaMalloc(&d_surf, sizeof(float4) * M) != cudaSuccess ||
+                       cudaMalloc(&fo.pts, sizeof(float4) * cap) != cudaSuccess || cudaMalloc(&fo.coef, sizeof(float4) * cap) != cudaSuccess ||
+                       cudaMalloc(&fo.src, sizeof(int) * cap) != cudaSuccess || cudaMalloc(&d_n, sizeof(int) * 4) != cudaSuccess ||
+                       cudaMalloc(&d_tf, sizeof(TransformF)) != cudaSuccess || cudaMalloc(&d_odom, sizeof(OdomState)) != cudaSuccess ||
+                       cudaMalloc(&d_partial, sizeof(double) * 32 * 1024) != cudaSuccess))
+    rc = LIO_ERR_CUDA;
+  if (rc != LIO_OK) lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+  if (rc == LIO_OK) {
+    const int hn[3] = {K, M, 0};
+    cudaMemcpy(d_map, map, sizeof(float4) * K, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_surf, surf, sizeof(float4) * M, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tf, tf7, sizeof(TransformF), cudaMemcpyHostToDevice);
+    cudaMemset(d_odom, 0, sizeof(OdomState));
+    fo.count = d_n + 2; fo.cap = cap;
+    const float cell = sqrtf(min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
+    rc = h.build(d_map, d_n, Kc, cell, 0, nullptr);
+    const int nb = std::max(1, std::min(sm, (cap + kOdomThreads - 1) / kOdomThreads));
+    for (int it = 0; it < max_iter && rc == LIO_OK; ++it) {
+      rc = calculate_features_dev(h, d_map, d_surf, d_n + 1, M, d_tf, min_match_sq_dis, min_plane_dis, fo, keep_features ? 1 : 0,
+                                  &d_odom->done, w, 0, nullptr);
+      if (rc != LIO_OK) break;
+      k_odom_reduce<<<nb, kOdomThreads>>>(fo.pts, fo.coef, fo.count, d_tf, d_odom, d_partial);
+      k_odom_solve<<<1, 32>>>(d_odom, d_tf, 0.05, 0.05);
+    }
+    if (rc == LIO_OK) {
+      int m = 0;
+      OdomState hs;
+      cudaError_t ce = cudaMemcpy(&m, d_n + 2, sizeof(int), cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(&hs, d_odom, sizeof(OdomState), cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(tf7, d_tf, sizeof(TransformF), cudaMemcpyDeviceToHost);
+      if (ce != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); rc = LIO_ERR_CUDA; }
+      else if (m > cap) { lio_set_last_error(__FILE__, __LINE__, "feature buffer overflow"); rc = LIO_ERR_CAPACITY; }
+      else {
+        *n_out = m;
+        if (iters) *iters = hs.iter;
+        if (m > 0) {
+          if (pts4) cudaMemcpy(pts4, fo.pts, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+          if (coef4) cudaMemcpy(coef4, fo.coef, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+          if (src) cudaMemcpy(src, fo.src, sizeof(int) * m, cudaMemcpyDeviceToHost);
+        }
+      }
+    }
+  }
+  void *fr[] = {d_map, d_surf, fo.pts, fo.coef, fo.src, d_n, d_tf, d_odom, d_partial};
+  for (void *q : fr) if (q) cudaFree(q);
+  h.destroy();
+  w.destroy();
+  return rc;
+}
+
 extern "C" int lio_asm_stream_bench(long long n_features, int iters, int device, double out[4]) {
   if (n_features <= 0 || iters <= 0 || !out) return LIO_ERR_INVALID;
   if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;

@@ -22,6 +22,7 @@ Preintegration::Preintegration(const V3 &a0, const V3 &g0, const V3 &ba, const V
 
 void Preintegration::push_back(double dt, const V3 &acc1, const V3 &gyr1) {
   sqrt_info_valid = false;
+  cache.reset();
   const V3 un_acc_0 = rotate(delta_q, acc0 - lin_ba);
   const V3 un_gyr = 0.5 * (gyr0 + gyr1) - lin_bg;
   const Q rq = delta_q * Q(1, un_gyr.x * dt / 2, un_gyr.y * dt / 2, un_gyr.z * dt / 2);
@@ -121,6 +122,22 @@ static void fill_pim(const Preintegration &p, PimData &d) {
 void Preintegration::to_data(PimData &d) {
   ensure_sqrt_info();
   fill_pim(*this, d);
+}
+
+const PimData &Preintegration::data() {
+  if (!cache || !sqrt_info_valid) {
+    if (!cache) cache = std::make_shared<PimData>();
+    to_data(*cache);
+  }
+  return *cache;
+}
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("arch=x86-64-v3", "default")))
+#endif
+void imu_factor_evaluate30(Preintegration &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                           double r[15], double (*J)[30]) {
+  imu_factor_eval30(pim.data(), pose_i, sb_i, pose_j, sb_j, r, J);
 }
 
 void imu_factor_evaluate(Preintegration &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,

@@ -30,6 +30,8 @@ struct Preintegration {
   void push_back(double dt, const hm::V3 &acc, const hm::V3 &gyr);
   void ensure_sqrt_info();
   void to_data(struct PimData &d);
+  const struct PimData &data();  // cached plain-data view (valid until the next push_back)
+  std::shared_ptr<struct PimData> cache;
 };
 
 // ImuFactor::Evaluate (include/factor/ImuFactor.h:53-167).  J blocks are 15x6 / 15x9 (tangent
@@ -37,6 +39,9 @@ struct Preintegration {
 // for residual-only evaluation.
 void imu_factor_evaluate(Preintegration &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
                          double r[15], double (*Ji)[6], double (*Jsi)[9], double (*Jj)[6], double (*Jsj)[9]);
+// Same with the combined 15 x 30 Jacobian over [pose_i | sb_i | pose_j | sb_j] (nullptr: residual only).
+void imu_factor_evaluate30(Preintegration &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                           double r[15], double (*J)[30]);
 
 // PivotPointPlaneFactor::Evaluate for ONE factor on the host (src/factor/PivotPointPlaneFactor.cc:43-137);
 // J blocks 1x7 row-major or nullptr.  Operator-seam entry (lio_ppp_evaluate), not used in the solve loop.

@@ -29,8 +29,9 @@ LIO_HD inline M3 right_tl(const Q &p) { return M3::I() * p.w - skew(p.vec()); }
 }  // namespace fi
 
 // whiten = false returns the raw residual and raw Jacobian blocks (the caller applies sqrt_info, e.g. in parallel)
-LIO_HD inline void imu_factor_eval_impl(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
-                         double r[15], double (*Ji)[6], double (*Jsi)[9], double (*Jj)[6], double (*Jsj)[9], bool whiten = true) {
+// Combined layout: J is 15 x 30 row-major over [pose_i(6) | sb_i(9) | pose_j(6) | sb_j(9)] tangent columns (or nullptr).
+LIO_HD inline void imu_factor_eval30(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                                     double r[15], double (*J)[30], bool whiten = true) {
   using namespace hm;
   using namespace fi;
   const V3 Pi(pose_i), Pj(pose_j), Vi(sb_i), Bai(sb_i + 3), Bgi(sb_i + 6), Vj(sb_j), Baj(sb_j + 3), Bgj(sb_j + 6);
@@ -53,52 +54,56 @@ LIO_HD inline void imu_factor_eval_impl(const PimData &pim, const double *pose_i
   for (int k = 0; k < 3; ++k) { raw[O_P + k] = rP[k]; raw[O_R + k] = rR[k]; raw[O_V + k] = rV[k]; raw[O_BA + k] = Baj[k] - Bai[k]; raw[O_BG + k] = Bgj[k] - Bgi[k]; }
   if (whiten) { for (int i = 0; i < 15; ++i) { double s = 0; for (int j = i; j < 15; ++j) s += pim.sqrt_info[i][j] * raw[j]; r[i] = s; } }
   else { for (int i = 0; i < 15; ++i) r[i] = raw[i]; }
-  if (!Ji) return;
+  if (!J) return;
   const M3 RiT = toR(Qi_inv);
-  double A0[15][6], A1[15][9], A2[15][6], A3[15][9];
-  for (int a = 0; a < 15; ++a) { for (int c = 0; c < 6; ++c) { A0[a][c] = 0; A2[a][c] = 0; } for (int c = 0; c < 9; ++c) { A1[a][c] = 0; A3[a][c] = 0; } }
-  put33(&A0[0][0], 6, O_P, 0, -RiT);
-  put33(&A0[0][0], 6, O_P, 3, skew(rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
+  double A[15][30];
+  for (int a = 0; a < 15; ++a) for (int c = 0; c < 30; ++c) A[a][c] = 0;
+  put33(&A[0][0], 30, O_P, 0, -RiT);
+  put33(&A[0][0], 30, O_P, 3, skew(rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
   {  // -(L(Qj^-1 Qi) R(corrected_delta_q)) top-left 3x3
     const Q ql = inverse(Qj) * Qi;
     M3 m = left_tl(ql) * right_tl(corrected_delta_q);
     const V3 qv = ql.vec(), pv = corrected_delta_q.vec();
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) m(a, b) -= qv[a] * pv[b];
-    put33(&A0[0][0], 6, O_R, 3, -m);
+    put33(&A[0][0], 30, O_R, 3, -m);
   }
-  put33(&A0[0][0], 6, O_V, 3, skew(rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi)));
-  put33(&A1[0][0], 9, O_P, 0, -RiT * sum_dt);
-  put33(&A1[0][0], 9, O_P, 3, -dp_dba);
-  put33(&A1[0][0], 9, O_P, 6, -dp_dbg);
-  put33(&A1[0][0], 9, O_R, 6, -(left_tl(inverse(Qj) * Qi * corrected_delta_q) * dq_dbg));
-  put33(&A1[0][0], 9, O_V, 0, -RiT);
-  put33(&A1[0][0], 9, O_V, 3, -dv_dba);
-  put33(&A1[0][0], 9, O_V, 6, -dv_dbg);
-  put33(&A1[0][0], 9, O_BA, 3, -M3::I());
-  put33(&A1[0][0], 9, O_BG, 6, -M3::I());
-  put33(&A2[0][0], 6, O_P, 0, RiT);
-  put33(&A2[0][0], 6, O_R, 3, left_tl(inverse(corrected_delta_q) * Qi_inv * Qj));
-  put33(&A3[0][0], 9, O_V, 0, RiT);
-  put33(&A3[0][0], 9, O_BA, 3, M3::I());
-  put33(&A3[0][0], 9, O_BG, 6, M3::I());
+  put33(&A[0][0], 30, O_V, 3, skew(rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi)));
+  put33(&A[0][0], 30, O_P, 6, -RiT * sum_dt);
+  put33(&A[0][0], 30, O_P, 9, -dp_dba);
+  put33(&A[0][0], 30, O_P, 12, -dp_dbg);
+  put33(&A[0][0], 30, O_R, 12, -(left_tl(inverse(Qj) * Qi * corrected_delta_q) * dq_dbg));
+  put33(&A[0][0], 30, O_V, 6, -RiT);
+  put33(&A[0][0], 30, O_V, 9, -dv_dba);
+  put33(&A[0][0], 30, O_V, 12, -dv_dbg);
+  put33(&A[0][0], 30, O_BA, 9, -M3::I());
+  put33(&A[0][0], 30, O_BG, 12, -M3::I());
+  put33(&A[0][0], 30, O_P, 15, RiT);
+  put33(&A[0][0], 30, O_R, 18, left_tl(inverse(corrected_delta_q) * Qi_inv * Qj));
+  put33(&A[0][0], 30, O_V, 21, RiT);
+  put33(&A[0][0], 30, O_BA, 24, M3::I());
+  put33(&A[0][0], 30, O_BG, 27, M3::I());
   if (!whiten) {
-    for (int i = 0; i < 15; ++i) {
-      for (int c = 0; c < 6; ++c) { Ji[i][c] = A0[i][c]; Jj[i][c] = A2[i][c]; }
-      for (int c = 0; c < 9; ++c) { Jsi[i][c] = A1[i][c]; Jsj[i][c] = A3[i][c]; }
-    }
+    for (int i = 0; i < 15; ++i) for (int c = 0; c < 30; ++c) J[i][c] = A[i][c];
     return;
   }
+  // J = sqrt_info (upper triangular) * A, row-wise axpy (stride-1 inner loop)
   for (int i = 0; i < 15; ++i) {
-    for (int c = 0; c < 6; ++c) {
-      double s0 = 0, s2 = 0;
-      for (int k = i; k < 15; ++k) { s0 += pim.sqrt_info[i][k] * A0[k][c]; s2 += pim.sqrt_info[i][k] * A2[k][c]; }
-      Ji[i][c] = s0; Jj[i][c] = s2;
+    for (int c = 0; c < 30; ++c) J[i][c] = 0;
+    for (int k = i; k < 15; ++k) {
+      const double s = pim.sqrt_info[i][k];
+      for (int c = 0; c < 30; ++c) J[i][c] += s * A[k][c];
     }
-    for (int c = 0; c < 9; ++c) {
-      double s1 = 0, s3 = 0;
-      for (int k = i; k < 15; ++k) { s1 += pim.sqrt_info[i][k] * A1[k][c]; s3 += pim.sqrt_info[i][k] * A3[k][c]; }
-      Jsi[i][c] = s1; Jsj[i][c] = s3;
-    }
+  }
+}
+
+LIO_HD inline void imu_factor_eval_impl(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                         double r[15], double (*Ji)[6], double (*Jsi)[9], double (*Jj)[6], double (*Jsj)[9], bool whiten = true) {
+  if (!Ji) { imu_factor_eval30(pim, pose_i, sb_i, pose_j, sb_j, r, nullptr, whiten); return; }
+  double J[15][30];
+  imu_factor_eval30(pim, pose_i, sb_i, pose_j, sb_j, r, J, whiten);
+  for (int i = 0; i < 15; ++i) {
+    for (int c = 0; c < 6; ++c) { Ji[i][c] = J[i][c]; Jj[i][c] = J[i][15 + c]; }
+    for (int c = 0; c < 9; ++c) { Jsi[i][c] = J[i][6 + c]; Jsj[i][c] = J[i][21 + c]; }
   }
 }
 

@@ -193,6 +193,39 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
   d.swap(ds);
 }
 
+LIO_MV void add_JtJ_mapped(const double *J, const double *r, int rows, int cols, const int *cm, Mat &H, Vec &g) {
+  // contiguous fast path when the mapped columns are consecutive
+  bool contiguous = true;
+  for (int a = 1; a < cols; ++a) if (cm[a] != cm[0] + a) contiguous = false;
+  const int n = H.c;
+  double tmp[64];
+  for (int a = 0; a < cols; ++a) {
+    double gs = 0;
+    for (int b = 0; b < cols; ++b) tmp[b] = 0.0;
+    for (int k = 0; k < rows; ++k) {
+      const double ja = J[k * cols + a];
+      const double *jr = J + k * cols;
+      for (int b = 0; b < cols; ++b) tmp[b] += ja * jr[b];
+      gs += ja * r[k];
+    }
+    g[cm[a]] += gs;
+    double *hrow = &H.d[(size_t)cm[a] * n];
+    if (contiguous) { double *dst = hrow + cm[0]; for (int b = 0; b < cols; ++b) dst[b] += tmp[b]; }
+    else for (int b = 0; b < cols; ++b) hrow[cm[b]] += tmp[b];
+  }
+}
+
+LIO_MV void matvec(const Mat &A, const Vec &x, Vec &y) {
+  y.assign(A.r, 0.0);
+  for (int i = 0; i < A.r; ++i) {
+    const double *row = &A.d[(size_t)i * A.c];
+    double s = 0;
+#pragma omp simd reduction(+ : s)
+    for (int j = 0; j < A.c; ++j) s += row[j] * x[j];
+    y[i] = s;
+  }
+}
+
 // C = A * A^T restricted to the first `kc` columns of A scaled by w: C(r,c) = sum_k A(r,k) w[k] A(c,k)
 LIO_MV void weighted_gram(const Mat &A, const Vec &w, const std::vector<int> &cols, Mat &C) {
   const int n = A.r, kc = (int)cols.size();

@@ -154,6 +154,10 @@ bool cholesky(Mat &a);
 void cholesky_solve(const Mat &L, Vec &b);
 // symmetric eigen-decomposition (ascending eigenvalues, eigenvectors in columns)
 void sym_eigen(const Mat &A, Vec &evals, Mat &evecs);
+// H(cm[a], cm[b]) += sum_k J[k][a] J[k][b];  g[cm[a]] += sum_k J[k][a] r[k]   (J: rows x cols row-major, cm: column map)
+void add_JtJ_mapped(const double *J, const double *r, int rows, int cols, const int *cm, Mat &H, Vec &g);
+// y = A x (multiversioned)
+void matvec(const Mat &A, const Vec &x, Vec &y);
 // C(r,c) = sum_{k in cols} A(r,k) w[k] A(c,k)
 void weighted_gram(const Mat &A, const Vec &w, const std::vector<int> &cols, Mat &C);
 

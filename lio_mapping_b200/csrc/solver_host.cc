@@ -9,6 +9,9 @@
 namespace lio {
 using namespace hm;
 
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("arch=x86-64-v3", "default")))
+#endif
 void dogleg_solve(const DoglegOptions &opt, DoglegProblem &P, DoglegSummary *sum) {
   const int n = P.n;
   *sum = DoglegSummary();

@@ -33,3 +33,31 @@ def calculate_features(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0
                                                       min_match_sq_dis, min_plane_dis, pts, coef, src, C.byref(n), device),
                "lio_calculate_features_host")
     return pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy()
+
+
+def laser_odom(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, keep_features=False, max_iter=10, device: int = 0):
+    """Estimator::CalculateLaserOdom on explicit arrays (lio_laser_odom_host).
+
+    Returns (tf7, pts, coef, src, iterations)."""
+    _lib.require_device()
+    m = np.ascontiguousarray(map_pts, np.float32).reshape(-1, 4)
+    s = np.ascontiguousarray(surf, np.float32).reshape(-1, 4)
+    cap = max(s.shape[0] * (max_iter if keep_features else 1), 1)
+    pts = np.zeros((cap, 4), np.float32)
+    coef = np.zeros((cap, 4), np.float32)
+    src = np.zeros(cap, np.int32)
+    tf = np.ascontiguousarray(tf7, np.float32).copy()
+    n, it = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().lio_laser_odom_host(m, m.shape[0], s, s.shape[0], tf, min_match_sq_dis, min_plane_dis,
+                                              1 if keep_features else 0, max_iter, pts, coef, src, C.byref(n), C.byref(it), device),
+               "lio_laser_odom_host")
+    return tf, pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy(), it.value
+
+
+def transform_to_end(cloud, tf7_es, time_factor=10.0, device: int = 0):
+    """TransformToEnd (lio_transform_to_end_host): returns the motion-compensated copy of `cloud`."""
+    _lib.require_device()
+    c = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4).copy()
+    _lib.check(_lib.lib().lio_transform_to_end_host(c, c.shape[0], np.ascontiguousarray(tf7_es, np.float32), time_factor, device),
+               "lio_transform_to_end_host")
+    return c

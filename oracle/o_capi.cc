@@ -321,3 +321,10 @@ void orc_est_get_prior(void *h, double *J, double *r) {
 }
 
 }  // extern "C"
+
+extern "C" void orc_transform_to_end(float *cloud, int n, const float *tf7, float time_factor) {
+  Cloud c((const PointXYZI *)cloud, (const PointXYZI *)cloud + n);
+  Transform t = make_tf(tf7);
+  TransformToEnd(c, t, time_factor);
+  std::memcpy(cloud, c.data(), sizeof(PointXYZI) * n);
+}

@@ -156,6 +156,16 @@ def laser_odom(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, keep
     return tf, pts[:n].copy(), coef[:n].copy(), src[:n].copy(), int(it[0])
 
 
+def transform_to_end(cloud, tf7, time_factor=10.0):
+    """TransformToEnd (Estimator.cc:62-103) on a copy of `cloud`."""
+    L = lib()
+    c = np.ascontiguousarray(cloud, np.float32).reshape(-1, 4).copy()
+    L.orc_transform_to_end.argtypes = [f32p, C.c_int, f32p, C.c_float]
+    L.orc_transform_to_end.restype = None
+    L.orc_transform_to_end(c, c.shape[0], np.ascontiguousarray(tf7, np.float32), time_factor)
+    return c
+
+
 # =================================================================================================
 # fp64 factors / solver / estimator bindings
 def _bind_factors(L):

@@ -234,3 +234,26 @@ def test_benchmark_configuration_parity(oracle):
         assert np.abs(xg[:, :3] - xo[:, :3]).max() <= 1e-4 * scale, (k, np.abs(xg[:, :3] - xo[:, :3]).max())
         assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-4
         assert abs(sg["final_cost"] - so["final_cost"]) <= 1e-2 * so["final_cost"], (k, sg["final_cost"], so["final_cost"])
+
+
+def test_window_solve_parity_with_deskew(oracle):
+    """enable_deskew && !cutoff_deskew: the incoming less-flat cloud goes through TransformToEnd (k_deskew on the
+    device, float sinf/acosf vs libm) before the 0.4 m voxel grid.  A last-ulp coordinate change can move a point
+    across a voxel face, so frame sizes agree within a handful of points and states at the north-star bound."""
+    seq = helpers.Sequence(oracle, "vlp16", n_total=9, distort=True)
+    W = 5
+    eo, eg = _mk(oracle, seq, W, opt_extrinsic=0, enable_deskew=1, cutoff_deskew=0)
+    for k in range(W, 9):
+        helpers.feed_scan(eo, seq, k)
+        helpers.feed_scan(eg, seq, k)
+        so, sg = eo.summary(), eg.summary()
+        fo, fg = eo.frame(W), eg.frame(W)     # newest frame (pushed at ProcessScan entry)
+        assert abs(fg.shape[0] - fo.shape[0]) <= 3
+        if fg.shape[0] == fo.shape[0]:
+            assert np.abs(fg[:, :3] - fo[:, :3]).max() < 0.4    # same voxel population (centroids may shift by one member)
+            assert np.median(np.abs(fg[:, :3] - fo[:, :3]).max(axis=1)) < 1e-5
+        assert abs(sg["num_features"] - so["num_features"]) <= 0.005 * so["num_features"]
+        xo, xg = eo.states(), eg.states()
+        scale = max(1.0, np.abs(xo[:, :3]).max())
+        assert np.abs(xg[:, :3] - xo[:, :3]).max() <= 1e-4 * scale
+        assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-4

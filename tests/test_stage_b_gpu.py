@@ -66,3 +66,59 @@ def test_calculate_features_edge_cases(oracle):
     po, co, so = oracle.calculate_features(m, s, tf7)
     pg, cg, sg = ops.calculate_features(m, s, tf7)
     assert np.array_equal(sg, so) and np.array_equal(cg, co)
+
+
+@pytest.mark.parametrize("kind,keep", [("vlp16", False), ("hdl64", False), ("vlp16", True)])
+def test_laser_odom_parity(oracle, kind, keep):
+    """CalculateLaserOdom: same iteration count, same feature sets, pose within float round-off of the oracle.
+
+    The 6x6 normal equations are accumulated in double from float rows on both sides but in a different
+    order (tree vs sequential), so the solved float update may differ in the last ulp: tolerance 2e-5."""
+    from lio_mapping_b200 import ops
+    sensor, clouds, poses = helpers.frame_clouds(oracle, kind, 4)
+    m = helpers.build_map(oracle, clouds, poses)
+    _, _, tf7 = helpers.rel_transform(poses[0], poses[3])
+    tf0 = tf7.copy()
+    tf0[4:] += np.array([0.05, -0.04, 0.02], np.float32)   # perturbed initial guess: the GN loop has work to do
+    to, po, co, so, ito = oracle.laser_odom(m, clouds[3], tf0, keep_features=int(keep))
+    tg, pg, cg, sg, itg = ops.laser_odom(m, clouds[3], tf0, keep_features=keep)
+    assert itg == ito and ito >= 2
+    assert np.allclose(tg, to, atol=2e-5, rtol=0)
+    # converged pose is closer to the unperturbed transform than the initial guess
+    assert np.linalg.norm(tg[4:] - tf7[4:]) < 0.5 * np.linalg.norm(tf0[4:] - tf7[4:])
+    assert abs(sg.shape[0] - so.shape[0]) <= max(2, so.shape[0] // 2000)
+    if sg.shape[0] == so.shape[0] and np.array_equal(sg, so):
+        assert np.allclose(pg, po, atol=1e-4, rtol=0)
+        assert np.allclose(cg, co, atol=1e-4, rtol=0)
+
+
+def test_laser_odom_first_round_is_exact(oracle):
+    """One round only: features are computed from identical inputs -> bit-exact, pose within round-off."""
+    from lio_mapping_b200 import ops
+    sensor, clouds, poses = helpers.frame_clouds(oracle, "vlp16", 3)
+    m = helpers.build_map(oracle, clouds, poses)
+    _, _, tf7 = helpers.rel_transform(poses[0], poses[2])
+    to, po, co, so, ito = oracle.laser_odom(m, clouds[2], tf7, max_iter=1)
+    tg, pg, cg, sg, itg = ops.laser_odom(m, clouds[2], tf7, max_iter=1)
+    assert itg == ito == 1
+    assert np.array_equal(sg, so) and np.array_equal(pg, po) and np.array_equal(cg, co)
+    assert np.allclose(tg, to, atol=2e-6, rtol=0)
+
+
+def test_transform_to_end_parity(oracle):
+    """TransformToEnd / k_deskew: float32 with device sinf/acosf vs libm -> 2e-6 relative to the point range."""
+    from lio_mapping_b200 import ops
+    rng = np.random.default_rng(5)
+    n = 50000
+    pts = rng.uniform(-60, 60, size=(n, 3)).astype(np.float32)
+    ring = rng.integers(0, 64, size=n).astype(np.float32)
+    rel = (rng.uniform(0, 0.1, size=n)).astype(np.float32)
+    cloud = np.concatenate([pts, (ring + rel)[:, None]], 1).astype(np.float32)
+    for q, p in [((0.01, -0.02, 0.05, 0.9985), (0.8, -0.1, 0.02)), ((0, 0, 0, 1), (0.5, 0, 0)), ((0, 0, 1e-5, 1), (0, 0, 0))]:
+        q = np.asarray(q, np.float64); q /= np.linalg.norm(q)
+        tf7 = np.concatenate([q, p]).astype(np.float32)
+        o = oracle.transform_to_end(cloud, tf7, 10.0)
+        g = ops.transform_to_end(cloud, tf7, 10.0)
+        assert np.array_equal(g[:, 3], o[:, 3])            # relative time channel is exact
+        assert np.max(np.abs(g[:, :3] - o[:, :3])) < 2e-6 * 100.0
+    assert ops.transform_to_end(np.zeros((0, 4), np.float32), tf7).shape == (0, 4)
