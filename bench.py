@@ -241,7 +241,8 @@ def main():
         torch.cuda.cudart().cudaProfilerStart()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches, iters, solve_t, feats = 0, [], [], []
-    brk = {"t_build_map": [], "t_features": [], "t_solve": [], "t_marg": [], "t_total": []}
+    brk = {"t_build_map": [], "t_features": [], "t_solve": [], "t_marg": [], "t_total": [], "t_lin_wait": [], "t_lin_host": [],
+           "t_lin_lidar": [], "t_marg_wait": []}
     for s in range(args.steps):
         flush.fill_(1.0)                                      # flush L2 between timed steps (outside the event pair)
         barrier()

@@ -189,6 +189,9 @@ typedef struct lio_est_config {   /* EstimatorConfig (Estimator.h:77-108), lidar
   int max_scan_points;           /* capacity of the incoming laser_cloud_surf_last_ */
   int device_solver;             /* 1: dogleg loop + dense Cholesky resident on the GPU (no host sync inside a solve);
                                     0 (default, faster at n <= 171 in round 1): host controller around the fused kernel */
+  int overlap_marginalization;   /* 1 (default): the Schur-complement / eigen algebra of scan k's marginalisation runs on a
+                                    worker thread beside scan k+1's device front end (started at that call's entry, joined
+                                    before its solve); 0: inline at the end of scan k, the reference's order.  Same result. */
 } lio_est_config;
 
 typedef struct lio_est lio_est;

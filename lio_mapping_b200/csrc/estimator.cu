@@ -9,6 +9,7 @@
 //   SlideWindow :2570-2666                  -> slide_window
 // There is no CPU path for the per-point work: without a CUDA device create() fails.
 #include "assemble.cuh"
+#include <future>
 #include "factors_host.h"
 #include "factors_impl.h"
 #include "knn.cuh"
@@ -322,8 +323,25 @@ struct MargPrior {
   double x0_ex[7];
 };
 
+// Marginalisation split in two: the linearised system (A, b) of the dropped + kept blocks is built right after the
+// solve (it needs the device reduction and the converged parameters); the dense algebra (Schur complement + two
+// symmetric eigen-decompositions, ~n^3) is a pure function of that snapshot and runs on a worker thread while the next
+// scan's front end (deskew, voxel grid, local map, k-NN features) keeps the device busy.  The worker is started at
+// the ENTRY of the next lio_est_process_scan_* call, not earlier, so none of it runs outside a caller's timed step.
+struct MargJob {
+  bool stashed = false, running = false;
+  int O = 0;
+  Mat A;
+  Vec b;
+  std::vector<double> x0_pose, x0_sb;
+  double x0_ex[7];
+  std::future<MargPrior> fut;
+};
+
 struct lio_est {
   lio_est_config cfg;
+  MargJob mjob;
+  double t_marg_wait = 0;
   int W = 0, O = 0, device = 0;
   cudaStream_t stream = 0;
   int sm_count = 148;
@@ -380,6 +398,9 @@ struct lio_est {
   bool turn_off = true;
   int odom_iters = 0;
   double t_build = 0, t_feat = 0, t_solve = 0, t_marg = 0, t_total = 0;
+  bool S_pending = false;
+  long long S_pending_feats = 0;
+  double t_lin_wait = 0, t_lin_host = 0, t_lin_lidar = 0;  // per scan: blocked on the device / host factor work / lidar block expansion
   int launches = 0;
   Mat H0;
   Vec g0;
@@ -464,10 +485,12 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
   c->max_num_iterations = 10; c->odom_max_iterations = 10;
   c->max_frame_points = 1 << 16; c->max_scan_points = 1 << 18;
   c->device_solver = 0;
+  c->overlap_marginalization = 1;
 }
 
 extern "C" int lio_est_destroy(lio_est *e) {
   if (!e) return LIO_OK;
+  if (e->mjob.running) { e->mjob.fut.wait(); e->mjob.running = false; }
   cudaSetDevice(e->device);
   for (float4 *p : e->slot_ptr) if (p) cudaFree(p);
   for (FeatureOut &f : e->feats) { if (f.pts) cudaFree(f.pts); if (f.coef) cudaFree(f.coef); if (f.src) cudaFree(f.src); }
@@ -804,7 +827,9 @@ static int build_local_map(lio_est *e) {
 // ---- stage C: lidar reduction at the current parameter values ------------------------------------
 struct FrameTerms { double R[9], t[3], M[6 * 18]; };
 
-static int eval_lidar(lio_est *e, std::vector<FrameTerms> &ft) {
+static int eval_lidar_wait(lio_est *e);
+// Enqueues the fused lidar reduction at the current parameters (no host synchronisation); eval_lidar_wait() completes it.
+static int eval_lidar_launch(lio_est *e, std::vector<FrameTerms> &ft) {
   const int O = e->O, pivot = e->W - O;
   ft.resize(O + 1);
   AsmParams ap;
@@ -833,13 +858,28 @@ static int eval_lidar(lio_est *e, std::vector<FrameTerms> &ft) {
     if (rc != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
   }
   EST_CUDA(cudaMemcpyAsync(e->h_S, e->asmw.out, sizeof(double) * O * kAsmStride, cudaMemcpyDeviceToHost, e->stream));
+  e->S_pending = true;
+  e->S_pending_feats = nfeat;
+  return LIO_OK;
+}
+
+static int eval_lidar_wait(lio_est *e) {
+  if (!e->S_pending) return LIO_OK;
+  const double t0 = now_s();
   EST_CUDA(cudaStreamSynchronize(e->stream));
+  e->t_lin_wait += now_s() - t0;
+  e->S_pending = false;
   if (e->ev0 && e->ev1) {
     float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
+    if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += e->S_pending_feats; }
   }
   e->S_valid = true;
   return LIO_OK;
+}
+
+static int eval_lidar(lio_est *e, std::vector<FrameTerms> &ft) {
+  int rc = eval_lidar_launch(e, ft);
+  return rc != LIO_OK ? rc : eval_lidar_wait(e);
 }
 
 // tangent layout: [pose_k(6) sb_k(9)] k=0..O, then ex(6)
@@ -904,15 +944,9 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
   if (H.r != n) H = Mat(n, n); else H.zero();
   g.assign(n, 0.0);
   std::vector<FrameTerms> ft;
-  if (eval_lidar(e, ft) != LIO_OK) return false;
+  if (eval_lidar_launch(e, ft) != LIO_OK) return false;  // the device reduces the lidar factors while the host does the rest
+  const double th0 = now_s();
   double cp = 0, ci = 0, cm = 0;
-  if (e->cfg.point_distance_factor) {
-    for (int i = 1; i <= O; ++i) {
-      const double *S = e->h_S + (i - 1) * kAsmStride;
-      cp += 0.5 * S[28];
-      add_lidar_block(S, ft[i].M, &H, &g, off_pose(0), off_pose(i), oe);
-    }
-  }
   if (e->cfg.imu_factor) {
     for (int i = 0; i < O; ++i) {
       const int j = i + 1;
@@ -960,6 +994,17 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
     }
     for (int k = 0; k < 6; ++k) cprior += 0.5 * r[k] * r[k];
   }
+  e->t_lin_host += now_s() - th0;
+  if (eval_lidar_wait(e) != LIO_OK) return false;
+  if (e->cfg.point_distance_factor) {
+    const double tl0 = now_s();
+    for (int i = 1; i <= O; ++i) {
+      const double *S = e->h_S + (i - 1) * kAsmStride;
+      cp += 0.5 * S[28];
+      add_lidar_block(S, ft[i].M, &H, &g, off_pose(0), off_pose(i), oe);
+    }
+    e->t_lin_lidar += now_s() - tl0;
+  }
   cost = cp + ci + cm + cprior;
   if (c_pim) *c_pim = ci;
   if (c_ppp) *c_ppp = cp;
@@ -967,6 +1012,7 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
   return std::isfinite(cost);
 }
 
+static void prior_join(lio_est *e);
 // ---- marginalisation (MarginalizationInfo::PreMarginalize / Marginalize, MarginalizationFactor.cc:132-311)
 static int marginalize(lio_est *e) {
   const int O = e->O, pivot = e->W - O;
@@ -1008,6 +1054,25 @@ static int marginalize(lio_est *e) {
     if (rc != LIO_OK) return rc;
     for (int i = 1; i <= O; ++i) add_lidar_block(e->h_S + (i - 1) * kAsmStride, ft[i].M, &A, &b, idx_pose(0), idx_pose(i), idx_ex);
   }
+  MargJob &job = e->mjob;
+  job.O = O;
+  job.A.r = A.r; job.A.c = A.c; job.A.d.swap(A.d);
+  job.b.swap(b);
+  job.x0_pose.resize(7 * O); job.x0_sb.resize(9 * O);
+  for (int k = 1; k <= O; ++k) {  // addr_shift: block i -> i-1 in the next window
+    std::memcpy(&job.x0_pose[7 * (k - 1)], e->para_pose[k].data(), 7 * sizeof(double));
+    std::memcpy(&job.x0_sb[9 * (k - 1)], e->para_sb[k].data(), 9 * sizeof(double));
+  }
+  std::memcpy(job.x0_ex, e->para_ex, sizeof(job.x0_ex));
+  job.stashed = true;
+  if (!e->cfg.overlap_marginalization) prior_join(e);
+  return LIO_OK;
+}
+
+// Schur complement + eigen square-root form (MarginalizationInfo::Marginalize, MarginalizationFactor.cc:206-311) of a
+// stashed system; layout [pose_0 (6), sb_0 (9) | pose_1, sb_1, ..., pose_O, sb_O, ex].  Pure function: worker-thread safe.
+static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, std::vector<double> x0_sb, const double *x0_ex) {
+  const int m = 15, nr = 15 * O + 6;
   // Schur complement with the eigen pseudo-inverse (eps = 1e-8)
   const double eps = 1e-8;
   Mat Amm(m, m);
@@ -1048,14 +1113,31 @@ static int marginalize(lio_est *e) {
     for (int k : kept) sb += V2(r, k) * vb[k];
     np.bp[r] = sb;
   }
-  np.x0_pose.resize(7 * O); np.x0_sb.resize(9 * O);
-  for (int k = 1; k <= O; ++k) {  // addr_shift: block i -> i-1 in the next window
-    std::memcpy(&np.x0_pose[7 * (k - 1)], e->para_pose[k].data(), 7 * sizeof(double));
-    std::memcpy(&np.x0_sb[9 * (k - 1)], e->para_sb[k].data(), 9 * sizeof(double));
-  }
-  std::memcpy(np.x0_ex, e->para_ex, sizeof(np.x0_ex));
-  e->prior = np;
-  return LIO_OK;
+  np.x0_pose = std::move(x0_pose);
+  np.x0_sb = std::move(x0_sb);
+  std::memcpy(np.x0_ex, x0_ex, sizeof(np.x0_ex));
+  return np;
+}
+
+static void marg_start(lio_est *e) {
+  MargJob &job = e->mjob;
+  if (!job.stashed || job.running) return;
+  job.stashed = false;
+  job.running = true;
+  job.fut = std::async(std::launch::async, [&job]() {
+    return marg_algebra(std::move(job.A), std::move(job.b), job.O, std::move(job.x0_pose), std::move(job.x0_sb), job.x0_ex);
+  });
+}
+
+// Makes e->prior current: runs a stashed job (inline start) and waits for a running one.
+static void prior_join(lio_est *e) {
+  MargJob &job = e->mjob;
+  if (job.stashed) marg_start(e);
+  if (!job.running) return;
+  const double t0 = now_s();
+  e->prior = job.fut.get();
+  job.running = false;
+  e->t_marg_wait += now_s() - t0;
 }
 
 static int solve_optimization(lio_est *e) {
@@ -1063,6 +1145,7 @@ static int solve_optimization(lio_est *e) {
   e->turn_off = true;
   int rc = build_local_map(e);
   if (rc != LIO_OK) return rc;
+  prior_join(e);  // the previous scan's marginalisation algebra ran beside the front end above
   const double t0 = now_s();
   e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
   vector_to_double(e);
@@ -1072,6 +1155,7 @@ static int solve_optimization(lio_est *e) {
   double cost;
   if (!linearize(e, H, g, cost, &e->cost_pim, &e->cost_ppp, &e->cost_marg)) { lio_set_last_error(__FILE__, __LINE__, "non-finite cost at the initial point"); return LIO_ERR_NUMERIC; }
   if (e->cfg.imu_factor) e->turn_off = e->cost_pim > 1e3;
+  const bool ex_constant_before = e->ex_constant, prior_before = e->prior.valid;
   {
     const double ratio = e->cost_marg / (e->cost_ppp + e->cost_pim);
     if (!e->convergence_flag && !e->turn_off && ratio <= 2 && ratio != 0) e->convergence_flag = true;
@@ -1084,8 +1168,12 @@ static int solve_optimization(lio_est *e) {
   const bool ex_free = !e->ex_constant;
   P.n = 15 * (O + 1) + (ex_free ? 6 : 0);
   bool first = true;
+  // the gate evaluation above is the solver's first linearisation when the gates left the problem structure unchanged
+  bool reuse_gate = (ex_constant_before == e->ex_constant && prior_before == e->prior.valid);
   P.linearize = [&](Mat &Hh, Vec &gg, double &c) {
-    bool ok = linearize(e, Hh, gg, c, nullptr, nullptr, nullptr);
+    bool ok = true;
+    if (reuse_gate && first) { Hh.d.swap(H.d); Hh.r = H.r; Hh.c = H.c; gg.swap(g); c = cost; }
+    else ok = linearize(e, Hh, gg, c, nullptr, nullptr, nullptr);
     if (ok && first) { e->H0 = Hh; e->g0 = gg; e->cost0 = c; e->have_H0 = true; first = false; }
     return ok;
   };
@@ -1130,6 +1218,7 @@ static int solve_optimization_dev(lio_est *e) {
   e->turn_off = true;
   int rc = build_local_map(e);
   if (rc != LIO_OK) return rc;
+  prior_join(e);  // the previous scan's marginalisation algebra ran beside the front end above
   const double t0 = now_s();
   e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
   vector_to_double(e);
@@ -1253,8 +1342,10 @@ static int slide_window(lio_est *e) {  // Estimator.cc:2570-2666
 static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max) {
   const int W = e->W;
   cudaStream_t st = e->stream;
+  marg_start(e);
   const double t0 = now_s();
   e->launches = 0;
+  e->t_lin_wait = e->t_lin_host = e->t_lin_lidar = e->t_marg_wait = 0;
   e->have_H0 = false;
   if (!e->tmp_pre) { lio_set_last_error(__FILE__, __LINE__, "process_scan before finish_init"); return LIO_ERR_INVALID; }
   push_shift(e->pre, e->tmp_pre);
@@ -1353,6 +1444,7 @@ extern "C" int lio_est_get_states(lio_est *e, double *out) {
 
 extern "C" int lio_est_summary(lio_est *e, double *o) {
   if (!e || !o) return LIO_ERR_INVALID;
+  const bool has_prior = e->prior.valid || e->mjob.stashed || e->mjob.running;  // does not force the pending algebra
   for (int k = 0; k < 32; ++k) o[k] = 0;
   o[0] = e->summary.iterations; o[1] = e->summary.successful_steps; o[2] = e->summary.termination;
   o[3] = e->summary.initial_cost; o[4] = e->summary.final_cost; o[5] = e->cost_pim; o[6] = e->cost_ppp; o[7] = e->cost_marg;
@@ -1361,7 +1453,8 @@ extern "C" int lio_est_summary(lio_est *e, double *o) {
   for (int v : e->h_feat_n) nf += v;
   o[11] = (double)nf; o[12] = e->odom_iters;
   o[13] = e->t_build; o[14] = e->t_feat; o[15] = e->t_solve; o[16] = e->t_marg; o[17] = e->t_total;
-  o[18] = e->prior.valid ? 1 : 0; o[19] = e->summary.evaluations; o[20] = e->summary.evaluations; o[21] = e->launches;
+  o[18] = has_prior ? 1 : 0; o[19] = e->summary.evaluations; o[20] = e->summary.evaluations; o[21] = e->launches;
+  o[22] = e->t_lin_wait; o[23] = e->t_lin_host; o[24] = e->t_lin_lidar; o[25] = e->t_marg_wait;
   return LIO_OK;
 }
 
@@ -1422,11 +1515,13 @@ extern "C" int lio_est_get_local_transform(lio_est *e, int frame, float tf7[7]) 
 }
 extern "C" int lio_est_prior_dim(lio_est *e, int *n) {
   if (!e || !n) return LIO_ERR_INVALID;
+  prior_join(e);
   *n = e->prior.valid ? e->prior.n : 0;
   return LIO_OK;
 }
 extern "C" int lio_est_get_prior(lio_est *e, double *Hp, double *bp) {
   if (!e || !Hp || !bp) return LIO_ERR_INVALID;
+  prior_join(e);
   if (!e->prior.valid) return LIO_ERR_INVALID;
   std::memcpy(Hp, e->prior.Hp.d.data(), sizeof(double) * e->prior.n * e->prior.n);
   std::memcpy(bp, e->prior.bp.data(), sizeof(double) * e->prior.n);

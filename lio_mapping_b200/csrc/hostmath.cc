@@ -12,27 +12,110 @@
 namespace lio {
 namespace hm {
 
-// Right-looking (outer-product) lower Cholesky: after step k the trailing lower triangle has the rank-1
-// update  a[i][j] -= l_ik * l_jk  applied row by row (contiguous axpy, no reduction to reassociate).
-LIO_MV bool cholesky(Mat &a) {
-  const int n = a.r;
-  std::vector<double> col(n);
-  double *A = a.d.data();
-  for (int k = 0; k < n; ++k) {
+// Unblocked right-looking (outer-product) lower Cholesky on the square [k0, k1) diagonal block: the rank-1 update
+// a[i][j] -= l_ik * l_jk is applied row by row (contiguous axpy, no reduction to reassociate).
+static inline bool chol_diag(double *A, int n, int k0, int k1) {
+  double col[64];
+  for (int k = k0; k < k1; ++k) {
     const double s = A[(size_t)k * n + k];
     if (!(s > 0.0) || !std::isfinite(s)) return false;
     const double l = std::sqrt(s), il = 1.0 / l;
     A[(size_t)k * n + k] = l;
-    for (int i = k + 1; i < n; ++i) {
+    for (int i = k + 1; i < k1; ++i) {
       const double v = A[(size_t)i * n + k] * il;
       A[(size_t)i * n + k] = v;
-      col[i] = v;
+      col[i - k0] = v;
     }
-    for (int i = k + 1; i < n; ++i) {
+    for (int i = k + 1; i < k1; ++i) {
       double *ri = A + (size_t)i * n;
-      const double lik = col[i];
-      const double *c = col.data();
-      for (int j = k + 1; j <= i; ++j) ri[j] -= lik * c[j];
+      const double lik = col[i - k0];
+      for (int j = k + 1; j <= i; ++j) ri[j] -= lik * col[j - k0];
+    }
+  }
+  return true;
+}
+
+typedef double v4d __attribute__((vector_size(32)));
+typedef double v4du __attribute__((vector_size(32), aligned(8)));
+
+// Blocked lower Cholesky (block width kCholNb): diagonal block, panel triangular solve, then the trailing update
+// C -= P P^T through a 4 x 8 register tile over the transposed panel, so the trailing matrix is read and written once
+// per block instead of once per column.  Only the lower triangle of the result is meaningful (tiles that straddle the
+// diagonal also write above it).
+constexpr int kCholNb = 24;
+
+LIO_MV bool cholesky(Mat &a) {
+  const int n = a.r;
+  double *A = a.d.data();
+  if (n <= 2 * kCholNb) return chol_diag(A, n, 0, n);
+  std::vector<double> PTbuf((size_t)kCholNb * n + 8);
+  double *PT = PTbuf.data();
+  for (int kb = 0; kb < n; kb += kCholNb) {
+    const int nb = std::min(kCholNb, n - kb), i0 = kb + nb, m = n - i0;
+    if (!chol_diag(A, n, kb, i0)) return false;
+    if (m <= 0) break;
+    // panel X L_kk^T = A[i0:, kb:i0], solved on the transposed copy: L_kk PT = B^T is a forward substitution whose
+    // updates are axpys over contiguous rows of PT (no short reductions)
+    for (int i = i0; i < n; ++i) {
+      const double *x = A + (size_t)i * n + kb;
+      for (int k = 0; k < nb; ++k) PT[(size_t)k * m + (i - i0)] = x[k];
+    }
+    for (int j = 0; j < nb; ++j) {
+      const double *lj = A + (size_t)(kb + j) * n + kb;
+      double *pj = PT + (size_t)j * m;
+      int t = 0;
+      for (; t + 1 < j; t += 2) {
+        const double l0 = lj[t], l1 = lj[t + 1];
+        const double *q0 = PT + (size_t)t * m, *q1 = q0 + m;
+        for (int c2 = 0; c2 < m; ++c2) pj[c2] -= l0 * q0[c2] + l1 * q1[c2];
+      }
+      for (; t < j; ++t) {
+        const double l0 = lj[t];
+        const double *q0 = PT + (size_t)t * m;
+        for (int c2 = 0; c2 < m; ++c2) pj[c2] -= l0 * q0[c2];
+      }
+      const double inv = 1.0 / lj[j];
+      for (int c2 = 0; c2 < m; ++c2) pj[c2] *= inv;
+    }
+    for (int i = i0; i < n; ++i) {
+      double *x = A + (size_t)i * n + kb;
+      for (int k = 0; k < nb; ++k) x[k] = PT[(size_t)k * m + (i - i0)];
+    }
+    // trailing update, rows i (4 at a time), columns j <= i (8 at a time)
+    for (int i = i0; i < n; i += 4) {
+      const int rows = std::min(4, n - i), jmax = i + rows - 1;
+      for (int jb = i0; jb <= jmax; jb += 8) {
+        const int w = std::min(8, n - jb);
+        if (rows == 4 && w == 8) {
+          v4d c00 = {0, 0, 0, 0}, c01 = c00, c10 = c00, c11 = c00, c20 = c00, c21 = c00, c30 = c00, c31 = c00;
+          const double *p0 = A + (size_t)i * n + kb, *p1 = p0 + n, *p2 = p1 + n, *p3 = p2 + n;
+          const double *pt = PT + (jb - i0);
+          for (int k = 0; k < nb; ++k, pt += m) {
+            const v4d b0 = *(const v4du *)pt, b1 = *(const v4du *)(pt + 4);
+            const double a0 = p0[k], a1 = p1[k], a2 = p2[k], a3 = p3[k];
+            c00 += a0 * b0; c01 += a0 * b1;
+            c10 += a1 * b0; c11 += a1 * b1;
+            c20 += a2 * b0; c21 += a2 * b1;
+            c30 += a3 * b0; c31 += a3 * b1;
+          }
+          double *r0 = A + (size_t)i * n + jb, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n;
+          *(v4du *)r0 -= c00; *(v4du *)(r0 + 4) -= c01;
+          *(v4du *)r1 -= c10; *(v4du *)(r1 + 4) -= c11;
+          *(v4du *)r2 -= c20; *(v4du *)(r2 + 4) -= c21;
+          *(v4du *)r3 -= c30; *(v4du *)(r3 + 4) -= c31;
+        } else {
+          for (int r = 0; r < rows; ++r) {
+            const double *pr = A + (size_t)(i + r) * n + kb;
+            double *cr = A + (size_t)(i + r) * n + jb;
+            for (int cidx = 0; cidx < w; ++cidx) {
+              const double *pt = PT + (jb - i0) + cidx;
+              double s = 0;
+              for (int k = 0; k < nb; ++k) s += pr[k] * pt[(size_t)k * m];
+              cr[cidx] -= s;
+            }
+          }
+        }
+      }
     }
   }
   return true;

@@ -15,7 +15,8 @@ from . import _lib
 
 SUMMARY_KEYS = ["iterations", "successful", "termination", "initial_cost", "final_cost", "cost_pim", "cost_ppp", "cost_marg",
                 "turn_off", "convergence_flag", "map_size", "num_features", "odom_iters", "t_build_map", "t_features",
-                "t_solve", "t_marg", "t_total", "has_prior", "linearizations", "cost_evals", "launches"]
+                "t_solve", "t_marg", "t_total", "has_prior", "linearizations", "cost_evals", "launches", "t_lin_wait", "t_lin_host",
+                "t_lin_lidar", "t_marg_wait"]
 
 
 def _d(a):
