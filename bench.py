@@ -133,6 +133,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="hdl64", choices=["hdl64", "vlp16", "stress128"])
+    ap.add_argument("--overlap-marginalization", type=int, default=1, choices=[0, 1],
+                    help="0: marginalisation algebra inline (reference order); 1: on a worker thread beside the next scan's front end")
     ap.add_argument("--cpu-sample", type=int, default=4, help="scans of the cpu_baseline sample (rank 0, N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -182,7 +184,7 @@ def main():
     pp = PointProcessor(sensor.lower_deg, sensor.upper_deg, sensor.rings, max_points=max_pts, device=local_rank, stream=stream)
     est = estimator.Estimator(device=local_rank, stream=stream, window_size=W, opt_window_size=W,
                               max_frame_points=1 << 16 if kind != "stress128" else 1 << 18,
-                              max_scan_points=max_pts, **est_cfg)
+                              max_scan_points=max_pts, overlap_marginalization=args.overlap_marginalization, **est_cfg)
     if world > 1:
         class _Arr:
             def __init__(self, ptr, n):
@@ -211,11 +213,13 @@ def main():
 
     def step_dev(k):
         t = dev_raw[k]
+        est.begin_scan()                                     # sweep k arrived: background marginalisation of scan k-1 starts here
         pp.process_device(t.data_ptr(), t.shape[0])
         scenario.feed_imu(est, scn, k)
         est.process_scan_dev(lf_ptr, nptr.value, max_pts)
 
     def step_host(k):
+        est.begin_scan()
         pp.SetInputCloud(scn.raw[k]); pp.Process()           # H2D of the sweep inside
         scenario.feed_imu(est, scn, k)
         est.process_scan_dev(lf_ptr, nptr.value, max_pts)
@@ -274,7 +278,8 @@ def main():
         return 0
     # ---- e2e pass (host buffers, fresh estimator, same scans) --------------------------------------
     est2 = estimator.Estimator(device=local_rank, stream=stream, window_size=W, opt_window_size=W,
-                               max_frame_points=1 << 16 if kind != "stress128" else 1 << 18, max_scan_points=max_pts, **est_cfg)
+                               max_frame_points=1 << 16 if kind != "stress128" else 1 << 18, max_scan_points=max_pts,
+                               overlap_marginalization=args.overlap_marginalization, **est_cfg)
     if world > 1:
         est2.set_shard(rank, world, allreduce)
     est_saved, est = est, est2
@@ -320,6 +325,8 @@ def main():
                            "l2": "flushed between timed steps (256 MB write outside the event pair)",
                            "parallelism": "frames sharded 1..O over %d rank(s), NCCL allreduce of O x 29 doubles per evaluation" % world,
                            "e2e_vs_device_pass_max_pos_diff_m": drift,
+                           "overlap_marginalization": args.overlap_marginalization,
+                           "ms_per_timed_step": [round(float(v), 3) for v in ms],
                            "host_wall_ms_per_scan": {kk: 1e3 * float(np.mean(v)) for kk, v in brk.items()}},
                 "roofline": {"kernel": "asm_ppp (fused PivotPointPlane residual+Jacobian+JtJ reduction)", "bound": "hbm",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,

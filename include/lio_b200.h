@@ -209,9 +209,15 @@ int lio_est_init_frame(lio_est *est, int k, const double state16[16], const floa
 int lio_est_finish_init(lio_est *est, const double acc_last[3], const double gyr_last[3]);
 /* Estimator::ProcessImu (Estimator.cc:338-427) */
 int lio_est_process_imu(lio_est *est, double dt, const double acc[3], const double gyr[3], double stamp);
+/* The same for n consecutive messages (dt[n], acc3[n][3], gyr3[n][3], stamp[n]) in one call: bag playback / batched drivers. */
+int lio_est_process_imu_batch(lio_est *est, int n, const double *dt, const double *acc3, const double *gyr3, const double *stamp);
 /* Estimator::ProcessLaserOdom, INITED branch (Estimator.cc:618-774): de-skew + VoxelGrid + SolveOptimization +
  * SlideWindow.  surf_last = laser_cloud_surf_last_ (surface_points_less_flat of the new sweep), HOST buffer. */
 int lio_est_process_scan_host(lio_est *est, const float *surf_last, int n);
+/* Optional: announce that the next sweep has arrived (call before stage A / lio_pp_process_*).  Starts the background
+ * marginalisation algebra of the previous scan now instead of at the lio_est_process_scan_* entry, so it also overlaps
+ * the feature extraction of the new sweep.  No effect with overlap_marginalization = 0. */
+int lio_est_begin_scan(lio_est *est);
 /* Same with the cloud already on the device (e.g. lio_pp_cloud_dev(LIO_PP_SURF_LESS_FLAT)); n is read
  * from *n_dev on the device, n_max bounds it. */
 int lio_est_process_scan_dev(lio_est *est, const float *surf_last_dev, const int *n_dev, int n_max);

@@ -102,6 +102,8 @@ def lib():
     L.lio_est_finish_init.argtypes = [vp, f64p, f64p]
     L.lio_est_process_imu.argtypes = [vp, C.c_double, f64p, f64p, C.c_double]
     L.lio_est_process_scan_host.argtypes = [vp, f32p, ip]
+    L.lio_est_begin_scan.argtypes = [vp]
+    L.lio_est_process_imu_batch.argtypes = [vp, ip, f64p, f64p, f64p, f64p]
     L.lio_est_process_scan_dev.argtypes = [vp, vp, vp, ip]
     L.lio_est_get_states.argtypes = [vp, f64p]
     L.lio_est_summary.argtypes = [vp, f64p]

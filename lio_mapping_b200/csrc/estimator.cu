@@ -667,6 +667,15 @@ extern "C" int lio_est_process_imu(lio_est *e, double dt, const double a[3], con
   return LIO_OK;
 }
 
+extern "C" int lio_est_process_imu_batch(lio_est *e, int n, const double *dt, const double *acc3, const double *gyr3, const double *stamp) {
+  if (!e || n < 0 || (n > 0 && (!dt || !acc3 || !gyr3 || !stamp))) return LIO_ERR_INVALID;
+  for (int k = 0; k < n; ++k) {
+    const int rc = lio_est_process_imu(e, dt[k], acc3 + 3 * k, gyr3 + 3 * k, stamp[k]);
+    if (rc != LIO_OK) return rc;
+  }
+  return LIO_OK;
+}
+
 // ---- parameter <-> state ---------------------------------------------------------------------------
 static void vector_to_double(lio_est *e) {  // Estimator.cc:2440-2478
   const int pivot = e->W - e->O;
@@ -1398,6 +1407,12 @@ static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_
   rc = slide_window(e);
   if (rc != LIO_OK) return rc;
   e->t_total = now_s() - t0;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_begin_scan(lio_est *e) {
+  if (!e) return LIO_ERR_INVALID;
+  if (e->cfg.overlap_marginalization) marg_start(e);
   return LIO_OK;
 }
 

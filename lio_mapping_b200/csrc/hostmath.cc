@@ -4,7 +4,7 @@
 #include "hostmath.h"
 
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
-#define LIO_MV __attribute__((target_clones("arch=x86-64-v3", "default")))
+#define LIO_MV __attribute__((target_clones("arch=x86-64-v4", "arch=x86-64-v3", "default")))
 #else
 #define LIO_MV
 #endif
@@ -219,6 +219,7 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
   e[n - 1] = 0.0;
   double f = 0.0, tst1 = 0.0;
   const double eps = 2.220446049250313e-16;
+  Vec rc(n, 0.0), rs(n, 0.0);
   for (int l = 0; l < n; ++l) {
     tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
     int m = l;
@@ -227,7 +228,7 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
       for (int iter = 0; iter < 300; ++iter) {
         double g = d[l];
         double p = (d[l + 1] - g) / (2.0 * e[l]);
-        double r = std::hypot(p, 1.0);
+        double r = std::sqrt(p * p + 1.0);
         if (p < 0) r = -r;
         d[l] = e[l] / (p + r);
         d[l + 1] = e[l] * (p + r);
@@ -238,22 +239,56 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
         p = d[m];
         double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
         const double el1 = e[l + 1];
+        // scalar QL recurrence first (it does not read Z) ...
         for (int i = m - 1; i >= l; --i) {
           c3 = c2; c2 = c; s2 = s;
           g = c * e[i];
           h = c * p;
-          r = std::hypot(p, e[i]);
+          r = std::sqrt(p * p + e[i] * e[i]);
           e[i + 1] = s * r;
           s = e[i] / r;
           c = p / r;
           p = c * d[i] - s * g;
           d[i + 1] = h + s * (c * g + s * d[i]);
-          double *ca = col(i), *cb = col(i + 1);
-          for (int k = 0; k < n; ++k) {
-            const double hb = cb[k], ha = ca[k];
-            cb[k] = s * ha + c * hb;
-            ca[k] = c * ha - s * hb;
+          rc[i] = c; rs[i] = s;
+        }
+        // ... then the plane rotations (i, i+1), i = m-1 .. l, applied to Z in row chunks: the column shared by two
+        // successive rotations is carried in registers, so each element is loaded and stored once per rotation
+        constexpr int KC = 32;
+        int k0 = 0;
+        for (; k0 + KC <= n; k0 += KC) {
+          double carry[KC];
+          const double *cm = col(m) + k0;
+          for (int k = 0; k < KC; ++k) carry[k] = cm[k];
+          for (int i = m - 1; i >= l; --i) {
+            const double ci = rc[i], si = rs[i];
+            double *ca = col(i) + k0, *cb = col(i + 1) + k0;
+#pragma omp simd
+            for (int k = 0; k < KC; ++k) {
+              const double ha = ca[k], hb = carry[k];
+              cb[k] = si * ha + ci * hb;
+              carry[k] = ci * ha - si * hb;
+            }
           }
+          double *cl = col(l) + k0;
+          for (int k = 0; k < KC; ++k) cl[k] = carry[k];
+        }
+        if (k0 < n) {
+          const int kc = n - k0;
+          double carry[KC];
+          const double *cm = col(m) + k0;
+          for (int k = 0; k < kc; ++k) carry[k] = cm[k];
+          for (int i = m - 1; i >= l; --i) {
+            const double ci = rc[i], si = rs[i];
+            double *ca = col(i) + k0, *cb = col(i + 1) + k0;
+            for (int k = 0; k < kc; ++k) {
+              const double ha = ca[k], hb = carry[k];
+              cb[k] = si * ha + ci * hb;
+              carry[k] = ci * ha - si * hb;
+            }
+          }
+          double *cl = col(l) + k0;
+          for (int k = 0; k < kc; ++k) cl[k] = carry[k];
         }
         p = -s * s2 * c3 * el1 * e[l] / dl1;
         e[l] = s * p;

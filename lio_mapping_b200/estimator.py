@@ -149,9 +149,20 @@ class Estimator:
     def process_imu(self, dt, acc, gyr, stamp):
         _lib.check(_lib.lib().lio_est_process_imu(self.h, float(dt), _d(acc), _d(gyr), float(stamp)), "lio_est_process_imu")
 
+    def process_imu_batch(self, dt, acc, gyr, stamp):
+        """n consecutive ProcessImu calls in one C-ABI crossing (arrays of n, n x 3, n x 3, n)."""
+        dt = np.ascontiguousarray(dt, np.float64)
+        _lib.check(_lib.lib().lio_est_process_imu_batch(self.h, dt.shape[0], dt, np.ascontiguousarray(acc, np.float64),
+                                                        np.ascontiguousarray(gyr, np.float64), np.ascontiguousarray(stamp, np.float64)),
+                   "lio_est_process_imu_batch")
+
     def process_scan(self, surf_last):
         s = np.ascontiguousarray(surf_last, np.float32).reshape(-1, 4)
         _lib.check(_lib.lib().lio_est_process_scan_host(self.h, s, s.shape[0]), "lio_est_process_scan_host")
+
+    def begin_scan(self):
+        """Announce the next sweep (starts the previous scan's background marginalisation algebra)."""
+        _lib.check(_lib.lib().lio_est_begin_scan(self.h), "lio_est_begin_scan")
 
     def process_scan_dev(self, dev_ptr: int, n_dev_ptr: int, n_max: int):
         _lib.check(_lib.lib().lio_est_process_scan_dev(self.h, C.c_void_p(dev_ptr), C.c_void_p(n_dev_ptr), n_max),

@@ -77,6 +77,14 @@ def warm_start(est, scn: Scenario, W: int, surf_ds_of, make_pim, pose_noise: flo
 def feed_imu(est, scn: Scenario, k: int):
     tt, acc, gyr = scn.imu[k]
     last = scn.t[k - 1]
+    if hasattr(est, "process_imu_batch"):   # product: one C-ABI crossing for the scan's IMU messages
+        cache = scn.__dict__.setdefault("_imu_batches", {})
+        if k not in cache:
+            tt64 = np.ascontiguousarray(tt, np.float64)
+            cache[k] = (np.ascontiguousarray(np.diff(np.concatenate([[last], tt64]))), np.ascontiguousarray(acc, np.float64),
+                        np.ascontiguousarray(gyr, np.float64), tt64)
+        est.process_imu_batch(*cache[k])
+        return
     for j in range(len(tt)):
         est.process_imu(tt[j] - last, acc[j], gyr[j], tt[j])
         last = tt[j]
