@@ -115,6 +115,14 @@ int lio_voxel_grid_host(const float *cloud, int n, float leaf, float *out, int c
 int lio_calculate_features_host(const float *map, int K, const float *surf, int M, const float *tf7,
                                 float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
                                 int *n_out, int device);
+/* Point-to-line branch of Estimator::CalculateFeatures (Estimator.cc:1101-1227, compiled out in the reference build:
+ * USE_CORNER is undefined, Estimator.h:55-56) == the live corner matching of PointMapping::OptimizeTransformTobeMapped
+ * (PointMapping.cc:381-512): 5-NN in the corner map, centroid + 3x3 covariance eigen-decomposition, line accepted iff
+ * lambda_3 > 3 lambda_2; a line is emitted as TWO consecutive half-weight plane-like features (normal_to_point and
+ * normal_cross_point), which go through the same PivotPointPlaneFactor / fused stage-C kernel.
+ * corner_map (K x float4) = local corner map, corner (M x float4) = corner stack of the frame; outputs sized 2*M. */
+int lio_calculate_line_features_host(const float *corner_map, int K, const float *corner, int M, const float *tf7,
+                                     float min_match_sq_dis, float *pts4, float *coef4, int32_t *src, int *n_out, int device);
 /* TransformToEnd (Estimator.cc:62-103): in-place motion compensation of a sweep whose intensity carries
  * ring + relative time; tf7_es = transform_es {qx,qy,qz,qw,px,py,pz}; time_factor = 10 at the call site
  * (Estimator.cc:560).  float32, device sinf/acosf: parity tolerance 2e-6 relative to the range. */
@@ -253,6 +261,25 @@ typedef int (*lio_allreduce_fn)(void *user, double *buf_dev, int count);
 int lio_est_set_shard(lio_est *est, int rank, int world, lio_allreduce_fn fn, void *user);
 /* Owner rank of window frame pivot+frame_rel (frame_rel = 1..O) under `world` ranks: (frame_rel-1) % world. */
 int lio_est_frame_owner(int frame_rel, int world);
+
+/* ------------------------------------------------------------------------------------------
+ * /compact_data wire format (host only; no device needed).  Encoder PointOdometry.cc:732-762, decoder
+ * PointMapping::CompactDataHandler PointMapping.cc:171-238: point 0 = transform_sum_.pos, point 1 = quaternion
+ * (x, y, z | intensity = w), point 2 = (corner_size, surf_size, full_size) as floats, then corner || surf || full.
+ * Clouds are packed (x, y, z, intensity) float4; tf7 = {qx,qy,qz,qw,px,py,pz}.
+ * ---------------------------------------------------------------------------------------- */
+/* out_xyzi sized cap_points float4; *n_points = 3 + nc + ns + nf.  LIO_ERR_CAPACITY when a size is >= 2^24 (not exact as
+ * a float) or the output is too small. */
+int lio_compact_encode(const float tf7[7], const float *corner, int nc, const float *surf, int ns, const float *full, int nf,
+                       float *out_xyzi, int cap_points, int *n_points);
+/* Header check of the decoder (:180-195): LIO_ERR_INVALID when n_points < 4 or 3 + sizes != n_points. */
+int lio_compact_sizes(const float *xyzi, int n_points, int sizes[3]);
+/* corner / surf / full sized by lio_compact_sizes. */
+int lio_compact_decode(const float *xyzi, int n_points, float tf7[7], float *corner, float *surf, float *full);
+/* packed float4 <-> the 32-byte pcl::PointXYZI records a sensor_msgs/PointCloud2 of this type carries
+ * (x, y, z at 0/4/8, data[3] = 1.0f, intensity at 16). */
+int lio_xyzi_to_pcl32(const float *xyzi, int n, uint8_t *out32);
+int lio_pcl32_to_xyzi(const uint8_t *in32, int n, float *xyzi);
 
 #ifdef __cplusplus
 }

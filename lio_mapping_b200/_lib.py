@@ -80,6 +80,12 @@ def lib():
     L.lio_voxel_grid_host.argtypes = [f32p, ip, C.c_float, f32p, ip, C.POINTER(ip), ip]
     L.lio_calculate_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, f32p, f32p, i32p,
                                               C.POINTER(ip), ip]
+    L.lio_calculate_line_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, f32p, f32p, i32p, C.POINTER(ip), ip]
+    L.lio_compact_encode.argtypes = [f32p, f32p, ip, f32p, ip, f32p, ip, f32p, ip, C.POINTER(ip)]
+    L.lio_compact_sizes.argtypes = [f32p, ip, i32p]
+    L.lio_compact_decode.argtypes = [f32p, ip, f32p, f32p, f32p, f32p]
+    L.lio_xyzi_to_pcl32.argtypes = [f32p, ip, u8p]
+    L.lio_pcl32_to_xyzi.argtypes = [u8p, ip, f32p]
     L.lio_transform_to_end_host.argtypes = [f32p, ip, f32p, C.c_float, ip]
     L.lio_laser_odom_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, ip, f32p, f32p, i32p,
                                       C.POINTER(ip), C.POINTER(ip), ip]

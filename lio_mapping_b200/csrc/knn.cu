@@ -145,9 +145,61 @@ constexpr unsigned long long kInfKey = 0x7f8000007fffffffull;  // (+inf, INT_MAX
 constexpr int kGroup = 8;                               // lanes cooperating on one query
 constexpr int kQueriesPerBlock = kKnnThreads / kGroup;  // 16
 
+// cyclic Jacobi eigen-decomposition of a symmetric 3x3 (float), ascending eigenvalues, vectors in columns — the same
+// operation order as the oracle's sym_eigen_jacobi<float>(3, ...) (stand-in for SelfAdjointEigenSolver<Matrix3f>)
+__device__ __forceinline__ void sym_eigen3(const float *Ain, float *evals, float *V) {
+  float A[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) { A[i] = Ain[i]; V[i] = (i % 4 == 0) ? 1.f : 0.f; }
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    float off = 0.f, diag = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      diag += A[i * 3 + i] * A[i * 3 + i];
+#pragma unroll
+      for (int j = i + 1; j < 3; ++j) off += A[i * 3 + j] * A[i * 3 + j];
+    }
+    if (off <= FLT_EPSILON * FLT_EPSILON * diag || off == 0.f) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        const float apq = A[p * 3 + q];
+        if (apq == 0.f) continue;
+        const float theta = (A[q * 3 + q] - A[p * 3 + p]) / (2.f * apq);
+        const float t = (theta >= 0.f ? 1.f : -1.f) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
+        const float c = 1.f / sqrtf(t * t + 1.f), sn = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { float a = A[k * 3 + p], b = A[k * 3 + q]; A[k * 3 + p] = c * a - sn * b; A[k * 3 + q] = sn * a + c * b; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { float a = A[p * 3 + k], b = A[q * 3 + k]; A[p * 3 + k] = c * a - sn * b; A[q * 3 + k] = sn * a + c * b; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { float a = V[k * 3 + p], b = V[k * 3 + q]; V[k * 3 + p] = c * a - sn * b; V[k * 3 + q] = sn * a + c * b; }
+      }
+  }
+  // ascending order of the diagonal (3-element sort, first index wins ties like the oracle's comparator sort)
+  int i0 = 0, i1 = 1, i2 = 2;
+  if (A[i1 * 3 + i1] < A[i0 * 3 + i0]) { int t = i0; i0 = i1; i1 = t; }
+  if (A[i2 * 3 + i2] < A[i1 * 3 + i1]) { int t = i1; i1 = i2; i2 = t; }
+  if (A[i1 * 3 + i1] < A[i0 * 3 + i0]) { int t = i0; i0 = i1; i1 = t; }
+  float Vc[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) Vc[i] = V[i];
+  const int idx[3] = {i0, i1, i2};
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    evals[j] = A[idx[j] * 3 + idx[j]];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) V[k * 3 + j] = Vc[k * 3 + idx[j]];
+  }
+}
+
+// kFit = 0: point-to-plane (Estimator::CalculateFeatures surf branch), one feature per accepted query;
+// kFit = 1: point-to-line (USE_CORNER branch :1101-1227 / PointMapping.cc:381-512), two half-weight features.
 // One 8-lane group per query: lane g scans cells g, g+8, g+16, g+24 of the 3x3x3 block keeping a local
 // sorted top-5; the groups' lists are merged by five rounds of a (d^2, idx) min-reduction (shuffles), which
 // yields exactly the sequence a single sorted scan would; lane 0 of the group then fits the plane.
+template <int kFit>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const int *__restrict__ hcount,
           const int *__restrict__ hstart, int hmask, float inv_cell, const float4 *__restrict__ cellpts, float min_match_sq_dis,
@@ -176,7 +228,7 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
   const int q = ltile * kQueriesPerBlock + (threadIdx.x / kGroup);
   const unsigned gmask = 0xffu << ((lane_id() / kGroup) * kGroup);
   bool valid = false;
-  float4 po = make_float4(0, 0, 0, 0), co = make_float4(0, 0, 0, 0);
+  float4 po = make_float4(0, 0, 0, 0), co = make_float4(0, 0, 0, 0), co2 = make_float4(0, 0, 0, 0);
   const bool active = q < n;
   float sx = 0.f, sy = 0.f, sz = 0.f;
   float4 p = make_float4(0, 0, 0, 0);
@@ -245,7 +297,7 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
   }
   if (active && g == 0) {
     const float d5 = __uint_as_float((unsigned)(top_k[4] >> 32));
-    if (top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+    if (kFit == 0 && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
       float A[5][3], Bv[5], X[3];
       float nx[5], ny[5], nz[5];
 #pragma unroll
@@ -283,13 +335,75 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
         }
       }
     }
+    if (kFit == 1 && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+      float nx[5], ny[5], nz[5];
+      float vcx = 0.f, vcy = 0.f, vcz = 0.f;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float4 m = __ldg(cellpts + top_p[j]);
+        nx[j] = m.x; ny[j] = m.y; nz[j] = m.z;
+        vcx += m.x; vcy += m.y; vcz += m.z;
+      }
+      vcx /= 5.0f; vcy /= 5.0f; vcz /= 5.0f;
+      float a00 = 0.f, a10 = 0.f, a20 = 0.f, a11 = 0.f, a21 = 0.f, a22 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        const float ax = nx[j] - vcx, ay = ny[j] - vcy, az = nz[j] - vcz;
+        a00 += ax * ax; a10 += ax * ay; a20 += ax * az; a11 += ay * ay; a21 += ay * az; a22 += az * az;
+      }
+      float A1[9], D1[3], V1[9];
+      A1[0] = a00 / 5.0f; A1[4] = a11 / 5.0f; A1[8] = a22 / 5.0f;
+      A1[3] = A1[1] = a10 / 5.0f; A1[6] = A1[2] = a20 / 5.0f; A1[7] = A1[5] = a21 / 5.0f;
+      sym_eigen3(A1, D1, V1);
+      if (D1[2] > 3 * D1[1]) {
+        // `vc + 0.1 * V(k,2)`: double arithmetic, rounded to float on assignment
+        const float x1 = (float)((double)vcx + 0.1 * (double)V1[2]), y1 = (float)((double)vcy + 0.1 * (double)V1[5]),
+                    z1 = (float)((double)vcz + 0.1 * (double)V1[8]);
+        const float x2 = (float)((double)vcx - 0.1 * (double)V1[2]), y2 = (float)((double)vcy - 0.1 * (double)V1[5]),
+                    z2 = (float)((double)vcz - 0.1 * (double)V1[8]);
+        const float u0 = sx - x1, u1 = sy - y1, u2 = sz - z1;   // X0 - X1
+        const float v0 = sx - x2, v1 = sy - y2, v2 = sz - z2;   // X0 - X2
+        const float ax = u1 * v2 - u2 * v1, ay = u2 * v0 - u0 * v2, az = u0 * v1 - u1 * v0;   // a012_vec
+        const float lx = x1 - x2, ly = y1 - y2, lz = z1 - z2;   // X1 - X2
+        float tx = ly * az - lz * ay, ty = lz * ax - lx * az, tz = lx * ay - ly * ax;         // (X1-X2) x a012_vec
+        {
+          const float zz = tx * tx + ty * ty + tz * tz;
+          if (zz > 0.f) { const float nn = sqrtf(zz); tx = tx / nn; ty = ty / nn; tz = tz / nn; }
+        }
+        const float cx2 = ly * tz - lz * ty, cy2 = lz * tx - lx * tz, cz2 = lx * ty - ly * tx;  // normal_cross_point
+        const float a012 = sqrtf(ax * ax + ay * ay + az * az);
+        const float l12 = sqrtf(lx * lx + ly * ly + lz * lz);
+        const float ld2 = a012 / l12;
+        const float qx = sx - tx * ld2, qy = sy - ty * ld2, qz = sz - tz * ld2;   // point_proj
+        const float ld_p1 = -(tx * qx + ty * qy + tz * qz);
+        const float ld_p2 = -(cx2 * qx + cy2 * qy + cz2 * qz);
+        const float s = 1.f - 0.9f * fabsf(ld2);
+        float zx, zy, zz;
+        assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
+        const float e0 = tf.px - sx, e1 = tf.py - sy, e2 = tf.pz - sz;
+        const float squared_side1 = e0 * e0 + e1 * e1 + e2 * e2;
+        const float f0 = zx - sx, f1 = zy - sy, f2 = zz - sz;
+        const float squared_side2 = f0 * f0 + f1 * f1 + f2 * f2;
+        const float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
+        const float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * sqrtf(3.0f) * sqrtf(squared_side1);
+        const bool in_fov = (check1 < 0.f && check2 > 0.f);
+        if ((double)s > 0.1 && in_fov) {
+          valid = true;
+          po = make_float4(p.x, p.y, p.z, s * 0.5f);   // halving is exact
+          co = make_float4((s * tx) * 0.5f, (s * ty) * 0.5f, (s * tz) * 0.5f, (s * ld_p1) * 0.5f);
+          co2 = make_float4((s * cx2) * 0.5f, (s * cy2) * 0.5f, (s * cz2) * 0.5f, (s * ld_p2) * 0.5f);
+        }
+      }
+    }
   }
   int tot;
-  const int lpos = block_scan_excl(valid ? 1 : 0, sscan, &tot);   // thread order == query order
+  constexpr int kPer = kFit == 1 ? 2 : 1;
+  const int lpos = block_scan_excl(valid ? kPer : 0, sscan, &tot);   // thread order == query order
   const int excl = lookback_exclusive(status + F.tile0, ltile, tot, &sbc);
   if (valid) {
     const int o = base_count + excl + lpos;
     F.out_p[o] = po; F.out_c[o] = co; F.out_src[o] = q;
+    if (kFit == 1) { F.out_p[o + 1] = po; F.out_c[o + 1] = co2; F.out_src[o + 1] = q; }
   }
   if (ltile == ntiles - 1 && threadIdx.x == 0) *F.out_count = base_count + excl + tot;
 }
@@ -318,14 +432,18 @@ void knn_plan(KnnBatch &b) {
 }
 
 int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
-                             KnnWork &work, cudaStream_t st, int *launches) {
+                             KnnWork &work, cudaStream_t st, int *launches, int fit) {
   if (b.nframes <= 0) return LIO_OK;
   knn_plan(b);
   if (b.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
   cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * b.ntiles, st);
   cudaMemsetAsync(work.ticket, 0, sizeof(int), st);
-  knn_plane<<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
-                                              min_plane_dis, done_flag, work.status, work.ticket);
+  if (fit == 1)
+    knn_plane<1><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+                                                   min_plane_dis, done_flag, work.status, work.ticket);
+  else
+    knn_plane<0><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+                                                   min_plane_dis, done_flag, work.status, work.ticket);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
@@ -334,14 +452,14 @@ int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_
 
 int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
                            const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
-                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches) {
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches, int fit) {
   (void)map;
   KnnBatch b;
   b.nframes = 1;
   KnnFrame &f = b.f[0];
   f.surf = surf; f.n_dev = nsurf_dev; f.n_bound = nsurf_max; f.tf = tf_dev;
   f.out_p = out.pts; f.out_c = out.coef; f.out_src = out.src; f.out_count = out.count; f.append = append; f.tile0 = 0;
-  return calculate_features_batch(h, b, min_match_sq_dis, min_plane_dis, done_flag, work, st, launches);
+  return calculate_features_batch(h, b, min_match_sq_dis, min_plane_dis, done_flag, work, st, launches, fit);
 }
 
 }  // namespace lio
@@ -349,9 +467,26 @@ int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *s
 // ---- C-ABI: Estimator::CalculateFeatures on explicit host arrays (parity entry) -----------------
 using namespace lio;
 
+static int calculate_features_host_impl(const float *map, int K, const float *surf, int M, const float *tf7,
+                                        float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
+                                        int *n_out, int device, int fit);
+
 extern "C" int lio_calculate_features_host(const float *map, int K, const float *surf, int M, const float *tf7,
                                            float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
                                            int *n_out, int device) {
+  return calculate_features_host_impl(map, K, surf, M, tf7, min_match_sq_dis, min_plane_dis, pts4, coef4, src, n_out, device, 0);
+}
+
+extern "C" int lio_calculate_line_features_host(const float *corner_map, int K, const float *corner, int M, const float *tf7,
+                                                float min_match_sq_dis, float *pts4, float *coef4, int32_t *src, int *n_out,
+                                                int device) {
+  return calculate_features_host_impl(corner_map, K, corner, M, tf7, min_match_sq_dis, 0.f, pts4, coef4, src, n_out, device, 1);
+}
+
+static int calculate_features_host_impl(const float *map, int K, const float *surf, int M, const float *tf7,
+                                        float min_match_sq_dis, float min_plane_dis, float *pts4, float *coef4, int32_t *src,
+                                        int *n_out, int device, int fit) {
+  const int per = fit == 1 ? 2 : 1;
   if (!map || !surf || !tf7 || !n_out || K < 0 || M < 0) return LIO_ERR_INVALID;
   if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
   LIO_CUDA_OK(cudaSetDevice(device));
@@ -367,8 +502,8 @@ extern "C" int lio_calculate_features_host(const float *map, int K, const float 
   int Kc = K > 0 ? K : 1;
   if (h.init(Kc) != 0 || w.init(M) != 0) rc = LIO_ERR_CUDA;
   if (rc == LIO_OK && (cudaMalloc(&d_map, sizeof(float4) * Kc) != cudaSuccess || cudaMalloc(&d_surf, sizeof(float4) * M) != cudaSuccess ||
-                       cudaMalloc(&fo.pts, sizeof(float4) * M) != cudaSuccess || cudaMalloc(&fo.coef, sizeof(float4) * M) != cudaSuccess ||
-                       cudaMalloc(&fo.src, sizeof(int) * M) != cudaSuccess || cudaMalloc(&d_n, sizeof(int) * 4) != cudaSuccess ||
+                       cudaMalloc(&fo.pts, sizeof(float4) * M * per) != cudaSuccess || cudaMalloc(&fo.coef, sizeof(float4) * M * per) != cudaSuccess ||
+                       cudaMalloc(&fo.src, sizeof(int) * M * per) != cudaSuccess || cudaMalloc(&d_n, sizeof(int) * 4) != cudaSuccess ||
                        cudaMalloc(&d_tf, sizeof(TransformF)) != cudaSuccess))
     rc = LIO_ERR_CUDA;
   if (rc == LIO_OK) {
@@ -377,11 +512,11 @@ extern "C" int lio_calculate_features_host(const float *map, int K, const float 
     cudaMemcpy(d_surf, surf, sizeof(float4) * M, cudaMemcpyHostToDevice);
     cudaMemcpy(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice);
     cudaMemcpy(d_tf, tf7, sizeof(TransformF), cudaMemcpyHostToDevice);
-    fo.count = d_n + 2; fo.cap = M;
+    fo.count = d_n + 2; fo.cap = M * per;
     // cell edge >= search radius (with margin, see header)
     float cell = sqrtf(min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
     rc = h.build(d_map, d_n, Kc, cell, 0, nullptr);
-    if (rc == LIO_OK) rc = calculate_features_dev(h, d_map, d_surf, d_n + 1, M, d_tf, min_match_sq_dis, min_plane_dis, fo, 0, nullptr, w, 0, nullptr);
+    if (rc == LIO_OK) rc = calculate_features_dev(h, d_map, d_surf, d_n + 1, M, d_tf, min_match_sq_dis, min_plane_dis, fo, 0, nullptr, w, 0, nullptr, fit);
     if (rc == LIO_OK) {
       int m = 0;
       cudaError_t e = cudaMemcpy(&m, d_n + 2, sizeof(int), cudaMemcpyDeviceToHost);

@@ -63,13 +63,15 @@ struct KnnWork {
 // CalculateFeatures for several frames against the same map in ONE launch (tiles are dealt frame-major so each
 // frame's accepted features are compacted in query order).
 int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
-                             KnnWork &work, cudaStream_t st, int *launches);
+                             KnnWork &work, cudaStream_t st, int *launches, int fit = 0);
 
+// fit = 0: point-to-plane (surf branch); fit = 1: point-to-line (USE_CORNER branch, Estimator.cc:1101-1227), which
+// emits two consecutive half-weight features per accepted query (out buffers sized 2 x queries).
 // Estimator::CalculateFeatures (Estimator.cc:970-1097) for one frame.  Appends to `out` starting at
 // *out.count when `append` is non-zero, else overwrites from 0.  `done_flag` (optional device int):
 // when non-null and *done_flag != 0 the launch is a no-op (used by the LaserOdom iteration chain).
 int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
                            const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
-                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches);
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches, int fit = 0);
 
 }  // namespace lio

@@ -61,3 +61,19 @@ def transform_to_end(cloud, tf7_es, time_factor=10.0, device: int = 0):
     _lib.check(_lib.lib().lio_transform_to_end_host(c, c.shape[0], np.ascontiguousarray(tf7_es, np.float32), time_factor, device),
                "lio_transform_to_end_host")
     return c
+
+
+def calculate_line_features(corner_map, corner, tf7, min_match_sq_dis=1.0, device: int = 0):
+    """Point-to-line matching (lio_calculate_line_features_host): two half-weight features per accepted corner point."""
+    _lib.require_device()
+    m = np.ascontiguousarray(corner_map, np.float32).reshape(-1, 4)
+    s = np.ascontiguousarray(corner, np.float32).reshape(-1, 4)
+    cap = max(2 * s.shape[0], 1)
+    pts = np.zeros((cap, 4), np.float32)
+    coef = np.zeros((cap, 4), np.float32)
+    src = np.zeros(cap, np.int32)
+    n = C.c_int()
+    _lib.check(_lib.lib().lio_calculate_line_features_host(m, m.shape[0], s, s.shape[0], np.ascontiguousarray(tf7, np.float32),
+                                                           min_match_sq_dis, pts, coef, src, C.byref(n), device),
+               "lio_calculate_line_features_host")
+    return pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy()

@@ -91,6 +91,8 @@ struct StageBConfig {  // lidar subset of EstimatorConfig, include/imu_processor
 void PointAssociateToMap(const PointXYZI &pi, PointXYZI &po, const Transform &t);
 void CalculateFeatures(const KdTree &kd, const Cloud &map, const Cloud &surf_stack, const Transform &local_transform,
                        const StageBConfig &cfg, std::vector<PointPlaneFeature> &features);
+void CalculateLineFeatures(const KdTree &kd, const Cloud &map, const Cloud &corner_stack, const Transform &local_transform,
+                           const StageBConfig &cfg, std::vector<PointPlaneFeature> &features);
 void CalculateLaserOdom(const KdTree &kd, const Cloud &map, const Cloud &surf_stack, Transform &local_transform,
                         const StageBConfig &cfg, std::vector<PointPlaneFeature> &features, int *iters_done);
 

@@ -119,6 +119,17 @@ int orc_calculate_features(const float *map, int K, const float *surf, int M, co
   copy_feats(feats, pts4, coef4, src);
   return (int)feats.size();
 }
+// Point-to-line branch (Estimator.cc:1101-1227 / PointMapping.cc:381-512); outputs sized 2*M.
+int orc_calculate_line_features(const float *map, int K, const float *corner, int M, const float *tf7, float min_match_sq_dis,
+                                float *pts4, float *coef4, int *src) {
+  Cloud cm((const PointXYZI *)map, (const PointXYZI *)map + K), cs((const PointXYZI *)corner, (const PointXYZI *)corner + M);
+  KdTree kd; kd.Build(cm);
+  StageBConfig cfg; cfg.min_match_sq_dis = min_match_sq_dis;
+  std::vector<PointPlaneFeature> feats;
+  CalculateLineFeatures(kd, cm, cs, make_tf(tf7), cfg, feats);
+  copy_feats(feats, pts4, coef4, src);
+  return (int)feats.size();
+}
 // Estimator::CalculateLaserOdom; tf7 is in/out; outputs sized M*(keep_features? max_iter : 1).
 int orc_laser_odom(const float *map, int K, const float *surf, int M, float *tf7, float min_match_sq_dis, float min_plane_dis,
                    int keep_features, int max_iter, float *pts4, float *coef4, int *src, int *iters) {

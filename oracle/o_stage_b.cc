@@ -85,6 +85,97 @@ void CalculateFeatures(const KdTree &kd, const Cloud &map, const Cloud &surf_sta
   }
 }
 
+// Point-to-line branch of Estimator::CalculateFeatures (src/imu_processor/Estimator.cc:1101-1227; compiled out there
+// because USE_CORNER is undefined, include/imu_processor/Estimator.h:55-56) == the live corner matching of
+// PointMapping::OptimizeTransformTobeMapped (src/point_processor/PointMapping.cc:381-512): 5-NN in the corner map,
+// centroid + 3x3 covariance, SelfAdjointEigenSolver, line iff lambda_3 > 3 lambda_2, and the line encoded as TWO
+// half-weight plane-like features (normal_to_point and normal_cross_point).  The FOV test uses the query's own
+// transform like the surf branch (:1063-1086; PointMapping keeps point_on_z_axis_ = T * (0,0,10) the same way).
+// Mixed precision kept as written: `0.1 * mat_V1(k,2)` is a double product rounded to float on assignment.
+// SelfAdjointEigenSolver<Matrix3f> is restated by cyclic Jacobi (o_linalg.h, parity unpinned w.r.t. Eigen's QL path;
+// the eigenvector sign only flips coeff2, whose squared residual is unchanged).
+void CalculateLineFeatures(const KdTree &kd, const Cloud &map, const Cloud &corner_stack, const Transform &local_transform,
+                           const StageBConfig &cfg, std::vector<PointPlaneFeature> &features) {
+  if (!cfg.keep_features) features.clear();
+  int point_search_idx[5];
+  float point_search_sq_dis[5];
+  PointXYZI point_ori, point_sel, point_proj;
+  PointXYZI point_on_z_axis;
+  point_on_z_axis.x = 0.0f; point_on_z_axis.y = 0.0f; point_on_z_axis.z = 10.0f; point_on_z_axis.intensity = 0.f;
+  PointAssociateToMap(point_on_z_axis, point_on_z_axis, local_transform);
+  for (size_t i = 0; i < corner_stack.size(); i++) {
+    point_ori = corner_stack[i];
+    PointAssociateToMap(point_ori, point_sel, local_transform);
+    kd.Knn(point_sel, 5, point_search_idx, point_search_sq_dis);
+    if (!(point_search_sq_dis[4] < cfg.min_match_sq_dis)) continue;
+    float vc[3] = {0, 0, 0};
+    for (int j = 0; j < 5; j++) {
+      const PointXYZI &m = map[point_search_idx[j]];
+      vc[0] += m.x; vc[1] += m.y; vc[2] += m.z;
+    }
+    vc[0] /= 5.0f; vc[1] /= 5.0f; vc[2] /= 5.0f;  // Vector3f /= 5.0: the scalar is cast to float
+    float a00 = 0, a10 = 0, a20 = 0, a11 = 0, a21 = 0, a22 = 0;
+    for (int j = 0; j < 5; j++) {
+      const PointXYZI &m = map[point_search_idx[j]];
+      float ax = m.x - vc[0], ay = m.y - vc[1], az = m.z - vc[2];
+      a00 += ax * ax; a10 += ax * ay; a20 += ax * az; a11 += ay * ay; a21 += ay * az; a22 += az * az;
+    }
+    // mat_A1 = mat_a / 5.0; only the lower triangle is written and SelfAdjointEigenSolver reads only it
+    float A1[9];
+    A1[0] = a00 / 5.0f; A1[4] = a11 / 5.0f; A1[8] = a22 / 5.0f;
+    A1[3] = A1[1] = a10 / 5.0f; A1[6] = A1[2] = a20 / 5.0f; A1[7] = A1[5] = a21 / 5.0f;
+    float D1[3], V1[9];
+    sym_eigen_jacobi<float>(3, A1, D1, V1);
+    if (!(D1[2] > 3 * D1[1])) continue;
+    float x0 = point_sel.x, y0 = point_sel.y, z0 = point_sel.z;
+    float x1 = (float)((double)vc[0] + 0.1 * (double)V1[0 * 3 + 2]);
+    float y1 = (float)((double)vc[1] + 0.1 * (double)V1[1 * 3 + 2]);
+    float z1 = (float)((double)vc[2] + 0.1 * (double)V1[2 * 3 + 2]);
+    float x2 = (float)((double)vc[0] - 0.1 * (double)V1[0 * 3 + 2]);
+    float y2 = (float)((double)vc[1] - 0.1 * (double)V1[1 * 3 + 2]);
+    float z2 = (float)((double)vc[2] - 0.1 * (double)V1[2 * 3 + 2]);
+    Vec3<float> X0(x0, y0, z0), X1(x1, y1, z1), X2(x2, y2, z2);
+    Vec3<float> a012_vec = (X0 - X1).cross(X0 - X2);
+    Vec3<float> l12_vec = X1 - X2;
+    Vec3<float> ntp = l12_vec.cross(a012_vec);
+    {  // .normalized(): v / sqrt(squaredNorm) when squaredNorm > 0
+      float z = ntp.x * ntp.x + ntp.y * ntp.y + ntp.z * ntp.z;
+      if (z > 0.f) { float nn = std::sqrt(z); ntp = Vec3<float>(ntp.x / nn, ntp.y / nn, ntp.z / nn); }
+    }
+    Vec3<float> ncp = l12_vec.cross(ntp);
+    float a012 = std::sqrt(a012_vec.x * a012_vec.x + a012_vec.y * a012_vec.y + a012_vec.z * a012_vec.z);
+    float l12 = std::sqrt(l12_vec.x * l12_vec.x + l12_vec.y * l12_vec.y + l12_vec.z * l12_vec.z);
+    float la = ntp.x, lb = ntp.y, lc = ntp.z;
+    float ld2 = a012 / l12;
+    point_proj = point_sel;
+    point_proj.x -= la * ld2; point_proj.y -= lb * ld2; point_proj.z -= lc * ld2;
+    float ld_p1 = -(ntp.x * point_proj.x + ntp.y * point_proj.y + ntp.z * point_proj.z);
+    float ld_p2 = -(ncp.x * point_proj.x + ncp.y * point_proj.y + ncp.z * point_proj.z);
+    float s = 1 - 0.9f * std::fabs(ld2);
+    PointXYZI coeff1, coeff2;
+    coeff1.x = s * la; coeff1.y = s * lb; coeff1.z = s * lc; coeff1.intensity = s * ld_p1;
+    coeff2.x = s * ncp.x; coeff2.y = s * ncp.y; coeff2.z = s * ncp.z; coeff2.intensity = s * ld_p2;
+    PointXYZI transform_pos;
+    transform_pos.x = local_transform.pos.x; transform_pos.y = local_transform.pos.y; transform_pos.z = local_transform.pos.z;
+    float squared_side1 = SqDiff(transform_pos, point_sel);
+    float squared_side2 = SqDiff(point_on_z_axis, point_sel);
+    float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * std::sqrt(3.0f) * std::sqrt(squared_side1);
+    float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * std::sqrt(3.0f) * std::sqrt(squared_side1);
+    bool is_in_laser_fov = (check1 < 0 && check2 > 0);
+    if (s > 0.1 && is_in_laser_fov) {
+      for (int h = 0; h < 2; ++h) {
+        const PointXYZI &c = h == 0 ? coeff1 : coeff2;
+        PointPlaneFeature f;
+        f.score = s * 0.5;
+        f.point[0] = point_ori.x; f.point[1] = point_ori.y; f.point[2] = point_ori.z;
+        f.coeffs[0] = c.x * 0.5; f.coeffs[1] = c.y * 0.5; f.coeffs[2] = c.z * 0.5; f.coeffs[3] = c.intensity * 0.5;
+        f.src_index = (int)i;
+        features.push_back(f);
+      }
+    }
+  }
+}
+
 void CalculateLaserOdom(const KdTree &kd, const Cloud &map, const Cloud &surf_stack, Transform &local_transform,
                         const StageBConfig &cfg, std::vector<PointPlaneFeature> &features, int *iters_done) {
   bool is_degenerate = false;

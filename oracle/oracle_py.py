@@ -141,6 +141,21 @@ def calculate_features(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0
     return pts[:n].copy(), coef[:n].copy(), src[:n].copy()
 
 
+def calculate_line_features(corner_map, corner, tf7, min_match_sq_dis=1.0):
+    L = lib()
+    m = np.ascontiguousarray(corner_map, np.float32).reshape(-1, 4)
+    s = np.ascontiguousarray(corner, np.float32).reshape(-1, 4)
+    cap = max(2 * s.shape[0], 1)
+    pts = np.zeros((cap, 4), np.float32)
+    coef = np.zeros((cap, 4), np.float32)
+    src = np.zeros(cap, np.int32)
+    L.orc_calculate_line_features.argtypes = [f32p, C.c_int, f32p, C.c_int, f32p, C.c_float, f32p, f32p, i32p]
+    L.orc_calculate_line_features.restype = C.c_int
+    n = L.orc_calculate_line_features(m, m.shape[0], s, s.shape[0], np.ascontiguousarray(tf7, np.float32), min_match_sq_dis,
+                                      pts, coef, src)
+    return pts[:n].copy(), coef[:n].copy(), src[:n].copy()
+
+
 def laser_odom(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, keep_features=0, max_iter=10):
     L = lib()
     m = np.ascontiguousarray(map_pts, np.float32).reshape(-1, 4)
@@ -154,6 +169,32 @@ def laser_odom(map_pts, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, keep
     n = L.orc_laser_odom(m, m.shape[0], s, s.shape[0], tf, min_match_sq_dis, min_plane_dis, keep_features, max_iter,
                          pts, coef, src, it)
     return tf, pts[:n].copy(), coef[:n].copy(), src[:n].copy(), int(it[0])
+
+
+def compact_encode(tf7, corner, surf, full):
+    """PointOdometry.cc:732-762: the compact cloud as (n, 4) float32."""
+    L = lib()
+    c, s, f = [np.ascontiguousarray(a, np.float32).reshape(-1, 4) for a in (corner, surf, full)]
+    out = np.zeros((3 + c.shape[0] + s.shape[0] + f.shape[0], 4), np.float32)
+    L.orc_compact_encode.argtypes = [f32p, f32p, C.c_int, f32p, C.c_int, f32p, C.c_int, f32p]
+    L.orc_compact_encode.restype = C.c_int
+    n = L.orc_compact_encode(np.ascontiguousarray(tf7, np.float32), c, c.shape[0], s, s.shape[0], f, f.shape[0], out)
+    return out[:n]
+
+
+def compact_decode(compact):
+    """PointMapping::CompactDataHandler (PointMapping.cc:171-238); None on the reference's error paths."""
+    L = lib()
+    d = np.ascontiguousarray(compact, np.float32).reshape(-1, 4)
+    n = d.shape[0]
+    tf7 = np.zeros(7, np.float32)
+    outs = [np.zeros((max(n, 1), 4), np.float32) for _ in range(3)]
+    sz = np.zeros(3, np.int32)
+    L.orc_compact_decode.argtypes = [f32p, C.c_int, f32p, f32p, f32p, f32p, i32p]
+    L.orc_compact_decode.restype = C.c_int
+    if not L.orc_compact_decode(d, n, tf7, outs[0], outs[1], outs[2], sz):
+        return None
+    return tf7, outs[0][:sz[0]], outs[1][:sz[1]], outs[2][:sz[2]]
 
 
 def transform_to_end(cloud, tf7, time_factor=10.0):

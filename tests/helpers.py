@@ -4,15 +4,16 @@ import numpy as np
 from lio_mapping_b200 import synth
 
 
-def frame_clouds(oracle, kind, n_frames, t0=1.0, seed0=10):
-    """surface_points_less_flat of n_frames consecutive sweeps + their ground-truth lidar poses."""
+def frame_clouds(oracle, kind, n_frames, t0=1.0, seed0=10, which="less_flat", leaf=0.4):
+    """One stage-A feature cloud (default surface_points_less_flat) of n_frames consecutive sweeps, voxel filtered,
+    + their ground-truth lidar poses."""
     sensor, scene, traj = synth.default_config(kind)
     clouds, poses = [], []
     for f in range(n_frames):
         t_end = t0 + 0.1 * f
         sw = synth.make_sweep(sensor, scene, traj, t_end, seed=seed0 + f, distort=False)
         r = oracle.stage_a(sw, sensor.lower_deg, sensor.upper_deg, sensor.rings)
-        clouds.append(oracle.voxel_grid(r["less_flat"], 0.4))
+        clouds.append(oracle.voxel_grid(r[which], leaf))
         p, R, _, _, _ = traj.state(np.array(t_end))
         poses.append((R, p))
     return sensor, clouds, poses

@@ -70,3 +70,57 @@ def test_knn_oracle_vs_bruteforce(oracle):
     ref = np.argsort(d, axis=1, kind="stable")[:, :5]
     assert np.array_equal(np.sort(idx, 1), np.sort(ref, 1))
     assert np.all(np.diff(d2, axis=1) >= 0)
+
+
+def test_line_features_geometry_float64_crosscheck(oracle):
+    """Pins the oracle's point-to-line restatement (Estimator.cc:1101-1227 / PointMapping.cc:381-512) against an
+    independent float64 derivation: brute-force 5-NN, numpy eigh of the covariance, and the geometric meaning of
+    the two emitted planes (orthonormal normals, both contain the fitted line, joint distance == point-line distance)."""
+    from tests import helpers
+    sensor, clouds, poses = helpers.frame_clouds(oracle, "vlp16", 4, which="less_sharp", leaf=0.2)
+    m = helpers.build_map(oracle, clouds, poses, leaf=0.2)
+    _, _, tf7 = helpers.rel_transform(poses[0], poses[2])
+    pts, coef, src = oracle.calculate_line_features(m, clouds[2], tf7)
+    assert pts.shape[0] >= 40 and pts.shape[0] % 2 == 0
+    R, t, _ = helpers.rel_transform(poses[0], poses[2])
+    R = R.astype(np.float64); t = t.astype(np.float64)
+    M = m[:, :3].astype(np.float64)
+    accepted = set(src[0::2].tolist())
+    n_checked = 0
+    for qi in range(clouds[2].shape[0]):
+        x0 = R @ clouds[2][qi, :3].astype(np.float64) + t
+        d2 = ((M - x0) ** 2).sum(1)
+        nn = np.argsort(d2, kind="stable")[:5]
+        if d2[nn[4]] >= 1.0 - 1e-4:
+            if d2[nn[4]] >= 1.0 + 1e-4:
+                assert qi not in accepted
+            continue
+        P = M[nn]
+        vc = P.mean(0)
+        w, V = np.linalg.eigh(np.cov((P - vc).T, bias=True))
+        is_line = w[2] > 3 * w[1]
+        if abs(w[2] - 3 * w[1]) < 1e-3 * w[2]:
+            continue                       # too close to the threshold for a float32 / float64 comparison
+        if not is_line:
+            assert qi not in accepted
+            continue
+        v = V[:, 2]
+        dist = np.linalg.norm(np.cross(x0 - vc, v))
+        s = 1 - 0.9 * dist
+        if qi not in accepted:
+            continue                       # rejected by score / FOV: checked in the GPU-vs-oracle test, not re-derived here
+        k = src[0::2].tolist().index(qi)
+        c1, c2 = coef[2 * k].astype(np.float64) * 2, coef[2 * k + 1].astype(np.float64) * 2   # undo the half weights
+        assert abs(pts[2 * k, 3] * 2 - s) < 2e-4
+        n1, n2 = c1[:3] / s, c2[:3] / s
+        # normal_to_point is a unit vector; normal_cross_point = (X1 - X2) x normal_to_point keeps |X1 - X2| = 0.2 as its
+        # length in the reference (Estimator.cc:1160) - restated as written, not normalised
+        assert abs(np.linalg.norm(n1) - 1) < 1e-4 and abs(np.linalg.norm(n2) - 0.2) < 1e-4
+        assert abs(n1 @ n2) < 1e-4 and abs(n1 @ v) < 2e-3 and abs(n2 @ v) < 2e-3
+        # plane 1 contains the foot point of x0 on the line with signed distance == point-line distance; plane 2 contains x0's
+        # projection too: residuals (w.x + b)/s at x0 are (dist, 0)
+        r1 = (c1[:3] @ x0 + c1[3]) / s
+        r2 = (c2[:3] @ x0 + c2[3]) / s
+        assert abs(r1 - dist) < 2e-3 and abs(r2) < 2e-3
+        n_checked += 1
+    assert n_checked >= 20

@@ -122,3 +122,38 @@ def test_transform_to_end_parity(oracle):
         assert np.array_equal(g[:, 3], o[:, 3])            # relative time channel is exact
         assert np.max(np.abs(g[:, :3] - o[:, :3])) < 2e-6 * 100.0
     assert ops.transform_to_end(np.zeros((0, 4), np.float32), tf7).shape == (0, 4)
+
+
+@pytest.mark.parametrize("kind", ["vlp16", "hdl64"])
+def test_calculate_line_features_parity(oracle, kind):
+    """Point-to-line branch (USE_CORNER / PointMapping corner matching): bit-exact against the oracle."""
+    from lio_mapping_b200 import ops
+    sensor, clouds, poses = helpers.frame_clouds(oracle, kind, 4, which="less_sharp", leaf=0.2)
+    m = helpers.build_map(oracle, clouds, poses, leaf=0.2)
+    for fi, jitter in [(1, 0.0), (3, 0.03)]:
+        _, _, tf7 = helpers.rel_transform(poses[0], poses[fi])
+        tf7 = tf7.copy()
+        tf7[4:] += jitter
+        po, co, so = oracle.calculate_line_features(m, clouds[fi], tf7)
+        pg, cg, sg = ops.calculate_line_features(m, clouds[fi], tf7)
+        assert so.shape[0] >= 0.2 * clouds[fi].shape[0], "scenario too sparse to be meaningful"
+        assert so.shape[0] % 2 == 0 and np.array_equal(so[0::2], so[1::2])      # two features per accepted corner point
+        assert np.array_equal(sg, so)
+        assert np.array_equal(pg, po)
+        assert np.array_equal(cg, co)
+
+
+def test_calculate_line_features_edge_cases(oracle):
+    from lio_mapping_b200 import ops
+    rng = np.random.default_rng(4)
+    tf7 = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    # isotropic blob: lambda_3 > 3 lambda_2 fails almost everywhere; exact collinear map: always a line
+    blob = np.concatenate([rng.normal(0, 0.2, size=(400, 3)) + [5, 0, 0], np.zeros((400, 1))], 1).astype(np.float32)
+    t = np.linspace(-3, 3, 300)
+    line = np.stack([5 + 0 * t, 0.5 + 0 * t, t, 0 * t], 1).astype(np.float32)
+    q = np.concatenate([rng.normal(0, 0.1, size=(200, 3)) + [5, 0.5, 0], np.zeros((200, 1))], 1).astype(np.float32)
+    for m in (blob, line, np.concatenate([blob, line]), line[:4]):
+        po, co, so = oracle.calculate_line_features(m, q, tf7)
+        pg, cg, sg = ops.calculate_line_features(m, q, tf7)
+        assert np.array_equal(sg, so) and np.array_equal(pg, po) and np.array_equal(cg, co)
+    assert ops.calculate_line_features(line, np.zeros((0, 4), np.float32), tf7)[0].shape == (0, 4)
