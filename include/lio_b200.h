@@ -135,6 +135,19 @@ int lio_laser_odom_host(const float *map, int K, const float *surf, int M, float
                         float min_plane_dis, int keep_features, int max_iter, float *pts4, float *coef4, int32_t *src,
                         int *n_out, int *iters, int device);
 
+/* PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:325-753): scan-to-map 6-DoF float Gauss-Newton of
+ * transform_tobe_mapped_ (tf7, in/out) against explicit corner / surf maps (laser_cloud_corner_from_map_ /
+ * laser_cloud_surf_from_map_; the cube-map store that selects them is outside this operator).  Per round: corner matching
+ * (:381-512, one feature per line), surf matching (:514-606, sign-normalised plane), skip when fewer than 50 matches
+ * (:609-611), 6x6 normal equations + colPivHouseholderQr + first-round degeneracy projection + quaternion update (:613-715),
+ * exit when delta_r < delta_r_abort (deg) and delta_t < delta_t_abort (cm).  Returns immediately (tf7 untouched) when
+ * Kc <= 10 or Ks <= 100 (:327-329).  Optional outputs (sized Mc + Ms): the matches of the last executed round, corner
+ * then surf; *iters = rounds executed. */
+int lio_scan_to_map_host(const float *corner_map, int Kc, const float *surf_map, int Ks, const float *corner, int Mc,
+                         const float *surf, int Ms, float *tf7, float min_match_sq_dis, float min_plane_dis, int max_iter,
+                         double delta_r_abort, double delta_t_abort, float *pts4, float *coef4, int32_t *src, int *n_out,
+                         int *iters, int device);
+
 /* ------------------------------------------------------------------------------------------
  * fp64 factor operators — the ceres::CostFunction::Evaluate seam.
  * Same contract as the reference: residuals always written, each jacobian pointer may be NULL,

@@ -137,7 +137,7 @@ constexpr int kOdomThreads = 256;
 
 __global__ void __launch_bounds__(kOdomThreads)
 k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, const int *__restrict__ n_dev,
-              const TransformF *__restrict__ tf_dev, OdomState *__restrict__ st, double *__restrict__ partial) {
+              const TransformF *__restrict__ tf_dev, OdomState *__restrict__ st, double *__restrict__ partial, int d2_from_coef = 0) {
   __shared__ double sred[kOdomThreads / 32][27];
   __shared__ bool is_last;
   if (st->done) return;
@@ -172,7 +172,8 @@ k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, c
     row[3] = c.x; row[4] = c.y; row[5] = c.z;
     float rx, ry, rz;
     qmul_vec(tf.qx, tf.qy, tf.qz, tf.qw, p.x, p.y, p.z, rx, ry, rz);
-    float d2 = c.x * (rx + tf.px) + c.y * (ry + tf.py) + c.z * (rz + tf.pz) + c.w;
+    // CalculateLaserOdom: d2 = w . (R p + t) + b (Estimator.cc:1282-1284); scan-to-map: d2 = coeff.intensity (PointMapping.cc:634)
+    float d2 = d2_from_coef ? c.w : c.x * (rx + tf.px) + c.y * (ry + tf.py) + c.z * (rz + tf.pz) + c.w;
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
@@ -244,12 +245,18 @@ __device__ void sym_eigen6(const float *Ain, float *evals, float *V) {
   for (int j = 0; j < 6; ++j) { evals[j] = A[idx[j] * 6 + idx[j]]; for (int k = 0; k < 6; ++k) V[k * 6 + j] = Vc[k * 6 + idx[j]]; }
 }
 
-__global__ void k_odom_solve(OdomState *__restrict__ st, TransformF *__restrict__ tf_dev, double delta_r_abort, double delta_t_abort) {
+// round < 0: CalculateLaserOdom (the first executed round carries the degeneracy analysis);  round >= 0: scan-to-map loop
+// index of PointMapping::OptimizeTransformTobeMapped, where a round with fewer than min_features matches is skipped
+// entirely (`continue`, PointMapping.cc:609-611) and the degeneracy analysis belongs to loop index 0 only.
+__global__ void k_odom_solve(OdomState *__restrict__ st, TransformF *__restrict__ tf_dev, double delta_r_abort, double delta_t_abort,
+                             int round = -1, const int *__restrict__ n_dev = nullptr, int min_features = 0) {
   if (threadIdx.x != 0 || st->done) return;
+  if (n_dev && *n_dev < min_features) { st->iter += 1; return; }
+  const bool first_round = round < 0 ? (st->iter == 0) : (round == 0);
   float A[6][6], B[6], X[6], AtA[36];
   for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) { A[a][b] = (float)st->AtA[a * 6 + b]; AtA[a * 6 + b] = A[a][b]; } B[a] = (float)st->AtB[a]; }
   colpiv_qr_solve<6, 6>(A, B, X);
-  if (st->iter == 0) {
+  if (first_round) {
     float E[6], V[36], V2[36];
     sym_eigen6(AtA, E, V);
     for (int k = 0; k < 36; ++k) V2[k] = V[k];
@@ -1699,6 +1706,100 @@ extern "C" int lio_transform_to_end_host(float *cloud, int n, const float *tf7_e
   if (dn) cudaFree(dn);
   if (ce != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); return LIO_ERR_CUDA; }
   return LIO_OK;
+}
+
+// ---- C-ABI: PointMapping::OptimizeTransformTobeMapped on explicit host arrays (parity entry) ------------------------
+extern "C" int lio_scan_to_map_host(const float *corner_map, int Kc, const float *surf_map, int Ks, const float *corner, int Mc,
+                                    const float *surf, int Ms, float *tf7, float min_match_sq_dis, float min_plane_dis, int max_iter,
+                                    double delta_r_abort, double delta_t_abort, float *pts4, float *coef4, int32_t *src, int *n_out,
+                                    int *iters, int device) {
+  if (!corner_map || !surf_map || !corner || !surf || !tf7 || Kc < 0 || Ks < 0 || Mc < 0 || Ms < 0 || max_iter < 0) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  if (n_out) *n_out = 0;
+  if (iters) *iters = 0;
+  if (Kc <= 10 || Ks <= 100 || max_iter == 0) return LIO_OK;  // PointMapping.cc:327-329: nothing to optimise against
+  const int cap = std::max(1, Mc + Ms);
+  CellHash hc, hs;
+  KnnWork w;
+  float4 *d_cmap = nullptr, *d_smap = nullptr, *d_corner = nullptr, *d_surf = nullptr;
+  FeatureOut fo;
+  int *d_n = nullptr;
+  TransformF *d_tf = nullptr;
+  OdomState *d_odom = nullptr;
+  double *d_partial = nullptr;
+  float *d_z = nullptr;
+  int rc = LIO_OK, sm = 148;
+  cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+  if (hc.init(Kc) != 0 || hs.init(Ks) != 0 || w.init(std::max(Mc, Ms) + 1) != 0) rc = LIO_ERR_CUDA;
+  auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
+  if (rc == LIO_OK && !(alloc((void **)&d_cmap, sizeof(float4) * Kc) && alloc((void **)&d_smap, sizeof(float4) * Ks) &&
+                        alloc((void **)&d_corner, sizeof(float4) * Mc) && alloc((void **)&d_surf, sizeof(float4) * Ms) &&
+                        alloc((void **)&fo.pts, sizeof(float4) * cap) && alloc((void **)&fo.coef, sizeof(float4) * cap) &&
+                        alloc((void **)&fo.src, sizeof(int) * cap) && alloc((void **)&d_n, sizeof(int) * 8) &&
+                        alloc((void **)&d_tf, sizeof(TransformF)) && alloc((void **)&d_odom, sizeof(OdomState)) &&
+                        alloc((void **)&d_partial, sizeof(double) * 32 * 1024) && alloc((void **)&d_z, sizeof(float) * 4)))
+    rc = LIO_ERR_CUDA;
+  if (rc != LIO_OK) lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+  if (rc == LIO_OK) {
+    const int hn[5] = {Kc, Ks, Mc, Ms, 0};
+    cudaMemcpy(d_cmap, corner_map, sizeof(float4) * Kc, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_smap, surf_map, sizeof(float4) * Ks, cudaMemcpyHostToDevice);
+    if (Mc) cudaMemcpy(d_corner, corner, sizeof(float4) * Mc, cudaMemcpyHostToDevice);
+    if (Ms) cudaMemcpy(d_surf, surf, sizeof(float4) * Ms, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice);
+    cudaMemcpy(d_tf, tf7, sizeof(TransformF), cudaMemcpyHostToDevice);
+    cudaMemset(d_odom, 0, sizeof(OdomState));
+    {  // point_on_z_axis_ = T0 * (0, 0, 10), fixed for the whole optimisation (PointMapping.cc:803-806); float, no FMA
+      const float qx = tf7[0], qy = tf7[1], qz = tf7[2], qw = tf7[3], vx = 0.0f, vy = 0.0f, vz = 10.0f;
+      volatile float ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
+      volatile float ux2 = ux + ux, uy2 = uy + uy, uz2 = uz + uz;
+      volatile float cx = qy * uz2 - qz * uy2, cy = qz * ux2 - qx * uz2, cz = qx * uy2 - qy * ux2;
+      volatile float ax = ux2 * qw, ay = uy2 * qw, az = uz2 * qw;
+      volatile float rx = vx + ax, ry = vy + ay, rz = vz + az;
+      volatile float sx = rx + cx, sy = ry + cy, sz = rz + cz;
+      const float hz[4] = {sx + tf7[4], sy + tf7[5], sz + tf7[6], 0.f};
+      cudaMemcpy(d_z, hz, sizeof(hz), cudaMemcpyHostToDevice);
+    }
+    fo.count = d_n + 4; fo.cap = cap;
+    const float cell = sqrtf(min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
+    rc = hc.build(d_cmap, d_n, Kc, cell, 0, nullptr);
+    if (rc == LIO_OK) rc = hs.build(d_smap, d_n + 1, Ks, cell, 0, nullptr);
+    const int nb = std::max(1, std::min(sm, (cap + kOdomThreads - 1) / kOdomThreads));
+    for (int it = 0; it < max_iter && rc == LIO_OK; ++it) {
+      rc = calculate_features_dev(hc, d_cmap, d_corner, d_n + 2, std::max(Mc, 1), d_tf, min_match_sq_dis, min_plane_dis, fo, 0,
+                                  &d_odom->done, w, 0, nullptr, 3, d_z);
+      if (rc == LIO_OK)
+        rc = calculate_features_dev(hs, d_smap, d_surf, d_n + 3, std::max(Ms, 1), d_tf, min_match_sq_dis, min_plane_dis, fo, 1,
+                                    &d_odom->done, w, 0, nullptr, 2, d_z);
+      if (rc != LIO_OK) break;
+      k_odom_reduce<<<nb, kOdomThreads>>>(fo.pts, fo.coef, fo.count, d_tf, d_odom, d_partial, 1);
+      k_odom_solve<<<1, 32>>>(d_odom, d_tf, delta_r_abort, delta_t_abort, it, fo.count, 50);
+    }
+    if (rc == LIO_OK) {
+      int m = 0;
+      OdomState hs2;
+      cudaError_t ce = cudaMemcpy(&m, d_n + 4, sizeof(int), cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(&hs2, d_odom, sizeof(OdomState), cudaMemcpyDeviceToHost);
+      if (ce == cudaSuccess) ce = cudaMemcpy(tf7, d_tf, sizeof(TransformF), cudaMemcpyDeviceToHost);
+      if (ce != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); rc = LIO_ERR_CUDA; }
+      else if (m > cap) { lio_set_last_error(__FILE__, __LINE__, "feature buffer overflow"); rc = LIO_ERR_CAPACITY; }
+      else {
+        if (n_out) *n_out = m;
+        if (iters) *iters = hs2.iter;
+        if (m > 0) {
+          if (pts4) cudaMemcpy(pts4, fo.pts, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+          if (coef4) cudaMemcpy(coef4, fo.coef, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+          if (src) cudaMemcpy(src, fo.src, sizeof(int) * m, cudaMemcpyDeviceToHost);
+        }
+      }
+    }
+  }
+  void *fr[] = {d_cmap, d_smap, d_corner, d_surf, fo.pts, fo.coef, fo.src, d_n, d_tf, d_odom, d_partial, d_z};
+  for (void *q : fr) if (q) cudaFree(q);
+  hc.destroy(); hs.destroy();
+  w.destroy();
+  return rc;
 }
 
 // ---- C-ABI: Estimator::CalculateLaserOdom on explicit host arrays (parity entry) ---------------------------------

@@ -297,7 +297,7 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
   }
   if (active && g == 0) {
     const float d5 = __uint_as_float((unsigned)(top_k[4] >> 32));
-    if (kFit == 0 && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+    if ((kFit == 0 || kFit == 2) && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
       float A[5][3], Bv[5], X[3];
       float nx[5], ny[5], nz[5];
 #pragma unroll
@@ -320,7 +320,8 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
         const float dist = sqrtf(sx * sx + sy * sy + sz * sz);
         const float s = 1.f - 0.9f * fabsf(pd2) / sqrtf(dist);
         float zx, zy, zz;
-        assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
+        if (F.zaxis) { zx = F.zaxis[0]; zy = F.zaxis[1]; zz = F.zaxis[2]; }
+        else assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
         const float e0 = tf.px - sx, e1 = tf.py - sy, e2 = tf.pz - sz;
         const float squared_side1 = e0 * e0 + e1 * e1 + e2 * e2;
         const float f0 = zx - sx, f1 = zy - sy, f2 = zz - sz;
@@ -331,11 +332,12 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
         if ((double)s > 0.1 && in_fov) {
           valid = true;
           po = make_float4(p.x, p.y, p.z, s);
-          co = make_float4(s * pa, s * pb, s * pc, s * pd);
+          if (kFit == 2) co = pd2 > 0.f ? make_float4(s * pa, s * pb, s * pc, s * pd2) : make_float4(-s * pa, -s * pb, -s * pc, -s * pd2);
+          else co = make_float4(s * pa, s * pb, s * pc, s * pd);
         }
       }
     }
-    if (kFit == 1 && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+    if ((kFit == 1 || kFit == 3) && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
       float nx[5], ny[5], nz[5];
       float vcx = 0.f, vcy = 0.f, vcz = 0.f;
 #pragma unroll
@@ -379,7 +381,8 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
         const float ld_p2 = -(cx2 * qx + cy2 * qy + cz2 * qz);
         const float s = 1.f - 0.9f * fabsf(ld2);
         float zx, zy, zz;
-        assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
+        if (F.zaxis) { zx = F.zaxis[0]; zy = F.zaxis[1]; zz = F.zaxis[2]; }
+        else assoc_to_map(tf, 0.0f, 0.0f, 10.0f, zx, zy, zz);
         const float e0 = tf.px - sx, e1 = tf.py - sy, e2 = tf.pz - sz;
         const float squared_side1 = e0 * e0 + e1 * e1 + e2 * e2;
         const float f0 = zx - sx, f1 = zy - sy, f2 = zz - sz;
@@ -389,9 +392,14 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
         const bool in_fov = (check1 < 0.f && check2 > 0.f);
         if ((double)s > 0.1 && in_fov) {
           valid = true;
-          po = make_float4(p.x, p.y, p.z, s * 0.5f);   // halving is exact
-          co = make_float4((s * tx) * 0.5f, (s * ty) * 0.5f, (s * tz) * 0.5f, (s * ld_p1) * 0.5f);
-          co2 = make_float4((s * cx2) * 0.5f, (s * cy2) * 0.5f, (s * cz2) * 0.5f, (s * ld_p2) * 0.5f);
+          if (kFit == 3) {
+            po = make_float4(p.x, p.y, p.z, s);
+            co = make_float4(s * tx, s * ty, s * tz, s * ld2);
+          } else {
+            po = make_float4(p.x, p.y, p.z, s * 0.5f);   // halving is exact
+            co = make_float4((s * tx) * 0.5f, (s * ty) * 0.5f, (s * tz) * 0.5f, (s * ld_p1) * 0.5f);
+            co2 = make_float4((s * cx2) * 0.5f, (s * cy2) * 0.5f, (s * cz2) * 0.5f, (s * ld_p2) * 0.5f);
+          }
         }
       }
     }
@@ -438,7 +446,13 @@ int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_
   if (b.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
   cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * b.ntiles, st);
   cudaMemsetAsync(work.ticket, 0, sizeof(int), st);
-  if (fit == 1)
+  if (fit == 2)
+    knn_plane<2><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+                                                   min_plane_dis, done_flag, work.status, work.ticket);
+  else if (fit == 3)
+    knn_plane<3><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+                                                   min_plane_dis, done_flag, work.status, work.ticket);
+  else if (fit == 1)
     knn_plane<1><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
                                                    min_plane_dis, done_flag, work.status, work.ticket);
   else
@@ -452,13 +466,13 @@ int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_
 
 int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
                            const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
-                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches, int fit) {
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches, int fit, const float *zaxis_dev) {
   (void)map;
   KnnBatch b;
   b.nframes = 1;
   KnnFrame &f = b.f[0];
   f.surf = surf; f.n_dev = nsurf_dev; f.n_bound = nsurf_max; f.tf = tf_dev;
-  f.out_p = out.pts; f.out_c = out.coef; f.out_src = out.src; f.out_count = out.count; f.append = append; f.tile0 = 0;
+  f.out_p = out.pts; f.out_c = out.coef; f.out_src = out.src; f.out_count = out.count; f.append = append; f.tile0 = 0; f.zaxis = zaxis_dev;
   return calculate_features_batch(h, b, min_match_sq_dis, min_plane_dis, done_flag, work, st, launches, fit);
 }
 

@@ -44,6 +44,7 @@ struct KnnFrame {
   int *out_src, *out_count;
   int append;
   int tile0;
+  const float *zaxis = nullptr;  // optional device float[3]: a fixed point_on_z_axis_ for the FOV test (PointMapping.cc:803-806)
 };
 
 struct KnnBatch {
@@ -65,6 +66,8 @@ struct KnnWork {
 int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
                              KnnWork &work, cudaStream_t st, int *launches, int fit = 0);
 
+// fit = 2 / 3: the scan-to-map flavours of PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:514-606 surf with the
+// sign-normalised coefficient and intensity = s |pd2|; :381-512 corner with ONE feature per line, intensity = s ld2).
 // fit = 0: point-to-plane (surf branch); fit = 1: point-to-line (USE_CORNER branch, Estimator.cc:1101-1227), which
 // emits two consecutive half-weight features per accepted query (out buffers sized 2 x queries).
 // Estimator::CalculateFeatures (Estimator.cc:970-1097) for one frame.  Appends to `out` starting at
@@ -72,6 +75,6 @@ int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_
 // when non-null and *done_flag != 0 the launch is a no-op (used by the LaserOdom iteration chain).
 int calculate_features_dev(const CellHash &h, const float4 *map, const float4 *surf, const int *nsurf_dev, int nsurf_max,
                            const TransformF *tf_dev, float min_match_sq_dis, float min_plane_dis, FeatureOut out, int append,
-                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches, int fit = 0);
+                           const int *done_flag, KnnWork &work, cudaStream_t st, int *launches, int fit = 0, const float *zaxis_dev = nullptr);
 
 }  // namespace lio

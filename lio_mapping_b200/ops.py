@@ -77,3 +77,21 @@ def calculate_line_features(corner_map, corner, tf7, min_match_sq_dis=1.0, devic
                                                            min_match_sq_dis, pts, coef, src, C.byref(n), device),
                "lio_calculate_line_features_host")
     return pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy()
+
+
+def scan_to_map(corner_map, surf_map, corner, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, max_iter=10,
+                delta_r_abort=0.05, delta_t_abort=0.05, device: int = 0):
+    """PointMapping::OptimizeTransformTobeMapped (lio_scan_to_map_host): returns (tf7, pts, coef, src, iterations)."""
+    _lib.require_device()
+    a = [np.ascontiguousarray(x, np.float32).reshape(-1, 4) for x in (corner_map, surf_map, corner, surf)]
+    pad = [x if x.shape[0] else np.zeros((1, 4), np.float32) for x in a]
+    cap = max(a[2].shape[0] + a[3].shape[0], 1)
+    pts = np.zeros((cap, 4), np.float32)
+    coef = np.zeros((cap, 4), np.float32)
+    src = np.zeros(cap, np.int32)
+    tf = np.ascontiguousarray(tf7, np.float32).copy()
+    n, it = C.c_int(), C.c_int()
+    _lib.check(_lib.lib().lio_scan_to_map_host(pad[0], a[0].shape[0], pad[1], a[1].shape[0], pad[2], a[2].shape[0], pad[3], a[3].shape[0],
+                                               tf, min_match_sq_dis, min_plane_dis, max_iter, delta_r_abort, delta_t_abort, pts, coef, src,
+                                               C.byref(n), C.byref(it), device), "lio_scan_to_map_host")
+    return tf, pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy(), it.value

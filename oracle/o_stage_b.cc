@@ -6,6 +6,7 @@
 //   RotatePoint                         include/utils/geometry_utils.h:288-299
 //   Estimator::CalculateFeatures        src/imu_processor/Estimator.cc:970-1097
 //   Estimator::CalculateLaserOdom       src/imu_processor/Estimator.cc:1242-1359
+//   PointMapping::OptimizeTransformTobeMapped  src/point_processor/PointMapping.cc:325-753 (scan-to-map GN)
 // Eigen pieces restated in o_linalg.h (colPivHouseholderQr, SelfAdjointEigenSolver, quaternion).
 #include "o_api.h"
 #include <cmath>
@@ -250,6 +251,172 @@ void CalculateLaserOdom(const KdTree &kd, const Cloud &map, const Cloud &surf_st
     if (delta_r < cfg.delta_r_abort && delta_t < cfg.delta_t_abort) break;
   }
   if (iters_done) *iters_done = it_done;
+}
+
+// PointMapping::OptimizeTransformTobeMapped (src/point_processor/PointMapping.cc:325-753), scan-to-map 6-DoF float
+// Gauss-Newton against explicit corner / surf maps (the cube-map store that selects them is outside this operator):
+//   corner matching :381-512  (ONE feature per line: coeff = s (la, lb, lc), intensity = s ld2)
+//   surf matching   :514-606  (sign-normalised plane: coeff.intensity = s |pd2|)
+//   6x6 GN          :608-715  (rows [-w^T (R [p]x), w^T], rhs -coeff.intensity; first-iteration degeneracy projection)
+// point_on_z_axis_ is set ONCE from the initial transform (PointMapping.cc:803-806) and not moved by the iterations.
+// features_out (optional): the (point_ori, coeff) pairs of the LAST executed feature pass, corner then surf.
+void OptimizeTransformTobeMapped(const Cloud &corner_map, const Cloud &surf_map, const Cloud &corner_stack, const Cloud &surf_stack,
+                                 Transform &tobe, const StageBConfig &cfg, int *iters_done, std::vector<PointPlaneFeature> *features_out) {
+  if (iters_done) *iters_done = 0;
+  if (corner_map.size() <= 10 || surf_map.size() <= 100) return;  // :327-329
+  KdTree kd_corner, kd_surf;
+  kd_corner.Build(corner_map);
+  kd_surf.Build(surf_map);
+  PointXYZI point_on_z_axis;
+  point_on_z_axis.x = 0.0f; point_on_z_axis.y = 0.0f; point_on_z_axis.z = 10.0f; point_on_z_axis.intensity = 0.f;
+  PointAssociateToMap(point_on_z_axis, point_on_z_axis, tobe);
+  bool is_degenerate = false;
+  float matP[6][6] = {};
+  for (int a = 0; a < 6; ++a) matP[a][a] = 1.f;
+  int point_search_idx[5];
+  float point_search_sq_dis[5];
+  Cloud laser_cloud_ori, coeff_sel;
+  std::vector<int> src;
+  int it_done = 0;
+  for (size_t iter_count = 0; iter_count < (size_t)cfg.num_max_iterations; ++iter_count) {
+    it_done = (int)iter_count + 1;
+    laser_cloud_ori.clear(); coeff_sel.clear(); src.clear();
+    PointXYZI point_ori, point_sel, coeff;
+    auto in_fov = [&](const PointXYZI &ps) {
+      PointXYZI transform_pos;
+      transform_pos.x = tobe.pos.x; transform_pos.y = tobe.pos.y; transform_pos.z = tobe.pos.z;
+      float squared_side1 = SqDiff(transform_pos, ps);
+      float squared_side2 = SqDiff(point_on_z_axis, ps);
+      float check1 = 100.0f + squared_side1 - squared_side2 - 10.0f * std::sqrt(3.0f) * std::sqrt(squared_side1);
+      float check2 = 100.0f + squared_side1 - squared_side2 + 10.0f * std::sqrt(3.0f) * std::sqrt(squared_side1);
+      return check1 < 0 && check2 > 0;
+    };
+    for (size_t i = 0; i < corner_stack.size(); ++i) {
+      point_ori = corner_stack[i];
+      PointAssociateToMap(point_ori, point_sel, tobe);
+      kd_corner.Knn(point_sel, 5, point_search_idx, point_search_sq_dis);
+      if (!(point_search_sq_dis[4] < cfg.min_match_sq_dis)) continue;
+      float vc[3] = {0, 0, 0};
+      for (int j = 0; j < 5; j++) { const PointXYZI &m = corner_map[point_search_idx[j]]; vc[0] += m.x; vc[1] += m.y; vc[2] += m.z; }
+      vc[0] /= 5.0f; vc[1] /= 5.0f; vc[2] /= 5.0f;
+      float a00 = 0, a10 = 0, a20 = 0, a11 = 0, a21 = 0, a22 = 0;
+      for (int j = 0; j < 5; j++) {
+        const PointXYZI &m = corner_map[point_search_idx[j]];
+        float ax = m.x - vc[0], ay = m.y - vc[1], az = m.z - vc[2];
+        a00 += ax * ax; a10 += ax * ay; a20 += ax * az; a11 += ay * ay; a21 += ay * az; a22 += az * az;
+      }
+      float A1[9], D1[3], V1[9];
+      A1[0] = a00 / 5.0f; A1[4] = a11 / 5.0f; A1[8] = a22 / 5.0f;
+      A1[3] = A1[1] = a10 / 5.0f; A1[6] = A1[2] = a20 / 5.0f; A1[7] = A1[5] = a21 / 5.0f;
+      sym_eigen_jacobi<float>(3, A1, D1, V1);
+      if (!(D1[2] > 3 * D1[1])) continue;
+      float x1 = (float)((double)vc[0] + 0.1 * (double)V1[2]), y1 = (float)((double)vc[1] + 0.1 * (double)V1[5]),
+            z1 = (float)((double)vc[2] + 0.1 * (double)V1[8]);
+      float x2 = (float)((double)vc[0] - 0.1 * (double)V1[2]), y2 = (float)((double)vc[1] - 0.1 * (double)V1[5]),
+            z2 = (float)((double)vc[2] - 0.1 * (double)V1[8]);
+      Vec3<float> X0(point_sel.x, point_sel.y, point_sel.z), X1(x1, y1, z1), X2(x2, y2, z2);
+      Vec3<float> a012_vec = (X0 - X1).cross(X0 - X2);
+      Vec3<float> l12_vec = X1 - X2;
+      Vec3<float> ntp = l12_vec.cross(a012_vec);
+      {
+        float z = ntp.x * ntp.x + ntp.y * ntp.y + ntp.z * ntp.z;
+        if (z > 0.f) { float nn = std::sqrt(z); ntp = Vec3<float>(ntp.x / nn, ntp.y / nn, ntp.z / nn); }
+      }
+      float a012 = std::sqrt(a012_vec.x * a012_vec.x + a012_vec.y * a012_vec.y + a012_vec.z * a012_vec.z);
+      float l12 = std::sqrt(l12_vec.x * l12_vec.x + l12_vec.y * l12_vec.y + l12_vec.z * l12_vec.z);
+      float ld2 = a012 / l12;
+      float sc = 1 - 0.9f * std::fabs(ld2);
+      coeff.x = sc * ntp.x; coeff.y = sc * ntp.y; coeff.z = sc * ntp.z; coeff.intensity = sc * ld2;
+      if (sc > 0.1 && in_fov(point_sel)) { laser_cloud_ori.push_back(point_ori); coeff_sel.push_back(coeff); src.push_back((int)i); }
+    }
+    for (size_t i = 0; i < surf_stack.size(); ++i) {
+      point_ori = surf_stack[i];
+      PointAssociateToMap(point_ori, point_sel, tobe);
+      kd_surf.Knn(point_sel, 5, point_search_idx, point_search_sq_dis);
+      if (!(point_search_sq_dis[4] < cfg.min_match_sq_dis)) continue;
+      float A[5][3], B[5], X[3];
+      for (int j = 0; j < 5; j++) {
+        A[j][0] = surf_map[point_search_idx[j]].x; A[j][1] = surf_map[point_search_idx[j]].y; A[j][2] = surf_map[point_search_idx[j]].z;
+        B[j] = -1.f;
+      }
+      colpiv_householder_qr_solve<float, 5, 3>(A, B, X);
+      float pa = X[0], pb = X[1], pc = X[2], pd = 1;
+      float ps = std::sqrt(pa * pa + pb * pb + pc * pc);
+      pa /= ps; pb /= ps; pc /= ps; pd /= ps;
+      bool planeValid = true;
+      for (int j = 0; j < 5; j++) {
+        const PointXYZI &m = surf_map[point_search_idx[j]];
+        if (std::fabs(pa * m.x + pb * m.y + pc * m.z + pd) > cfg.min_plane_dis) { planeValid = false; break; }
+      }
+      if (!planeValid) continue;
+      float pd2 = pa * point_sel.x + pb * point_sel.y + pc * point_sel.z + pd;
+      float dist = std::sqrt(point_sel.x * point_sel.x + point_sel.y * point_sel.y + point_sel.z * point_sel.z);
+      float sc = 1 - 0.9f * std::fabs(pd2) / std::sqrt(dist);
+      if (pd2 > 0) { coeff.x = sc * pa; coeff.y = sc * pb; coeff.z = sc * pc; coeff.intensity = sc * pd2; }
+      else { coeff.x = -sc * pa; coeff.y = -sc * pb; coeff.z = -sc * pc; coeff.intensity = -sc * pd2; }
+      if (sc > 0.1 && in_fov(point_sel)) { laser_cloud_ori.push_back(point_ori); coeff_sel.push_back(coeff); src.push_back((int)i); }
+    }
+    const size_t n = laser_cloud_ori.size();
+    if (n < 50) continue;  // :609-611
+    Quat<float> R_SO3 = tobe.rot;
+    R_SO3.normalize();
+    float AtA[6][6] = {}, AtB[6] = {};
+    Mat3<float> Rm = tobe.rot.toRotationMatrix();
+    for (size_t i = 0; i < n; i++) {
+      Vec3<float> p(laser_cloud_ori[i].x, laser_cloud_ori[i].y, laser_cloud_ori[i].z);
+      Vec3<float> w(coeff_sel[i].x, coeff_sel[i].y, coeff_sel[i].z);
+      Mat3<float> RS = Rm * Skew(p);
+      float row[6];
+      for (int c = 0; c < 3; ++c) row[c] = -(w.x * RS(0, c) + w.y * RS(1, c) + w.z * RS(2, c));
+      row[3] = w.x; row[4] = w.y; row[5] = w.z;
+      float d2 = coeff_sel[i].intensity;
+      for (int a = 0; a < 6; ++a) {
+        for (int c = 0; c < 6; ++c) AtA[a][c] += row[a] * row[c];
+        AtB[a] += row[a] * (-d2);
+      }
+    }
+    float Aw[6][6], Bw[6], X[6];
+    for (int a = 0; a < 6; ++a) { for (int c = 0; c < 6; ++c) Aw[a][c] = AtA[a][c]; Bw[a] = AtB[a]; }
+    colpiv_householder_qr_solve<float, 6, 6>(Aw, Bw, X);
+    if (iter_count == 0) {
+      float E[6], V[36], V2[36];
+      sym_eigen_jacobi<float>(6, &AtA[0][0], E, V);
+      for (int k = 0; k < 36; ++k) V2[k] = V[k];
+      is_degenerate = false;
+      for (int i = 0; i < 6; ++i) {
+        if (E[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0; is_degenerate = true; }
+        else break;
+      }
+      for (int a = 0; a < 6; ++a)
+        for (int c = 0; c < 6; ++c) { float sm = 0; for (int k = 0; k < 6; ++k) sm += V2[a * 6 + k] * V[c * 6 + k]; matP[a][c] = sm; }
+    }
+    if (is_degenerate) {
+      float X2[6];
+      for (int a = 0; a < 6; ++a) { float sm = 0; for (int c = 0; c < 6; ++c) sm += matP[a][c] * X[c]; X2[a] = sm; }
+      for (int a = 0; a < 6; ++a) X[a] = X2[a];
+    }
+    tobe.pos.x += X[3]; tobe.pos.y += X[4]; tobe.pos.z += X[5];
+    tobe.rot = tobe.rot * DeltaQ(Vec3<float>(X[0], X[1], X[2]));
+    if (!std::isfinite(tobe.pos.x)) tobe.pos.x = 0.0f;
+    if (!std::isfinite(tobe.pos.y)) tobe.pos.y = 0.0f;
+    if (!std::isfinite(tobe.pos.z)) tobe.pos.z = 0.0f;
+    float ad = R_SO3.angularDistance(tobe.rot);
+    float delta_r = (float)(ad * 180.0 / M_PI);
+    float delta_t = std::sqrt(std::pow(X[3] * 100, 2) + std::pow(X[4] * 100, 2) + std::pow(X[5] * 100, 2));
+    if (delta_r < cfg.delta_r_abort && delta_t < cfg.delta_t_abort) break;
+  }
+  if (iters_done) *iters_done = it_done;
+  if (features_out) {
+    features_out->clear();
+    for (size_t i = 0; i < laser_cloud_ori.size(); ++i) {
+      PointPlaneFeature f;
+      f.score = 0;
+      f.point[0] = laser_cloud_ori[i].x; f.point[1] = laser_cloud_ori[i].y; f.point[2] = laser_cloud_ori[i].z;
+      f.coeffs[0] = coeff_sel[i].x; f.coeffs[1] = coeff_sel[i].y; f.coeffs[2] = coeff_sel[i].z; f.coeffs[3] = coeff_sel[i].intensity;
+      f.src_index = src[i];
+      features_out->push_back(f);
+    }
+  }
 }
 
 }  // namespace orc

@@ -157,3 +157,51 @@ def test_calculate_line_features_edge_cases(oracle):
         pg, cg, sg = ops.calculate_line_features(m, q, tf7)
         assert np.array_equal(sg, so) and np.array_equal(pg, po) and np.array_equal(cg, co)
     assert ops.calculate_line_features(line, np.zeros((0, 4), np.float32), tf7)[0].shape == (0, 4)
+
+
+@pytest.mark.parametrize("kind", ["vlp16", "hdl64"])
+def test_scan_to_map_parity(oracle, kind):
+    """PointMapping::OptimizeTransformTobeMapped: corner + surf matching and the 6-DoF float GN, device vs oracle.
+    Round 1 works on identical inputs (bit-exact matches); later rounds inherit the last-ulp difference of the 6x6
+    reduction order (double tree vs sequential float), so the pose is compared at 2e-5."""
+    from lio_mapping_b200 import ops
+    sensor, sc, poses = helpers.frame_clouds(oracle, kind, 4)
+    _, cc, _ = helpers.frame_clouds(oracle, kind, 4, which="less_sharp", leaf=0.2)
+    smap = helpers.build_map(oracle, sc, poses)
+    cmap = helpers.build_map(oracle, cc, poses, leaf=0.2)
+    _, _, tf7 = helpers.rel_transform(poses[0], poses[3])
+    tf0 = tf7.copy()
+    tf0[4:] += np.array([0.05, -0.04, 0.02], np.float32)
+    # one round: identical matches, in the reference's order (corner block then surf block)
+    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, cc[3], sc[3], tf0, max_iter=1)
+    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, cc[3], sc[3], tf0, max_iter=1)
+    assert itg == ito == 1
+    assert np.array_equal(sg, so) and np.array_equal(pg[:, :3], po[:, :3]) and np.array_equal(cg, co)
+    assert np.allclose(tg, to, atol=2e-6, rtol=0)
+    # full loop
+    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, cc[3], sc[3], tf0)
+    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, cc[3], sc[3], tf0)
+    assert itg == ito and 2 <= ito <= 10
+    assert np.allclose(tg, to, atol=2e-5, rtol=0)
+    assert np.linalg.norm(tg[4:] - tf7[4:]) < 0.5 * np.linalg.norm(tf0[4:] - tf7[4:])
+    assert abs(sg.shape[0] - so.shape[0]) <= max(2, so.shape[0] // 2000)
+
+
+def test_scan_to_map_guards(oracle):
+    """Map-size guard (PointMapping.cc:327-329) and the < 50 matches `continue` (:609-611): the pose is left untouched."""
+    from lio_mapping_b200 import ops
+    sensor, sc, poses = helpers.frame_clouds(oracle, "vlp16", 3)
+    _, cc, _ = helpers.frame_clouds(oracle, "vlp16", 3, which="less_sharp", leaf=0.2)
+    smap = helpers.build_map(oracle, sc, poses)
+    cmap = helpers.build_map(oracle, cc, poses, leaf=0.2)
+    tf0 = np.array([0, 0, 0, 1, 0.1, 0.2, 0.3], np.float32)
+    for cm, sm_ in ((cmap[:10], smap), (cmap, smap[:100])):
+        tg, pg, cg, sg, itg = ops.scan_to_map(cm, sm_, cc[2], sc[2], tf0)
+        to, po, co, so, ito = oracle.scan_to_map(cm, sm_, cc[2], sc[2], tf0)
+        assert np.array_equal(tg, tf0) and np.array_equal(to, tf0) and itg == ito == 0
+    # queries far from the map: no matches in any round -> 10 skipped rounds, pose unchanged
+    far = sc[2].copy(); far[:, :3] += 500.0
+    farc = cc[2].copy(); farc[:, :3] += 500.0
+    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, farc, far, tf0)
+    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, farc, far, tf0)
+    assert np.array_equal(tg, tf0) and np.array_equal(to, tf0) and itg == ito == 10 and sg.shape[0] == so.shape[0] == 0
