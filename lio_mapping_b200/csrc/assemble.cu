@@ -25,10 +25,11 @@ __device__ __forceinline__ float4 ld_stream(const float4 *p) {
   return v;
 }
 
-__device__ __forceinline__ void accumulate(double (&acc)[29], const double (&R)[9], const double (&t)[3], float4 pf, float4 cf) {
+// One feature: u = [a; p x a; r] with a = R^T w, r = a.(p + t) + b, and s = 1 + r^2.  Branch-free, so that the
+// kAsmPerThread features a thread handles per stage interleave (the chain a -> r -> s -> 1/s is latency bound otherwise).
+__device__ __forceinline__ void feature_terms(const double (&R)[9], const double (&t)[3], float4 pf, float4 cf, double (&u)[7], double &s) {
   const double px = pf.x, py = pf.y, pz = pf.z;
   const double wx = cf.x, wy = cf.y, wz = cf.z, b = cf.w;
-  double u[7];
   // a = R^T w
   u[0] = R[0] * wx + R[3] * wy + R[6] * wz;
   u[1] = R[1] * wx + R[4] * wy + R[7] * wz;
@@ -39,23 +40,12 @@ __device__ __forceinline__ void accumulate(double (&acc)[29], const double (&R)[
   u[5] = px * u[1] - py * u[0];
   // r = a.(p + t) + b
   u[6] = u[0] * (px + t[0]) + u[1] * (py + t[1]) + u[2] * (pz + t[2]) + b;
-  const double x = u[6] * u[6];
-  const double s = 1.0 + x;
-  const double c = 1.0 / s;  // rho'
-  // rho = log(1 + x): residuals are centimetres, so x is almost always < 1/16 where a 14-term alternating
-  // series (Horner, |err| < x^15/15 < 6e-20) replaces the library log (~3x fewer fp64 instructions)
-  double rho;
-  if (x < 0.0625) {
-    double p = -1.0 / 14.0;
-    p = fma(p, x, 1.0 / 13.0); p = fma(p, x, -1.0 / 12.0); p = fma(p, x, 1.0 / 11.0); p = fma(p, x, -1.0 / 10.0);
-    p = fma(p, x, 1.0 / 9.0); p = fma(p, x, -1.0 / 8.0); p = fma(p, x, 1.0 / 7.0); p = fma(p, x, -1.0 / 6.0);
-    p = fma(p, x, 1.0 / 5.0); p = fma(p, x, -1.0 / 4.0); p = fma(p, x, 1.0 / 3.0); p = fma(p, x, -0.5);
-    p = fma(p, x, 1.0);
-    rho = p * x;
-  } else {
-    rho = log(s);
-  }
-  acc[28] += rho;
+  s = 1.0 + u[6] * u[6];
+}
+
+// acc[0..27] += rho' [g;r][g;r]^T (upper triangle, row-major), rho' = 1/s
+__device__ __forceinline__ void accumulate_outer(double (&acc)[29], const double (&u)[7], double s) {
+  const double c = 1.0 / s;
   int k = 0;
 #pragma unroll
   for (int i = 0; i < 7; ++i) {
@@ -65,12 +55,24 @@ __device__ __forceinline__ void accumulate(double (&acc)[29], const double (&R)[
   }
 }
 
+// rho = log(1 + x) = log(s).  Residuals are centimetres, so x is almost always tiny: instead of one log per feature the
+// thread keeps the running PRODUCT of s (one DMUL, no dependency chain) and takes a single log when it folds (sum of
+// logs == log of the product; relative error <= n ulp on the product, i.e. <= n 2^-53 absolute on rho).  Large
+// residuals go through log directly so the product stays far from overflow (< 1.0625^kAsmFold).
+__device__ __forceinline__ void accumulate_rho(double (&acc)[29], double &prod, double s) {
+  const bool big = s >= 1.0625;
+  prod *= big ? 1.0 : s;
+  if (big) acc[28] += log(s);
+}
+
 // ---- TMA (bulk async copy) staging ---------------------------------------------------------------
 // The feature stream is staged through shared memory by the TMA unit: one elected thread arms an mbarrier
 // with the byte count and issues two cp.async.bulk (point tile + plane tile, 16 B aligned, contiguous 1-D:
 // no tensor map needed); all threads wait on the barrier phase, consume their float4s from shared memory and
 // hand the stage back with a CTA barrier.  kAsmStages tiles are in flight per CTA.
-constexpr int kAsmChunk = kAsmThreads;  // features per stage (one per thread)
+constexpr int kAsmPerThread = 2;                       // independent features a thread consumes per stage (ILP)
+constexpr int kAsmChunk = kAsmThreads * kAsmPerThread;  // features per stage
+constexpr int kAsmFold = 2048;                          // features per thread between folds of the (1 + x) product
 constexpr int kAsmStages = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -96,11 +98,12 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
   }
 }
 
-__global__ void __launch_bounds__(kAsmThreads)
+__global__ void __launch_bounds__(kAsmThreads, 2)
 asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ partial, double *__restrict__ out,
         unsigned *__restrict__ counter) {
-  __shared__ __align__(128) float4 s_pts[kAsmStages][kAsmChunk];
-  __shared__ __align__(128) float4 s_coef[kAsmStages][kAsmChunk];
+  extern __shared__ __align__(128) unsigned char asm_smem[];  // kAsmStages x (point tile | plane tile)
+  float4 (*s_pts)[kAsmChunk] = reinterpret_cast<float4 (*)[kAsmChunk]>(asm_smem);
+  float4 (*s_coef)[kAsmChunk] = reinterpret_cast<float4 (*)[kAsmChunk]>(asm_smem + sizeof(float4) * kAsmStages * kAsmChunk);
   __shared__ __align__(8) unsigned long long full_bar[kAsmStages];
   __shared__ double sred[kAsmThreads / 32][29];
   __shared__ bool is_last;
@@ -117,6 +120,7 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   double acc[29];
 #pragma unroll
   for (int k = 0; k < 29; ++k) acc[k] = 0.0;
+  double prod = 1.0;
   const int begin = (tile - F.tile0) * P.tile_feats;
   const int end = min(begin + P.tile_feats, F.n);
   const int nchunks = (end > begin) ? (end - begin + kAsmChunk - 1) / kAsmChunk : 0;
@@ -138,11 +142,26 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   for (int k = 0; k < nchunks; ++k) {
     const int s = k % kAsmStages;
     mbar_wait(&full_bar[s], (unsigned)((k / kAsmStages) & 1));
-    const int i = begin + k * kAsmChunk + threadIdx.x;
-    if (i < end) accumulate(acc, R, t, s_pts[s][threadIdx.x], s_coef[s][threadIdx.x]);
+    {
+      double u[kAsmPerThread][7], sv[kAsmPerThread];
+#pragma unroll
+      for (int j = 0; j < kAsmPerThread; ++j) {
+        const int li = j * kAsmThreads + threadIdx.x;
+        const bool ok = begin + k * kAsmChunk + li < end;   // past the end: all-zero feature (u = 0, s = 1) contributes nothing
+        float4 pf = s_pts[s][li], cf = s_coef[s][li];
+        if (!ok) { pf = make_float4(0.f, 0.f, 0.f, 0.f); cf = pf; }
+        feature_terms(R, t, pf, cf, u[j], sv[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < kAsmPerThread; ++j) accumulate_outer(acc, u[j], sv[j]);
+#pragma unroll
+      for (int j = 0; j < kAsmPerThread; ++j) accumulate_rho(acc, prod, sv[j]);
+    }
+    if (((k + 1) * kAsmPerThread) % kAsmFold == 0) { acc[28] += log(prod); prod = 1.0; }
     __syncthreads();  // stage s fully consumed
     if (threadIdx.x == 0 && k + kAsmStages < nchunks) issue(k + kAsmStages);
   }
+  acc[28] += log(prod);
   // warp reduce-scatter: each level halves the values a lane owns (30 shuffles instead of 29 x 5)
   {
     const unsigned lane = lane_id();
@@ -240,7 +259,15 @@ void asm_plan(AsmParams &p, int sm_count) {
 int asm_launch(const AsmParams &p, const double *Rt_dev, AsmWork &work, cudaStream_t st, int *launches) {
   if (p.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
   if (p.nframes <= 0) return LIO_OK;
-  asm_ppp<<<p.ntiles, kAsmThreads, 0, st>>>(p, Rt_dev, work.partial, work.out, work.counter);
+  constexpr size_t kSmem = 2 * sizeof(float4) * kAsmStages * kAsmChunk;
+  static bool attr_set[64] = {};  // per device: the opt-in above 48 KB is a per-context function attribute
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaFuncSetAttribute(asm_ppp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    attr_set[dev & 63] = true;
+  }
+  asm_ppp<<<p.ntiles, kAsmThreads, kSmem, st>>>(p, Rt_dev, work.partial, work.out, work.counter);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }

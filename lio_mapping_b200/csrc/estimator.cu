@@ -9,7 +9,10 @@
 //   SlideWindow :2570-2666                  -> slide_window
 // There is no CPU path for the per-point work: without a CUDA device create() fails.
 #include "assemble.cuh"
-#include <future>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include "factors_host.h"
 #include "factors_impl.h"
 #include "knn.cuh"
@@ -342,12 +345,54 @@ struct MargJob {
   Vec b;
   std::vector<double> x0_pose, x0_sb;
   double x0_ex[7];
-  std::future<MargPrior> fut;
+  MargPrior result;
+};
+
+// One persistent helper thread per estimator context (created on first use): starting a std::thread per scan costs
+// ~0.1 ms on the bench host, a condition-variable hand-off a few microseconds.
+struct Worker {
+  std::thread th;
+  std::mutex mu;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, busy = false, quit = false, started = false;
+  void submit(std::function<void()> f) {
+    std::unique_lock<std::mutex> lk(mu);
+    if (!started) { started = true; th = std::thread([this]() { loop(); }); }
+    job = std::move(f);
+    has_job = true; busy = true;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [this]() { return !busy; });
+  }
+  void loop() {
+    std::unique_lock<std::mutex> lk(mu);
+    while (true) {
+      cv.wait(lk, [this]() { return has_job || quit; });
+      if (quit) return;
+      std::function<void()> f = std::move(job);
+      has_job = false;
+      lk.unlock();
+      f();
+      lk.lock();
+      busy = false;
+      cv.notify_all();
+    }
+  }
+  ~Worker() {
+    if (started) {
+      { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [this]() { return !busy; }); quit = true; cv.notify_all(); }
+      th.join();
+    }
+  }
 };
 
 struct lio_est {
   lio_est_config cfg;
   MargJob mjob;
+  Worker worker;
   double t_marg_wait = 0;
   int W = 0, O = 0, device = 0;
   cudaStream_t stream = 0;
@@ -497,7 +542,7 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
 
 extern "C" int lio_est_destroy(lio_est *e) {
   if (!e) return LIO_OK;
-  if (e->mjob.running) { e->mjob.fut.wait(); e->mjob.running = false; }
+  if (e->mjob.running) { e->worker.wait(); e->mjob.running = false; }
   cudaSetDevice(e->device);
   for (float4 *p : e->slot_ptr) if (p) cudaFree(p);
   for (FeatureOut &f : e->feats) { if (f.pts) cudaFree(f.pts); if (f.coef) cudaFree(f.coef); if (f.src) cudaFree(f.src); }
@@ -1029,6 +1074,7 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
 }
 
 static void prior_join(lio_est *e);
+static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, std::vector<double> x0_sb, const double *x0_ex);
 // ---- marginalisation (MarginalizationInfo::PreMarginalize / Marginalize, MarginalizationFactor.cc:132-311)
 static int marginalize(lio_est *e) {
   const int O = e->O, pivot = e->W - O;
@@ -1081,7 +1127,10 @@ static int marginalize(lio_est *e) {
   }
   std::memcpy(job.x0_ex, e->para_ex, sizeof(job.x0_ex));
   job.stashed = true;
-  if (!e->cfg.overlap_marginalization) prior_join(e);
+  if (!e->cfg.overlap_marginalization) {  // the reference's order: finish the algebra before returning from this scan
+    job.stashed = false;
+    e->prior = marg_algebra(std::move(job.A), std::move(job.b), job.O, std::move(job.x0_pose), std::move(job.x0_sb), job.x0_ex);
+  }
   return LIO_OK;
 }
 
@@ -1111,7 +1160,7 @@ static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, 
   }
   Vec ev2;
   Mat V2;
-  sym_eigen(A2, ev2, V2);
+  sym_eigen(A2, ev2, V2, 1);  // threads > 1 measured slower on the bench host (thread start-up ~0.1 ms each)
   MargPrior np;
   np.valid = true;
   np.n = nr;
@@ -1140,8 +1189,8 @@ static void marg_start(lio_est *e) {
   if (!job.stashed || job.running) return;
   job.stashed = false;
   job.running = true;
-  job.fut = std::async(std::launch::async, [&job]() {
-    return marg_algebra(std::move(job.A), std::move(job.b), job.O, std::move(job.x0_pose), std::move(job.x0_sb), job.x0_ex);
+  e->worker.submit([&job]() {
+    job.result = marg_algebra(std::move(job.A), std::move(job.b), job.O, std::move(job.x0_pose), std::move(job.x0_sb), job.x0_ex);
   });
 }
 
@@ -1151,7 +1200,8 @@ static void prior_join(lio_est *e) {
   if (job.stashed) marg_start(e);
   if (!job.running) return;
   const double t0 = now_s();
-  e->prior = job.fut.get();
+  e->worker.wait();
+  e->prior = std::move(job.result);
   job.running = false;
   e->t_marg_wait += now_s() - t0;
 }

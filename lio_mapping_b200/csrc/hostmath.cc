@@ -2,6 +2,7 @@
 // All inner loops are stride-1 (right-looking Cholesky on rows, column-major eigen-solver) and the hot
 // functions are multiversioned (x86-64-v3 = AVX2+FMA when the CPU has it, baseline otherwise).
 #include "hostmath.h"
+#include <thread>
 
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
 #define LIO_MV __attribute__((target_clones("arch=x86-64-v4", "arch=x86-64-v3", "default")))
@@ -142,7 +143,72 @@ LIO_MV void cholesky_solve(const Mat &L, Vec &b) {
 
 // Householder tridiagonalisation + implicit-shift QL with accumulated transformations (EISPACK
 // tred2/tql2), on column-major storage: z(i,j) = Zt[j*n + i], so every inner loop walks a column.
-LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
+// Applies the recorded QL plane rotations to the rows [k0, k1) of Z (column-major: Zt[j * n + k]).  Rows are independent,
+// so the range is cut into chunks of KC rows that stay in L1 while ALL sweeps run over them; within a sweep the column
+// shared by two successive rotations is carried in registers (one load + one store per element and rotation).
+LIO_MV static void ql_apply_rows(double *Zt, int n, const double *rc, const double *rs, const std::vector<int> &sw_l,
+                                 const std::vector<int> &sw_m, const std::vector<long long> &sw_off, int k0, int k1) {
+  constexpr int KC = 32;
+  const size_t ns = sw_l.size();
+  for (int kb = k0; kb < k1; kb += KC) {
+    const int kc = std::min(KC, k1 - kb);
+    for (size_t sidx = 0; sidx < ns; ++sidx) {
+      const int l = sw_l[sidx], m = sw_m[sidx];
+      const double *c = rc + sw_off[sidx], *s = rs + sw_off[sidx];
+      double carry[KC];
+      const double *cm = Zt + (size_t)m * n + kb;
+      if (kc == KC) {
+        for (int k = 0; k < KC; ++k) carry[k] = cm[k];
+        for (int i = m - 1; i >= l; --i) {
+          const double ci = c[i], si = s[i];
+          const double *ca = Zt + (size_t)i * n + kb;
+          double *cb = Zt + (size_t)(i + 1) * n + kb;
+#pragma omp simd
+          for (int k = 0; k < KC; ++k) {
+            const double ha = ca[k], hb = carry[k];
+            cb[k] = si * ha + ci * hb;
+            carry[k] = ci * ha - si * hb;
+          }
+        }
+        double *cl = Zt + (size_t)l * n + kb;
+        for (int k = 0; k < KC; ++k) cl[k] = carry[k];
+      } else {
+        for (int k = 0; k < kc; ++k) carry[k] = cm[k];
+        for (int i = m - 1; i >= l; --i) {
+          const double ci = c[i], si = s[i];
+          const double *ca = Zt + (size_t)i * n + kb;
+          double *cb = Zt + (size_t)(i + 1) * n + kb;
+          for (int k = 0; k < kc; ++k) {
+            const double ha = ca[k], hb = carry[k];
+            cb[k] = si * ha + ci * hb;
+            carry[k] = ci * ha - si * hb;
+          }
+        }
+        double *cl = Zt + (size_t)l * n + kb;
+        for (int k = 0; k < kc; ++k) cl[k] = carry[k];
+      }
+    }
+  }
+}
+
+static void ql_apply(double *Zt, int n, const double *rc, const double *rs, const std::vector<int> &sw_l, const std::vector<int> &sw_m,
+                     const std::vector<long long> &sw_off, int threads) {
+  const int chunks = (n + 31) / 32;
+  threads = std::max(1, std::min(threads, chunks));
+  if (threads == 1) { ql_apply_rows(Zt, n, rc, rs, sw_l, sw_m, sw_off, 0, n); return; }
+  std::vector<std::thread> pool;
+  int k0 = 0;
+  for (int t = 0; t < threads; ++t) {
+    const int nch = chunks / threads + (t < chunks % threads ? 1 : 0);
+    const int k1 = std::min(n, k0 + 32 * nch);
+    if (t + 1 < threads) pool.emplace_back([=, &sw_l, &sw_m, &sw_off]() { ql_apply_rows(Zt, n, rc, rs, sw_l, sw_m, sw_off, k0, k1); });
+    else ql_apply_rows(Zt, n, rc, rs, sw_l, sw_m, sw_off, k0, k1);
+    k0 = k1;
+  }
+  for (auto &th : pool) th.join();
+}
+
+LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout, int threads) {
   const int n = A.r;
   d.assign(n, 0.0);
   Zout = Mat(n, n);
@@ -219,7 +285,10 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
   e[n - 1] = 0.0;
   double f = 0.0, tst1 = 0.0;
   const double eps = 2.220446049250313e-16;
-  Vec rc(n, 0.0), rs(n, 0.0);
+  Vec rc, rs;                       // recorded rotations of every QL sweep
+  std::vector<int> sw_l, sw_m;
+  std::vector<long long> sw_off;
+  rc.reserve((size_t)n * n); rs.reserve((size_t)n * n);
   for (int l = 0; l < n; ++l) {
     tst1 = std::max(tst1, std::fabs(d[l]) + std::fabs(e[l]));
     int m = l;
@@ -239,7 +308,11 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
         p = d[m];
         double c = 1.0, c2 = 1.0, c3 = 1.0, s = 0.0, s2 = 0.0;
         const double el1 = e[l + 1];
-        // scalar QL recurrence first (it does not read Z) ...
+        // scalar QL recurrence only (it never reads Z): the plane rotations (i, i+1), i = m-1 .. l, are recorded and
+        // applied to Z after the whole spectrum is known (ql_apply below)
+        sw_l.push_back(l); sw_m.push_back(m); sw_off.push_back((long long)rc.size() - l);  // rc[off + i] is rotation i
+        rc.resize(rc.size() + (size_t)(m - l)); rs.resize(rc.size());
+        double *rcp = rc.data() + sw_off.back(), *rsp = rs.data() + sw_off.back();
         for (int i = m - 1; i >= l; --i) {
           c3 = c2; c2 = c; s2 = s;
           g = c * e[i];
@@ -250,45 +323,7 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
           c = p / r;
           p = c * d[i] - s * g;
           d[i + 1] = h + s * (c * g + s * d[i]);
-          rc[i] = c; rs[i] = s;
-        }
-        // ... then the plane rotations (i, i+1), i = m-1 .. l, applied to Z in row chunks: the column shared by two
-        // successive rotations is carried in registers, so each element is loaded and stored once per rotation
-        constexpr int KC = 32;
-        int k0 = 0;
-        for (; k0 + KC <= n; k0 += KC) {
-          double carry[KC];
-          const double *cm = col(m) + k0;
-          for (int k = 0; k < KC; ++k) carry[k] = cm[k];
-          for (int i = m - 1; i >= l; --i) {
-            const double ci = rc[i], si = rs[i];
-            double *ca = col(i) + k0, *cb = col(i + 1) + k0;
-#pragma omp simd
-            for (int k = 0; k < KC; ++k) {
-              const double ha = ca[k], hb = carry[k];
-              cb[k] = si * ha + ci * hb;
-              carry[k] = ci * ha - si * hb;
-            }
-          }
-          double *cl = col(l) + k0;
-          for (int k = 0; k < KC; ++k) cl[k] = carry[k];
-        }
-        if (k0 < n) {
-          const int kc = n - k0;
-          double carry[KC];
-          const double *cm = col(m) + k0;
-          for (int k = 0; k < kc; ++k) carry[k] = cm[k];
-          for (int i = m - 1; i >= l; --i) {
-            const double ci = rc[i], si = rs[i];
-            double *ca = col(i) + k0, *cb = col(i + 1) + k0;
-            for (int k = 0; k < kc; ++k) {
-              const double ha = ca[k], hb = carry[k];
-              cb[k] = si * ha + ci * hb;
-              carry[k] = ci * ha - si * hb;
-            }
-          }
-          double *cl = col(l) + k0;
-          for (int k = 0; k < kc; ++k) cl[k] = carry[k];
+          rcp[i] = c; rsp[i] = s;
         }
         p = -s * s2 * c3 * el1 * e[l] / dl1;
         e[l] = s * p;
@@ -299,6 +334,7 @@ LIO_MV void sym_eigen(const Mat &A, Vec &d, Mat &Zout) {
     d[l] += f;
     e[l] = 0.0;
   }
+  ql_apply(Zt.data(), n, rc.data(), rs.data(), sw_l, sw_m, sw_off, threads);
   std::vector<int> idx(n);
   for (int i = 0; i < n; ++i) idx[i] = i;
   std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return d[a] < d[b]; });

@@ -153,7 +153,9 @@ inline double vnorm(const Vec &a) { return std::sqrt(vdot(a, a)); }
 bool cholesky(Mat &a);
 void cholesky_solve(const Mat &L, Vec &b);
 // symmetric eigen-decomposition (ascending eigenvalues, eigenvectors in columns)
-void sym_eigen(const Mat &A, Vec &evals, Mat &evecs);
+// threads > 1: the QL rotations are applied to disjoint row ranges of the eigenvector matrix by that many threads
+// (same arithmetic per element, bit-identical to threads = 1).
+void sym_eigen(const Mat &A, Vec &evals, Mat &evecs, int threads = 1);
 // H(cm[a], cm[b]) += sum_k J[k][a] J[k][b];  g[cm[a]] += sum_k J[k][a] r[k]   (J: rows x cols row-major, cm: column map)
 void add_JtJ_mapped(const double *J, const double *r, int rows, int cols, const int *cm, Mat &H, Vec &g);
 // y = A x (multiversioned)

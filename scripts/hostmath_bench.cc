@@ -1,5 +1,5 @@
 // Micro-benchmark of the host shell's dense kernels at the solver's sizes (n = 15 (O+1) [+6]).
-// build: g++ -O3 -std=c++17 -fopenmp-simd -I lio_mapping_b200/csrc scripts/hostmath_bench.cc lio_mapping_b200/csrc/hostmath.cc -o /tmp/hm_bench
+// build: g++ -O3 -std=c++17 -fopenmp-simd -pthread -I lio_mapping_b200/csrc scripts/hostmath_bench.cc lio_mapping_b200/csrc/hostmath.cc -o /tmp/hm_bench
 #include <chrono>
 #include <cstdio>
 #include <random>
@@ -32,9 +32,13 @@ int main(int argc, char **argv) {
   for (int r = 0; r < reps; ++r) { Vec y = mul(H, g); acc += y[3]; }
   double t_mul = (now() - t0) / reps;
   Vec d; Mat Z;
-  t0 = now();
-  for (int r = 0; r < 20; ++r) { sym_eigen(H, d, Z); acc += d[0]; }
-  double t_eig = (now() - t0) / 20;
+  double t_eig = 0;
+  for (int th : {4, 2, 1}) {
+    t0 = now();
+    for (int r = 0; r < 20; ++r) { sym_eigen(H, d, Z, th); acc += d[0]; }
+    t_eig = (now() - t0) / 20;
+    printf("sym_eigen n=%d threads=%d: %.1f us\n", n, th, t_eig * 1e6);
+  }
   printf("n=%d copy %.1f us  chol %.1f us  trisolve %.1f us  matvec %.1f us  mul %.1f us  sym_eigen %.1f us  (%g)\n", n, t_copy * 1e6, t_chol * 1e6,
          t_solve * 1e6, t_mv * 1e6, t_mul * 1e6, t_eig * 1e6, acc);
   return 0;
