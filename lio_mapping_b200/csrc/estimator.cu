@@ -393,6 +393,7 @@ struct lio_est {
   lio_est_config cfg;
   MargJob mjob;
   Worker worker;
+  struct ImuBlockStore { double JtJ[30 * 30], Jtr[30], cost; bool used; } imu_blocks_store[kMaxOpt];
   double t_marg_wait = 0;
   int W = 0, O = 0, device = 0;
   cudaStream_t stream = 0;
@@ -1008,13 +1009,36 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
   if (eval_lidar_launch(e, ft) != LIO_OK) return false;  // the device reduces the lidar factors while the host does the rest
   const double th0 = now_s();
   double cp = 0, ci = 0, cm = 0;
+  // ImuFactors: the upper half of the window is evaluated by the context's helper thread into private 30x30 blocks
+  // (adjacent factors overlap in H), the lower half directly into H on this thread; the blocks are added after the
+  // prior, right before the device result is needed.
+  typedef lio_est::ImuBlockStore ImuBlock;
+  ImuBlock *blk = e->imu_blocks_store;
+  const int i_split = (e->cfg.imu_factor && O >= 4) ? O / 2 : O;
+  auto imu_eval = [&](int i, double *r, double (*J)[30]) {
+    Preintegration &pim = *e->pre[pivot + i + 1];
+    if (pim.sum_dt > 10.0) return false;
+    imu_factor_evaluate30(pim, e->para_pose[i].data(), e->para_sb[i].data(), e->para_pose[i + 1].data(), e->para_sb[i + 1].data(), r, J);
+    return true;
+  };
+  if (e->cfg.imu_factor && i_split < O) {
+    e->worker.submit([&, i_split]() {
+      for (int i = i_split; i < O; ++i) {
+        double r[15], J[15][30];
+        ImuBlock &b = blk[i];
+        b.used = imu_eval(i, r, J);
+        if (!b.used) continue;
+        JtJ_dense(&J[0][0], r, 15, 30, b.JtJ, b.Jtr);
+        double sq = 0;
+        for (int k = 0; k < 15; ++k) sq += r[k] * r[k];
+        b.cost = 0.5 * sq;
+      }
+    });
+  }
   if (e->cfg.imu_factor) {
-    for (int i = 0; i < O; ++i) {
-      const int j = i + 1;
-      Preintegration &pim = *e->pre[pivot + j];
-      if (pim.sum_dt > 10.0) continue;
+    for (int i = 0; i < i_split; ++i) {
       double r[15], J[15][30];
-      imu_factor_evaluate30(pim, e->para_pose[i].data(), e->para_sb[i].data(), e->para_pose[j].data(), e->para_sb[j].data(), r, J);
+      if (!imu_eval(i, r, J)) continue;
       int cmap[30];
       for (int a = 0; a < 30; ++a) cmap[a] = 15 * i + a;  // pose_i, sb_i, pose_j, sb_j are contiguous in the tangent layout
       add_JtJ_mapped(&J[0][0], r, 15, 30, cmap, H, g);
@@ -1040,6 +1064,20 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
       const int nw = 15 * O;  // window part maps one to one
       for (int b = 0; b < nw; ++b) hrow[b] += row[b];
       if (ex_free) for (int b = nw; b < pr.n; ++b) hrow[15 * (O + 1) + (b - nw)] += row[b];
+    }
+  }
+  if (e->cfg.imu_factor && i_split < O) {
+    e->worker.wait();
+    for (int i = i_split; i < O; ++i) {
+      const ImuBlock &b = blk[i];
+      if (!b.used) continue;
+      for (int a = 0; a < 30; ++a) {
+        double *hrow = &H.d[(size_t)(15 * i + a) * n + 15 * i];
+        const double *src = b.JtJ + 30 * a;
+        for (int c = 0; c < 30; ++c) hrow[c] += src[c];
+        g[15 * i + a] += b.Jtr[a];
+      }
+      ci += b.cost;
     }
   }
   double cprior = 0;

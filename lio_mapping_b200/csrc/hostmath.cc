@@ -36,8 +36,75 @@ static inline bool chol_diag(double *A, int n, int k0, int k1) {
   return true;
 }
 
+
+// Trailing update of the blocked Cholesky: C[i][j] -= sum_k P[i][k] P[j][k] for i0 <= j <= i < n, with the panel P (rows
+// i0.., columns kb..kb+nb of A) read row-wise for the left factor and through its transposed copy PT (nb x m) for the
+// right one.  Register tile: 4 rows x (2 vectors) columns; tiles that straddle the diagonal also write above it.
+#define LIO_TRAIL_BODY(VT, VTU, VW)                                                                                     \
+  for (int i = i0; i < n; i += 4) {                                                                                    \
+    const int rows = std::min(4, n - i), jmax = i + rows - 1;                                                          \
+    for (int jb = i0; jb <= jmax; jb += 2 * VW) {                                                                      \
+      const int w = std::min(2 * VW, n - jb);                                                                          \
+      if (rows == 4 && w == 2 * VW) {                                                                                  \
+        VT c00 = {}, c01 = {}, c10 = {}, c11 = {}, c20 = {}, c21 = {}, c30 = {}, c31 = {};                               \
+        const double *p0 = A + (size_t)i * n + kb, *p1 = p0 + n, *p2 = p1 + n, *p3 = p2 + n;                            \
+        const double *pt = PT + (jb - i0);                                                                             \
+        for (int k = 0; k < nb; ++k, pt += m) {                                                                        \
+          const VT b0 = *(const VTU *)pt, b1 = *(const VTU *)(pt + VW);                                                \
+          const double a0 = p0[k], a1 = p1[k], a2 = p2[k], a3 = p3[k];                                                 \
+          c00 += a0 * b0; c01 += a0 * b1;                                                                              \
+          c10 += a1 * b0; c11 += a1 * b1;                                                                              \
+          c20 += a2 * b0; c21 += a2 * b1;                                                                              \
+          c30 += a3 * b0; c31 += a3 * b1;                                                                              \
+        }                                                                                                              \
+        double *r0 = A + (size_t)i * n + jb, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n;                                  \
+        *(VTU *)r0 -= c00; *(VTU *)(r0 + VW) -= c01;                                                                   \
+        *(VTU *)r1 -= c10; *(VTU *)(r1 + VW) -= c11;                                                                   \
+        *(VTU *)r2 -= c20; *(VTU *)(r2 + VW) -= c21;                                                                   \
+        *(VTU *)r3 -= c30; *(VTU *)(r3 + VW) -= c31;                                                                   \
+      } else {                                                                                                         \
+        for (int r = 0; r < rows; ++r) {                                                                               \
+          const double *pr = A + (size_t)(i + r) * n + kb;                                                             \
+          double *cr = A + (size_t)(i + r) * n + jb;                                                                   \
+          for (int cidx = 0; cidx < w; ++cidx) {                                                                       \
+            const double *pt = PT + (jb - i0) + cidx;                                                                  \
+            double s = 0;                                                                                              \
+            for (int k = 0; k < nb; ++k) s += pr[k] * pt[(size_t)k * m];                                               \
+            cr[cidx] -= s;                                                                                             \
+          }                                                                                                            \
+        }                                                                                                              \
+      }                                                                                                                \
+    }                                                                                                                  \
+  }
+
 typedef double v4d __attribute__((vector_size(32)));
 typedef double v4du __attribute__((vector_size(32), aligned(8)));
+typedef double v8d __attribute__((vector_size(64)));
+typedef double v8du __attribute__((vector_size(64), aligned(8)));
+
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target("arch=x86-64-v4"))) static void trailing_v4(double *A, int n, int kb, int nb, int i0, const double *PT, int m) {
+  LIO_TRAIL_BODY(v8d, v8du, 8)
+}
+__attribute__((target("arch=x86-64-v3"))) static void trailing_v3(double *A, int n, int kb, int nb, int i0, const double *PT, int m) {
+  LIO_TRAIL_BODY(v4d, v4du, 4)
+}
+#endif
+static void trailing_base(double *A, int n, int kb, int nb, int i0, const double *PT, int m) {
+  LIO_TRAIL_BODY(v4d, v4du, 4)
+}
+typedef void (*trailing_fn)(double *, int, int, int, int, const double *, int);
+static trailing_fn pick_trailing() {
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+  __builtin_cpu_init();
+  if (__builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx512dq") &&
+      __builtin_cpu_supports("avx512bw") && __builtin_cpu_supports("avx512cd"))
+    return trailing_v4;
+  if (__builtin_cpu_supports("avx2") && __builtin_cpu_supports("fma")) return trailing_v3;
+#endif
+  return trailing_base;
+}
+static const trailing_fn trailing = pick_trailing();
 
 // Blocked lower Cholesky (block width kCholNb): diagonal block, panel triangular solve, then the trailing update
 // C -= P P^T through a 4 x 8 register tile over the transposed panel, so the trailing matrix is read and written once
@@ -82,42 +149,7 @@ LIO_MV bool cholesky(Mat &a) {
       double *x = A + (size_t)i * n + kb;
       for (int k = 0; k < nb; ++k) x[k] = PT[(size_t)k * m + (i - i0)];
     }
-    // trailing update, rows i (4 at a time), columns j <= i (8 at a time)
-    for (int i = i0; i < n; i += 4) {
-      const int rows = std::min(4, n - i), jmax = i + rows - 1;
-      for (int jb = i0; jb <= jmax; jb += 8) {
-        const int w = std::min(8, n - jb);
-        if (rows == 4 && w == 8) {
-          v4d c00 = {0, 0, 0, 0}, c01 = c00, c10 = c00, c11 = c00, c20 = c00, c21 = c00, c30 = c00, c31 = c00;
-          const double *p0 = A + (size_t)i * n + kb, *p1 = p0 + n, *p2 = p1 + n, *p3 = p2 + n;
-          const double *pt = PT + (jb - i0);
-          for (int k = 0; k < nb; ++k, pt += m) {
-            const v4d b0 = *(const v4du *)pt, b1 = *(const v4du *)(pt + 4);
-            const double a0 = p0[k], a1 = p1[k], a2 = p2[k], a3 = p3[k];
-            c00 += a0 * b0; c01 += a0 * b1;
-            c10 += a1 * b0; c11 += a1 * b1;
-            c20 += a2 * b0; c21 += a2 * b1;
-            c30 += a3 * b0; c31 += a3 * b1;
-          }
-          double *r0 = A + (size_t)i * n + jb, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n;
-          *(v4du *)r0 -= c00; *(v4du *)(r0 + 4) -= c01;
-          *(v4du *)r1 -= c10; *(v4du *)(r1 + 4) -= c11;
-          *(v4du *)r2 -= c20; *(v4du *)(r2 + 4) -= c21;
-          *(v4du *)r3 -= c30; *(v4du *)(r3 + 4) -= c31;
-        } else {
-          for (int r = 0; r < rows; ++r) {
-            const double *pr = A + (size_t)(i + r) * n + kb;
-            double *cr = A + (size_t)(i + r) * n + jb;
-            for (int cidx = 0; cidx < w; ++cidx) {
-              const double *pt = PT + (jb - i0) + cidx;
-              double s = 0;
-              for (int k = 0; k < nb; ++k) s += pr[k] * pt[(size_t)k * m];
-              cr[cidx] -= s;
-            }
-          }
-        }
-      }
-    }
+    trailing(A, n, kb, nb, i0, PT, m);
   }
   return true;
 }
@@ -366,6 +398,21 @@ LIO_MV void add_JtJ_mapped(const double *J, const double *r, int rows, int cols,
     double *hrow = &H.d[(size_t)cm[a] * n];
     if (contiguous) { double *dst = hrow + cm[0]; for (int b = 0; b < cols; ++b) dst[b] += tmp[b]; }
     else for (int b = 0; b < cols; ++b) hrow[cm[b]] += tmp[b];
+  }
+}
+
+LIO_MV void JtJ_dense(const double *J, const double *r, int rows, int cols, double *JtJ, double *Jtr) {
+  for (int a = 0; a < cols; ++a) {
+    double *out = JtJ + (size_t)a * cols;
+    double gs = 0;
+    for (int b = 0; b < cols; ++b) out[b] = 0.0;
+    for (int k = 0; k < rows; ++k) {
+      const double ja = J[k * cols + a];
+      const double *jr = J + k * cols;
+      for (int b = 0; b < cols; ++b) out[b] += ja * jr[b];
+      gs += ja * r[k];
+    }
+    Jtr[a] = gs;
   }
 }
 

@@ -158,6 +158,8 @@ void cholesky_solve(const Mat &L, Vec &b);
 void sym_eigen(const Mat &A, Vec &evals, Mat &evecs, int threads = 1);
 // H(cm[a], cm[b]) += sum_k J[k][a] J[k][b];  g[cm[a]] += sum_k J[k][a] r[k]   (J: rows x cols row-major, cm: column map)
 void add_JtJ_mapped(const double *J, const double *r, int rows, int cols, const int *cm, Mat &H, Vec &g);
+// JtJ (cols x cols, row-major) = J^T J,  Jtr (cols) = J^T r   (J: rows x cols row-major)
+void JtJ_dense(const double *J, const double *r, int rows, int cols, double *JtJ, double *Jtr);
 // y = A x (multiversioned)
 void matvec(const Mat &A, const Vec &x, Vec &y);
 // C(r,c) = sum_{k in cols} A(r,k) w[k] A(c,k)
