@@ -22,7 +22,7 @@ namespace lio {
 
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr int kHashThreads = 256;
-constexpr int kKnnThreads = 128;
+constexpr int kKnnThreads = 256;
 
 __device__ __forceinline__ unsigned long long pack_cell(int cx, int cy, int cz) {
   const int off = 1 << 20;
@@ -143,7 +143,7 @@ __device__ __forceinline__ unsigned long long pack_key(float d, int mi) {
 constexpr unsigned long long kInfKey = 0x7f8000007fffffffull;  // (+inf, INT_MAX)
 
 constexpr int kGroup = 8;                               // lanes cooperating on one query
-constexpr int kQueriesPerBlock = kKnnThreads / kGroup;  // 16
+constexpr int kQueriesPerBlock = kKnnThreads / kGroup;  // 32: the fits of a block fill exactly one warp
 
 // cyclic Jacobi eigen-decomposition of a symmetric 3x3 (float), ascending eigenvalues, vectors in columns — the same
 // operation order as the oracle's sym_eigen_jacobi<float>(3, ...) (stand-in for SelfAdjointEigenSolver<Matrix3f>)
@@ -198,7 +198,9 @@ __device__ __forceinline__ void sym_eigen3(const float *Ain, float *evals, float
 // kFit = 1: point-to-line (USE_CORNER branch :1101-1227 / PointMapping.cc:381-512), two half-weight features.
 // One 8-lane group per query: lane g scans cells g, g+8, g+16, g+24 of the 3x3x3 block keeping a local
 // sorted top-5; the groups' lists are merged by five rounds of a (d^2, idx) min-reduction (shuffles), which
-// yields exactly the sequence a single sorted scan would; lane 0 of the group then fits the plane.
+// yields exactly the sequence a single sorted scan would.  The 32 merged neighbour lists of the block are handed to
+// warp 0 through shared memory, one query per LANE, so the long fit (QR / eigen, tests) issues once per block at full
+// lane occupancy instead of on one lane in eight of every warp.
 template <int kFit>
 __global__ void __launch_bounds__(kKnnThreads)
 knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const int *__restrict__ hcount,
@@ -295,9 +297,29 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
       bk[4] = kInfKey; bp[4] = -1;
     }
   }
-  if (active && g == 0) {
-    const float d5 = __uint_as_float((unsigned)(top_k[4] >> 32));
-    if ((kFit == 0 || kFit == 2) && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+  __shared__ int s_tp[kQueriesPerBlock][5];
+  __shared__ float s_d5[kQueriesPerBlock];
+  __shared__ float4 s_sel[kQueriesPerBlock], s_ori[kQueriesPerBlock];
+  if (g == 0) {
+    const int ql = threadIdx.x / kGroup;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) s_tp[ql][j] = top_p[j];
+    // d5 < 0 marks "no fit": inactive query or fewer than five neighbours in the 27 cells
+    s_d5[ql] = (active && top_k[4] != kInfKey) ? __uint_as_float((unsigned)(top_k[4] >> 32)) : -1.f;
+    s_sel[ql] = make_float4(sx, sy, sz, 0.f);
+    s_ori[ql] = p;
+  }
+  __syncthreads();
+  const int qf = ltile * kQueriesPerBlock + threadIdx.x;   // the query this thread fits (warp 0 only)
+  if (threadIdx.x < kQueriesPerBlock && s_d5[threadIdx.x] >= 0.f) {
+    const float d5 = s_d5[threadIdx.x];
+    int top_p[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) top_p[j] = s_tp[threadIdx.x][j];
+    const float4 sel = s_sel[threadIdx.x];
+    const float sx = sel.x, sy = sel.y, sz = sel.z;
+    const float4 p = s_ori[threadIdx.x];
+    if ((kFit == 0 || kFit == 2) && d5 < min_match_sq_dis) {
       float A[5][3], Bv[5], X[3];
       float nx[5], ny[5], nz[5];
 #pragma unroll
@@ -337,7 +359,7 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
         }
       }
     }
-    if ((kFit == 1 || kFit == 3) && top_k[4] != kInfKey && d5 < min_match_sq_dis) {
+    if ((kFit == 1 || kFit == 3) && d5 < min_match_sq_dis) {
       float nx[5], ny[5], nz[5];
       float vcx = 0.f, vcy = 0.f, vcz = 0.f;
 #pragma unroll
@@ -410,8 +432,8 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
   const int excl = lookback_exclusive(status + F.tile0, ltile, tot, &sbc);
   if (valid) {
     const int o = base_count + excl + lpos;
-    F.out_p[o] = po; F.out_c[o] = co; F.out_src[o] = q;
-    if (kFit == 1) { F.out_p[o + 1] = po; F.out_c[o + 1] = co2; F.out_src[o + 1] = q; }
+    F.out_p[o] = po; F.out_c[o] = co; F.out_src[o] = qf;
+    if (kFit == 1) { F.out_p[o + 1] = po; F.out_c[o + 1] = co2; F.out_src[o + 1] = qf; }
   }
   if (ltile == ntiles - 1 && threadIdx.x == 0) *F.out_count = base_count + excl + tot;
 }
