@@ -1759,14 +1759,24 @@ extern "C" int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, co
   return rc;
 }
 
-__global__ void k_fill_features(float4 *pts, float4 *coef, long long n) {
+// Synthetic feature stream shaped like a converged window: points within +-20 m, unit normals scaled by a score of 0.8,
+// and plane offsets chosen so that the residual under the frame's (R, t) of the benchmark is a few centimetres
+// (|r| <= 0.04 m), i.e. the regime the solver runs in (rho = log(1 + r^2) with r^2 << 1).
+__global__ void k_fill_features(float4 *pts, float4 *coef, long long n, long long per_frame) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   unsigned h = (unsigned)(i * 2654435761u);
   float a = (float)(h & 1023) * (1.0f / 1024.0f), b = (float)((h >> 10) & 1023) * (1.0f / 1024.0f), c = (float)((h >> 20) & 1023) * (1.0f / 1024.0f);
-  pts[i] = make_float4(40.f * (a - 0.5f), 40.f * (b - 0.5f), 4.f * c, 0.9f);
+  const float px = 40.f * (a - 0.5f), py = 40.f * (b - 0.5f), pz = 4.f * c;
+  pts[i] = make_float4(px, py, pz, 0.9f);
   float nx = a - 0.5f, ny = b - 0.5f, nz = c + 0.1f, nn = rsqrtf(nx * nx + ny * ny + nz * nz);
-  coef[i] = make_float4(0.8f * nx * nn, 0.8f * ny * nn, 0.8f * nz * nn, 0.05f * (a - b));
+  const float wx = 0.8f * nx * nn, wy = 0.8f * ny * nn, wz = 0.8f * nz * nn;
+  // same (R, t) as lio_asm_stream_bench builds for frame k: R = Rz(0.01 k) stored row-major, t = (0.1 k, 0.02 k, 0)
+  const int k = (int)(i / per_frame);
+  const double cs = cos(0.01 * k), sn = sin(0.01 * k);
+  const double ax = cs * wx + sn * wy, ay = -sn * wx + cs * wy, az = wz;   // a = R^T w
+  const double r0 = ax * (px + 0.1 * k) + ay * (py + 0.02 * k) + az * pz;
+  coef[i] = make_float4(wx, wy, wz, (float)(-r0) + 0.08f * (a - 0.5f));
 }
 
 // Streaming-rate measurement of the fused stage-C kernel on a synthetic feature stream of n features
@@ -1982,7 +1992,7 @@ extern "C" int lio_asm_stream_bench(long long n_features, int iters, int device,
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   double *dRt = nullptr;
   if (rc == LIO_OK) {
-    k_fill_features<<<(unsigned)((per * O + 255) / 256), 256>>>(dp, dc, per * O);
+    k_fill_features<<<(unsigned)((per * O + 255) / 256), 256>>>(dp, dc, per * O, per);
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     AsmParams ap;
     std::memset(&ap, 0, sizeof(ap));
