@@ -335,9 +335,17 @@ def main():
                              "avg_launch_us": avg_ms * 1e3, "bytes_per_launch": bytes_per_launch, "launches": prof["asm_launches"],
                              "peak_source": peak_src,
                              "note": "32 B/feature x features of the solve; ~4.8 MB per launch on this workload, i.e. launch-latency and L2 bound (SURVEY.md 7.3-4)"},
+                "roofline_knn": {"kernel": "knn_plane (frame-batched 5-NN + plane fit, the largest share of kernel time)", "bound": "hbm",
+                                 "achieved": (prof["bytes_per_query"] * prof["knn_queries"] / max(1, prof["knn_launches"])) /
+                                             (max(prof["knn_ms"], 1e-9) / max(1, prof["knn_launches"]) * 1e-3) / 1e9,
+                                 "peak": peak, "unit": "GB/s", "traffic": None,
+                                 "avg_launch_us": 1e3 * prof["knn_ms"] / max(1, prof["knn_launches"]),
+                                 "queries_per_launch": prof["knn_queries"] / max(1, prof["knn_launches"]),
+                                 "note": "128 B/query algorithmic (query + 5 neighbours + feature out); an L2-gather + ALU kernel, not HBM bound"},
                 "e2e": {"value": args.steps / e2e_t, "unit": "scans/s", "h2d_bytes_per_step": h2d // args.steps,
                         "d2h_bytes_per_step": d2h // args.steps},
                 "gpu_launches": launches, "clocks": clocks}
+        line["roofline_knn"]["frac"] = line["roofline_knn"]["achieved"] / peak
         if world == 1:
             try:   # the same kernel on a stream larger than L2 (512 MB): its HBM-resident streaming rate
                 sb = estimator.asm_stream_bench(1 << 26, 10, local_rank)

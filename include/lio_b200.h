@@ -265,8 +265,10 @@ int lio_est_last_normal_equations(lio_est *est, double *H, double *g, double *co
 /* Kernels launched by the last process_scan call. */
 int lio_est_last_launches(lio_est *est);
 /* CUDA-event timing of the fused residual+Jacobian kernel accumulated since the last reset (events recorded
- * on the estimator's stream around every launch): out = {sum ms, launches, features processed, bytes/feature}. */
-int lio_est_kernel_profile(lio_est *est, double out[4], int reset);
+ * on the estimator's stream around every launch): out[0..3] = {sum ms, launches, features processed, bytes/feature};
+ * out[4..7] = the same for the frame-batched k-NN + plane-fit launch of BuildLocalMap {sum ms, launches, queries,
+ * algorithmic bytes/query = 128}. */
+int lio_est_kernel_profile(lio_est *est, double out[8], int reset);
 /* Multi-GPU: frames i with (i-1) % world == rank are matched/assembled locally; the
  * callback must sum-allreduce `count` doubles in place on the DEVICE buffer `buf` across ranks
  * (e.g. ncclAllReduce / torch.distributed.all_reduce on the estimator's stream). */
@@ -293,6 +295,18 @@ int lio_compact_decode(const float *xyzi, int n_points, float tf7[7], float *cor
  * (x, y, z at 0/4/8, data[3] = 1.0f, intensity at 16). */
 int lio_xyzi_to_pcl32(const float *xyzi, int n, uint8_t *out32);
 int lio_pcl32_to_xyzi(const uint8_t *in32, int n, float *xyzi);
+
+/* ------------------------------------------------------------------------------------------
+ * Dense fp64 kernels of the host shell (host only; test seams).
+ * ---------------------------------------------------------------------------------------- */
+/* Lower Cholesky A = L L^T (blocked, the factorisation behind every dogleg step: Ceres DENSE_SCHUR at n <= 261,
+ * Estimator.cc:1909-1921) and the solve A x = b.  A n x n row-major symmetric (lower triangle read); L_out optional
+ * (n x n, upper triangle zeroed).  LIO_ERR_NUMERIC when A is not positive definite. */
+int lio_host_cholesky_solve(int n, const double *A, const double *b, double *L_out, double *x);
+/* Symmetric eigen-decomposition (Eigen::SelfAdjointEigenSolver call sites MarginalizationFactor.cc:276, :293):
+ * ascending eigenvalues, eigenvectors in the COLUMNS of evecs (n x n row-major).  threads > 1 applies the QL rotations
+ * on disjoint row ranges in parallel (bit-identical result). */
+int lio_host_sym_eigen(int n, const double *A, double *evals, double *evecs, int threads);
 
 #ifdef __cplusplus
 }

@@ -81,6 +81,8 @@ def lib():
     L.lio_calculate_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, f32p, f32p, i32p,
                                               C.POINTER(ip), ip]
     L.lio_calculate_line_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, f32p, f32p, i32p, C.POINTER(ip), ip]
+    L.lio_host_cholesky_solve.argtypes = [ip, f64p, f64p, f64p, f64p]
+    L.lio_host_sym_eigen.argtypes = [ip, f64p, f64p, f64p, ip]
     L.lio_compact_encode.argtypes = [f32p, f32p, ip, f32p, ip, f32p, ip, f32p, ip, C.POINTER(ip)]
     L.lio_compact_sizes.argtypes = [f32p, ip, i32p]
     L.lio_compact_decode.argtypes = [f32p, ip, f32p, f32p, f32p, f32p]

@@ -467,7 +467,10 @@ struct lio_est {
   // cached lidar reduction for the current parameter values
   bool S_valid = false;
   // CUDA-event timing of the fused kernel (on the launching stream)
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr;
+  double knn_ms_sum = 0;
+  long long knn_launch_count = 0, knn_query_sum = 0;
+  bool knn_timed = false;
   double asm_ms_sum = 0;
   long long asm_launch_count = 0, asm_feat_sum = 0;
 };
@@ -553,6 +556,8 @@ extern "C" int lio_est_destroy(lio_est *e) {
   e->ds.destroy();
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->evk0) cudaEventDestroy(e->evk0);
+  if (e->evk1) cudaEventDestroy(e->evk1);
   if (e->h_tf) cudaFreeHost(e->h_tf);
   if (e->h_S) cudaFreeHost(e->h_S);
   if (e->h_Rt) cudaFreeHost(e->h_Rt);
@@ -639,6 +644,7 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
     ok = ok && cudaMemset(e->d_counts, 0, sizeof(int) * 8) == cudaSuccess;
   }
   ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
+  ok = ok && cudaEventCreate(&e->evk0) == cudaSuccess && cudaEventCreate(&e->evk1) == cudaSuccess;
   for (int k = 0; k < 48 && ok; ++k) ok = ok && cudaEventCreate(&e->evp[k]) == cudaSuccess;
   e->use_dev_solver = cfg->device_solver != 0 && e->ds.supports(O) && cfg->max_num_iterations <= 22;
   if (e->use_dev_solver) ok = ok && e->ds.init(O) == 0;
@@ -850,8 +856,11 @@ static int build_local_map(lio_est *e) {
       f.out_p = e->feats[idx].pts; f.out_c = e->feats[idx].coef; f.out_src = e->feats[idx].src; f.out_count = e->feats[idx].count;
       f.append = 0; f.tile0 = 0;
     }
+    e->knn_timed = b.nframes > 0 && e->evk0 && e->evk1;
+    if (e->knn_timed) cudaEventRecord(e->evk0, st);
     rc = calculate_features_batch(e->hash, b, e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, nullptr, e->knn, st, &e->launches);
     if (rc != LIO_OK) return rc;
+    if (e->knn_timed) cudaEventRecord(e->evk1, st);
   }
   if (e->cfg.imu_factor && owns_frame(e, W)) {
     const int idx = W, slot = e->slot_of[W];
@@ -875,6 +884,15 @@ static int build_local_map(lio_est *e) {
   EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 6, e->d_slot_n + e->slot_of[W], sizeof(int), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaStreamSynchronize(st));
   e->size_surf_stack[W] = e->h_counts[W + 6];
+  if (e->knn_timed) {  // live duration of the frame-batched k-NN + plane-fit launch (its memsets included, ~2 us)
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, e->evk0, e->evk1) == cudaSuccess) {
+      long long nq = 0;
+      for (int idx = pivot + 1; idx <= W; ++idx)
+        if (owns_frame(e, idx) && !(idx == W && e->cfg.imu_factor)) nq += e->size_surf_stack[idx];
+      e->knn_ms_sum += ms; e->knn_launch_count += 1; e->knn_query_sum += nq;
+    }
+  }
   for (int k = 0; k <= W; ++k) e->h_feat_n[k] = e->h_counts[k];
   e->h_map_n = e->h_counts[W + 1 + 2];
   e->odom_iters = e->h_counts[W + 5];
@@ -1661,10 +1679,11 @@ extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, d
 }
 extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
 
-extern "C" int lio_est_kernel_profile(lio_est *e, double out[4], int reset) {
+extern "C" int lio_est_kernel_profile(lio_est *e, double out[8], int reset) {
   if (!e || !out) return LIO_ERR_INVALID;
   out[0] = e->asm_ms_sum; out[1] = (double)e->asm_launch_count; out[2] = (double)e->asm_feat_sum; out[3] = 32.0;
-  if (reset) { e->asm_ms_sum = 0; e->asm_launch_count = 0; e->asm_feat_sum = 0; }
+  out[4] = e->knn_ms_sum; out[5] = (double)e->knn_launch_count; out[6] = (double)e->knn_query_sum; out[7] = 128.0;
+  if (reset) { e->asm_ms_sum = 0; e->asm_launch_count = 0; e->asm_feat_sum = 0; e->knn_ms_sum = 0; e->knn_launch_count = 0; e->knn_query_sum = 0; }
   return LIO_OK;
 }
 

@@ -178,9 +178,10 @@ class Estimator:
         _lib.check(_lib.lib().lio_est_set_shard(self.h, rank, world, cb, None), "lio_est_set_shard")
 
     def kernel_profile(self, reset=False):
-        o = np.zeros(4)
+        o = np.zeros(8)
         _lib.check(_lib.lib().lio_est_kernel_profile(self.h, o, 1 if reset else 0), "kernel_profile")
-        return dict(asm_ms=o[0], asm_launches=int(o[1]), asm_features=int(o[2]), bytes_per_feature=o[3])
+        return dict(asm_ms=o[0], asm_launches=int(o[1]), asm_features=int(o[2]), bytes_per_feature=o[3],
+                    knn_ms=o[4], knn_launches=int(o[5]), knn_queries=int(o[6]), bytes_per_query=o[7])
 
     def states(self):
         out = np.zeros((self.W + 1, 16))
