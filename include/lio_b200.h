@@ -142,11 +142,13 @@ int lio_laser_odom_host(const float *map, int K, const float *surf, int M, float
  * (:609-611), 6x6 normal equations + colPivHouseholderQr + first-round degeneracy projection + quaternion update (:613-715),
  * exit when delta_r < delta_r_abort (deg) and delta_t < delta_t_abort (cm).  Returns immediately (tf7 untouched) when
  * Kc <= 10 or Ks <= 100 (:327-329).  Optional outputs (sized Mc + Ms): the matches of the last executed round, corner
- * then surf; *iters = rounds executed. */
+ * then surf; *iters = rounds executed.
+ * variant 1 = MapBuilder::OptimizeMap (MapBuilder.cc:624-1014): the same loop with the rotation information matrix
+ * J_r <- J_r R^-1 diag(5e-3, 5e-3, 1) (:905-911) and the left-multiplicative update rot = DeltaQ(x) * rot (:984-985). */
 int lio_scan_to_map_host(const float *corner_map, int Kc, const float *surf_map, int Ks, const float *corner, int Mc,
                          const float *surf, int Ms, float *tf7, float min_match_sq_dis, float min_plane_dis, int max_iter,
-                         double delta_r_abort, double delta_t_abort, float *pts4, float *coef4, int32_t *src, int *n_out,
-                         int *iters, int device);
+                         double delta_r_abort, double delta_t_abort, int variant, float *pts4, float *coef4, int32_t *src,
+                         int *n_out, int *iters, int device);
 
 /* ------------------------------------------------------------------------------------------
  * fp64 factor operators — the ceres::CostFunction::Evaluate seam.

@@ -89,7 +89,7 @@ def lib():
     L.lio_xyzi_to_pcl32.argtypes = [f32p, ip, u8p]
     L.lio_pcl32_to_xyzi.argtypes = [u8p, ip, f32p]
     L.lio_scan_to_map_host.argtypes = [f32p, ip, f32p, ip, f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, C.c_double, C.c_double,
-                                       f32p, f32p, i32p, C.POINTER(ip), C.POINTER(ip), ip]
+                                       ip, f32p, f32p, i32p, C.POINTER(ip), C.POINTER(ip), ip]
     L.lio_transform_to_end_host.argtypes = [f32p, ip, f32p, C.c_float, ip]
     L.lio_laser_odom_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, ip, f32p, f32p, i32p,
                                       C.POINTER(ip), C.POINTER(ip), ip]

@@ -140,7 +140,7 @@ constexpr int kOdomThreads = 256;
 
 __global__ void __launch_bounds__(kOdomThreads)
 k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, const int *__restrict__ n_dev,
-              const TransformF *__restrict__ tf_dev, OdomState *__restrict__ st, double *__restrict__ partial, int d2_from_coef = 0) {
+              const TransformF *__restrict__ tf_dev, OdomState *__restrict__ st, double *__restrict__ partial, int mode = 0) {
   __shared__ double sred[kOdomThreads / 32][27];
   __shared__ bool is_last;
   if (st->done) return;
@@ -155,6 +155,19 @@ k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, c
     R[0] = 1.f - (tyy + tzz); R[1] = txy - twz; R[2] = txz + twy;
     R[3] = txy + twz; R[4] = 1.f - (txx + tzz); R[5] = tyz - twx;
     R[6] = txz - twy; R[7] = tyz + twx; R[8] = 1.f - (txx + tyy);
+  }
+  // mode 2 (MapBuilder::OptimizeMap, MapBuilder.cc:905-911): J_r is post-multiplied by rot.inverse().toRotationMatrix()
+  // (inverse = conjugate / squaredNorm) and the rotation information matrix diag(5e-3, 5e-3, 1)
+  float Ri[9];
+  {
+    const float n2 = tf.qx * tf.qx + tf.qy * tf.qy + tf.qz * tf.qz + tf.qw * tf.qw;
+    const float ix = -tf.qx / n2, iy = -tf.qy / n2, iz = -tf.qz / n2, iw = tf.qw / n2;
+    const float tx = 2.f * ix, ty = 2.f * iy, tz = 2.f * iz;
+    const float twx = tx * iw, twy = ty * iw, twz = tz * iw, txx = tx * ix, txy = ty * ix, txz = tz * ix;
+    const float tyy = ty * iy, tyz = tz * iy, tzz = tz * iz;
+    Ri[0] = 1.f - (tyy + tzz); Ri[1] = txy - twz; Ri[2] = txz + twy;
+    Ri[3] = txy + twz; Ri[4] = 1.f - (txx + tzz); Ri[5] = tyz - twx;
+    Ri[6] = txz - twy; Ri[7] = tyz + twx; Ri[8] = 1.f - (txx + tyy);
   }
   double acc[27];
 #pragma unroll
@@ -172,11 +185,17 @@ k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, c
     float row[6];
 #pragma unroll
     for (int q = 0; q < 3; ++q) row[q] = -(c.x * RS[q] + c.y * RS[3 + q] + c.z * RS[6 + q]);
+    if (mode == 2) {
+      const float t0 = row[0] * Ri[0] + row[1] * Ri[3] + row[2] * Ri[6];
+      const float t1 = row[0] * Ri[1] + row[1] * Ri[4] + row[2] * Ri[7];
+      const float t2 = row[0] * Ri[2] + row[1] * Ri[5] + row[2] * Ri[8];
+      row[0] = t0 * 5e-3f; row[1] = t1 * 5e-3f; row[2] = t2 * 1.0f;
+    }
     row[3] = c.x; row[4] = c.y; row[5] = c.z;
     float rx, ry, rz;
     qmul_vec(tf.qx, tf.qy, tf.qz, tf.qw, p.x, p.y, p.z, rx, ry, rz);
     // CalculateLaserOdom: d2 = w . (R p + t) + b (Estimator.cc:1282-1284); scan-to-map: d2 = coeff.intensity (PointMapping.cc:634)
-    float d2 = d2_from_coef ? c.w : c.x * (rx + tf.px) + c.y * (ry + tf.py) + c.z * (rz + tf.pz) + c.w;
+    float d2 = mode != 0 ? c.w : c.x * (rx + tf.px) + c.y * (ry + tf.py) + c.z * (rz + tf.pz) + c.w;
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
@@ -252,7 +271,7 @@ __device__ void sym_eigen6(const float *Ain, float *evals, float *V) {
 // index of PointMapping::OptimizeTransformTobeMapped, where a round with fewer than min_features matches is skipped
 // entirely (`continue`, PointMapping.cc:609-611) and the degeneracy analysis belongs to loop index 0 only.
 __global__ void k_odom_solve(OdomState *__restrict__ st, TransformF *__restrict__ tf_dev, double delta_r_abort, double delta_t_abort,
-                             int round = -1, const int *__restrict__ n_dev = nullptr, int min_features = 0) {
+                             int round = -1, const int *__restrict__ n_dev = nullptr, int min_features = 0, int left_update = 0) {
   if (threadIdx.x != 0 || st->done) return;
   if (n_dev && *n_dev < min_features) { st->iter += 1; return; }
   const bool first_round = round < 0 ? (st->iter == 0) : (round == 0);
@@ -284,10 +303,18 @@ __global__ void k_odom_solve(OdomState *__restrict__ st, TransformF *__restrict_
   tf.px += X[3]; tf.py += X[4]; tf.pz += X[5];
   {  // rot = rot * DeltaQ(X[0..2])  (Hamilton product, not normalised)
     float dx = X[0] / 2.f, dy = X[1] / 2.f, dz = X[2] / 2.f, dw = 1.f;
-    float nw = tf.qw * dw - tf.qx * dx - tf.qy * dy - tf.qz * dz;
-    float nx = tf.qw * dx + tf.qx * dw + tf.qy * dz - tf.qz * dy;
-    float ny = tf.qw * dy + tf.qy * dw + tf.qz * dx - tf.qx * dz;
-    float nz = tf.qw * dz + tf.qz * dw + tf.qx * dy - tf.qy * dx;
+    float nw, nx, ny, nz;
+    if (left_update) {  // rot = DeltaQ(x) * rot  (MapBuilder.cc:984-985)
+      nw = dw * tf.qw - dx * tf.qx - dy * tf.qy - dz * tf.qz;
+      nx = dw * tf.qx + dx * tf.qw + dy * tf.qz - dz * tf.qy;
+      ny = dw * tf.qy + dy * tf.qw + dz * tf.qx - dx * tf.qz;
+      nz = dw * tf.qz + dz * tf.qw + dx * tf.qy - dy * tf.qx;
+    } else {
+      nw = tf.qw * dw - tf.qx * dx - tf.qy * dy - tf.qz * dz;
+      nx = tf.qw * dx + tf.qx * dw + tf.qy * dz - tf.qz * dy;
+      ny = tf.qw * dy + tf.qy * dw + tf.qz * dx - tf.qx * dz;
+      nz = tf.qw * dz + tf.qz * dw + tf.qx * dy - tf.qy * dx;
+    }
     tf.qx = nx; tf.qy = ny; tf.qz = nz; tf.qw = nw;
   }
   if (!isfinite(tf.px)) tf.px = 0.f;
@@ -393,6 +420,8 @@ struct lio_est {
   lio_est_config cfg;
   MargJob mjob;
   Worker worker;
+  Mat hp_exp;              // prior Hp scattered into the current tangent layout (cache of one solve)
+  bool hp_exp_valid = false;
   struct ImuBlockStore { double JtJ[30 * 30], Jtr[30], cost; bool used; } imu_blocks_store[kMaxOpt];
   double t_marg_wait = 0;
   int W = 0, O = 0, device = 0;
@@ -1021,10 +1050,31 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
   const bool ex_free = !e->ex_constant;
   const int n = 15 * (O + 1) + (ex_free ? 6 : 0);
   const int oe = ex_free ? 15 * (O + 1) : -1;
-  if (H.r != n) H = Mat(n, n); else H.zero();
-  g.assign(n, 0.0);
   std::vector<FrameTerms> ft;
   if (eval_lidar_launch(e, ft) != LIO_OK) return false;  // the device reduces the lidar factors while the host does the rest
+  // H starts as the prior's information matrix scattered into the tangent layout (constant over a solve: cached), or zero
+  const bool use_prior = e->cfg.marginalization_factor && e->prior.valid;
+  if (use_prior) {
+    if (!e->hp_exp_valid || e->hp_exp.r != n) {
+      const MargPrior &pr = e->prior;
+      e->hp_exp = Mat(n, n);
+      const int nw = 15 * O;  // window part maps one to one, the extrinsic block moves behind pose_O / sb_O
+      for (int a = 0; a < pr.n; ++a) {
+        const int ta = a < nw ? a : (ex_free ? 15 * (O + 1) + (a - nw) : -1);
+        if (ta < 0) continue;
+        const double *row = &pr.Hp.d[(size_t)a * pr.n];
+        double *hrow = &e->hp_exp.d[(size_t)ta * n];
+        for (int b = 0; b < nw; ++b) hrow[b] = row[b];
+        if (ex_free) for (int b = nw; b < pr.n; ++b) hrow[15 * (O + 1) + (b - nw)] = row[b];
+      }
+      e->hp_exp_valid = true;
+    }
+    if (H.r != n) H = Mat(n, n);
+    std::memcpy(H.d.data(), e->hp_exp.d.data(), sizeof(double) * (size_t)n * n);
+  } else {
+    if (H.r != n) H = Mat(n, n); else H.zero();
+  }
+  g.assign(n, 0.0);
   const double th0 = now_s();
   double cp = 0, ci = 0, cm = 0;
   // ImuFactors: the upper half of the window is evaluated by the context's helper thread into private 30x30 blocks
@@ -1075,13 +1125,7 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
     auto tmap = [&](int pi) { return pi < 15 * O ? pi : (ex_free ? 15 * (O + 1) + (pi - 15 * O) : -1); };
     for (int a = 0; a < pr.n; ++a) {
       const int ta = tmap(a);
-      if (ta < 0) continue;
-      g[ta] += Hdx[a] + pr.bp[a];
-      const double *row = &pr.Hp.d[(size_t)a * pr.n];
-      double *hrow = &H.d[(size_t)ta * n];
-      const int nw = 15 * O;  // window part maps one to one
-      for (int b = 0; b < nw; ++b) hrow[b] += row[b];
-      if (ex_free) for (int b = nw; b < pr.n; ++b) hrow[15 * (O + 1) + (b - nw)] += row[b];
+      if (ta >= 0) g[ta] += Hdx[a] + pr.bp[a];
     }
   }
   if (e->cfg.imu_factor && i_split < O) {
@@ -1186,6 +1230,7 @@ static int marginalize(lio_est *e) {
   if (!e->cfg.overlap_marginalization) {  // the reference's order: finish the algebra before returning from this scan
     job.stashed = false;
     e->prior = marg_algebra(std::move(job.A), std::move(job.b), job.O, std::move(job.x0_pose), std::move(job.x0_sb), job.x0_ex);
+    e->hp_exp_valid = false;
   }
   return LIO_OK;
 }
@@ -1258,6 +1303,7 @@ static void prior_join(lio_est *e) {
   const double t0 = now_s();
   e->worker.wait();
   e->prior = std::move(job.result);
+  e->hp_exp_valid = false;
   job.running = false;
   e->t_marg_wait += now_s() - t0;
 }
@@ -1828,9 +1874,10 @@ extern "C" int lio_transform_to_end_host(float *cloud, int n, const float *tf7_e
 // ---- C-ABI: PointMapping::OptimizeTransformTobeMapped on explicit host arrays (parity entry) ------------------------
 extern "C" int lio_scan_to_map_host(const float *corner_map, int Kc, const float *surf_map, int Ks, const float *corner, int Mc,
                                     const float *surf, int Ms, float *tf7, float min_match_sq_dis, float min_plane_dis, int max_iter,
-                                    double delta_r_abort, double delta_t_abort, float *pts4, float *coef4, int32_t *src, int *n_out,
-                                    int *iters, int device) {
-  if (!corner_map || !surf_map || !corner || !surf || !tf7 || Kc < 0 || Ks < 0 || Mc < 0 || Ms < 0 || max_iter < 0) return LIO_ERR_INVALID;
+                                    double delta_r_abort, double delta_t_abort, int variant, float *pts4, float *coef4, int32_t *src,
+                                    int *n_out, int *iters, int device) {
+  if (!corner_map || !surf_map || !corner || !surf || !tf7 || Kc < 0 || Ks < 0 || Mc < 0 || Ms < 0 || max_iter < 0 || variant < 0 || variant > 1)
+    return LIO_ERR_INVALID;
   if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
   LIO_CUDA_OK(cudaSetDevice(device));
   if (n_out) *n_out = 0;
@@ -1890,8 +1937,8 @@ extern "C" int lio_scan_to_map_host(const float *corner_map, int Kc, const float
         rc = calculate_features_dev(hs, d_smap, d_surf, d_n + 3, std::max(Ms, 1), d_tf, min_match_sq_dis, min_plane_dis, fo, 1,
                                     &d_odom->done, w, 0, nullptr, 2, d_z);
       if (rc != LIO_OK) break;
-      k_odom_reduce<<<nb, kOdomThreads>>>(fo.pts, fo.coef, fo.count, d_tf, d_odom, d_partial, 1);
-      k_odom_solve<<<1, 32>>>(d_odom, d_tf, delta_r_abort, delta_t_abort, it, fo.count, 50);
+      k_odom_reduce<<<nb, kOdomThreads>>>(fo.pts, fo.coef, fo.count, d_tf, d_odom, d_partial, variant == 1 ? 2 : 1);
+      k_odom_solve<<<1, 32>>>(d_odom, d_tf, delta_r_abort, delta_t_abort, it, fo.count, 50, variant == 1 ? 1 : 0);
     }
     if (rc == LIO_OK) {
       int m = 0;

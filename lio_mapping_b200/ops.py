@@ -80,8 +80,9 @@ def calculate_line_features(corner_map, corner, tf7, min_match_sq_dis=1.0, devic
 
 
 def scan_to_map(corner_map, surf_map, corner, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, max_iter=10,
-                delta_r_abort=0.05, delta_t_abort=0.05, device: int = 0):
-    """PointMapping::OptimizeTransformTobeMapped (lio_scan_to_map_host): returns (tf7, pts, coef, src, iterations)."""
+                delta_r_abort=0.05, delta_t_abort=0.05, variant: int = 0, device: int = 0):
+    """PointMapping::OptimizeTransformTobeMapped (lio_scan_to_map_host; variant 1 = MapBuilder::OptimizeMap):
+    returns (tf7, pts, coef, src, iterations)."""
     _lib.require_device()
     a = [np.ascontiguousarray(x, np.float32).reshape(-1, 4) for x in (corner_map, surf_map, corner, surf)]
     pad = [x if x.shape[0] else np.zeros((1, 4), np.float32) for x in a]
@@ -92,6 +93,6 @@ def scan_to_map(corner_map, surf_map, corner, surf, tf7, min_match_sq_dis=1.0, m
     tf = np.ascontiguousarray(tf7, np.float32).copy()
     n, it = C.c_int(), C.c_int()
     _lib.check(_lib.lib().lio_scan_to_map_host(pad[0], a[0].shape[0], pad[1], a[1].shape[0], pad[2], a[2].shape[0], pad[3], a[3].shape[0],
-                                               tf, min_match_sq_dis, min_plane_dis, max_iter, delta_r_abort, delta_t_abort, pts, coef, src,
+                                               tf, min_match_sq_dis, min_plane_dis, max_iter, delta_r_abort, delta_t_abort, variant, pts, coef, src,
                                                C.byref(n), C.byref(it), device), "lio_scan_to_map_host")
     return tf, pts[:n.value].copy(), coef[:n.value].copy(), src[:n.value].copy(), it.value

@@ -94,7 +94,8 @@ void CalculateFeatures(const KdTree &kd, const Cloud &map, const Cloud &surf_sta
 void CalculateLineFeatures(const KdTree &kd, const Cloud &map, const Cloud &corner_stack, const Transform &local_transform,
                            const StageBConfig &cfg, std::vector<PointPlaneFeature> &features);
 void OptimizeTransformTobeMapped(const Cloud &corner_map, const Cloud &surf_map, const Cloud &corner_stack, const Cloud &surf_stack,
-                                 Transform &tobe, const StageBConfig &cfg, int *iters_done, std::vector<PointPlaneFeature> *features_out);
+                                 Transform &tobe, const StageBConfig &cfg, int *iters_done, std::vector<PointPlaneFeature> *features_out,
+                                 int variant = 0);
 void CalculateLaserOdom(const KdTree &kd, const Cloud &map, const Cloud &surf_stack, Transform &local_transform,
                         const StageBConfig &cfg, std::vector<PointPlaneFeature> &features, int *iters_done);
 

@@ -133,14 +133,14 @@ int orc_calculate_line_features(const float *map, int K, const float *corner, in
 // PointMapping::OptimizeTransformTobeMapped on explicit arrays; tf7 in/out; feature outputs (last pass) sized Mc + Ms.
 int orc_scan_to_map(const float *cmap, int Kc, const float *smap, int Ks, const float *corner, int Mc, const float *surf, int Ms,
                     float *tf7, float min_match_sq_dis, float min_plane_dis, int max_iter, double delta_r_abort, double delta_t_abort,
-                    float *pts4, float *coef4, int *src, int *iters) {
+                    float *pts4, float *coef4, int *src, int *iters, int variant) {
   Cloud cm((const PointXYZI *)cmap, (const PointXYZI *)cmap + Kc), sm((const PointXYZI *)smap, (const PointXYZI *)smap + Ks),
       cs((const PointXYZI *)corner, (const PointXYZI *)corner + Mc), ss((const PointXYZI *)surf, (const PointXYZI *)surf + Ms);
   StageBConfig cfg; cfg.min_match_sq_dis = min_match_sq_dis; cfg.min_plane_dis = min_plane_dis; cfg.num_max_iterations = max_iter;
   cfg.delta_r_abort = delta_r_abort; cfg.delta_t_abort = delta_t_abort;
   Transform t = make_tf(tf7);
   std::vector<PointPlaneFeature> feats;
-  OptimizeTransformTobeMapped(cm, sm, cs, ss, t, cfg, iters, &feats);
+  OptimizeTransformTobeMapped(cm, sm, cs, ss, t, cfg, iters, &feats, variant);
   tf7[0] = t.rot.x; tf7[1] = t.rot.y; tf7[2] = t.rot.z; tf7[3] = t.rot.w; tf7[4] = t.pos.x; tf7[5] = t.pos.y; tf7[6] = t.pos.z;
   copy_feats(feats, pts4, coef4, src);
   return (int)feats.size();

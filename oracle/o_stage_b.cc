@@ -260,8 +260,12 @@ void CalculateLaserOdom(const KdTree &kd, const Cloud &map, const Cloud &surf_st
 //   6x6 GN          :608-715  (rows [-w^T (R [p]x), w^T], rhs -coeff.intensity; first-iteration degeneracy projection)
 // point_on_z_axis_ is set ONCE from the initial transform (PointMapping.cc:803-806) and not moved by the iterations.
 // features_out (optional): the (point_ori, coeff) pairs of the LAST executed feature pass, corner then surf.
+// variant 1 = MapBuilder::OptimizeMap (src/map_builder/MapBuilder.cc:624-1014), the same loop with a rotation
+// information matrix on the Jacobian, J_r = -w^T (R [p]x) R^-1 diag(5e-3, 5e-3, 1) (:905-911, non-DEBUG branch), and a
+// LEFT-multiplicative update rot = DeltaQ(x) * rot (:984-985).
 void OptimizeTransformTobeMapped(const Cloud &corner_map, const Cloud &surf_map, const Cloud &corner_stack, const Cloud &surf_stack,
-                                 Transform &tobe, const StageBConfig &cfg, int *iters_done, std::vector<PointPlaneFeature> *features_out) {
+                                 Transform &tobe, const StageBConfig &cfg, int *iters_done, std::vector<PointPlaneFeature> *features_out,
+                                 int variant) {
   if (iters_done) *iters_done = 0;
   if (corner_map.size() <= 10 || surf_map.size() <= 100) return;  // :327-329
   KdTree kd_corner, kd_surf;
@@ -362,12 +366,18 @@ void OptimizeTransformTobeMapped(const Cloud &corner_map, const Cloud &surf_map,
     R_SO3.normalize();
     float AtA[6][6] = {}, AtB[6] = {};
     Mat3<float> Rm = tobe.rot.toRotationMatrix();
+    Mat3<float> Rinv = tobe.rot.inverse().toRotationMatrix();
     for (size_t i = 0; i < n; i++) {
       Vec3<float> p(laser_cloud_ori[i].x, laser_cloud_ori[i].y, laser_cloud_ori[i].z);
       Vec3<float> w(coeff_sel[i].x, coeff_sel[i].y, coeff_sel[i].z);
       Mat3<float> RS = Rm * Skew(p);
       float row[6];
-      for (int c = 0; c < 3; ++c) row[c] = -(w.x * RS(0, c) + w.y * RS(1, c) + w.z * RS(2, c));
+      for (int c = 0; c < 3; ++c) row[c] = (-w.x) * RS(0, c) + (-w.y) * RS(1, c) + (-w.z) * RS(2, c);
+      if (variant == 1) {
+        float t3[3];
+        for (int c = 0; c < 3; ++c) t3[c] = row[0] * Rinv(0, c) + row[1] * Rinv(1, c) + row[2] * Rinv(2, c);
+        row[0] = t3[0] * 5e-3f; row[1] = t3[1] * 5e-3f; row[2] = t3[2] * 1.0f;
+      }
       row[3] = w.x; row[4] = w.y; row[5] = w.z;
       float d2 = coeff_sel[i].intensity;
       for (int a = 0; a < 6; ++a) {
@@ -396,7 +406,8 @@ void OptimizeTransformTobeMapped(const Cloud &corner_map, const Cloud &surf_map,
       for (int a = 0; a < 6; ++a) X[a] = X2[a];
     }
     tobe.pos.x += X[3]; tobe.pos.y += X[4]; tobe.pos.z += X[5];
-    tobe.rot = tobe.rot * DeltaQ(Vec3<float>(X[0], X[1], X[2]));
+    if (variant == 1) tobe.rot = DeltaQ(Vec3<float>(X[0], X[1], X[2])) * tobe.rot;
+    else tobe.rot = tobe.rot * DeltaQ(Vec3<float>(X[0], X[1], X[2]));
     if (!std::isfinite(tobe.pos.x)) tobe.pos.x = 0.0f;
     if (!std::isfinite(tobe.pos.y)) tobe.pos.y = 0.0f;
     if (!std::isfinite(tobe.pos.z)) tobe.pos.z = 0.0f;

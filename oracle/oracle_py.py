@@ -157,8 +157,9 @@ def calculate_line_features(corner_map, corner, tf7, min_match_sq_dis=1.0):
 
 
 def scan_to_map(corner_map, surf_map, corner, surf, tf7, min_match_sq_dis=1.0, min_plane_dis=0.2, max_iter=10,
-                delta_r_abort=0.05, delta_t_abort=0.05):
-    """PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:325-753): returns (tf7, pts, coef, src, iterations)."""
+                delta_r_abort=0.05, delta_t_abort=0.05, variant=0):
+    """PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:325-753; variant 1 = MapBuilder::OptimizeMap,
+    MapBuilder.cc:624-1014): returns (tf7, pts, coef, src, iterations)."""
     L = lib()
     a = [np.ascontiguousarray(x, np.float32).reshape(-1, 4) for x in (corner_map, surf_map, corner, surf)]
     cap = max(a[2].shape[0] + a[3].shape[0], 1)
@@ -166,10 +167,10 @@ def scan_to_map(corner_map, surf_map, corner, surf, tf7, min_match_sq_dis=1.0, m
     tf = np.ascontiguousarray(tf7, np.float32).copy()
     it = np.zeros(1, np.int32)
     L.orc_scan_to_map.argtypes = [f32p, C.c_int, f32p, C.c_int, f32p, C.c_int, f32p, C.c_int, f32p, C.c_float, C.c_float, C.c_int,
-                                  C.c_double, C.c_double, f32p, f32p, i32p, i32p]
+                                  C.c_double, C.c_double, f32p, f32p, i32p, i32p, C.c_int]
     L.orc_scan_to_map.restype = C.c_int
     n = L.orc_scan_to_map(a[0], a[0].shape[0], a[1], a[1].shape[0], a[2], a[2].shape[0], a[3], a[3].shape[0], tf, min_match_sq_dis,
-                          min_plane_dis, max_iter, delta_r_abort, delta_t_abort, pts, coef, src, it)
+                          min_plane_dis, max_iter, delta_r_abort, delta_t_abort, pts, coef, src, it, variant)
     return tf, pts[:n].copy(), coef[:n].copy(), src[:n].copy(), int(it[0])
 
 

@@ -159,9 +159,10 @@ def test_calculate_line_features_edge_cases(oracle):
     assert ops.calculate_line_features(line, np.zeros((0, 4), np.float32), tf7)[0].shape == (0, 4)
 
 
-@pytest.mark.parametrize("kind", ["vlp16", "hdl64"])
-def test_scan_to_map_parity(oracle, kind):
-    """PointMapping::OptimizeTransformTobeMapped: corner + surf matching and the 6-DoF float GN, device vs oracle.
+@pytest.mark.parametrize("kind,variant", [("vlp16", 0), ("hdl64", 0), ("vlp16", 1), ("hdl64", 1)])
+def test_scan_to_map_parity(oracle, kind, variant):
+    """PointMapping::OptimizeTransformTobeMapped (variant 0) and MapBuilder::OptimizeMap (variant 1, rotation information
+    matrix + left-multiplicative update): corner + surf matching and the 6-DoF float GN, device vs oracle.
     Round 1 works on identical inputs (bit-exact matches); later rounds inherit the last-ulp difference of the 6x6
     reduction order (double tree vs sequential float), so the pose is compared at 2e-5."""
     from lio_mapping_b200 import ops
@@ -173,14 +174,14 @@ def test_scan_to_map_parity(oracle, kind):
     tf0 = tf7.copy()
     tf0[4:] += np.array([0.05, -0.04, 0.02], np.float32)
     # one round: identical matches, in the reference's order (corner block then surf block)
-    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, cc[3], sc[3], tf0, max_iter=1)
-    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, cc[3], sc[3], tf0, max_iter=1)
+    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, cc[3], sc[3], tf0, max_iter=1, variant=variant)
+    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, cc[3], sc[3], tf0, max_iter=1, variant=variant)
     assert itg == ito == 1
     assert np.array_equal(sg, so) and np.array_equal(pg[:, :3], po[:, :3]) and np.array_equal(cg, co)
     assert np.allclose(tg, to, atol=2e-6, rtol=0)
     # full loop
-    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, cc[3], sc[3], tf0)
-    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, cc[3], sc[3], tf0)
+    to, po, co, so, ito = oracle.scan_to_map(cmap, smap, cc[3], sc[3], tf0, variant=variant)
+    tg, pg, cg, sg, itg = ops.scan_to_map(cmap, smap, cc[3], sc[3], tf0, variant=variant)
     assert itg == ito and 2 <= ito <= 10
     assert np.allclose(tg, to, atol=2e-5, rtol=0)
     assert np.linalg.norm(tg[4:] - tf7[4:]) < 0.5 * np.linalg.norm(tf0[4:] - tf7[4:])
