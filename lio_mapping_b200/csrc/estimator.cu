@@ -9,6 +9,7 @@
 //   SlideWindow :2570-2666                  -> slide_window
 // There is no CPU path for the per-point work: without a CUDA device create() fails.
 #include "assemble.cuh"
+#include <atomic>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -376,41 +377,65 @@ struct MargJob {
 };
 
 // One persistent helper thread per estimator context (created on first use): starting a std::thread per scan costs
-// ~0.1 ms on the bench host, a condition-variable hand-off a few microseconds.
+// ~0.1 ms on the bench host.  Hand-off: the helper spins for kWorkerSpinUs after each job before it sleeps on the condition
+// variable, so the jobs of one solve (one every ~150 us) never pay a futex wake-up; between scans it sleeps.
 struct Worker {
+  static constexpr double kWorkerSpinUs = 400.0;
   std::thread th;
   std::mutex mu;
   std::condition_variable cv;
   std::function<void()> job;
-  bool has_job = false, busy = false, quit = false, started = false;
+  std::atomic<int> has_job{0}, busy{0}, sleeping{0};
+  bool quit = false, started = false;
+  static inline void relax() {
+#if defined(__x86_64__)
+    __builtin_ia32_pause();
+#endif
+  }
   void submit(std::function<void()> f) {
-    std::unique_lock<std::mutex> lk(mu);
+    wait();                                // the previous job has fully retired
     if (!started) { started = true; th = std::thread([this]() { loop(); }); }
     job = std::move(f);
-    has_job = true; busy = true;
-    cv.notify_all();
+    busy.store(1);
+    has_job.store(1);
+    if (sleeping.load()) { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
   }
   void wait() {
-    std::unique_lock<std::mutex> lk(mu);
-    cv.wait(lk, [this]() { return !busy; });
+    const double t0 = now_s();
+    while (busy.load()) {
+      relax();
+      if ((now_s() - t0) * 1e6 > kWorkerSpinUs) {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this]() { return busy.load() == 0; });
+        return;
+      }
+    }
   }
   void loop() {
-    std::unique_lock<std::mutex> lk(mu);
     while (true) {
-      cv.wait(lk, [this]() { return has_job || quit; });
-      if (quit) return;
-      std::function<void()> f = std::move(job);
-      has_job = false;
-      lk.unlock();
-      f();
-      lk.lock();
-      busy = false;
-      cv.notify_all();
+      const double t0 = now_s();
+      bool got = false;
+      while ((now_s() - t0) * 1e6 <= kWorkerSpinUs) {
+        if (has_job.load()) { got = true; break; }
+        relax();
+      }
+      if (!got) {
+        std::unique_lock<std::mutex> lk(mu);
+        sleeping.store(1);
+        cv.wait(lk, [this]() { return has_job.load() != 0 || quit; });
+        sleeping.store(0);
+        if (!has_job.load()) return;  // quit
+      }
+      has_job.store(0);
+      job();
+      busy.store(0);
+      { std::lock_guard<std::mutex> lk(mu); cv.notify_all(); }
     }
   }
   ~Worker() {
     if (started) {
-      { std::unique_lock<std::mutex> lk(mu); cv.wait(lk, [this]() { return !busy; }); quit = true; cv.notify_all(); }
+      wait();
+      { std::lock_guard<std::mutex> lk(mu); quit = true; cv.notify_all(); }
       th.join();
     }
   }
@@ -423,6 +448,7 @@ struct lio_est {
   Mat hp_exp;              // prior Hp scattered into the current tangent layout (cache of one solve)
   bool hp_exp_valid = false;
   struct ImuBlockStore { double JtJ[30 * 30], Jtr[30], cost; bool used; } imu_blocks_store[kMaxOpt];
+  std::atomic<int> imu_next{0}, imu_done{0};  // shared pool of ImuFactor indices of one linearisation (caller + helper)
   double t_marg_wait = 0;
   int W = 0, O = 0, device = 0;
   cudaStream_t stream = 0;
@@ -1044,6 +1070,25 @@ static void prior_dx(const lio_est *e, const MargPrior &pr, Vec &dx) {  // Margi
   pose_dx(e->para_ex, pr.x0_ex, &dx[15 * O]);
 }
 
+// Drains the ImuFactor pool of the current linearisation (called concurrently by the caller thread and the helper).
+static void imu_pool_run(lio_est *e, int O, int pivot) {
+  int i;
+  while ((i = e->imu_next.fetch_add(1)) < O) {
+    lio_est::ImuBlockStore &b = e->imu_blocks_store[i];
+    Preintegration &pim = *e->pre[pivot + i + 1];
+    b.used = !(pim.sum_dt > 10.0);
+    if (b.used) {
+      double r[15], J[15][30];
+      imu_factor_evaluate30(pim, e->para_pose[i].data(), e->para_sb[i].data(), e->para_pose[i + 1].data(), e->para_sb[i + 1].data(), r, J);
+      JtJ_dense(&J[0][0], r, 15, 30, b.JtJ, b.Jtr);
+      double sq = 0;
+      for (int k = 0; k < 15; ++k) sq += r[k] * r[k];
+      b.cost = 0.5 * sq;
+    }
+    e->imu_done.fetch_add(1);
+  }
+}
+
 // Full linearisation at the current parameter values.  n_t = tangent dim (ex block present iff !ex_constant).
 static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, double *c_ppp, double *c_marg) {
   const int O = e->O, pivot = e->W - O;
@@ -1077,11 +1122,10 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
   g.assign(n, 0.0);
   const double th0 = now_s();
   double cp = 0, ci = 0, cm = 0;
-  // ImuFactors: the upper half of the window is evaluated by the context's helper thread into private 30x30 blocks
-  // (adjacent factors overlap in H), the lower half directly into H on this thread; the blocks are added after the
-  // prior, right before the device result is needed.
-  typedef lio_est::ImuBlockStore ImuBlock;
-  ImuBlock *blk = e->imu_blocks_store;
+  // ImuFactors: factors [0, i_split) go directly into H on this thread; factors [i_split, O) form a pool that the context's
+  // helper thread and (after its own share and the prior) this thread drain together into private 30x30 blocks, which
+  // are added in index order afterwards - the result does not depend on who evaluated which block, and a helper that
+  // is late or descheduled costs nothing but its share.
   const int i_split = (e->cfg.imu_factor && O >= 4) ? O / 2 : O;
   auto imu_eval = [&](int i, double *r, double (*J)[30]) {
     Preintegration &pim = *e->pre[pivot + i + 1];
@@ -1090,18 +1134,10 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
     return true;
   };
   if (e->cfg.imu_factor && i_split < O) {
-    e->worker.submit([&, i_split]() {
-      for (int i = i_split; i < O; ++i) {
-        double r[15], J[15][30];
-        ImuBlock &b = blk[i];
-        b.used = imu_eval(i, r, J);
-        if (!b.used) continue;
-        JtJ_dense(&J[0][0], r, 15, 30, b.JtJ, b.Jtr);
-        double sq = 0;
-        for (int k = 0; k < 15; ++k) sq += r[k] * r[k];
-        b.cost = 0.5 * sq;
-      }
-    });
+    e->worker.wait();  // the previous pool job has retired before the counters are reset
+    e->imu_next.store(i_split);
+    e->imu_done.store(0);
+    e->worker.submit([e, O, pivot]() { imu_pool_run(e, O, pivot); });
   }
   if (e->cfg.imu_factor) {
     for (int i = 0; i < i_split; ++i) {
@@ -1129,9 +1165,11 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
     }
   }
   if (e->cfg.imu_factor && i_split < O) {
-    e->worker.wait();
+    imu_pool_run(e, O, pivot);
+    while (e->imu_done.load() < O - i_split) Worker::relax();  // at most one block still in flight on the helper
+    const lio_est::ImuBlockStore *blk = e->imu_blocks_store;
     for (int i = i_split; i < O; ++i) {
-      const ImuBlock &b = blk[i];
+      const lio_est::ImuBlockStore &b = blk[i];
       if (!b.used) continue;
       for (int a = 0; a < 30; ++a) {
         double *hrow = &H.d[(size_t)(15 * i + a) * n + 15 * i];
