@@ -36,42 +36,40 @@ static inline bool chol_diag(double *A, int n, int k0, int k1) {
   return true;
 }
 
-
 // Trailing update of the blocked Cholesky: C[i][j] -= sum_k P[i][k] P[j][k] for i0 <= j <= i < n, with the panel P (rows
 // i0.., columns kb..kb+nb of A) read row-wise for the left factor and through its transposed copy PT (nb x m) for the
 // right one.  Register tile: 4 rows x (2 vectors) columns; tiles that straddle the diagonal also write above it.
 #define LIO_TRAIL_BODY(VT, VTU, VW)                                                                                     \
   for (int i = i0; i < n; i += 4) {                                                                                    \
     const int rows = std::min(4, n - i), jmax = i + rows - 1;                                                          \
+    /* a short last row group re-reads its last valid row: the duplicates are computed and dropped */                  \
+    const double *p0 = A + (size_t)i * n + kb, *p1 = A + (size_t)std::min(i + 1, n - 1) * n + kb,                        \
+                 *p2 = A + (size_t)std::min(i + 2, n - 1) * n + kb, *p3 = A + (size_t)std::min(i + 3, n - 1) * n + kb;   \
     for (int jb = i0; jb <= jmax; jb += 2 * VW) {                                                                      \
       const int w = std::min(2 * VW, n - jb);                                                                          \
+      VT c00 = {}, c01 = {}, c10 = {}, c11 = {}, c20 = {}, c21 = {}, c30 = {}, c31 = {};                                 \
+      const double *pt = PT + (jb - i0);   /* rows of PT are padded to ldpt: lanes past m are finite and dropped */     \
+      for (int k = 0; k < nb; ++k, pt += ldpt) {                                                                       \
+        const VT b0 = *(const VTU *)pt, b1 = *(const VTU *)(pt + VW);                                                  \
+        const double a0 = p0[k], a1 = p1[k], a2 = p2[k], a3 = p3[k];                                                   \
+        c00 += a0 * b0; c01 += a0 * b1;                                                                                \
+        c10 += a1 * b0; c11 += a1 * b1;                                                                                \
+        c20 += a2 * b0; c21 += a2 * b1;                                                                                \
+        c30 += a3 * b0; c31 += a3 * b1;                                                                                \
+      }                                                                                                                \
       if (rows == 4 && w == 2 * VW) {                                                                                  \
-        VT c00 = {}, c01 = {}, c10 = {}, c11 = {}, c20 = {}, c21 = {}, c30 = {}, c31 = {};                               \
-        const double *p0 = A + (size_t)i * n + kb, *p1 = p0 + n, *p2 = p1 + n, *p3 = p2 + n;                            \
-        const double *pt = PT + (jb - i0);                                                                             \
-        for (int k = 0; k < nb; ++k, pt += m) {                                                                        \
-          const VT b0 = *(const VTU *)pt, b1 = *(const VTU *)(pt + VW);                                                \
-          const double a0 = p0[k], a1 = p1[k], a2 = p2[k], a3 = p3[k];                                                 \
-          c00 += a0 * b0; c01 += a0 * b1;                                                                              \
-          c10 += a1 * b0; c11 += a1 * b1;                                                                              \
-          c20 += a2 * b0; c21 += a2 * b1;                                                                              \
-          c30 += a3 * b0; c31 += a3 * b1;                                                                              \
-        }                                                                                                              \
         double *r0 = A + (size_t)i * n + jb, *r1 = r0 + n, *r2 = r1 + n, *r3 = r2 + n;                                  \
         *(VTU *)r0 -= c00; *(VTU *)(r0 + VW) -= c01;                                                                   \
         *(VTU *)r1 -= c10; *(VTU *)(r1 + VW) -= c11;                                                                   \
         *(VTU *)r2 -= c20; *(VTU *)(r2 + VW) -= c21;                                                                   \
         *(VTU *)r3 -= c30; *(VTU *)(r3 + VW) -= c31;                                                                   \
       } else {                                                                                                         \
+        double tmp[4][2 * VW];                                                                                         \
+        *(VTU *)&tmp[0][0] = c00; *(VTU *)&tmp[0][VW] = c01; *(VTU *)&tmp[1][0] = c10; *(VTU *)&tmp[1][VW] = c11;       \
+        *(VTU *)&tmp[2][0] = c20; *(VTU *)&tmp[2][VW] = c21; *(VTU *)&tmp[3][0] = c30; *(VTU *)&tmp[3][VW] = c31;       \
         for (int r = 0; r < rows; ++r) {                                                                               \
-          const double *pr = A + (size_t)(i + r) * n + kb;                                                             \
           double *cr = A + (size_t)(i + r) * n + jb;                                                                   \
-          for (int cidx = 0; cidx < w; ++cidx) {                                                                       \
-            const double *pt = PT + (jb - i0) + cidx;                                                                  \
-            double s = 0;                                                                                              \
-            for (int k = 0; k < nb; ++k) s += pr[k] * pt[(size_t)k * m];                                               \
-            cr[cidx] -= s;                                                                                             \
-          }                                                                                                            \
+          for (int cidx = 0; cidx < w; ++cidx) cr[cidx] -= tmp[r][cidx];                                               \
         }                                                                                                              \
       }                                                                                                                \
     }                                                                                                                  \
@@ -83,14 +81,14 @@ typedef double v8d __attribute__((vector_size(64)));
 typedef double v8du __attribute__((vector_size(64), aligned(8)));
 
 #if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
-__attribute__((target("arch=x86-64-v4"))) static void trailing_v4(double *A, int n, int kb, int nb, int i0, const double *PT, int m) {
+__attribute__((target("arch=x86-64-v4"))) static void trailing_v4(double *A, int n, int kb, int nb, int i0, const double *PT, int ldpt) {
   LIO_TRAIL_BODY(v8d, v8du, 8)
 }
-__attribute__((target("arch=x86-64-v3"))) static void trailing_v3(double *A, int n, int kb, int nb, int i0, const double *PT, int m) {
+__attribute__((target("arch=x86-64-v3"))) static void trailing_v3(double *A, int n, int kb, int nb, int i0, const double *PT, int ldpt) {
   LIO_TRAIL_BODY(v4d, v4du, 4)
 }
 #endif
-static void trailing_base(double *A, int n, int kb, int nb, int i0, const double *PT, int m) {
+static void trailing_base(double *A, int n, int kb, int nb, int i0, const double *PT, int ldpt) {
   LIO_TRAIL_BODY(v4d, v4du, 4)
 }
 typedef void (*trailing_fn)(double *, int, int, int, int, const double *, int);
@@ -116,40 +114,48 @@ LIO_MV bool cholesky(Mat &a) {
   const int n = a.r;
   double *A = a.d.data();
   if (n <= 2 * kCholNb) return chol_diag(A, n, 0, n);
-  std::vector<double> PTbuf((size_t)kCholNb * n + 8);
+  const int ldpt = ((n + 31) / 32) * 32 + 32;   // padded row length of the transposed panel (vector tiles over-read / over-write the pad)
+  std::vector<double> PTbuf((size_t)kCholNb * ldpt + 16, 0.0);
   double *PT = PTbuf.data();
   for (int kb = 0; kb < n; kb += kCholNb) {
     const int nb = std::min(kCholNb, n - kb), i0 = kb + nb, m = n - i0;
     if (!chol_diag(A, n, kb, i0)) return false;
     if (m <= 0) break;
     // panel X L_kk^T = A[i0:, kb:i0], solved on the transposed copy: L_kk PT = B^T is a forward substitution whose
-    // updates are axpys over contiguous rows of PT (no short reductions)
+    // updates are axpys over contiguous rows of PT (no short reductions).  Column chunks of kPc keep the nb x kPc working
+    // set in L1 and the accumulators of row j in registers across its j updates.
     for (int i = i0; i < n; ++i) {
       const double *x = A + (size_t)i * n + kb;
-      for (int k = 0; k < nb; ++k) PT[(size_t)k * m + (i - i0)] = x[k];
+      for (int k = 0; k < nb; ++k) PT[(size_t)k * ldpt + (i - i0)] = x[k];
     }
-    for (int j = 0; j < nb; ++j) {
-      const double *lj = A + (size_t)(kb + j) * n + kb;
-      double *pj = PT + (size_t)j * m;
-      int t = 0;
-      for (; t + 1 < j; t += 2) {
-        const double l0 = lj[t], l1 = lj[t + 1];
-        const double *q0 = PT + (size_t)t * m, *q1 = q0 + m;
-        for (int c2 = 0; c2 < m; ++c2) pj[c2] -= l0 * q0[c2] + l1 * q1[c2];
+    {
+      constexpr int kPc = 32;
+      double inv[kCholNb];
+      for (int j = 0; j < nb; ++j) inv[j] = 1.0 / A[(size_t)(kb + j) * n + kb + j];
+      for (int c0 = 0; c0 < m; c0 += kPc) {   // the padded tail of PT (finite values) is processed along and ignored
+        for (int j = 0; j < nb; ++j) {
+          const double *lj = A + (size_t)(kb + j) * n + kb;
+          double *pj = PT + (size_t)j * ldpt + c0;
+          double acc[kPc];
+#pragma omp simd
+          for (int c2 = 0; c2 < kPc; ++c2) acc[c2] = pj[c2];
+          for (int t = 0; t < j; ++t) {
+            const double l0 = lj[t];
+            const double *q0 = PT + (size_t)t * ldpt + c0;
+#pragma omp simd
+            for (int c2 = 0; c2 < kPc; ++c2) acc[c2] -= l0 * q0[c2];
+          }
+          const double iv = inv[j];
+#pragma omp simd
+          for (int c2 = 0; c2 < kPc; ++c2) pj[c2] = acc[c2] * iv;
+        }
       }
-      for (; t < j; ++t) {
-        const double l0 = lj[t];
-        const double *q0 = PT + (size_t)t * m;
-        for (int c2 = 0; c2 < m; ++c2) pj[c2] -= l0 * q0[c2];
-      }
-      const double inv = 1.0 / lj[j];
-      for (int c2 = 0; c2 < m; ++c2) pj[c2] *= inv;
     }
     for (int i = i0; i < n; ++i) {
       double *x = A + (size_t)i * n + kb;
-      for (int k = 0; k < nb; ++k) x[k] = PT[(size_t)k * m + (i - i0)];
+      for (int k = 0; k < nb; ++k) x[k] = PT[(size_t)k * ldpt + (i - i0)];
     }
-    trailing(A, n, kb, nb, i0, PT, m);
+    trailing(A, n, kb, nb, i0, PT, ldpt);
   }
   return true;
 }
