@@ -165,9 +165,16 @@ LIO_MV void cholesky_solve(const Mat &L, Vec &b) {
   const double *A = L.d.data();
   for (int i = 0; i < n; ++i) {
     const double *ri = A + (size_t)i * n;
-    double s = 0;
-#pragma omp simd reduction(+ : s)
-    for (int k = 0; k < i; ++k) s += ri[k] * b[k];
+    const double *bp = b.data();
+    // four interleaved partial sums: the reduction is not one latency chain
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    const int q = i / 4;
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+    for (int k = 0; k < q; ++k) {
+      s0 += ri[k] * bp[k]; s1 += ri[q + k] * bp[q + k]; s2 += ri[2 * q + k] * bp[2 * q + k]; s3 += ri[3 * q + k] * bp[3 * q + k];
+    }
+    double s = (s0 + s1) + (s2 + s3);
+    for (int k = 4 * q; k < i; ++k) s += ri[k] * bp[k];
     b[i] = (b[i] - s) / ri[i];
   }
   // back substitution in axpy form: x_i known -> subtract its column (= row i of L) from the rest
@@ -422,13 +429,27 @@ LIO_MV void JtJ_dense(const double *J, const double *r, int rows, int cols, doub
   }
 }
 
+// Four rows at a time: x is loaded once per four dot products and the four reductions are independent chains.
 LIO_MV void matvec(const Mat &A, const Vec &x, Vec &y) {
-  y.assign(A.r, 0.0);
-  for (int i = 0; i < A.r; ++i) {
-    const double *row = &A.d[(size_t)i * A.c];
+  const int nr = A.r, nc = A.c;
+  y.assign(nr, 0.0);
+  const double *xp = x.data();
+  int i = 0;
+  for (; i + 4 <= nr; i += 4) {
+    const double *r0 = &A.d[(size_t)i * nc], *r1 = r0 + nc, *r2 = r1 + nc, *r3 = r2 + nc;
+    double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+    for (int j = 0; j < nc; ++j) {
+      const double xj = xp[j];
+      s0 += r0[j] * xj; s1 += r1[j] * xj; s2 += r2[j] * xj; s3 += r3[j] * xj;
+    }
+    y[i] = s0; y[i + 1] = s1; y[i + 2] = s2; y[i + 3] = s3;
+  }
+  for (; i < nr; ++i) {
+    const double *row = &A.d[(size_t)i * nc];
     double s = 0;
 #pragma omp simd reduction(+ : s)
-    for (int j = 0; j < A.c; ++j) s += row[j] * x[j];
+    for (int j = 0; j < nc; ++j) s += row[j] * xp[j];
     y[i] = s;
   }
 }
@@ -442,13 +463,25 @@ LIO_MV void weighted_gram(const Mat &A, const Vec &w, const std::vector<int> &co
   C = Mat(n, n);
   for (int r = 0; r < n; ++r) {
     const double *br = &Bw.d[(size_t)r * kc];
-    for (int c = r; c < n; ++c) {
-      const double *bc = &B.d[(size_t)c * kc];
+    int cc = r;
+    for (; cc + 4 <= n; cc += 4) {  // four columns per pass: br is loaded once, four independent reductions
+      const double *b0 = &B.d[(size_t)cc * kc], *b1 = b0 + kc, *b2 = b1 + kc, *b3 = b2 + kc;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma omp simd reduction(+ : s0, s1, s2, s3)
+      for (int k = 0; k < kc; ++k) {
+        const double v = br[k];
+        s0 += v * b0[k]; s1 += v * b1[k]; s2 += v * b2[k]; s3 += v * b3[k];
+      }
+      const double sv[4] = {s0, s1, s2, s3};
+      for (int q = 0; q < 4; ++q) { C.d[(size_t)r * n + cc + q] = sv[q]; C.d[(size_t)(cc + q) * n + r] = sv[q]; }
+    }
+    for (; cc < n; ++cc) {
+      const double *bc = &B.d[(size_t)cc * kc];
       double s = 0;
 #pragma omp simd reduction(+ : s)
       for (int k = 0; k < kc; ++k) s += br[k] * bc[k];
-      C.d[(size_t)r * n + c] = s;
-      C.d[(size_t)c * n + r] = s;
+      C.d[(size_t)r * n + cc] = s;
+      C.d[(size_t)cc * n + r] = s;
     }
   }
 }

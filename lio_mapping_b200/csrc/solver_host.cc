@@ -58,7 +58,8 @@ void dogleg_solve(const DoglegOptions &opt, DoglegProblem &P, DoglegSummary *sum
       {
         Vec sg(n);
         for (int i = 0; i < n; ++i) sg[i] = gradient[i] / diagonal[i];
-        Vec Hsg = mul(H, sg);
+        Vec Hsg;
+        matvec(H, sg, Hsg);
         alpha = vdot(gradient, gradient) / vdot(sg, Hsg);
       }
       linear_ok = false;
@@ -97,7 +98,8 @@ void dogleg_solve(const DoglegOptions &opt, DoglegProblem &P, DoglegSummary *sum
         dogleg_step_norm = vnorm(step);
       }
       for (int i = 0; i < n; ++i) step[i] /= diagonal[i];
-      Vec Hs = mul(H, step);
+      Vec Hs;
+      matvec(H, step, Hs);
       model_cost_change = -vdot(step, g) - 0.5 * vdot(step, Hs);
       step_valid = model_cost_change > 0.0;
     }
