@@ -172,6 +172,9 @@ int lio_asm_ppp_host(const float *pts4, const float *coef4, int n, const double 
 /* Streaming-rate measurement of the fused stage-C kernel on n synthetic features (32 B each) split over 8 frames;
  * CUDA events around each launch.  out = {avg ms / launch, min ms, algorithmic bytes / launch, launches}. */
 int lio_asm_stream_bench(long long n_features, int iters, int device, double out[4]);
+/* Test seam: number of TMA stages between folds of the per-thread product of (1 + r^2) into the cost accumulator of the
+ * fused kernel (default 1024, i.e. one log per 2048 features and thread). */
+int lio_asm_set_fold_chunks(int chunks);
 
 /* IntegrationBase (include/imu_processor/IntegrationBase.h:72-388) */
 typedef struct lio_pim lio_pim;

@@ -97,6 +97,7 @@ def lib():
     L.lio_ppp_evaluate.argtypes = [f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p, f64p]
     L.lio_ppp_evaluate_batch_host.argtypes = [f32p, f32p, ip, f64p, f64p, f64p, f64p, f64p, ip]
     L.lio_asm_ppp_host.argtypes = [f32p, f32p, ip, f64p, f64p, f64p, ip]
+    L.lio_asm_set_fold_chunks.argtypes = [ip]
     L.lio_asm_stream_bench.argtypes = [C.c_longlong, ip, ip, f64p]
     L.lio_pim_create.argtypes = [f64p, f64p, f64p, f64p, f64p, C.POINTER(vp)]
     L.lio_pim_destroy.argtypes = [vp]

@@ -157,7 +157,7 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
 #pragma unroll
       for (int j = 0; j < kAsmPerThread; ++j) accumulate_rho(acc, prod, sv[j]);
     }
-    if (((k + 1) * kAsmPerThread) % kAsmFold == 0) { acc[28] += log(prod); prod = 1.0; }
+    if ((k + 1) % P.fold_chunks == 0) { acc[28] += log(prod); prod = 1.0; }
     __syncthreads();  // stage s fully consumed
     if (threadIdx.x == 0 && k + kAsmStages < nchunks) issue(k + kAsmStages);
   }
@@ -238,7 +238,11 @@ void AsmWork::destroy() {
   partial = out = nullptr; counter = nullptr;
 }
 
+static int g_fold_chunks = kAsmFold / kAsmPerThread;
+void asm_set_fold_chunks(int chunks) { g_fold_chunks = chunks < 1 ? 1 : chunks; }
+
 void asm_plan(AsmParams &p, int sm_count) {
+  p.fold_chunks = g_fold_chunks;
   long long total = 0;
   for (int k = 0; k < p.nframes; ++k) total += p.f[k].n;
   // aim at ~4 tiles per SM, at least 2 loads per thread, tile a multiple of the block size

@@ -21,6 +21,7 @@ struct AsmParams {
   int nframes;
   int tile_feats;  // features per tile (multiple of the block size)
   int ntiles;
+  int fold_chunks; // stages between folds of the per-thread (1 + r^2) product into the cost (set by asm_plan)
 };
 
 struct AsmWork {
@@ -32,6 +33,8 @@ struct AsmWork {
   void destroy();
 };
 
+// Test seam: stages between folds of the running (1 + r^2) product (default 1024 = 2048 features per thread).
+void asm_set_fold_chunks(int chunks);
 // Fills tile0 / ntiles / tile_feats of `p` from the per-frame counts (host side).
 void asm_plan(AsmParams &p, int sm_count);
 // Launches the fused kernel; results land in work.out (device), kAsmStride doubles per frame:

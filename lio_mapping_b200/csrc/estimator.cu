@@ -2078,6 +2078,11 @@ extern "C" int lio_laser_odom_host(const float *map, int K, const float *surf, i
   return rc;
 }
 
+extern "C" int lio_asm_set_fold_chunks(int chunks) {
+  asm_set_fold_chunks(chunks);
+  return LIO_OK;
+}
+
 extern "C" int lio_asm_stream_bench(long long n_features, int iters, int device, double out[4]) {
   if (n_features <= 0 || iters <= 0 || !out) return LIO_ERR_INVALID;
   if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;

@@ -48,6 +48,32 @@ def test_asm_ppp_kernel_vs_numpy(n):
     assert abs(cost - cr) <= 1e-11 * max(1.0, cr)
 
 
+def test_asm_ppp_product_fold_and_large_residuals():
+    """The cost is accumulated as a per-thread running product of (1 + r^2) that is folded into a log every few stages;
+    residuals with r^2 >= 1/16 bypass the product.  Force one fold per stage and mix both regimes."""
+    from lio_mapping_b200 import estimator, synth, _lib
+    from tests.test_shard_gloo import s_blocks
+    rng = np.random.default_rng(11)
+    n = 1500000                                            # 5 stages per tile on 148 SMs: several folds per thread
+    p = rng.uniform(-30, 30, (n, 4)).astype(np.float32)
+    w = rng.normal(size=(n, 3)); w /= np.linalg.norm(w, axis=1, keepdims=True)
+    q = rng.normal(size=4); q /= np.linalg.norm(q)
+    R = synth.quat_to_rot(q); t = rng.normal(size=3)
+    a = w @ R                                              # rows: R^T w
+    r_target = np.where(rng.uniform(size=n) < 0.9, rng.normal(0, 0.03, n), rng.normal(0, 3.0, n))   # 10 % outliers
+    b = r_target - np.einsum("ij,ij->i", a, p[:, :3].astype(np.float64) + t)
+    c = np.concatenate([w, b[:, None]], 1).astype(np.float32)
+    Sr, cr = s_blocks((p.astype(np.float64), c.astype(np.float64)), R, t)
+    try:
+        for fold in (1, 2, 1024):
+            _lib.check(_lib.lib().lio_asm_set_fold_chunks(fold), "fold")
+            S, cost = estimator.asm_ppp(p, c, R, t)
+            assert np.abs(S - Sr).max() <= 1e-11 * max(1.0, np.abs(Sr).max())
+            assert abs(cost - cr) <= 1e-11 * max(1.0, cr), (fold, cost, cr)
+    finally:
+        _lib.lib().lio_asm_set_fold_chunks(1024)
+
+
 @pytest.fixture(scope="module")
 def vlp_seq(oracle):
     return helpers.Sequence(oracle, "vlp16", n_total=10, distort=False)
