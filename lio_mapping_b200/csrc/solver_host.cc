@@ -5,6 +5,7 @@
 // One device evaluation per iteration: the candidate evaluation already carries H and g, which are
 // reused when the step is accepted.
 #include "solver_host.h"
+#include <cstring>
 
 namespace lio {
 using namespace hm;
@@ -18,8 +19,8 @@ void dogleg_solve(const DoglegOptions &opt, DoglegProblem &P, DoglegSummary *sum
   if (n == 0) { sum->termination = 1; return; }
   Vec x, cand;
   P.get_state(x);
-  Mat H(n, n), Hc(n, n);
-  Vec g(n), gc(n);
+  Mat H(n, n), Hc(n, n), A(n, n);
+  Vec g(n), gc(n), rhs(n);
   double x_cost = 0;
   if (!P.linearize(H, g, x_cost)) { sum->termination = 2; return; }
   sum->evaluations = 1;
@@ -64,9 +65,9 @@ void dogleg_solve(const DoglegOptions &opt, DoglegProblem &P, DoglegSummary *sum
       }
       linear_ok = false;
       while (mu < max_mu) {
-        Mat A = H;
+        std::memcpy(A.d.data(), H.d.data(), sizeof(double) * (size_t)n * n);   // workspace reused across iterations
         for (int i = 0; i < n; ++i) A(i, i) += mu * diagonal[i] * diagonal[i];
-        Vec rhs = g;
+        rhs = g;
         bool ok = cholesky(A);
         if (ok) {
           cholesky_solve(A, rhs);
