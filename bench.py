@@ -135,6 +135,8 @@ def main():
     ap.add_argument("--workload", default="hdl64", choices=["hdl64", "vlp16", "stress128"])
     ap.add_argument("--overlap-marginalization", type=int, default=1, choices=[0, 1],
                     help="0: marginalisation algebra inline (reference order); 1: on a worker thread beside the next scan's front end")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU exchange of the S blocks: fused peer-memory stores (default) or an NCCL allreduce callback")
     ap.add_argument("--cpu-sample", type=int, default=4, help="scans of the cpu_baseline sample (rank 0, N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -194,7 +196,29 @@ def main():
             t = torch.as_tensor(_Arr(ptr, count), device=dev)
             dist.all_reduce(t)
             return 0
-        est.set_shard(rank, world, allreduce)
+
+        exchange = {"kind": "nccl allreduce (torch.distributed) of O x 32 doubles per evaluation"}
+
+        def attach(e):
+            """Preferred: fused exchange over peer memory (IPC handles all-gathered once); fallback: NCCL allreduce callback."""
+            if args.exchange == "nccl":
+                e.set_shard(rank, world, allreduce)
+                return
+            try:
+                mine = torch.from_numpy(e.exchange_handle()).to(dev)
+                allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
+                dist.all_gather(allh, mine)
+                e.set_peers(rank, world, handles=[h.cpu().numpy() for h in allh])
+                ok = torch.ones(1, device=dev)
+            except Exception as exc:   # no P2P / IPC on this box
+                print(f"[bench] peer exchange unavailable on rank {rank}: {exc!r}", file=sys.stderr)
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) < 0.5:
+                e.set_shard(rank, world, allreduce)
+            else:
+                exchange["kind"] = "fused into the stage-C kernel tail: P2P stores of the owned S blocks into every rank's buffer + epoch flags (CUDA IPC peer memory)"
+        attach(est)
 
     def surf_ds_of(k):
         pp.SetInputCloud(scn.raw[k]); pp.Process()
@@ -283,7 +307,7 @@ def main():
                                max_frame_points=1 << 16 if kind != "stress128" else 1 << 18, max_scan_points=max_pts,
                                overlap_marginalization=args.overlap_marginalization, **est_cfg)
     if world > 1:
-        est2.set_shard(rank, world, allreduce)
+        attach(est2)
     est_saved, est = est, est2
     scenario.warm_start(est, scn, W, surf_ds_of,
                         lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=est_cfg["acc_n"], gyr_n=est_cfg["gyr_n"],
@@ -325,7 +349,7 @@ def main():
                 "config": {"workload": workload, "window": W, "opt_window": W, "points_per_scan": int(scn.raw[W].shape[0]),
                            "features_per_solve": float(np.mean(feats)), "gn_iterations_per_scan": float(np.mean(iters)),
                            "l2": "flushed between timed steps (256 MB write outside the event pair)",
-                           "parallelism": "frames sharded 1..O over %d rank(s), NCCL allreduce of O x 29 doubles per evaluation" % world,
+                           "parallelism": "frames sharded 1..O over %d rank(s)%s" % (world, ("; exchange: " + exchange["kind"]) if world > 1 else ""),
                            "e2e_vs_device_pass_max_pos_diff_m": drift,
                            "overlap_marginalization": args.overlap_marginalization,
                            "ms_per_timed_step": [round(float(v), 3) for v in ms],

@@ -279,6 +279,17 @@ int lio_est_kernel_profile(lio_est *est, double out[8], int reset);
  * (e.g. ncclAllReduce / torch.distributed.all_reduce on the estimator's stream). */
 typedef int (*lio_allreduce_fn)(void *user, double *buf_dev, int count);
 int lio_est_set_shard(lio_est *est, int rank, int world, lio_allreduce_fn fn, void *user);
+/* Fused exchange over peer memory (preferred on one NVLink / NVSwitch node; `fn` may then be NULL in set_shard).  Every
+ * rank owns one small device exchange buffer; once each rank knows the device pointers of all of them (its own, and the
+ * peers' opened through CUDA IPC with lio_ipc_export / lio_ipc_open, or raw pointers when the contexts share a process),
+ * the last CTA of the fused stage-C kernel stores the S blocks of the frames it owns straight into EVERY rank's buffer
+ * (P2P stores) and publishes an epoch with system-scope release; a one-warp kernel on each rank acquires the epochs of
+ * all ranks before the 2.5 kB result goes to the host.  No collective call, no extra pass over the data. */
+int lio_est_exchange_buffer(lio_est *est, void **dev_ptr, size_t *bytes);
+int lio_est_set_peers(lio_est *est, int world, void *const *peer_ptrs /* [world], entry [rank] ignored */);
+int lio_ipc_export(const void *dev_ptr, unsigned char handle[64]);      /* cudaIpcGetMemHandle */
+int lio_ipc_open(const unsigned char handle[64], void **dev_ptr);       /* cudaIpcOpenMemHandle, lazy peer access */
+int lio_ipc_close(void *dev_ptr);
 /* Owner rank of window frame pivot+frame_rel (frame_rel = 1..O) under `world` ranks: (frame_rel-1) % world. */
 int lio_est_frame_owner(int frame_rel, int world);
 

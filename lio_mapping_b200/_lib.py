@@ -114,6 +114,11 @@ def lib():
     L.lio_est_process_imu.argtypes = [vp, C.c_double, f64p, f64p, C.c_double]
     L.lio_est_process_scan_host.argtypes = [vp, f32p, ip]
     L.lio_est_begin_scan.argtypes = [vp]
+    L.lio_est_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lio_est_set_peers.argtypes = [vp, ip, C.POINTER(vp)]
+    L.lio_ipc_export.argtypes = [vp, u8p]
+    L.lio_ipc_open.argtypes = [u8p, C.POINTER(vp)]
+    L.lio_ipc_close.argtypes = [vp]
     L.lio_est_process_imu_batch.argtypes = [vp, ip, f64p, f64p, f64p, f64p]
     L.lio_est_process_scan_dev.argtypes = [vp, vp, vp, ip]
     L.lio_est_get_states.argtypes = [vp, f64p]

@@ -207,6 +207,7 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   // (independent L2 loads, so the chain pipelines); deterministic and no second launch.
   for (int q = threadIdx.x; q < P.nframes * 29; q += kAsmThreads) {
     const int f = q / 29, k = q - f * 29;
+    if (P.npeers > 0 && !((P.owned_mask >> f) & 1u)) continue;   // a peer reduces this frame and writes the row here
     const int t0 = P.f[f].tile0;
     const int t1 = (f + 1 < P.nframes) ? P.f[f + 1].tile0 : P.ntiles;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
@@ -218,7 +219,21 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
       v3 += __ldcg(partial + (size_t)(tt + 3) * kAsmStride + k);
     }
     for (; tt < t1; ++tt) v0 += __ldcg(partial + (size_t)tt * kAsmStride + k);
-    out[f * kAsmStride + k] = (v0 + v1) + (v2 + v3);
+    const double v = (v0 + v1) + (v2 + v3);
+    if (P.npeers > 0) {
+#pragma unroll 1
+      for (int pr = 0; pr < P.npeers; ++pr) P.peer_out[pr][f * kAsmStride + k] = v;   // own buffer included
+    } else {
+      out[f * kAsmStride + k] = v;
+    }
+  }
+  if (P.npeers > 0) {
+    __threadfence_system();   // rows visible system-wide before the flags
+    __syncthreads();
+    if (threadIdx.x < (unsigned)P.npeers) {
+      unsigned *fl = P.peer_flag[threadIdx.x] + P.self;
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl), "r"(P.epoch) : "memory");
+    }
   }
   if (threadIdx.x == 0) *counter = 0u;
 }
@@ -242,7 +257,7 @@ static int g_fold_chunks = kAsmFold / kAsmPerThread;
 void asm_set_fold_chunks(int chunks) { g_fold_chunks = chunks < 1 ? 1 : chunks; }
 
 void asm_plan(AsmParams &p, int sm_count) {
-  p.fold_chunks = g_fold_chunks;
+  p.fold_chunks = g_fold_chunks;   // (the exchange fields are set by the caller; zero-initialised params mean single GPU)
   long long total = 0;
   for (int k = 0; k < p.nframes; ++k) total += p.f[k].n;
   // aim at ~4 tiles per SM, at least 2 loads per thread, tile a multiple of the block size

@@ -14,6 +14,7 @@ struct AsmFrame {
   int tile0;           // first tile index of this frame
 };
 
+constexpr int kMaxPeers = 8;
 constexpr int kAsmRtStride = 12;  // per frame: R_lpi (9, row-major) then R_lpi^T P_lpi (3), in a DEVICE buffer
 
 struct AsmParams {
@@ -22,6 +23,14 @@ struct AsmParams {
   int tile_feats;  // features per tile (multiple of the block size)
   int ntiles;
   int fold_chunks; // stages between folds of the per-thread (1 + r^2) product into the cost (set by asm_plan)
+  // Fused exchange over peer memory (multi-GPU, frames sharded by rank): the last CTA writes the S blocks of the frames
+  // this rank owns into its own AND every peer's result buffer (P2P stores over NVLink), then publishes `epoch` in each
+  // peer's flag slot with system-scope release.  npeers == 0: single-GPU behaviour (all rows written locally).
+  unsigned owned_mask;              // bit f set: frame f is reduced by this rank
+  int npeers, self;                 // ranks in the exchange (including this one), this rank's index
+  unsigned epoch;                   // evaluation counter, identical on all ranks
+  double *peer_out[kMaxPeers];      // result buffers (this rank's own at [self]), already offset to the epoch's parity
+  unsigned *peer_flag[kMaxPeers];   // flag arrays (one slot per source rank)
 };
 
 struct AsmWork {

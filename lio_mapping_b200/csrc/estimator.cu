@@ -366,6 +366,11 @@ struct MargPrior {
 // symmetric eigen-decompositions, ~n^3) is a pure function of that snapshot and runs on a worker thread while the next
 // scan's front end (deskew, voxel grid, local map, k-NN features) keeps the device busy.  The worker is started at
 // the ENTRY of the next lio_est_process_scan_* call, not earlier, so none of it runs outside a caller's timed step.
+constexpr size_t kXRowBytes = sizeof(double) * kMaxOpt * kAsmStride;
+constexpr size_t kXFlagOff = 2 * kXRowBytes;
+constexpr size_t kXErrOff = kXFlagOff + sizeof(unsigned) * kMaxPeers;
+constexpr size_t kXBytes = kXErrOff + 64;
+
 struct MargJob {
   bool stashed = false, running = false;
   int O = 0;
@@ -445,6 +450,12 @@ struct lio_est {
   lio_est_config cfg;
   MargJob mjob;
   Worker worker;
+  // fused exchange over peer memory (multi-GPU): one device allocation per rank, laid out as
+  //   [2 parities][kMaxOpt * kAsmStride doubles] | unsigned flag[kMaxPeers] | int err
+  char *xbuf = nullptr;
+  char *peer_base[kMaxPeers] = {};
+  int npeers = 0;
+  unsigned xepoch = 0;
   Mat hp_exp;              // prior Hp scattered into the current tangent layout (cache of one solve)
   bool hp_exp_valid = false;
   struct ImuBlockStore { double JtJ[30 * 30], Jtr[30], cost; bool used; } imu_blocks_store[kMaxOpt];
@@ -613,6 +624,7 @@ extern "C" int lio_est_destroy(lio_est *e) {
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evk0) cudaEventDestroy(e->evk0);
   if (e->evk1) cudaEventDestroy(e->evk1);
+  if (e->xbuf) cudaFree(e->xbuf);
   if (e->h_tf) cudaFreeHost(e->h_tf);
   if (e->h_S) cudaFreeHost(e->h_S);
   if (e->h_Rt) cudaFreeHost(e->h_Rt);
@@ -671,7 +683,8 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   ok = ok && cudaMalloc(&e->d_odom, sizeof(OdomState)) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_odom_partial, sizeof(double) * 32 * 1024) == cudaSuccess;
   ok = ok && cudaMallocHost((void **)&e->h_tf, sizeof(TransformF) * (W + 1)) == cudaSuccess;
-  ok = ok && cudaMallocHost((void **)&e->h_S, sizeof(double) * kMaxOpt * kAsmStride) == cudaSuccess;
+  ok = ok && cudaMallocHost((void **)&e->h_S, sizeof(double) * (kMaxOpt * kAsmStride + 2)) == cudaSuccess;  // + exchange error flag
+  if (ok) std::memset(e->h_S, 0, sizeof(double) * (kMaxOpt * kAsmStride + 2));
   ok = ok && cudaMallocHost((void **)&e->h_Rt, sizeof(double) * kMaxOpt * kAsmRtStride) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_Rt, sizeof(double) * kMaxOpt * kAsmRtStride) == cudaSuccess;
   ok = ok && cudaMallocHost((void **)&e->h_counts, sizeof(int) * (W + 16)) == cudaSuccess;
@@ -700,6 +713,7 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   }
   ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
   ok = ok && cudaEventCreate(&e->evk0) == cudaSuccess && cudaEventCreate(&e->evk1) == cudaSuccess;
+  ok = ok && cudaMalloc(&e->xbuf, kXBytes) == cudaSuccess && cudaMemset(e->xbuf, 0, kXBytes) == cudaSuccess;
   for (int k = 0; k < 48 && ok; ++k) ok = ok && cudaEventCreate(&e->evp[k]) == cudaSuccess;
   e->use_dev_solver = cfg->device_solver != 0 && e->ds.supports(O) && cfg->max_num_iterations <= 22;
   if (e->use_dev_solver) ok = ok && e->ds.init(O) == 0;
@@ -959,6 +973,22 @@ static int build_local_map(lio_est *e) {
   return LIO_OK;
 }
 
+// ---- fused exchange over peer memory -----------------------------------------------------------------
+// Waits until every rank has published `epoch` in this rank's flag array (the rows travel with the asm_ppp tails of the
+// peers as P2P stores; system-scope release / acquire).  Bounded: a peer that never arrives sets *err instead of hanging.
+__global__ void k_xwait(const unsigned *__restrict__ flags, int npeers, unsigned epoch, int *__restrict__ err) {
+  const int p = threadIdx.x;
+  if (p >= npeers) return;
+  const long long t0 = clock64();
+  while (true) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + p) : "memory");
+    if ((int)(v - epoch) >= 0) break;
+    if (clock64() - t0 > 6000000000LL) { *err = 1; break; }   // ~3 s
+    __nanosleep(64);
+  }
+}
+
 // ---- stage C: lidar reduction at the current parameter values ------------------------------------
 struct FrameTerms { double R[9], t[3], M[6 * 18]; };
 
@@ -984,15 +1014,36 @@ static int eval_lidar_launch(lio_est *e, std::vector<FrameTerms> &ft) {
   asm_plan(ap, e->sm_count);
   long long nfeat = 0;
   for (int k = 0; k < ap.nframes; ++k) nfeat += ap.f[k].n;
+  const bool peers = e->world > 1 && e->npeers == e->world;
+  if (e->world > 1 && !peers && !e->allreduce) {
+    lio_set_last_error(__FILE__, __LINE__, "sharded context without an exchange: call lio_est_set_peers or pass an allreduce callback");
+    return LIO_ERR_INVALID;
+  }
+  const double *result = e->asmw.out;
+  if (peers) {  // the kernel's tail scatters the owned rows to every rank and publishes the epoch
+    ap.npeers = e->npeers; ap.self = e->rank; ap.epoch = ++e->xepoch;
+    const size_t par = (size_t)(ap.epoch & 1u) * kXRowBytes;
+    for (int i = 1; i <= O; ++i) if (owns_frame(e, pivot + i)) ap.owned_mask |= 1u << (i - 1);
+    for (int r = 0; r < e->npeers; ++r) {
+      ap.peer_out[r] = reinterpret_cast<double *>(e->peer_base[r] + par);
+      ap.peer_flag[r] = reinterpret_cast<unsigned *>(e->peer_base[r] + kXFlagOff);
+    }
+    result = reinterpret_cast<const double *>(e->xbuf + par);
+  }
   if (e->ev0) cudaEventRecord(e->ev0, e->stream);
   int rc = asm_launch(ap, e->d_Rt, e->asmw, e->stream, &e->launches);
   if (rc != LIO_OK) return rc;
   if (e->ev1) cudaEventRecord(e->ev1, e->stream);
-  if (e->world > 1 && e->allreduce) {
+  if (peers) {
+    k_xwait<<<1, 32, 0, e->stream>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
+                                     reinterpret_cast<int *>(e->xbuf + kXErrOff));
+    ++e->launches;
+    EST_CUDA(cudaMemcpyAsync(e->h_S + kMaxOpt * kAsmStride, e->xbuf + kXErrOff, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
+  } else if (e->world > 1 && e->allreduce) {
     rc = e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride);
     if (rc != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
   }
-  EST_CUDA(cudaMemcpyAsync(e->h_S, e->asmw.out, sizeof(double) * O * kAsmStride, cudaMemcpyDeviceToHost, e->stream));
+  EST_CUDA(cudaMemcpyAsync(e->h_S, result, sizeof(double) * O * kAsmStride, cudaMemcpyDeviceToHost, e->stream));
   e->S_pending = true;
   e->S_pending_feats = nfeat;
   return LIO_OK;
@@ -1004,6 +1055,7 @@ static int eval_lidar_wait(lio_est *e) {
   EST_CUDA(cudaStreamSynchronize(e->stream));
   e->t_lin_wait += now_s() - t0;
   e->S_pending = false;
+  if (*reinterpret_cast<const int *>(e->h_S + kMaxOpt * kAsmStride)) { lio_set_last_error(__FILE__, __LINE__, "peer exchange timed out (a rank did not publish its rows)"); return LIO_ERR_CUDA; }
   if (e->ev0 && e->ev1) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += e->S_pending_feats; }
@@ -1637,8 +1689,48 @@ extern "C" int lio_est_frame_owner(int frame_rel, int world) {  // frame_rel in 
 
 extern "C" int lio_est_set_shard(lio_est *e, int rank, int world, lio_allreduce_fn fn, void *user) {
   if (!e || world < 1 || rank < 0 || rank >= world) return LIO_ERR_INVALID;
-  if (world > 1 && !fn) return LIO_ERR_INVALID;
   e->rank = rank; e->world = world; e->allreduce = fn; e->allreduce_user = user;
+  e->npeers = 0;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_exchange_buffer(lio_est *e, void **dev_ptr, size_t *bytes) {
+  if (!e || !dev_ptr) return LIO_ERR_INVALID;
+  *dev_ptr = e->xbuf;
+  if (bytes) *bytes = kXBytes;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_set_peers(lio_est *e, int world, void *const *peer_ptrs) {
+  if (!e || !peer_ptrs || world != e->world || world < 2 || world > kMaxPeers) return LIO_ERR_INVALID;
+  for (int r = 0; r < world; ++r) {
+    e->peer_base[r] = r == e->rank ? e->xbuf : static_cast<char *>(peer_ptrs[r]);
+    if (!e->peer_base[r]) return LIO_ERR_INVALID;
+  }
+  e->npeers = world;
+  return LIO_OK;
+}
+
+extern "C" int lio_ipc_export(const void *dev_ptr, unsigned char handle[64]) {
+  if (!dev_ptr || !handle) return LIO_ERR_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaIpcMemHandle_t h;
+  LIO_CUDA_OK(cudaIpcGetMemHandle(&h, const_cast<void *>(dev_ptr)));
+  std::memcpy(handle, &h, 64);
+  return LIO_OK;
+}
+
+extern "C" int lio_ipc_open(const unsigned char handle[64], void **dev_ptr) {
+  if (!handle || !dev_ptr) return LIO_ERR_INVALID;
+  cudaIpcMemHandle_t h;
+  std::memcpy(&h, handle, 64);
+  LIO_CUDA_OK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return LIO_OK;
+}
+
+extern "C" int lio_ipc_close(void *dev_ptr) {
+  if (!dev_ptr) return LIO_OK;
+  LIO_CUDA_OK(cudaIpcCloseMemHandle(dev_ptr));
   return LIO_OK;
 }
 

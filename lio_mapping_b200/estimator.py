@@ -177,6 +177,36 @@ class Estimator:
         self._cb = cb
         _lib.check(_lib.lib().lio_est_set_shard(self.h, rank, world, cb, None), "lio_est_set_shard")
 
+    def exchange_buffer(self) -> int:
+        """Device pointer of this rank's exchange buffer (peer-memory exchange of the S blocks)."""
+        p = C.c_void_p()
+        _lib.check(_lib.lib().lio_est_exchange_buffer(self.h, C.byref(p), None), "lio_est_exchange_buffer")
+        return p.value
+
+    def exchange_handle(self) -> np.ndarray:
+        """64-byte CUDA IPC handle of the exchange buffer, to be all-gathered across ranks."""
+        h = np.zeros(64, np.uint8)
+        _lib.check(_lib.lib().lio_ipc_export(C.c_void_p(self.exchange_buffer()), h), "lio_ipc_export")
+        return h
+
+    def set_peers(self, rank, world, ptrs=None, handles=None):
+        """Switch the sharded solve to the fused peer-memory exchange.  ptrs: device pointers of every rank's exchange
+        buffer valid in this process (same-process contexts), or handles: (world, 64) uint8 IPC handles (one per rank)."""
+        self.set_shard(rank, world, None)
+        arr = (C.c_void_p * world)()
+        self._peer_open = []
+        for r in range(world):
+            if r == rank:
+                arr[r] = self.exchange_buffer()
+            elif ptrs is not None:
+                arr[r] = int(ptrs[r])
+            else:
+                p = C.c_void_p()
+                _lib.check(_lib.lib().lio_ipc_open(np.ascontiguousarray(handles[r], np.uint8), C.byref(p)), "lio_ipc_open")
+                self._peer_open.append(p.value)
+                arr[r] = p.value
+        _lib.check(_lib.lib().lio_est_set_peers(self.h, world, arr), "lio_est_set_peers")
+
     def kernel_profile(self, reset=False):
         o = np.zeros(8)
         _lib.check(_lib.lib().lio_est_kernel_profile(self.h, o, 1 if reset else 0), "kernel_profile")

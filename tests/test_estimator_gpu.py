@@ -219,6 +219,48 @@ def test_two_rank_shard_equals_single(oracle, vlp_seq):
         assert np.abs(e.states() - x).max() <= 1e-9 * max(1.0, np.abs(x).max())
 
 
+def test_two_rank_peer_exchange_equals_single(oracle, vlp_seq):
+    """The fused peer-memory exchange (owned S rows stored into every rank's buffer by the stage-C kernel tail, epoch
+    flags with system-scope release / acquire): two estimator contexts of one process exchange through raw device
+    pointers on one GPU and reproduce the single-rank solve."""
+    import threading
+    from lio_mapping_b200 import estimator
+    W = 5
+    cfg = dict(odom_max_iterations=1, prior_factor=1)
+    import torch
+    ref = estimator.Estimator(window_size=W, opt_window_size=W, max_frame_points=1 << 15, max_scan_points=1 << 17, **cfg)
+    # each rank on its own non-blocking stream: a rank's flag-wait kernel must not serialise with its peer's kernels
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    ranks = [estimator.Estimator(stream=streams[r].cuda_stream, window_size=W, opt_window_size=W, max_frame_points=1 << 15,
+                                 max_scan_points=1 << 17, **cfg) for r in range(2)]
+    mk = lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=0.2, gyr_n=0.02)
+    for e in [ref] + ranks:
+        helpers.warm_start(e, vlp_seq, oracle, W, pose_noise=0.01, seed=1, make_pim=mk)
+    torch.cuda.synchronize()
+    ptrs = [e.exchange_buffer() for e in ranks]
+    for r, e in enumerate(ranks):
+        e.set_peers(r, 2, ptrs=ptrs)
+    errs = []
+
+    def run(r):
+        try:
+            for k in range(W, 9):
+                helpers.feed_scan(ranks[r], vlp_seq, k)
+        except Exception as exc:   # pragma: no cover
+            errs.append(exc)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t_ in th:
+        t_.start()
+    for k in range(W, 9):
+        helpers.feed_scan(ref, vlp_seq, k)
+    for t_ in th:
+        t_.join(timeout=300)
+    assert not errs, errs
+    x = ref.states()
+    for e in ranks:
+        assert np.abs(e.states() - x).max() <= 1e-9 * max(1.0, np.abs(x).max())
+
+
 def test_device_solver_equals_host_solver(oracle, vlp_seq):
     """The GPU-resident dogleg loop and the host controller take the same steps."""
     from lio_mapping_b200 import estimator
