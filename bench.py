@@ -357,10 +357,11 @@ def main():
                            "ms_per_timed_step": [round(float(v), 3) for v in ms],
                            "host_wall_ms_per_scan": {kk: 1e3 * float(np.mean(v)) for kk, v in brk.items()}},
                 "roofline": {"kernel": "asm_ppp (fused PivotPointPlane residual+Jacobian+JtJ reduction)", "bound": "hbm",
-                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": 3.83e6 if kind == "hdl64" else None,
                              "avg_launch_us": avg_ms * 1e3, "bytes_per_launch": bytes_per_launch, "launches": prof["asm_launches"],
                              "peak_source": peak_src,
-                             "note": "32 B/feature x features of the solve; ~4.8 MB per launch on this workload, i.e. launch-latency and L2 bound (SURVEY.md 7.3-4)"},
+                             "note": "32 B/feature x features of the solve (3.9 MB per launch on HDL-64): launch-latency bound, ~12 us fixed cost; traffic = dram__bytes_read+write per launch from profiles/r1a_asm_ppp_full_hdl64.csv (ncu --set full of this workload: every byte read once); the streaming rate of the same kernel is in roofline_stream"},
                 "roofline_knn": {"kernel": "knn_plane (frame-batched 5-NN + plane fit, the largest share of kernel time)", "bound": "hbm",
                                  "achieved": (prof["bytes_per_query"] * prof["knn_queries"] / max(1, prof["knn_launches"])) /
                                              (max(prof["knn_ms"], 1e-9) / max(1, prof["knn_launches"]) * 1e-3) / 1e9,
