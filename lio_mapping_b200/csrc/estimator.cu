@@ -382,10 +382,10 @@ struct MargJob {
 };
 
 // One persistent helper thread per estimator context (created on first use): starting a std::thread per scan costs
-// ~0.1 ms on the bench host.  Hand-off: the helper spins for kWorkerSpinUs after each job before it sleeps on the condition
+// ~0.1 ms on the bench host.  Hand-off: the helper spins for spin_us after each job before it sleeps on the condition
 // variable, so the jobs of one solve (one every ~150 us) never pay a futex wake-up; between scans it sleeps.
 struct Worker {
-  static constexpr double kWorkerSpinUs = 400.0;
+  double spin_us = 400.0;   // hand-off spin window; shortened for sharded runs (one process per GPU shares the host cores)
   std::thread th;
   std::mutex mu;
   std::condition_variable cv;
@@ -409,7 +409,7 @@ struct Worker {
     const double t0 = now_s();
     while (busy.load()) {
       relax();
-      if ((now_s() - t0) * 1e6 > kWorkerSpinUs) {
+      if ((now_s() - t0) * 1e6 > spin_us) {
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [this]() { return busy.load() == 0; });
         return;
@@ -420,7 +420,7 @@ struct Worker {
     while (true) {
       const double t0 = now_s();
       bool got = false;
-      while ((now_s() - t0) * 1e6 <= kWorkerSpinUs) {
+      while ((now_s() - t0) * 1e6 <= spin_us) {
         if (has_job.load()) { got = true; break; }
         relax();
       }
@@ -1691,6 +1691,7 @@ extern "C" int lio_est_set_shard(lio_est *e, int rank, int world, lio_allreduce_
   if (!e || world < 1 || rank < 0 || rank >= world) return LIO_ERR_INVALID;
   e->rank = rank; e->world = world; e->allreduce = fn; e->allreduce_user = user;
   e->npeers = 0;
+  e->worker.spin_us = world > 1 ? std::max(25.0, 400.0 / world) : 400.0;  // N processes share the host: spin less
   return LIO_OK;
 }
 
