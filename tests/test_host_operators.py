@@ -75,3 +75,20 @@ def test_preintegration_and_imu_factor_match_oracle(oracle):
     assert np.allclose(rg, ro, rtol=1e-9, atol=1e-9 * np.abs(ro).max())
     for a, b in zip(Jg, Jo):
         assert np.allclose(a, b, rtol=1e-9, atol=1e-9 * np.abs(b).max())
+
+
+def test_header_is_plain_c99_and_c_client_links(tmp_path):
+    """include/lio_b200.h must be consumable by a C compiler (extern "C" boundary, plain pointers and sizes) and a C
+    client must link against the shared library; without a device the client stops after the host-only entry points."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "minimal"
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "examples", "minimal.c"), "-L" + os.path.join(root, "lio_mapping_b200"), "-llio_b200",
+           "-Wl,-rpath," + os.path.join(root, "lio_mapping_b200"), "-lm", "-o", str(exe)]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.stdout, run.stderr)
+    assert "liblio_b200 version" in run.stdout
