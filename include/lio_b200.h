@@ -323,6 +323,13 @@ int lio_host_cholesky_solve(int n, const double *A, const double *b, double *L_o
  * ascending eigenvalues, eigenvectors in the COLUMNS of evecs (n x n row-major).  threads > 1 applies the QL rotations
  * on disjoint row ranges in parallel (bit-identical result). */
 int lio_host_sym_eigen(int n, const double *A, double *evals, double *evecs, int threads);
+/* The trust-region / traditional-dogleg controller that stands in for ceres::Solve (options of Estimator.cc:1909-1921,
+ * Ceres 1.14 defaults otherwise) on a toy nonlinear least-squares problem assembled on the host:
+ * r_k = a_k . x + amp sin(b_k . x) - y_k  (A, B: m x n row-major), optional CauchyLoss(1.0) with the Ceres corrector.
+ * x in/out; summary[8] = {iterations, successful steps, termination (0 no convergence, 1 convergence, 2 failure),
+ * initial cost, final cost, evaluations}. */
+int lio_host_dogleg_toy(int n, int m, const double *A, const double *B, const double *y, double amp, int use_cauchy, double *x,
+                        int max_iter, double *summary);
 
 #ifdef __cplusplus
 }

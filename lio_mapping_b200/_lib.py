@@ -83,6 +83,7 @@ def lib():
     L.lio_calculate_line_features_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, f32p, f32p, i32p, C.POINTER(ip), ip]
     L.lio_host_cholesky_solve.argtypes = [ip, f64p, f64p, f64p, f64p]
     L.lio_host_sym_eigen.argtypes = [ip, f64p, f64p, f64p, ip]
+    L.lio_host_dogleg_toy.argtypes = [ip, ip, f64p, f64p, f64p, C.c_double, ip, f64p, ip, f64p]
     L.lio_compact_encode.argtypes = [f32p, f32p, ip, f32p, ip, f32p, ip, f32p, ip, C.POINTER(ip)]
     L.lio_compact_sizes.argtypes = [f32p, ip, i32p]
     L.lio_compact_decode.argtypes = [f32p, ip, f32p, f32p, f32p, f32p]

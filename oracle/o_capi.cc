@@ -354,3 +354,45 @@ extern "C" void orc_transform_to_end(float *cloud, int n, const float *tf7, floa
   TransformToEnd(c, t, time_factor);
   std::memcpy(cloud, c.data(), sizeof(PointXYZI) * n);
 }
+
+// ---- toy nonlinear least squares through the oracle's Ceres-style Problem / Solve (controller parity on the CPU) --------
+// residual k:  r_k = a_k . x + amp * sin(b_k . x) - y_k   (1-dim blocks over ONE n-dim Euclidean parameter block),
+// optional CauchyLoss(1.0).  summary = {iterations, successful steps, termination, initial cost, final cost, linearizations}.
+namespace {
+struct ToyCost : orc::CostFunction {
+  const double *a, *b;
+  double y, amp;
+  int n;
+  ToyCost(const double *a_, const double *b_, double y_, double amp_, int n_) : a(a_), b(b_), y(y_), amp(amp_), n(n_) {
+    num_residuals = 1;
+    block_sizes = {n_};
+  }
+  bool Evaluate(double const *const *parameters, double *residuals, double **jacobians) const override {
+    const double *x = parameters[0];
+    double s = 0, t = 0;
+    for (int j = 0; j < n; ++j) { s += a[j] * x[j]; t += b[j] * x[j]; }
+    residuals[0] = s + amp * std::sin(t) - y;
+    if (jacobians && jacobians[0]) {
+      const double cb = amp * std::cos(t);
+      for (int j = 0; j < n; ++j) jacobians[0][j] = a[j] + cb * b[j];
+    }
+    return true;
+  }
+};
+}  // namespace
+
+extern "C" int orc_toy_solve(int n, int m, const double *A, const double *B, const double *y, double amp, int use_cauchy, double *x,
+                             int max_iter, double *summary) {
+  orc::Problem P;
+  P.AddParameterBlock(x, n, false);
+  orc::CauchyLoss loss(1.0);
+  for (int k = 0; k < m; ++k)
+    P.AddResidualBlock(std::make_shared<ToyCost>(A + (size_t)k * n, B + (size_t)k * n, y[k], amp, n), use_cauchy ? &loss : nullptr, {x});
+  orc::SolverOptions opt;
+  opt.max_num_iterations = max_iter;
+  orc::SolverSummary sum;
+  orc::Solve(opt, &P, &sum);
+  summary[0] = sum.num_iterations; summary[1] = sum.num_successful_steps; summary[2] = sum.termination;
+  summary[3] = sum.initial_cost; summary[4] = sum.final_cost; summary[5] = sum.num_linearizations;
+  return 0;
+}

@@ -215,6 +215,18 @@ def compact_decode(compact):
     return tf7, outs[0][:sz[0]], outs[1][:sz[1]], outs[2][:sz[2]]
 
 
+def toy_solve(A, B, y, x0, amp=0.05, use_cauchy=False, max_iter=10):
+    """Toy nonlinear least squares through the oracle's Problem / Solve (Ceres-1.14 restatement): returns (x, summary)."""
+    L = lib()
+    A = np.ascontiguousarray(A, np.float64); B = np.ascontiguousarray(B, np.float64)
+    m, n = A.shape
+    x = np.ascontiguousarray(x0, np.float64).copy()
+    s = np.zeros(8)
+    L.orc_toy_solve.argtypes = [C.c_int, C.c_int, f64p, f64p, f64p, C.c_double, C.c_int, f64p, C.c_int, f64p]
+    L.orc_toy_solve(n, m, A, B, np.ascontiguousarray(y, np.float64), amp, int(use_cauchy), x, max_iter, s)
+    return x, dict(iterations=int(s[0]), successful=int(s[1]), termination=int(s[2]), initial_cost=s[3], final_cost=s[4])
+
+
 def transform_to_end(cloud, tf7, time_factor=10.0):
     """TransformToEnd (Estimator.cc:62-103) on a copy of `cloud`."""
     L = lib()
