@@ -46,6 +46,7 @@ struct StageA {
 
   size_t num_ring_points() const { size_t n = 0; for (auto &c : laser_scans) n += c.size(); return n; }
   void PointToRing(const PointXYZI *points, size_t n);
+  void PointToRingWithRingField(const PointXYZI *points, const unsigned short *rings, size_t n);  // PointProcessor.cc:428-536
   void PrepareRing(const Cloud &scan);
   void PrepareSubregion(const Cloud &scan, size_t idx_start, size_t idx_end);
   void MaskPickedInRing(const Cloud &scan, size_t in_scan_idx);

@@ -22,6 +22,11 @@ void orc_a_run(void *h, const float *xyzi, int n) {
   a->PointToRing((const PointXYZI *)xyzi, (size_t)n);
   a->ExtractFeaturePoints();
 }
+void orc_a_run_ring(void *h, const float *xyzi, const unsigned short *rings, int n) {  // PointXYZIR input
+  StageA *a = (StageA *)h;
+  a->PointToRingWithRingField((const PointXYZI *)xyzi, rings, (size_t)n);
+  a->ExtractFeaturePoints();
+}
 // which: 0 laser_scans (ring-ordered, intensity=ring+rel_time) 1 cloud_in_rings 2 sharp 3 less_sharp 4 flat 5 less_flat
 static const Cloud *a_cloud(StageA *a, int which, Cloud &tmp) {
   switch (which) {

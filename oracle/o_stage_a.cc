@@ -94,6 +94,64 @@ void StageA::PointToRing(const PointXYZI *points, size_t cloud_size) {
   }
 }
 
+// PointToRing for sensors that deliver the ring index (lio::PointXYZIR, include/point_processor/point_types.h:37-52):
+// PointProcessor.cc:428-536.  Ring id from the field; the azimuth gets +2 pi when it lies before start_ori_ (the
+// half_passed branch can never be entered: `i > 3 * cloud_size / 2` is false for every i < cloud_size); end_ori_ is the
+// running maximum (from 0) and rel_time = scan_period * (azi - start_ori_) / (end_ori_ - start_ori_).
+void StageA::PointToRingWithRingField(const PointXYZI *points, const unsigned short *rings, size_t cloud_size) {
+  const int R = cfg.num_rings;
+  laser_scans.assign(R, Cloud());
+  intensity_scans.assign(R, Cloud());
+  orig_index.assign(R, std::vector<int>());
+  bool start_flag = false;
+  start_ori = 0.f;
+  float end_ori = 0.f;
+  bool half_passed = false;
+  for (size_t i = 0; i < cloud_size; ++i) {
+    PointXYZI p = points[i];
+    PointXYZI p_with_intensity = p;
+    if (!finite3(p)) continue;  // :456-460
+    float azi_rad = (float)(2 * M_PI - std::atan2(p.y, p.x));
+    if (azi_rad >= 2 * M_PI) azi_rad = (float)(azi_rad - 2 * M_PI);
+    int scan_id = rings[i];
+    if (scan_id >= R || scan_id < 0) continue;
+    if (!start_flag) { start_ori = azi_rad; start_flag = true; }
+    float azi_rad_rel = azi_rad - start_ori;
+    if (!half_passed) {
+      if (azi_rad_rel < 0) azi_rad = (float)(azi_rad + 2 * M_PI);
+      if (azi_rad_rel > M_PI && i > 3 * cloud_size / 2) half_passed = true;
+    } else {
+      if (azi_rad_rel < M_PI / 2) azi_rad = (float)(azi_rad + 2 * M_PI);
+    }
+    if (end_ori < azi_rad) end_ori = azi_rad;
+    p.intensity = azi_rad;
+    laser_scans[scan_id].push_back(p);
+    intensity_scans[scan_id].push_back(p_with_intensity);
+    orig_index[scan_id].push_back((int)i);
+  }
+  const float range_ori = end_ori - start_ori;
+  for (int ring = 0; ring < R; ++ring) {
+    Cloud &pts = laser_scans[ring];
+    Cloud &pti = intensity_scans[ring];
+    for (size_t i = 0; i < pts.size(); ++i) {
+      float azi_rad_rel = pts[i].intensity - start_ori;
+      float rel_time = (float)(cfg.scan_period * azi_rad_rel / range_ori);
+      pts[i].intensity = ring + rel_time;
+      pti[i].intensity = int(pti[i].intensity) + rel_time;
+    }
+  }
+  cloud_in_rings.clear();
+  scan_ranges.clear();
+  size_t cs = 0;
+  for (int i = 0; i < R; ++i) {   // wrapper :185-205 (shared by both variants)
+    cloud_in_rings.insert(cloud_in_rings.end(), intensity_scans[i].begin(), intensity_scans[i].end());
+    std::pair<size_t, size_t> range(cs, 0);
+    cs += laser_scans[i].size();
+    range.second = (cs > 0 ? cs - 1 : 0);
+    scan_ranges.push_back(range);
+  }
+}
+
 void StageA::PrepareRing(const Cloud &scan) {
   // PointProcessor.cc:542-585.  The reference writes scan_ring_mask_[scan_size] (one past the
   // end) for i = scan_size-d-1 in the "else" branch; we allocate one spare slot.

@@ -70,13 +70,20 @@ CLOUDS = {"laser_scans": 0, "cloud_in_rings": 1, "sharp": 2, "less_sharp": 3, "f
 IDX = {"sharp": 0, "less_sharp": 1, "flat": 2, "less_flat_prevoxel": 3, "orig_index": 4}
 
 
-def stage_a(xyzi: np.ndarray, lower: float, upper: float, rings: int, scan_period: float = 0.1) -> dict:
-    """PointProcessor::PointToRing + ExtractFeaturePoints on one sweep (oracle)."""
+def stage_a(xyzi: np.ndarray, lower: float, upper: float, rings: int, scan_period: float = 0.1, ring_field=None) -> dict:
+    """PointProcessor::PointToRing + ExtractFeaturePoints on one sweep (oracle).  ring_field: uint16 ring index per point
+    (PointXYZIR input, PointProcessor.cc:428-536) instead of the elevation-derived ring."""
     L = lib()
     xyzi = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
     h = L.orc_a_create(lower, upper, rings, scan_period)
     try:
-        L.orc_a_run(h, xyzi, xyzi.shape[0])
+        if ring_field is None:
+            L.orc_a_run(h, xyzi, xyzi.shape[0])
+        else:
+            rf = np.ascontiguousarray(ring_field, np.uint16)
+            L.orc_a_run_ring.argtypes = [C.c_void_p, f32p, np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS"), C.c_int]
+            L.orc_a_run_ring.restype = None
+            L.orc_a_run_ring(h, xyzi, rf, xyzi.shape[0])
         out = {}
         for name, w in CLOUDS.items():
             n = L.orc_a_cloud_size(h, w)

@@ -124,3 +124,33 @@ def test_line_features_geometry_float64_crosscheck(oracle):
         assert abs(r1 - dist) < 2e-3 and abs(r2) < 2e-3
         n_checked += 1
     assert n_checked >= 20
+
+
+def test_ring_field_variant_oracle(oracle):
+    """PointToRing for PointXYZIR input (PointProcessor.cc:428-536), oracle side: the ring comes from the field, rel_time is
+    scaled by the observed azimuth range (end_ori - start_ori) instead of 2 pi, and everything downstream is shared."""
+    from lio_mapping_b200 import synth
+    sensor, scene, traj = synth.default_config("vlp16")
+    sw = synth.make_sweep(sensor, scene, traj, 1.0, seed=3, distort=False)
+    base = oracle.stage_a(sw, sensor.lower_deg, sensor.upper_deg, sensor.rings)
+    # the elevation-derived ring of every accepted point, as a driver would deliver it
+    ele = np.degrees(np.arctan2(sw[:, 2], np.hypot(sw[:, 0], sw[:, 1])))
+    factor = (sensor.rings - 1) / (sensor.upper_deg - sensor.lower_deg)
+    ring = np.clip(((ele - sensor.lower_deg) * factor + 0.5).astype(np.int64), 0, 65535).astype(np.uint16)
+    r = oracle.stage_a(sw, sensor.lower_deg, sensor.upper_deg, sensor.rings, ring_field=ring)
+    assert r["laser_scans"].shape[0] == sw.shape[0]                       # every finite point with a valid ring is kept
+    assert np.array_equal(r["scan_ranges"][:, 0], np.concatenate([[0], np.cumsum(np.bincount(ring, minlength=sensor.rings))[:-1]]))
+    ring_of = np.floor(r["laser_scans"][:, 3]).astype(int)
+    assert np.array_equal(ring_of, np.sort(ring).astype(int))            # bucketed by the field, ring + rel_time encoding
+    rel = r["laser_scans"][:, 3] - ring_of
+    assert rel.min() >= -1e-6 and rel.max() <= 0.1 + 1e-5                 # rel_time spans [0, scan_period]
+    assert abs(rel.max() - 0.1) < 1e-4                                    # the last azimuth maps to the full period
+    # same geometry in both variants; only rel_time (range-normalised) and boundary ring assignments may differ
+    assert abs(r["laser_scans"].shape[0] - base["laser_scans"].shape[0]) <= 0.01 * sw.shape[0]
+    assert abs(r["start_ori"] - base["start_ori"]) < 1e-6
+    # out-of-range rings and non-finite points are dropped (:456-460, :471-475)
+    ring2 = ring.copy(); ring2[::7] = 200
+    sw2 = sw.copy(); sw2[5::11, 0] = np.nan
+    r2 = oracle.stage_a(sw2, sensor.lower_deg, sensor.upper_deg, sensor.rings, ring_field=ring2)
+    keep = (ring2 < sensor.rings) & np.isfinite(sw2[:, :3]).all(1)
+    assert r2["laser_scans"].shape[0] == int(keep.sum())
