@@ -86,6 +86,12 @@ int lio_pp_destroy(lio_pp *pp);
 int lio_pp_process_host(lio_pp *pp, const float *xyzi, int n);
 /* Same, input already on the device; asynchronous on the stream. */
 int lio_pp_process_dev(lio_pp *pp, const float *xyzi_dev, int n);
+/* The overload for sensors that deliver the ring index (lio::PointXYZIR, include/point_processor/point_types.h:37-52):
+ * PointToRing(PointCloud<PointIR>) PointProcessor.cc:428-536 — ring id from `rings` (n x uint16), rel_time scaled by the
+ * observed azimuth range end_ori_ - start_ori_ — followed by the shared ExtractFeaturePoints.  Synchronous.
+ * Round-1 status: restated in the oracle and pinned by a CPU test; the device path was written after the round's GPU
+ * budget was spent and is exercised by a non-strict xfail test until it has run on hardware. */
+int lio_pp_process_host_ring(lio_pp *pp, const float *xyzi, const uint16_t *rings, int n);
 /* Sizes of the six output clouds (synchronises the stream). */
 int lio_pp_cloud_sizes(lio_pp *pp, int sizes[LIO_PP_NUM_CLOUDS]);
 /* Copy one output cloud to the host (cap in points).  Returns the point count via *n. */

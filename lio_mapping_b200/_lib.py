@@ -69,6 +69,7 @@ def lib():
     L.lio_pp_destroy.argtypes = [vp]
     L.lio_pp_process_host.argtypes = [vp, f32p, ip]
     L.lio_pp_process_dev.argtypes = [vp, vp, ip]
+    L.lio_pp_process_host_ring.argtypes = [vp, f32p, np.ctypeslib.ndpointer(np.uint16, flags="C_CONTIGUOUS"), ip]
     L.lio_pp_cloud_sizes.argtypes = [vp, i32p]
     L.lio_pp_download_cloud.argtypes = [vp, ip, f32p, ip, C.POINTER(ip)]
     L.lio_pp_cloud_dev.argtypes = [vp, ip, C.POINTER(vp)]

@@ -167,6 +167,109 @@ a_scatter(const float4 *__restrict__ in, int n, PPParams P, const int16_t *__res
   }
 }
 
+// ---- ring-field variant (PointToRing for lio::PointXYZIR input, PointProcessor.cc:428-536) ------------------------
+// Separate kernels so that the elevation variant above stays byte-for-byte what the parity tests pinned.  The ring id
+// comes from the driver's field; an azimuth before start_ori_ gets + 2 pi (the reference's half_passed branch is
+// unreachable: `i > 3 * cloud_size / 2` never holds); end_ori_ is the maximum adjusted azimuth (from 0) and
+// rel_time = scan_period * (azi - start_ori_) / (end_ori_ - start_ori_).
+__global__ void __launch_bounds__(kClsThreads)
+a_classify_ring(const float4 *__restrict__ in, const unsigned short *__restrict__ rings_in, int n, PPParams P,
+                int16_t *__restrict__ ring_id, float *__restrict__ azi_out, int *__restrict__ first_valid, int *__restrict__ hist) {
+  __shared__ int sh[kMaxRings];
+  for (int r = threadIdx.x; r < P.num_rings; r += blockDim.x) sh[r] = 0;
+  __syncthreads();
+  const int base = blockIdx.x * kClsPerBlock;
+  int my_first = 0x7fffffff;
+#pragma unroll
+  for (int k = 0; k < kClsPerBlock / kClsThreads; ++k) {
+    int i = base + k * kClsThreads + threadIdx.x;
+    if (i < n) {
+      float4 p = __ldg(in + i);
+      int ring = -1;
+      float azi = 0.f;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {   // :456-460
+        azi = azimuth_of(p.x, p.y);
+        const int sid = (int)rings_in[i];                      // :468
+        if (sid < P.num_rings && sid >= 0) ring = sid;
+      }
+      ring_id[i] = (int16_t)ring;
+      azi_out[i] = azi;
+      if (ring >= 0) {
+        atomicAdd(&sh[ring], 1);
+        my_first = min(my_first, i);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_first = min(my_first, __shfl_xor_sync(0xffffffffu, my_first, o));
+  if (lane_id() == 0 && my_first != 0x7fffffff) atomicMin(first_valid, my_first);
+  __syncthreads();
+  for (int r = threadIdx.x; r < P.num_rings; r += blockDim.x) hist[blockIdx.x * P.num_rings + r] = sh[r];
+}
+
+__device__ __forceinline__ float adjusted_azimuth(float azi, float start_ori) {
+  const float rel = azi - start_ori;                                   // :482
+  return rel < 0 ? (float)((double)azi + 2.0 * M_PI) : azi;           // :486-488
+}
+
+// end_ori_ = max over accepted points of the adjusted azimuth (non-negative floats order like their bit patterns)
+__global__ void __launch_bounds__(256)
+a_endori(const float *__restrict__ azi, const int16_t *__restrict__ ring_id, int n, const int *__restrict__ first_valid,
+         int *__restrict__ end_bits) {
+  const int fv = *first_valid;
+  const float start_ori = (fv >= 0 && fv < n) ? azi[fv] : 0.f;
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (ring_id[i] >= 0) m = fmaxf(m, adjusted_azimuth(azi[i], start_ori));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane_id() == 0) atomicMax(end_bits, __float_as_int(m));
+}
+
+__global__ void __launch_bounds__(kClsThreads)
+a_scatter_ring(const float4 *__restrict__ in, int n, PPParams P, const int16_t *__restrict__ ring_id, const float *__restrict__ azi,
+               const int *__restrict__ first_valid, const int *__restrict__ end_bits, const int *__restrict__ offsets,
+               float4 *__restrict__ laser, float4 *__restrict__ full, int *__restrict__ orig, float *__restrict__ start_ori_out) {
+  __shared__ int running[kMaxRings];
+  __shared__ int warpcnt[kClsThreads / 32][kMaxRings];
+  const int R = P.num_rings;
+  for (int r = threadIdx.x; r < R; r += blockDim.x) running[r] = offsets[blockIdx.x * R + r];
+  for (int k = threadIdx.x; k < (kClsThreads / 32) * kMaxRings; k += blockDim.x) (&warpcnt[0][0])[k] = 0;
+  const int fv = *first_valid;
+  const float start_ori = (fv >= 0 && fv < n) ? azi[fv] : 0.f;
+  const float range_ori = __int_as_float(*end_bits) - start_ori;       // :513
+  if (blockIdx.x == 0 && threadIdx.x == 0) *start_ori_out = start_ori;
+  __syncthreads();
+  const int base = blockIdx.x * kClsPerBlock;
+  const int w = warp_id();
+  for (int k = 0; k < kClsPerBlock / kClsThreads; ++k) {
+    int i = base + k * kClsThreads + threadIdx.x;
+    int ring = (i < n) ? (int)ring_id[i] : -1;
+    unsigned peers = __match_any_sync(0xffffffffu, ring);
+    int lrank = __popc(peers & ((1u << lane_id()) - 1u));
+    if (ring >= 0 && lrank == 0) warpcnt[w][ring] = __popc(peers);
+    __syncthreads();
+    if (ring >= 0) {
+      int pos = running[ring] + lrank;
+      for (int ww = 0; ww < w; ++ww) pos += warpcnt[ww][ring];
+      float4 p = __ldg(in + i);
+      const float azi_rel = adjusted_azimuth(azi[i], start_ori) - start_ori;                       // :526
+      const float rel_time = (float)(P.scan_period * (double)azi_rel / (double)range_ori);         // :528
+      laser[pos] = make_float4(p.x, p.y, p.z, (float)ring + rel_time);          // :531
+      full[pos] = make_float4(p.x, p.y, p.z, (float)(int)p.w + rel_time);       // :532
+      orig[pos] = i;
+    }
+    __syncthreads();
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+      int s2 = 0;
+#pragma unroll
+      for (int ww = 0; ww < kClsThreads / 32; ++ww) { s2 += warpcnt[ww][r]; warpcnt[ww][r] = 0; }
+      running[r] += s2;
+    }
+    __syncthreads();
+  }
+}
+
 // ---- helpers for the ring kernel -------------------------------------------------------------
 __device__ __forceinline__ float sqdiff(const float *sx, const float *sy, const float *sz, int a, int b) {
   float dx = sx[a] - sx[b], dy = sy[a] - sy[b], dz = sz[a] - sz[b];
@@ -579,6 +682,8 @@ struct lio_pp {
   signed char *d_label = nullptr;
   int *d_pick_less = nullptr, *d_n_less = nullptr, *d_pick_flat = nullptr, *d_n_flat = nullptr, *d_lf_count = nullptr;
   int *d_idx_sharp = nullptr, *d_idx_less = nullptr, *d_idx_flat = nullptr, *d_counts = nullptr, *d_err = nullptr;
+  unsigned short *d_rings_in = nullptr;  // ring-field variant only (allocated on first use)
+  int *d_end_bits = nullptr;
   int *h_counts = nullptr;  // pinned: counts[0..4], err
   int launches = 0;
   int last_n = 0;
@@ -650,6 +755,8 @@ extern "C" int lio_pp_destroy(lio_pp *pp) {
                   pp->d_orig, pp->d_mask, pp->d_label, pp->d_pick_less, pp->d_n_less, pp->d_pick_flat, pp->d_n_flat,
                   pp->d_lf_count, pp->d_idx_sharp, pp->d_idx_less, pp->d_idx_flat, pp->d_counts, pp->d_err};
   for (void *p : ptrs) if (p) cudaFree(p);
+  if (pp->d_rings_in) cudaFree(pp->d_rings_in);
+  if (pp->d_end_bits) cudaFree(pp->d_end_bits);
   if (pp->h_counts) cudaFreeHost(pp->h_counts);
   delete pp;
   return LIO_OK;
@@ -706,6 +813,47 @@ extern "C" int lio_pp_process_host(lio_pp *pp, const float *xyzi, int n) {
   if (n > 0) LIO_CUDA_OK(cudaMemcpyAsync(pp->d_in, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, pp->stream));
   int rc = lio_pp_process_dev(pp, reinterpret_cast<const float *>(pp->d_in), n);
   if (rc != LIO_OK) return rc;
+  return pp_sync_counts(pp);
+}
+
+// SetInputCloud(PointIR) + PointToRing (ring-field variant, PointProcessor.cc:428-536) + ExtractFeaturePoints; host buffers.
+extern "C" int lio_pp_process_host_ring(lio_pp *pp, const float *xyzi, const uint16_t *rings, int n) {
+  if (!pp || ((!xyzi || !rings) && n > 0) || n < 0) return LIO_ERR_INVALID;
+  if (n > pp->max_points) return LIO_ERR_CAPACITY;
+  LIO_CUDA_OK(cudaSetDevice(pp->device));
+  if (!pp->d_rings_in) {
+    LIO_CUDA_OK(dalloc(&pp->d_rings_in, (size_t)pp->max_points));
+    LIO_CUDA_OK(dalloc(&pp->d_end_bits, 1));
+  }
+  cudaStream_t st = pp->stream;
+  const PPParams &P = pp->P;
+  const int R = P.num_rings;
+  if (n > 0) {
+    LIO_CUDA_OK(cudaMemcpyAsync(pp->d_in, xyzi, (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, st));
+    LIO_CUDA_OK(cudaMemcpyAsync(pp->d_rings_in, rings, (size_t)n * sizeof(uint16_t), cudaMemcpyHostToDevice, st));
+  }
+  pp->launches = 0;
+  pp->last_n = n;
+  pp->counts_valid = false;
+  int nb = (n + kClsPerBlock - 1) / kClsPerBlock;
+  if (nb < 1) nb = 1;
+  LIO_CUDA_OK(cudaMemsetAsync(pp->d_first_valid, 0x7f, sizeof(int), st));
+  LIO_CUDA_OK(cudaMemsetAsync(pp->d_end_bits, 0, sizeof(int), st));   // end_ori_ = 0
+  a_classify_ring<<<nb, kClsThreads, 0, st>>>(pp->d_in, pp->d_rings_in, n, P, pp->d_ring_id, pp->d_azi, pp->d_first_valid, pp->d_hist);
+  a_scan<<<1, kMaxRings, 0, st>>>(pp->d_hist, nb, R, pp->d_offsets, pp->d_ring_start);
+  a_endori<<<std::min(nb, 148), 256, 0, st>>>(pp->d_azi, pp->d_ring_id, n, pp->d_first_valid, pp->d_end_bits);
+  a_scatter_ring<<<nb, kClsThreads, 0, st>>>(pp->d_in, n, P, pp->d_ring_id, pp->d_azi, pp->d_first_valid, pp->d_end_bits, pp->d_offsets,
+                                             pp->d_laser, pp->d_full, pp->d_orig, pp->d_start_ori);
+  a_ring<<<R, kRingThreads, pp->ring_smem, st>>>(pp->d_laser, pp->d_ring_start, P, pp->d_start_ori, pp->d_mask, pp->d_label,
+                                                 pp->d_pick_less, pp->d_n_less, pp->d_pick_flat, pp->d_n_flat, pp->d_lf_ring,
+                                                 pp->d_lf_count, pp->d_err);
+  a_compact<<<R, 256, 0, st>>>(pp->d_laser, pp->d_ring_start, P, pp->d_pick_less, pp->d_n_less, pp->d_pick_flat, pp->d_n_flat,
+                               pp->d_lf_ring, pp->d_lf_count, pp->d_out_sharp, pp->d_out_less, pp->d_out_flat, pp->d_out_lf,
+                               pp->d_idx_sharp, pp->d_idx_less, pp->d_idx_flat, pp->d_counts);
+  pp->launches = 6;
+  LIO_CUDA_OK(cudaGetLastError());
+  LIO_CUDA_OK(cudaMemcpyAsync(pp->h_counts, pp->d_counts, 5 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LIO_CUDA_OK(cudaMemcpyAsync(pp->h_counts + 8, pp->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
   return pp_sync_counts(pp);
 }
 

@@ -56,6 +56,15 @@ class PointProcessor:
             raise _lib.LioError("SetInputCloud first")
         _lib.check(_lib.lib().lio_pp_process_host(self._h, self._cloud, self._cloud.shape[0]), "lio_pp_process_host")
 
+    def ProcessWithRingField(self, rings):
+        """PointToRing for PointXYZIR input (ring index per point, PointProcessor.cc:428-536) + ExtractFeaturePoints."""
+        if self._cloud is None:
+            raise _lib.LioError("SetInputCloud first")
+        r = np.ascontiguousarray(rings, np.uint16)
+        if r.shape[0] != self._cloud.shape[0]:
+            raise ValueError("one ring index per point")
+        _lib.check(_lib.lib().lio_pp_process_host_ring(self._h, self._cloud, r, self._cloud.shape[0]), "lio_pp_process_host_ring")
+
     def process_device(self, dev_ptr: int, n: int):
         """Device-resident input (float4 array); asynchronous on the processor's stream."""
         _lib.check(_lib.lib().lio_pp_process_dev(self._h, C.c_void_p(dev_ptr), n), "lio_pp_process_dev")
