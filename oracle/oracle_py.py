@@ -465,3 +465,58 @@ class Estimator:
             self.L.orc_est_destroy(self.h)
         except Exception:
             pass
+
+
+# =================================================================================================
+# rolling cube map of PointMapping (oracle only: groundwork, see oracle/o_cubemap.cc)
+class CubeMap:
+    L_, W_, H_ = 21, 21, 11
+
+    def __init__(self):
+        self.L = lib()
+        i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+        self.L.orc_cm_create.restype = C.c_void_p
+        self.L.orc_cm_destroy.argtypes = [C.c_void_p]
+        self.L.orc_cm_recentre.argtypes = [C.c_void_p, f32p, i32p]
+        self.L.orc_cm_select.argtypes = [C.c_void_p, f32p, f32p, i32p, i64p, i64p, i32p]
+        self.L.orc_cm_cube_size.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
+        self.L.orc_cm_cube_copy.argtypes = [C.c_void_p, C.c_longlong, C.c_int, f32p]
+        self.L.orc_cm_update.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int, i64p, C.c_int, f32p, i32p]
+        self.h = self.L.orc_cm_create()
+
+    def __del__(self):
+        try:
+            self.L.orc_cm_destroy(self.h)
+        except Exception:
+            pass
+
+    @staticmethod
+    def to_index(i, j, k):
+        return i + 21 * j + 21 * 21 * k
+
+    def recentre(self, pos):
+        out = np.zeros(6, np.int32)
+        self.L.orc_cm_recentre(self.h, np.ascontiguousarray(pos, np.float32), out)
+        return tuple(out[:3].tolist()), tuple(out[3:].tolist())
+
+    def select(self, pos, zaxis, centre):
+        v = np.zeros(125, np.int64); s = np.zeros(125, np.int64); n = np.zeros(2, np.int32)
+        self.L.orc_cm_select(self.h, np.ascontiguousarray(pos, np.float32), np.ascontiguousarray(zaxis, np.float32),
+                             np.ascontiguousarray(centre, np.int32), v, s, n)
+        return v[:n[0]].copy(), s[:n[1]].copy()
+
+    def cube(self, index, which):
+        n = self.L.orc_cm_cube_size(self.h, int(index), 0 if which == "corner" else 1)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        if n:
+            self.L.orc_cm_cube_copy(self.h, int(index), 0 if which == "corner" else 1, out)
+        return out[:n]
+
+    def update(self, corner, surf, valid, tf7, margin_centre):
+        c = np.ascontiguousarray(corner, np.float32).reshape(-1, 4); s = np.ascontiguousarray(surf, np.float32).reshape(-1, 4)
+        cp = c if c.shape[0] else np.zeros((1, 4), np.float32)
+        sp = s if s.shape[0] else np.zeros((1, 4), np.float32)
+        v = np.ascontiguousarray(valid, np.int64)
+        vp = v if v.shape[0] else np.zeros(1, np.int64)
+        self.L.orc_cm_update(self.h, cp, c.shape[0], sp, s.shape[0], vp, v.shape[0], np.ascontiguousarray(tf7, np.float32),
+                             np.ascontiguousarray(margin_centre, np.int32))

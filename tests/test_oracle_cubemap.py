@@ -1,0 +1,86 @@
+"""Rolling cube map of lio::PointMapping, oracle restatement (oracle/o_cubemap.cc; no device counterpart yet): invariants
+of re-centring (PointMapping.cc:809-931), cube selection (:944-1003) and UpdateMapDatabase (:1112-1208)."""
+import numpy as np
+
+
+def _cube_of(v, cen):
+    c = int((v + 25.0) / 50.0) + cen
+    return c - 1 if v + 25.0 < 0 else c
+
+
+def test_recentre_keeps_world_to_cube_relation(oracle):
+    cm = oracle.CubeMap()
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], np.float32)
+    centre, cen = cm.recentre([0.0, 0.0, 0.0])
+    assert centre == (10, 10, 5) and cen == (10, 10, 5)
+    rng = np.random.default_rng(0)
+    pts = np.concatenate([rng.uniform(-120, 120, (500, 2)), rng.uniform(-40, 40, (500, 1)), rng.uniform(0, 9, (500, 1))], 1).astype(np.float32)
+    cm.update(pts[:200], pts[200:], [], ident, cen)
+    # walk the sensor far enough that the arrays shift along +x, -y and +z
+    for pos in ([380.0, 0.0, 0.0], [410.0, -370.0, 0.0], [410.0, -370.0, 160.0]):
+        centre, cen = cm.recentre(pos)
+        assert all(3 <= c < n - 3 for c, n in zip(centre, (21, 21, 11)))
+        assert centre == tuple(_cube_of(p, c) for p, c in zip(pos, cen))
+        # every stored point is still found in the cube its world position maps to under the new centre
+        kept = 0
+        for name, block in (("corner", pts[:200]), ("surf", pts[200:])):
+            for p in block:
+                ijk = [_cube_of(float(p[a]), cen[a]) for a in range(3)]
+                if all(0 <= ijk[a] < n for a, n in zip(range(3), (21, 21, 11))):
+                    cube = cm.cube(oracle.CubeMap.to_index(*ijk), name)
+                    assert (cube == p).all(1).any()
+                    kept += 1
+        assert kept > 0
+
+
+def test_select_matches_angle_criterion(oracle):
+    cm = oracle.CubeMap()
+    pos = np.array([3.0, -7.0, 1.0], np.float32)
+    centre, cen = cm.recentre(pos)
+    R = np.eye(3)                                         # sensor z axis = world z
+    zaxis = (pos + R @ np.array([0, 0, 10.0])).astype(np.float32)
+    valid, surround = cm.select(pos, zaxis, centre)
+    assert len(surround) == 125 and set(valid) <= set(surround)
+    assert oracle.CubeMap.to_index(*centre) in set(surround)
+    # independent statement: a cube is valid iff one of its corners sees the z axis under an angle in (30, 150) degrees
+    vset = set(valid.tolist())
+    for i in range(centre[0] - 2, centre[0] + 3):
+        for j in range(centre[1] - 2, centre[1] + 3):
+            for k in range(centre[2] - 2, centre[2] + 3):
+                c = 50.0 * (np.array([i, j, k]) - np.array(cen))
+                ang = []
+                for s in np.array(np.meshgrid([-1, 1], [-1, 1], [-1, 1])).T.reshape(-1, 3):
+                    d = c + 25.0 * s - pos
+                    ang.append(np.degrees(np.arccos(np.clip(d @ (zaxis - pos) / (np.linalg.norm(d) * 10.0), -1, 1))))
+                ang = np.array(ang)
+                inside = ((ang > 30.0) & (ang < 150.0)).any()
+                near = (np.abs(ang - 30.0) < 1e-3).any() or (np.abs(ang - 150.0) < 1e-3).any()
+                if not near:
+                    assert (oracle.CubeMap.to_index(i, j, k) in vset) == inside
+
+
+def test_update_inserts_and_filters_valid_cubes(oracle):
+    cm = oracle.CubeMap()
+    pos = np.zeros(3, np.float32)
+    centre, cen = cm.recentre(pos)
+    valid, _ = cm.select(pos, np.array([0, 0, 10.0], np.float32), centre)
+    rng = np.random.default_rng(3)
+    surf = np.concatenate([rng.uniform(-20, 20, (4000, 3)), rng.uniform(0, 5, (4000, 1))], 1).astype(np.float32)
+    corner = np.concatenate([rng.uniform(-20, 20, (800, 3)), rng.uniform(0, 5, (800, 1))], 1).astype(np.float32)
+    tf7 = np.array([0, 0, np.sin(0.1), np.cos(0.1), 1.0, 2.0, 0.5], np.float32)
+    cm.update(corner, surf, valid, tf7, cen)
+    idx = oracle.CubeMap.to_index(*centre)
+    assert idx in set(valid.tolist())                      # the sensor's own cube sees the horizon band
+    got_s, got_c = cm.cube(idx, "surf"), cm.cube(idx, "corner")
+    # expected: points mapped by PointAssociateToMap, those falling into the centre cube, voxel-filtered at 0.4 / 0.2
+    Rm = np.array([[np.cos(0.2), -np.sin(0.2), 0], [np.sin(0.2), np.cos(0.2), 0], [0, 0, 1]], np.float32)
+    for got, src, leaf in ((got_s, surf, 0.4), (got_c, corner, 0.2)):
+        w = oracle.transform_cloud(src, Rm, tf7[4:])       # same rotation up to float rounding of the quaternion product
+        inside = np.all((w[:, :3] >= -25.0) & (w[:, :3] < 25.0), axis=1)
+        exp = oracle.voxel_grid(w[inside], leaf)
+        assert abs(got.shape[0] - exp.shape[0]) <= max(2, exp.shape[0] // 200)
+        assert got.shape[0] <= inside.sum()                # filtered (sparse clouds may keep every point)
+    # a second identical update grows the cube by at most the new points and filters again (idempotent size up to merging)
+    n1 = cm.cube(idx, "surf").shape[0]
+    cm.update(corner, surf, valid, tf7, cen)
+    assert cm.cube(idx, "surf").shape[0] <= n1 + 5
