@@ -8,6 +8,7 @@
 //                                                      corners lies within +-60 deg of the sensor's z axis)
 //   map extraction          PointMapping.cc:1005-1011 (concatenate the valid cubes, corner and surf separately)
 //   UpdateMapDatabase       PointMapping.cc:1112-1208 (insert the down-sampled stacks, re-filter the touched valid cubes)
+//   PointMapping::Process   PointMapping.cc:765-1052  (imu_inited_ == false path, num_stack_frames_ == 1)
 // No device counterpart exists yet: this file is groundwork for it and is pinned by invariants only.
 #include "o_api.h"
 #include <cmath>
@@ -131,10 +132,69 @@ struct CubeMap {
   }
 };
 
+// PointMapping::Process with imu_inited_ == false and num_stack_frames_ == 1 (PointMapping.cc:765-1052): associate the
+// odometry increment, bring the last features to the map frame, re-centre / select cubes, pull the map, take the stacks
+// back to the sensor frame and down-sample them, optimise against the map, update the map database.
+struct PointMappingOracle {
+  CubeMap map;
+  Transform sum, bef, aft, tobe;   // transform_sum_, transform_bef_mapped_, transform_aft_mapped_, transform_tobe_mapped_
+  StageBConfig cfg;
+  int last_iters = 0;
+  size_t last_corner_from_map = 0, last_surf_from_map = 0;
+  static void PointAssociateTobeMapped(const PointXYZI &pi, PointXYZI &po, const Transform &t) {  // :316-323
+    Vec3<float> v(pi.x - t.pos.x, pi.y - t.pos.y, pi.z - t.pos.z);
+    Vec3<float> o = t.rot.conjugate() * v;
+    po.x = o.x; po.y = o.y; po.z = o.z; po.intensity = pi.intensity;
+  }
+  void Process(const Cloud &corner_last, const Cloud &surf_last, const Transform &transform_sum) {
+    sum = transform_sum;
+    {  // TransformAssociateToMap :753-756
+      Transform incre = bef.inverse() * sum;
+      tobe = tobe * incre;
+    }
+    Cloud corner_stack, surf_stack;
+    PointXYZI point_sel;
+    for (const PointXYZI &p : corner_last) { PointAssociateToMap(p, point_sel, tobe); corner_stack.push_back(point_sel); }
+    for (const PointXYZI &p : surf_last) { PointAssociateToMap(p, point_sel, tobe); surf_stack.push_back(point_sel); }
+    PointXYZI point_on_z_axis;
+    point_on_z_axis.x = 0.0f; point_on_z_axis.y = 0.0f; point_on_z_axis.z = 10.0f; point_on_z_axis.intensity = 0.f;
+    PointAssociateToMap(point_on_z_axis, point_on_z_axis, tobe);
+    int ci, cj, ck;
+    map.Recentre(tobe.pos, ci, cj, ck);
+    std::vector<size_t> valid, surround;
+    map.Select(tobe.pos, point_on_z_axis, ci, cj, ck, valid, surround);
+    Cloud corner_from_map, surf_from_map;
+    map.FromMap(valid, corner_from_map, surf_from_map);
+    last_corner_from_map = corner_from_map.size(); last_surf_from_map = surf_from_map.size();
+    for (PointXYZI &p : corner_stack) PointAssociateTobeMapped(p, p, tobe);
+    for (PointXYZI &p : surf_stack) PointAssociateTobeMapped(p, p, tobe);
+    Cloud corner_ds, surf_ds;
+    VoxelGridFilter(corner_stack, map.corner_leaf, corner_ds);
+    VoxelGridFilter(surf_stack, map.surf_leaf, surf_ds);
+    const bool optimised = !(corner_from_map.size() <= 10 || surf_from_map.size() <= 100);
+    last_iters = 0;
+    OptimizeTransformTobeMapped(corner_from_map, surf_from_map, corner_ds, surf_ds, tobe, cfg, &last_iters, nullptr, 0);
+    if (optimised) { bef = sum; aft = tobe; }   // TransformUpdate() sits behind the early return of the optimiser (:327-329, :716)
+    map.UpdateMapDatabase(corner_ds, surf_ds, valid, tobe, map.cen_l, map.cen_w, map.cen_h);
+  }
+};
+
 }  // namespace orc
 
 using namespace orc;
 extern "C" {
+void *orc_pm_create() { return new PointMappingOracle(); }
+void orc_pm_destroy(void *h) { delete (PointMappingOracle *)h; }
+// transform_sum as tf7 (qx,qy,qz,qw,px,py,pz); out: tobe tf7, then {iterations, corner_from_map, surf_from_map}
+void orc_pm_process(void *h, const float *corner, int nc, const float *surf, int ns, const float *sum7, float *tobe7, int *info3) {
+  PointMappingOracle *m = (PointMappingOracle *)h;
+  Cloud c((const PointXYZI *)corner, (const PointXYZI *)corner + nc), s((const PointXYZI *)surf, (const PointXYZI *)surf + ns);
+  Transform t(Quat<float>(sum7[3], sum7[0], sum7[1], sum7[2]), Vec3<float>(sum7[4], sum7[5], sum7[6]));
+  m->Process(c, s, t);
+  tobe7[0] = m->tobe.rot.x; tobe7[1] = m->tobe.rot.y; tobe7[2] = m->tobe.rot.z; tobe7[3] = m->tobe.rot.w;
+  tobe7[4] = m->tobe.pos.x; tobe7[5] = m->tobe.pos.y; tobe7[6] = m->tobe.pos.z;
+  info3[0] = m->last_iters; info3[1] = (int)m->last_corner_from_map; info3[2] = (int)m->last_surf_from_map;
+}
 void *orc_cm_create() { return new CubeMap(); }
 void orc_cm_destroy(void *h) { delete (CubeMap *)h; }
 // out: centre cube (3), map centre after the shifts (3)

@@ -520,3 +520,28 @@ class CubeMap:
         vp = v if v.shape[0] else np.zeros(1, np.int64)
         self.L.orc_cm_update(self.h, cp, c.shape[0], sp, s.shape[0], vp, v.shape[0], np.ascontiguousarray(tf7, np.float32),
                              np.ascontiguousarray(margin_centre, np.int32))
+
+
+class PointMappingOracle:
+    """PointMapping::Process (imu_inited_ == false path, PointMapping.cc:765-1052) around the cube map (oracle only)."""
+
+    def __init__(self):
+        self.L = lib()
+        self.L.orc_pm_create.restype = C.c_void_p
+        self.L.orc_pm_destroy.argtypes = [C.c_void_p]
+        self.L.orc_pm_process.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int, f32p, f32p, i32p]
+        self.h = self.L.orc_pm_create()
+
+    def __del__(self):
+        try:
+            self.L.orc_pm_destroy(self.h)
+        except Exception:
+            pass
+
+    def process(self, corner_last, surf_last, transform_sum7):
+        c = np.ascontiguousarray(corner_last, np.float32).reshape(-1, 4); s = np.ascontiguousarray(surf_last, np.float32).reshape(-1, 4)
+        tobe = np.zeros(7, np.float32); info = np.zeros(3, np.int32)
+        self.L.orc_pm_process(self.h, c if c.shape[0] else np.zeros((1, 4), np.float32), c.shape[0],
+                              s if s.shape[0] else np.zeros((1, 4), np.float32), s.shape[0],
+                              np.ascontiguousarray(transform_sum7, np.float32), tobe, info)
+        return tobe, dict(iterations=int(info[0]), corner_from_map=int(info[1]), surf_from_map=int(info[2]))

@@ -84,3 +84,33 @@ def test_update_inserts_and_filters_valid_cubes(oracle):
     n1 = cm.cube(idx, "surf").shape[0]
     cm.update(corner, surf, valid, tf7, cen)
     assert cm.cube(idx, "surf").shape[0] <= n1 + 5
+
+
+def test_point_mapping_process_tracks_a_drifting_odometry(oracle):
+    """PointMapping::Process in a loop (oracle): the odometry input drifts, the scan-to-map optimisation against the growing cube
+    map pulls the mapped pose back towards the ground truth."""
+    from lio_mapping_b200 import synth
+    from tests import helpers
+    sensor, scene, traj = synth.default_config("vlp16")
+    pm = oracle.PointMappingOracle()
+    p0 = R0 = None
+    err_odom, err_map = [], []
+    for f in range(7):
+        t_end = 1.0 + 0.1 * f
+        sw = synth.make_sweep(sensor, scene, traj, t_end, seed=40 + f, distort=False)
+        r = oracle.stage_a(sw, sensor.lower_deg, sensor.upper_deg, sensor.rings)
+        p, R, _, _, _ = traj.state(np.array(t_end))
+        if f == 0:
+            p0, R0 = p, R
+        Rrel, trel, tf7 = helpers.rel_transform((R0, p0), (R, p))
+        drift = np.array([0.03, -0.02, 0.01], np.float32) * f               # accumulated odometry error
+        tf_odom = tf7.copy(); tf_odom[4:] += drift
+        tobe, info = pm.process(r["less_sharp"], r["less_flat"], tf_odom)
+        if f == 0:
+            assert info["iterations"] == 0 and info["surf_from_map"] == 0     # empty map: the optimiser returns at its guard
+        else:
+            assert info["surf_from_map"] > 100 and info["corner_from_map"] > 10 and info["iterations"] >= 1
+        err_odom.append(float(np.linalg.norm(tf_odom[4:] - tf7[4:])))
+        err_map.append(float(np.linalg.norm(tobe[4:] - tf7[4:])))
+    # the mapped pose stays within a few centimetres while the raw odometry has drifted by ~0.2 m
+    assert err_odom[-1] > 0.15 and err_map[-1] < 0.05 and max(err_map[1:]) < 0.06, (err_odom, err_map)
