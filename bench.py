@@ -107,7 +107,7 @@ def run_reference(args, scn, W, est_cfg):
     scenario.warm_start(eo, scn, W, lambda k: O.voxel_grid(stage_a(k), est_cfg["surf_filter_size"]),
                         lambda a, g: O.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=est_cfg["acc_n"], gyr_n=est_cfg["gyr_n"],
                                            acc_w=est_cfg["acc_w"], gyr_w=est_cfg["gyr_w"], g_norm=est_cfg["g_norm"]))
-    times, iters, solve_t = [], [], []
+    times, iters, solve_t, states = [], [], [], {}
     k0 = W
     for s in range(args.warmup + args.steps):
         k = k0 + s
@@ -116,13 +116,31 @@ def run_reference(args, scn, W, est_cfg):
         scenario.feed_imu(eo, scn, k)
         eo.process_scan(r["less_flat"])
         dt = time.perf_counter() - t0
+        states[k] = eo.states()
         if s >= args.warmup:
             times.append(dt)
             sm = eo.summary()
             iters.append(sm["iterations"]); solve_t.append(sm["t_solve"])
     total = float(np.sum(times))
     return dict(scans_per_s=len(times) / total, ms_per_step=1e3 * total / len(times),
-                gn_iter_ms=1e3 * float(np.sum(solve_t)) / max(1.0, float(np.sum(iters))), steps=len(times))
+                gn_iter_ms=1e3 * float(np.sum(solve_t)) / max(1.0, float(np.sum(iters))), steps=len(times), states=states)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def asm_traffic(kind):
+    """dram__bytes_read+write per asm_ppp launch from the committed `ncu --set full` capture of the SAME workload
+    (profiles/asm_ppp_traffic.json), else None."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "asm_ppp_traffic.json")))
+        return t.get(kind, {}).get("traffic_bytes_per_launch")
+    except Exception:
+        return None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -156,13 +174,13 @@ def main():
             return 0
         scn = scenario.Scenario(kind, n_total=n_total)
         r = run_reference(args, scn, W, est_cfg)
-        cores = 4
+        cores = 4   # threads the restatement actually uses: 1 (front end, kNN, dogleg: Ceres num_threads = 1) + 4 only inside ThreadsConstructA
         line = {"impl": "reference", "metric": METRIC, "value": r["scans_per_s"], "unit": "scans/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f32 features / f64 solve", "data": "synthetic",
                 "gn_iter_ms": r["gn_iter_ms"],
                 "config": {"workload": workload, "window": W, "opt_window": W, "points_per_scan": int(scn.raw[W].shape[0])},
-                "cpu_baseline": {"value": r["scans_per_s"], "unit": "scans/s", "cores": cores, "kind": "port",
+                "cpu_baseline": {"value": r["scans_per_s"], "unit": "scans/s", "cores": cores, "host_cores": host_cores(), "kind": "port",
                                  "sample": "%d scans of the same workload (oracle/: CPU restatement; the reference needs Eigen/PCL/Ceres/ROS, absent here); 1 thread + 4 marginalisation threads" % r["steps"]},
                 "e2e": {"value": r["scans_per_s"], "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -315,8 +333,9 @@ def main():
                                                    acc_w=est_cfg["acc_w"], gyr_w=est_cfg["gyr_w"], g_norm=est_cfg["g_norm"]))
     k = W
     barrier()
+    e2e_states = {}
     for _ in range(args.warmup):
-        step_host(k); k += 1
+        e2e_states[k] = step_host(k); k += 1
     e2e_t = 0.0
     h2d = d2h = 0
     for s in range(args.steps):
@@ -326,6 +345,7 @@ def main():
         st = step_host(k)
         torch.cuda.synchronize()
         e2e_t += time.perf_counter() - t0
+        e2e_states[k] = st
         sm = est.summary()
         h2d += scn.raw[k].shape[0] * 16 + (W + 1) * 28 + 4
         d2h += int(sm["linearizations"] + 2) * W * 32 * 8 + (W + 8) * 4 + 28
@@ -354,14 +374,15 @@ def main():
                            "parallelism": "frames sharded 1..O over %d rank(s)%s" % (world, ("; exchange: " + exchange["kind"]) if world > 1 else ""),
                            "e2e_vs_device_pass_max_pos_diff_m": drift,
                            "overlap_marginalization": args.overlap_marginalization,
+                           "timing": "value: CUDA events around each scan (device-resident sweep); e2e: host perf_counter around the C-ABI calls; the bench host is shared, runs differ by about +-10 %",
                            "ms_per_timed_step": [round(float(v), 3) for v in ms],
                            "host_wall_ms_per_scan": {kk: 1e3 * float(np.mean(v)) for kk, v in brk.items()}},
                 "roofline": {"kernel": "asm_ppp (fused PivotPointPlane residual+Jacobian+JtJ reduction)", "bound": "hbm",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": 3.83e6 if kind == "hdl64" else None,
+                             "traffic": asm_traffic(kind),
                              "avg_launch_us": avg_ms * 1e3, "bytes_per_launch": bytes_per_launch, "launches": prof["asm_launches"],
                              "peak_source": peak_src,
-                             "note": "32 B/feature x features of the solve (3.9 MB per launch on HDL-64): launch-latency bound, ~12 us fixed cost; traffic = dram__bytes_read+write per launch from profiles/r1a_asm_ppp_full_hdl64.csv (ncu --set full of this workload: every byte read once); the streaming rate of the same kernel is in roofline_stream"},
+                             "note": "32 B/feature x features of the solve (3.9 MB per launch on HDL-64): launch-latency bound, ~12 us fixed cost; traffic = dram__bytes_read+write per launch from the committed ncu --set full capture of this workload (profiles/asm_ppp_traffic.json; null when there is none); the streaming rate of the same kernel is in roofline_stream"},
                 "roofline_knn": {"kernel": "knn_plane (frame-batched 5-NN + plane fit, the largest share of kernel time)", "bound": "hbm",
                                  "achieved": (prof["bytes_per_query"] * prof["knn_queries"] / max(1, prof["knn_launches"])) /
                                              (max(prof["knn_ms"], 1e-9) / max(1, prof["knn_launches"]) * 1e-3) / 1e9,
@@ -385,12 +406,27 @@ def main():
             try:
                 ra = argparse.Namespace(warmup=1, steps=min(args.cpu_sample, n_total - W - 2))
                 r = run_reference(ra, scn, W, est_cfg)
-                line["cpu_baseline"] = {"value": r["scans_per_s"], "unit": "scans/s", "cores": 4, "kind": "port",
+                line["cpu_baseline"] = {"value": r["scans_per_s"], "unit": "scans/s", "cores": 4, "host_cores": host_cores(), "kind": "port",
                                         "gn_iter_ms": r["gn_iter_ms"],
                                         "sample": "%d scans of the same workload through oracle/ (CPU restatement of the reference; 1 thread + 4 marginalisation threads)" % r["steps"]}
+                # parity of THIS run: the oracle consumed the same scans from the same start as the e2e pass
+                common = sorted(set(r["states"]) & set(e2e_states))
+                perr, qerr = 0.0, 0.0
+                for kk in common:
+                    xo, xg = r["states"][kk], e2e_states[kk]
+                    perr = max(perr, float(np.abs(xg[:, :3] - xo[:, :3]).max() / max(1.0, np.abs(xo[:, :3]).max())))
+                    qerr = max(qerr, float(np.abs(xg[:, 3:7] - xo[:, 3:7]).max()))
+                line["parity"] = {"max_rel_pos_err": perr, "max_quat_err": qerr, "scans": len(common), "tolerance": 1e-4,
+                                  "ok": bool(common) and perr <= 1e-4 and qerr <= 1e-4,
+                                  "against": "oracle/ (CPU restatement of the reference) on the same scans, window states after every scan"}
             except Exception as exc:  # the baseline leg must not take the bench line down
                 line["cpu_baseline"] = {"value": None, "unit": "scans/s", "cores": 0, "kind": "port", "sample": "failed: %r" % (exc,)}
         print(json.dumps(line))
+        if "parity" in line and not line["parity"]["ok"]:
+            print("[bench] PARITY FAILED: %r" % (line["parity"],), file=sys.stderr)
+            if world > 1:
+                dist.destroy_process_group()
+            return 3
     if world > 1:
         dist.destroy_process_group()
     return 0

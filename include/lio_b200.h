@@ -244,14 +244,18 @@ int lio_est_process_imu(lio_est *est, double dt, const double acc[3], const doub
 /* The same for n consecutive messages (dt[n], acc3[n][3], gyr3[n][3], stamp[n]) in one call: bag playback / batched drivers. */
 int lio_est_process_imu_batch(lio_est *est, int n, const double *dt, const double *acc3, const double *gyr3, const double *stamp);
 /* Estimator::ProcessLaserOdom, INITED branch (Estimator.cc:618-774): de-skew + VoxelGrid + SolveOptimization +
- * SlideWindow.  surf_last = laser_cloud_surf_last_ (surface_points_less_flat of the new sweep), HOST buffer. */
+ * SlideWindow.  surf_last = laser_cloud_surf_last_ (surface_points_less_flat of the new sweep), HOST buffer.
+ * Error behaviour: the window bookkeeping (pre-integration buffer, frame slots) advances before the device work, as in
+ * the reference.  If a scan fails after that point (LIO_ERR_CAPACITY: down-sampled scan > max_frame_points, local map or
+ * feature buffers full, voxel index overflow; LIO_ERR_NUMERIC; LIO_ERR_CUDA) the context is POISONED: every later
+ * lio_est_process_scan_* call returns LIO_ERR_INVALID until the context is destroyed and re-created. */
 int lio_est_process_scan_host(lio_est *est, const float *surf_last, int n);
 /* Optional: announce that the next sweep has arrived (call before stage A / lio_pp_process_*).  Starts the background
  * marginalisation algebra of the previous scan now instead of at the lio_est_process_scan_* entry, so it also overlaps
  * the feature extraction of the new sweep.  No effect with overlap_marginalization = 0. */
 int lio_est_begin_scan(lio_est *est);
 /* Same with the cloud already on the device (e.g. lio_pp_cloud_dev(LIO_PP_SURF_LESS_FLAT)); n is read
- * from *n_dev on the device, n_max bounds it. */
+ * from *n_dev on the device and clamped there to n_max (n_max itself is clamped to max_scan_points). */
 int lio_est_process_scan_dev(lio_est *est, const float *surf_last_dev, const int *n_dev, int n_max);
 /* Device pointer to the point count of one stage-A output cloud, to chain stage A into the estimator. */
 int lio_pp_cloud_count_dev(lio_pp *pp, int which, const int **n_dev);

@@ -461,6 +461,7 @@ struct lio_est {
   struct ImuBlockStore { double JtJ[30 * 30], Jtr[30], cost; bool used; } imu_blocks_store[kMaxOpt];
   std::atomic<int> imu_next{0}, imu_done{0};  // shared pool of ImuFactor indices of one linearisation (caller + helper)
   double t_marg_wait = 0;
+  bool poisoned = false;   // a scan failed half-way: the window bookkeeping is inconsistent, every later call fails fast
   int W = 0, O = 0, device = 0;
   cudaStream_t stream = 0;
   int sm_count = 148;
@@ -902,7 +903,7 @@ static int build_local_map(lio_est *e) {
   EST_CUDA(cudaMemcpyAsync(e->d_tf, e->h_tf, sizeof(TransformF) * (W + 1), cudaMemcpyHostToDevice, st));
   k_concat<<<std::max(1, std::min(e->sm_count * 4, (e->local_cap + 255) / 256)), 256, 0, st>>>(cp, e->d_local, e->d_counts + 1, e->local_cap);
   ++e->launches;
-  int rc = e->vg.run(e->d_local, e->d_counts + 1, e->local_cap, e->cfg.surf_filter_size, e->d_map, e->d_counts + 2, nullptr, st, &e->launches);
+  int rc = e->vg.run(e->d_local, e->d_counts + 1, e->local_cap, e->cfg.surf_filter_size, e->d_map, e->local_cap, e->d_counts + 2, nullptr, st, &e->launches);
   if (rc != LIO_OK) return rc;
   const float cell = std::sqrt(e->cfg.min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
   rc = e->hash.build(e->d_map, e->d_counts + 2, e->local_cap, cell, st, &e->launches);
@@ -951,7 +952,17 @@ static int build_local_map(lio_est *e) {
   EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 5, &e->d_odom->iter, sizeof(int), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaMemcpyAsync(e->h_tf + W, e->d_tf + W, sizeof(TransformF), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 6, e->d_slot_n + e->slot_of[W], sizeof(int), cudaMemcpyDeviceToHost, st));
+  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 7, e->vg.overflow_flag(), sizeof(int), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaStreamSynchronize(st));
+  if (e->h_counts[W + 6] > e->cfg.max_frame_points) {   // vg_emit stopped storing at the capacity but kept counting
+    lio_set_last_error(__FILE__, __LINE__, "down-sampled scan exceeds max_frame_points");
+    return LIO_ERR_CAPACITY;
+  }
+  if (e->h_counts[W + 7]) {   // PCL: "Leaf size is too small for the input dataset. Integer indices would overflow."
+    cudaMemsetAsync(e->vg.overflow_flag(), 0, sizeof(int), st);
+    lio_set_last_error(__FILE__, __LINE__, "voxel grid index overflow (leaf size too small for the cloud extent)");
+    return LIO_ERR_CAPACITY;
+  }
   e->size_surf_stack[W] = e->h_counts[W + 6];
   if (e->knn_timed) {  // live duration of the frame-batched k-NN + plane-fit launch (its memsets included, ~2 us)
     float ms = 0.f;
@@ -1055,7 +1066,12 @@ static int eval_lidar_wait(lio_est *e) {
   EST_CUDA(cudaStreamSynchronize(e->stream));
   e->t_lin_wait += now_s() - t0;
   e->S_pending = false;
-  if (*reinterpret_cast<const int *>(e->h_S + kMaxOpt * kAsmStride)) { lio_set_last_error(__FILE__, __LINE__, "peer exchange timed out (a rank did not publish its rows)"); return LIO_ERR_CUDA; }
+  if (*reinterpret_cast<const int *>(e->h_S + kMaxOpt * kAsmStride)) {
+    cudaMemsetAsync(e->xbuf + kXErrOff, 0, sizeof(int), e->stream);   // the flag is one-shot: clear it with the report
+    *reinterpret_cast<int *>(e->h_S + kMaxOpt * kAsmStride) = 0;
+    lio_set_last_error(__FILE__, __LINE__, "peer exchange timed out (a rank did not publish its rows)");
+    return LIO_ERR_CUDA;
+  }
   if (e->ev0 && e->ev1) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->ev0, e->ev1) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += e->S_pending_feats; }
@@ -1597,7 +1613,22 @@ static int slide_window(lio_est *e) {  // Estimator.cc:2570-2666
   return LIO_OK;
 }
 
+static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max);
+// The pre-integration buffer, the slot rotation and size_surf_stack advance before the fallible device work.  A failure
+// after that point leaves the window half-slid, so the context is poisoned: later calls return LIO_ERR_INVALID instead of
+// running on inconsistent state (documented in lio_b200.h).
 static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max) {
+  if (e->poisoned) {
+    lio_set_last_error(__FILE__, __LINE__, "estimator context poisoned by an earlier failed scan: destroy and re-create it");
+    return LIO_ERR_INVALID;
+  }
+  if (!e->tmp_pre) { lio_set_last_error(__FILE__, __LINE__, "process_scan before finish_init"); return LIO_ERR_INVALID; }
+  const int rc = process_scan_body(e, scan_dev, n_dev, n_max);
+  if (rc != LIO_OK) e->poisoned = true;
+  return rc;
+}
+
+static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max) {
   const int W = e->W;
   cudaStream_t st = e->stream;
   marg_start(e);
@@ -1647,7 +1678,7 @@ static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_
     ++e->launches;
     src = e->d_scan;
   }
-  int rc = e->vg.run(src, n_dev, n_max, e->cfg.surf_filter_size, e->slot_ptr[slot], e->d_slot_n + slot, nullptr, st, &e->launches);
+  int rc = e->vg.run(src, n_dev, n_max, e->cfg.surf_filter_size, e->slot_ptr[slot], e->cfg.max_frame_points, e->d_slot_n + slot, nullptr, st, &e->launches);
   if (rc != LIO_OK) return rc;
   EST_CUDA(cudaMemcpyAsync(e->d_own_n + slot, e->d_slot_n + slot, sizeof(int), cudaMemcpyDeviceToDevice, st));
   push_shift(e->size_surf_stack, 0);
@@ -1677,7 +1708,7 @@ extern "C" int lio_est_process_scan_host(lio_est *e, const float *surf_last, int
 
 extern "C" int lio_est_process_scan_dev(lio_est *e, const float *surf_last_dev, const int *n_dev, int n_max) {
   if (!e || !surf_last_dev || !n_dev || n_max <= 0) return LIO_ERR_INVALID;
-  if (n_max > e->cfg.max_scan_points) n_max = e->cfg.max_scan_points;
+  if (n_max > e->cfg.max_scan_points) n_max = e->cfg.max_scan_points;   // the voxel filter clamps *n_dev to n_max on the device
   LIO_CUDA_OK(cudaSetDevice(e->device));
   return process_scan_common(e, reinterpret_cast<const float4 *>(surf_last_dev), n_dev, n_max);
 }

@@ -821,10 +821,8 @@ extern "C" int lio_pp_process_host_ring(lio_pp *pp, const float *xyzi, const uin
   if (!pp || ((!xyzi || !rings) && n > 0) || n < 0) return LIO_ERR_INVALID;
   if (n > pp->max_points) return LIO_ERR_CAPACITY;
   LIO_CUDA_OK(cudaSetDevice(pp->device));
-  if (!pp->d_rings_in) {
-    LIO_CUDA_OK(dalloc(&pp->d_rings_in, (size_t)pp->max_points));
-    LIO_CUDA_OK(dalloc(&pp->d_end_bits, 1));
-  }
+  if (!pp->d_rings_in) LIO_CUDA_OK(dalloc(&pp->d_rings_in, (size_t)pp->max_points));
+  if (!pp->d_end_bits) LIO_CUDA_OK(dalloc(&pp->d_end_bits, 1));
   cudaStream_t st = pp->stream;
   const PPParams &P = pp->P;
   const int R = P.num_rings;

@@ -20,10 +20,13 @@ __device__ __forceinline__ float ord2f(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__global__ void vg_reset(unsigned *bbox, int *ticket) {
+// Also publishes n_eff = min(*n_dev, n_max): every later kernel of the filter (and the radix sort) reads the clamped
+// count, so a caller-side count above the grid / scratch bound cannot run past the buffers.
+__global__ void vg_reset(unsigned *bbox, int *ticket, const int *__restrict__ n_dev, int n_max, int *__restrict__ n_eff) {
   if (threadIdx.x < 3) bbox[threadIdx.x] = 0xffffffffu;
   else if (threadIdx.x < 6) bbox[threadIdx.x] = 0u;
   if (threadIdx.x == 6) *ticket = 0;
+  if (threadIdx.x == 7) { int n = *n_dev; *n_eff = n < 0 ? 0 : (n > n_max ? n_max : n); }
 }
 
 __global__ void __launch_bounds__(256)
@@ -66,7 +69,7 @@ vg_keys(const float4 *__restrict__ in, const int *__restrict__ n_dev, const unsi
     sp[3] = xb0 - mb0 + 1;
     sp[4] = (xb0 - mb0 + 1) * (xb1 - mb1 + 1);
     sp[5] = ovf;
-    if (blockIdx.x == 0) *overflow = ovf;
+    if (blockIdx.x == 0 && ovf) *overflow = 1;   // sticky until the host reads and clears it
   }
   __syncthreads();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -84,8 +87,8 @@ constexpr int kEmitThreads = 256;
 
 __global__ void __launch_bounds__(kEmitThreads)
 vg_emit(const float4 *__restrict__ in, const int *__restrict__ n_dev, const unsigned *__restrict__ keys,
-        const unsigned *__restrict__ vals, float4 *__restrict__ out, int *__restrict__ nout_dev, unsigned *__restrict__ vox_key_out,
-        unsigned long long *__restrict__ status, int *__restrict__ ticket) {
+        const unsigned *__restrict__ vals, float4 *__restrict__ out, int out_cap, int *__restrict__ nout_dev,
+        unsigned *__restrict__ vox_key_out, unsigned long long *__restrict__ status, int *__restrict__ ticket) {
   __shared__ int sscan[40];
   __shared__ int stile, sbc;
   const int n = *n_dev;
@@ -116,8 +119,10 @@ vg_emit(const float4 *__restrict__ in, const int *__restrict__ n_dev, const unsi
       ++cnt;
     }
     float fn = (float)cnt;
-    out[excl + lpos] = make_float4(ax / fn, ay / fn, az / fn, ai / fn);
-    if (vox_key_out) vox_key_out[excl + lpos] = v;
+    if (excl + lpos < out_cap) {   // the count below keeps growing: the host compares it with the capacity
+      out[excl + lpos] = make_float4(ax / fn, ay / fn, az / fn, ai / fn);
+      if (vox_key_out) vox_key_out[excl + lpos] = v;
+    }
   }
   if (tile == ntiles - 1 && threadIdx.x == 0) *nout_dev = excl + tot;
 }
@@ -134,7 +139,8 @@ int VoxelGrid::init(int cap_) {
   nstatus = (cap + kEmitThreads - 1) / kEmitThreads + 1;
   if (cudaMalloc(&status, sizeof(unsigned long long) * nstatus) != cudaSuccess) return -1;
   if (cudaMalloc(&bbox, sizeof(unsigned) * 8) != cudaSuccess) return -1;
-  if (cudaMalloc(&ticket, sizeof(int) * 2) != cudaSuccess) return -1;
+  if (cudaMalloc(&ticket, sizeof(int) * 4) != cudaSuccess) return -1;
+  if (cudaMemset(ticket, 0, sizeof(int) * 4) != cudaSuccess) return -1;
   return 0;
 }
 
@@ -144,12 +150,13 @@ void VoxelGrid::destroy() {
   keys_a = vals_a = keys_b = vals_b = nullptr; rs.tile_hist = nullptr; status = nullptr; bbox = nullptr; ticket = nullptr;
 }
 
-int VoxelGrid::run(const float4 *in, const int *n_dev, int n_max, float leaf, float4 *out, int *nout_dev, unsigned *vox_key_out,
-                   cudaStream_t st, int *launches) {
+int VoxelGrid::run(const float4 *in, const int *n_dev_in, int n_max, float leaf, float4 *out, int out_cap, int *nout_dev,
+                   unsigned *vox_key_out, cudaStream_t st, int *launches) {
   if (n_max > cap) return LIO_ERR_CAPACITY;
   if (n_max <= 0) n_max = 1;
   int *overflow = ticket + 1;
-  vg_reset<<<1, 32, 0, st>>>(bbox, ticket);
+  int *n_dev = ticket + 2;   // clamped copy of the caller's count
+  vg_reset<<<1, 32, 0, st>>>(bbox, ticket, n_dev_in, n_max, n_dev);
   int nblk = (n_max + 255) / 256;
   int bb_blocks = nblk < 592 ? nblk : 592;
   vg_bbox<<<bb_blocks, 256, 0, st>>>(in, n_dev, bbox);
@@ -159,7 +166,7 @@ int VoxelGrid::run(const float4 *in, const int *n_dev, int n_max, float leaf, fl
   const unsigned *k = which ? keys_b : keys_a, *v = which ? vals_b : vals_a;
   int etiles = (n_max + kEmitThreads - 1) / kEmitThreads;
   cudaMemsetAsync(status, 0, sizeof(unsigned long long) * (size_t)(etiles + 1), st);
-  vg_emit<<<etiles, kEmitThreads, 0, st>>>(in, n_dev, k, v, out, nout_dev, vox_key_out, status, ticket);
+  vg_emit<<<etiles, kEmitThreads, 0, st>>>(in, n_dev, k, v, out, out_cap, nout_dev, vox_key_out, status, ticket);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
@@ -189,7 +196,7 @@ extern "C" int lio_voxel_grid_host(const float *cloud, int n, float leaf, float 
   if (rc == LIO_OK) {
     cudaMemcpy(d_in, cloud, sizeof(float4) * n, cudaMemcpyHostToDevice);
     cudaMemcpy(d_n, &n, sizeof(int), cudaMemcpyHostToDevice);
-    rc = vg.run(d_in, d_n, n, leaf, d_out, d_n + 1, nullptr, 0, nullptr);
+    rc = vg.run(d_in, d_n, n, leaf, d_out, n, d_n + 1, nullptr, 0, nullptr);
     if (rc == LIO_OK) {
       int m = 0;
       cudaError_t e = cudaMemcpy(&m, d_n + 1, sizeof(int), cudaMemcpyDeviceToHost);

@@ -1,0 +1,98 @@
+"""Full-window parity (product estimator through the C-ABI vs the CPU oracle) on the configurations that are actually
+benchmarked and shipped, not only on the small VLP-16 windows of test_estimator_gpu.py:
+
+  * HDL-64 outdoor_test_config_64, window 10/10      - BASELINE.json configs[2], the bench's headline workload;
+  * stress 128 x 4096, window 15/15                  - BASELINE.json configs[4];
+  * window 7 / opt 5 (outdoor yaml:12-13) and window 12 / opt 7 + keep_features (indoor yaml:12-13, :68): pivot_idx > 0,
+    i.e. the frame merge of BuildLocalMap (Estimator.cc:1384, 1409-1441) and the pivot slide of SlideWindow (:2570-2635);
+  * keep_features = 1 inside the estimator (Estimator.cc:978-980: LaserOdom rounds append to the newest frame's features).
+
+Tolerances: pose <= 1e-4 relative (north_star), quaternion 1e-4, feature count 0.5 % (10 float LaserOdom rounds reduce in
+a different order), local map identical on the first scan (identical inputs by construction)."""
+import numpy as np
+import pytest
+
+from lio_mapping_b200 import scenario
+from tests import helpers
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(oracle, seq, W, O, max_frame_points, **cfg):
+    from lio_mapping_b200 import estimator
+    eo = oracle.Estimator(window_size=W, opt_window_size=O, **cfg)
+    eg = estimator.Estimator(window_size=W, opt_window_size=O, max_frame_points=max_frame_points,
+                             max_scan_points=max(len(c) for c in seq.less_flat) + 16, **cfg)
+    n5 = dict(acc_n=cfg.get("acc_n", 0.2), gyr_n=cfg.get("gyr_n", 0.02))
+    helpers.warm_start(eo, seq, oracle, W, pose_noise=0.01, seed=1, make_pim=lambda a, g: oracle.Pim(a, g, np.zeros(3), np.zeros(3), **n5))
+    helpers.warm_start(eg, seq, oracle, W, pose_noise=0.01, seed=1, make_pim=lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), **n5))
+    return eo, eg
+
+
+def _run(oracle, seq, W, O, n_scans, max_frame_points, cost_tol=1e-2, **cfg):
+    eo, eg = _pair(oracle, seq, W, O, max_frame_points, **cfg)
+    worst = 0.0
+    for k in range(W, W + n_scans):
+        helpers.feed_scan(eo, seq, k)
+        helpers.feed_scan(eg, seq, k)
+        so, sg = eo.summary(), eg.summary()
+        if k == W:
+            assert sg["map_size"] == so["map_size"]
+            assert np.array_equal(eg.local_map(), eo.local_map())
+        assert abs(sg["map_size"] - so["map_size"]) <= 2 + 1e-4 * so["map_size"], (k, sg["map_size"], so["map_size"])
+        assert abs(sg["num_features"] - so["num_features"]) <= 0.005 * so["num_features"], (k, sg["num_features"], so["num_features"])
+        assert sg["has_prior"] == so["has_prior"], k
+        xo, xg = eo.states(), eg.states()
+        scale = max(1.0, np.abs(xo[:, :3]).max())
+        err = np.abs(xg[:, :3] - xo[:, :3]).max() / scale
+        worst = max(worst, err)
+        assert err <= 1e-4, (k, err)                                       # north_star: pose error <= 1e-4 relative
+        assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-4, k
+        assert np.abs(xg[:, 7:10] - xo[:, 7:10]).max() <= 1e-3 * max(1.0, np.abs(xo[:, 7:10]).max()), k
+        assert abs(sg["final_cost"] - so["final_cost"]) <= cost_tol * so["final_cost"], (k, sg["final_cost"], so["final_cost"])
+        assert np.abs(eg.extrinsic() - eo.extrinsic()).max() <= 1e-4, k
+    return worst
+
+
+def test_hdl64_window10_parity(oracle):
+    """The bench's headline workload (HDL-64, outdoor_test_config_64, W = O = 10), three consecutive scans."""
+    seq = helpers.Sequence(oracle, "hdl64", n_total=13, distort=False)
+    _run(oracle, seq, 10, 10, 3, 1 << 16, **scenario.EST_CFG["hdl64"])
+
+
+def test_stress128_window15_parity(oracle):
+    """BASELINE.json configs[4]: 128 x 4096 sweep, W = O = 15, two scans (the second one carries the first prior)."""
+    seq = helpers.Sequence(oracle, "stress128", n_total=17, distort=False)
+    _run(oracle, seq, 15, 15, 2, 1 << 18, **scenario.EST_CFG["stress128"])
+
+
+def test_outdoor_shipped_window_7_5(oracle):
+    """config/outdoor_test_config_64.yaml:12-13: window 7, opt window 5 (pivot_idx = 2) on HDL-64 sweeps."""
+    seq = helpers.Sequence(oracle, "hdl64", n_total=12, distort=False)
+    _run(oracle, seq, 7, 5, 5, 1 << 16, **scenario.EST_CFG["hdl64"])
+
+
+def test_indoor_shipped_window_12_7_keep_features(oracle):
+    """config/indoor_test_config.yaml:12-13, :50, :68: window 12, opt window 7 (pivot_idx = 5), prior_factor 0,
+    keep_features 1 on VLP-16 sweeps."""
+    seq = helpers.Sequence(oracle, "vlp16", n_total=17, distort=False)
+    cfg = dict(scenario.EST_CFG["vlp16"], prior_factor=0, keep_features=1)
+    _run(oracle, seq, 12, 7, 5, 1 << 15, **cfg)
+
+
+def test_keep_features_in_estimator(oracle):
+    """keep_features = 1 with W = O: the newest frame's feature list grows over the LaserOdom rounds (Estimator.cc:978-980)
+    and all of them enter the window problem."""
+    seq = helpers.Sequence(oracle, "vlp16", n_total=9, distort=False)
+    cfg = dict(scenario.EST_CFG["vlp16"], keep_features=1, opt_extrinsic=0)
+    eo, eg = _pair(oracle, seq, 5, 5, 1 << 15, **cfg)
+    for k in range(5, 9):
+        helpers.feed_scan(eo, seq, k)
+        helpers.feed_scan(eg, seq, k)
+        so, sg = eo.summary(), eg.summary()
+        no, ng = eo.features(5)[0].shape[0], eg.features(5)[0].shape[0]
+        assert no > 1.5 * eo.features(4)[0].shape[0]          # really accumulated over several rounds
+        assert abs(ng - no) <= 0.01 * no, (k, ng, no)
+        xo, xg = eo.states(), eg.states()
+        assert np.abs(xg[:, :3] - xo[:, :3]).max() <= 1e-4 * max(1.0, np.abs(xo[:, :3]).max()), k
+        assert np.abs(xg[:, 3:7] - xo[:, 3:7]).max() <= 1e-4, k

@@ -1,14 +1,11 @@
 """Ring-field variant of stage A (PointToRing for lio::PointXYZIR input, PointProcessor.cc:428-536) on the device vs the
-oracle.  The device entry was written after the round's GPU budget was spent, so it has not run on hardware yet: the test
-is a NON-STRICT xfail (it reports XPASS when the path works, XFAIL when it does not) and the file sorts last so that a
-fault here cannot disturb the verified suite."""
+oracle (first run on hardware: round-1 driver GPU tests, both cases passed)."""
 import numpy as np
 import pytest
 
 from lio_mapping_b200 import synth
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="ring-field device entry not yet run on hardware (round 1)")]
+pytestmark = pytest.mark.gpu
 
 
 def _rings_of(sw, sensor):
