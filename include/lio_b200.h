@@ -182,6 +182,11 @@ int lio_asm_stream_bench(long long n_features, int iters, int device, double out
  * fused kernel (default 1024, i.e. one log per 2048 features and thread). */
 int lio_asm_set_fold_chunks(int chunks);
 
+/* Test seam of the device-resident solver: solves A x = b (A symmetric positive definite, n x n row-major, n <= 216) with
+ * the tiled shared-memory Cholesky (fp64 tensor-core MMA trailing update) that the dogleg step of the device solver uses
+ * in place of Ceres' dense factorisation (Estimator.cc:1911 DENSE_SCHUR).  *ok = 0 when a pivot is not positive. */
+int lio_dev_cholesky_solve_host(const double *A, const double *b, int n, double *x, int *ok, int device);
+
 /* IntegrationBase (include/imu_processor/IntegrationBase.h:72-388) */
 typedef struct lio_pim lio_pim;
 int lio_pim_create(const double acc0[3], const double gyr0[3], const double ba[3], const double bg[3],
@@ -279,6 +284,11 @@ int lio_est_get_prior(lio_est *est, double *Hp, double *bp);
 int lio_est_last_normal_equations(lio_est *est, double *H, double *g, double *cost, int *n);
 /* Kernels launched by the last process_scan call. */
 int lio_est_last_launches(lio_est *est);
+/* Diagnostic: phase timestamps of the device-resident solver's step kernel for the evaluations of the last solve:
+ * out[24][12] (row = evaluation; [0] / [11] = GPU wall clock in ns at kernel entry / exit, [1..10] = SM clock at the phase
+ * boundaries entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit).  Zeros when the
+ * host controller is in use. */
+int lio_est_solver_trace(lio_est *est, long long *out, int cap);
 /* CUDA-event timing of the fused residual+Jacobian kernel accumulated since the last reset (events recorded
  * on the estimator's stream around every launch): out[0..3] = {sum ms, launches, features processed, bytes/feature};
  * out[4..7] = the same for the frame-batched k-NN + plane-fit launch of BuildLocalMap {sum ms, launches, queries,

@@ -101,6 +101,7 @@ def lib():
     L.lio_asm_ppp_host.argtypes = [f32p, f32p, ip, f64p, f64p, f64p, ip]
     L.lio_asm_set_fold_chunks.argtypes = [ip]
     L.lio_asm_stream_bench.argtypes = [C.c_longlong, ip, ip, f64p]
+    L.lio_dev_cholesky_solve_host.argtypes = [f64p, f64p, ip, f64p, C.POINTER(ip), ip]
     L.lio_pim_create.argtypes = [f64p, f64p, f64p, f64p, f64p, C.POINTER(vp)]
     L.lio_pim_destroy.argtypes = [vp]
     L.lio_pim_push_back.argtypes = [vp, C.c_double, f64p, f64p]
@@ -136,6 +137,7 @@ def lib():
     L.lio_est_get_prior.argtypes = [vp, f64p, f64p]
     L.lio_est_last_normal_equations.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(ip)]
     L.lio_est_last_launches.argtypes = [vp]
+    L.lio_est_solver_trace.argtypes = [vp, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), ip]
     L.lio_est_frame_owner.argtypes = [ip, ip]
     L.lio_est_kernel_profile.argtypes = [vp, f64p, ip]
     L.lio_est_set_shard.argtypes = [vp, ip, ip, ALLREDUCE_FN, vp]

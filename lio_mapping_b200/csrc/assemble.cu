@@ -107,6 +107,7 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   __shared__ __align__(8) unsigned long long full_bar[kAsmStages];
   __shared__ double sred[kAsmThreads / 32][29];
   __shared__ bool is_last;
+  if (P.skip_flag && *P.skip_flag) return;
   const int tile = blockIdx.x;
   int fi = 0;
 #pragma unroll 1

@@ -987,9 +987,11 @@ static int build_local_map(lio_est *e) {
 // ---- fused exchange over peer memory -----------------------------------------------------------------
 // Waits until every rank has published `epoch` in this rank's flag array (the rows travel with the asm_ppp tails of the
 // peers as P2P stores; system-scope release / acquire).  Bounded: a peer that never arrives sets *err instead of hanging.
-__global__ void k_xwait(const unsigned *__restrict__ flags, int npeers, unsigned epoch, int *__restrict__ err) {
+__global__ void k_xwait(const unsigned *__restrict__ flags, int npeers, unsigned epoch, int *__restrict__ err,
+                        const int *__restrict__ skip = nullptr) {
   const int p = threadIdx.x;
   if (p >= npeers) return;
+  if (skip && *skip) return;   // the device solver has terminated: its asm_ppp launches publish nothing any more
   const long long t0 = clock64();
   while (true) {
     unsigned v;
@@ -1539,24 +1541,59 @@ static int solve_optimization_dev(lio_est *e) {
     f.pts = fo.pts; f.coef = fo.coef;
     f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
     nfeat += f.n;
+    double Mtmp[108];   // frame terms of the initial point; the solver writes the candidates' terms itself
+    ppp_frame_terms(e->para_pose[0].data(), e->para_pose[i].data(), e->para_ex, e->h_Rt + (i - 1) * kAsmRtStride,
+                    e->h_Rt + (i - 1) * kAsmRtStride + 9, Mtmp);
   }
+  EST_CUDA(cudaMemcpyAsync(e->d_Rt, e->h_Rt, sizeof(double) * O * kAsmRtStride, cudaMemcpyHostToDevice, st));
   asm_plan(ap, e->sm_count);
-  rc = dev_solver_terms(e->ds, e->d_Rt, st, &e->launches);
-  if (rc != LIO_OK) return rc;
+  ap.skip_flag = &e->ds.st->done;
+  const bool peers = e->world > 1 && e->npeers == e->world;
+  if (e->world > 1 && !peers && !e->allreduce) {
+    lio_set_last_error(__FILE__, __LINE__, "sharded context without an exchange: call lio_est_set_peers or pass an allreduce callback");
+    return LIO_ERR_INVALID;
+  }
+  if (peers) {
+    ap.npeers = e->npeers; ap.self = e->rank;
+    for (int i = 1; i <= O; ++i) if (owns_frame(e, pivot + i)) ap.owned_mask |= 1u << (i - 1);
+  }
   const int nevals = e->cfg.max_num_iterations + 1;
   for (int ev = 0; ev < nevals; ++ev) {
+    rc = dev_solver_factors(e->ds, ev, st, &e->launches);   // ImuFactors / prior / M_i on the second stream, beside asm_ppp
+    if (rc != LIO_OK) return rc;
+    const double *result = e->asmw.out;
+    if (peers) {
+      ap.epoch = ++e->xepoch;
+      const size_t par = (size_t)(ap.epoch & 1u) * kXRowBytes;
+      for (int r = 0; r < e->npeers; ++r) {
+        ap.peer_out[r] = reinterpret_cast<double *>(e->peer_base[r] + par);
+        ap.peer_flag[r] = reinterpret_cast<unsigned *>(e->peer_base[r] + kXFlagOff);
+      }
+      result = reinterpret_cast<const double *>(e->xbuf + par);
+    }
     cudaEventRecord(e->evp[2 * ev], st);
     rc = asm_launch(ap, e->d_Rt, e->asmw, st, &e->launches);
     if (rc != LIO_OK) return rc;
     cudaEventRecord(e->evp[2 * ev + 1], st);
-    if (e->world > 1 && e->allreduce) {
+    if (peers) {
+      k_xwait<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
+                                reinterpret_cast<int *>(e->xbuf + kXErrOff), &e->ds.st->done);
+      ++e->launches;
+    } else if (e->world > 1 && e->allreduce) {
       if (e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride) != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
     }
-    rc = dev_solver_step(e->ds, e->asmw.out, e->d_Rt, ev, st, &e->launches);
+    rc = dev_solver_step(e->ds, result, e->d_Rt, ev, st, &e->launches);
     if (rc != LIO_OK) return rc;
   }
+  if (peers) EST_CUDA(cudaMemcpyAsync(e->h_S + kMaxOpt * kAsmStride, e->xbuf + kXErrOff, sizeof(int), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaMemcpyAsync(&S, e->ds.st, offsetof(DevSolveState, scale), cudaMemcpyDeviceToHost, st));
   EST_CUDA(cudaStreamSynchronize(st));
+  if (peers && *reinterpret_cast<const int *>(e->h_S + kMaxOpt * kAsmStride)) {
+    cudaMemsetAsync(e->xbuf + kXErrOff, 0, sizeof(int), st);
+    *reinterpret_cast<int *>(e->h_S + kMaxOpt * kAsmStride) = 0;
+    lio_set_last_error(__FILE__, __LINE__, "peer exchange timed out (a rank did not publish its rows)");
+    return LIO_ERR_CUDA;
+  }
   for (int ev = 0; ev < std::min(nevals, S.evaluations); ++ev) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
@@ -1886,6 +1923,14 @@ extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, d
   return LIO_OK;
 }
 extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
+
+extern "C" int lio_est_solver_trace(lio_est *e, long long *out, int cap) {
+  if (!e || !out || cap < 24 * 12) return LIO_ERR_INVALID;
+  if (!e->use_dev_solver) { std::memset(out, 0, sizeof(long long) * 24 * 12); return LIO_OK; }
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  LIO_CUDA_OK(cudaMemcpy(out, reinterpret_cast<const char *>(e->ds.st) + offsetof(DevSolveState, dbg), sizeof(long long) * 24 * 12, cudaMemcpyDeviceToHost));
+  return LIO_OK;
+}
 
 extern "C" int lio_est_kernel_profile(lio_est *e, double out[8], int reset) {
   if (!e || !out) return LIO_ERR_INVALID;

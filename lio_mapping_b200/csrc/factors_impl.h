@@ -28,10 +28,11 @@ LIO_HD inline M3 left_tl(const Q &q) { return M3::I() * q.w + skew(q.vec()); }
 LIO_HD inline M3 right_tl(const Q &p) { return M3::I() * p.w - skew(p.vec()); }
 }  // namespace fi
 
-// whiten = false returns the raw residual and raw Jacobian blocks (the caller applies sqrt_info, e.g. in parallel)
-// Combined layout: J is 15 x 30 row-major over [pose_i(6) | sb_i(9) | pose_j(6) | sb_j(9)] tangent columns (or nullptr).
-LIO_HD inline void imu_factor_eval30(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
-                                     double r[15], double (*J)[30], bool whiten = true) {
+// Raw (un-whitened) ImuFactor residual and Jacobian: raw[15]; A (15 x 30 over [pose_i(6) | sb_i(9) | pose_j(6) | sb_j(9)]
+// tangent columns, row stride ld, or nullptr).  Only the structurally non-zero 3x3 blocks of A are written: the caller
+// zeroes the buffer first.
+LIO_HD inline void imu_factor_raw(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                                  double raw[15], double *A, int ld) {
   using namespace hm;
   using namespace fi;
   const V3 Pi(pose_i), Pj(pose_j), Vi(sb_i), Bai(sb_i + 3), Bgi(sb_i + 6), Vj(sb_j), Baj(sb_j + 3), Bgj(sb_j + 6);
@@ -50,38 +51,46 @@ LIO_HD inline void imu_factor_eval30(const PimData &pim, const double *pose_i, c
   const V3 rP = rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt) - corrected_delta_p;
   const V3 rR = 2.0 * (inverse(corrected_delta_q) * (Qi_inv * Qj)).vec();
   const V3 rV = rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi) - corrected_delta_v;
-  double raw[15];
   for (int k = 0; k < 3; ++k) { raw[O_P + k] = rP[k]; raw[O_R + k] = rR[k]; raw[O_V + k] = rV[k]; raw[O_BA + k] = Baj[k] - Bai[k]; raw[O_BG + k] = Bgj[k] - Bgi[k]; }
-  if (whiten) { for (int i = 0; i < 15; ++i) { double s = 0; for (int j = i; j < 15; ++j) s += pim.sqrt_info[i][j] * raw[j]; r[i] = s; } }
-  else { for (int i = 0; i < 15; ++i) r[i] = raw[i]; }
-  if (!J) return;
+  if (!A) return;
   const M3 RiT = toR(Qi_inv);
-  double A[15][30];
-  for (int a = 0; a < 15; ++a) for (int c = 0; c < 30; ++c) A[a][c] = 0;
-  put33(&A[0][0], 30, O_P, 0, -RiT);
-  put33(&A[0][0], 30, O_P, 3, skew(rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
+  put33(A, ld, O_P, 0, -RiT);
+  put33(A, ld, O_P, 3, skew(rotate(Qi_inv, -0.5 * g_vec * sum_dt * sum_dt + Pj - Pi - Vi * sum_dt)));
   {  // -(L(Qj^-1 Qi) R(corrected_delta_q)) top-left 3x3
     const Q ql = inverse(Qj) * Qi;
     M3 m = left_tl(ql) * right_tl(corrected_delta_q);
     const V3 qv = ql.vec(), pv = corrected_delta_q.vec();
     for (int a = 0; a < 3; ++a) for (int b = 0; b < 3; ++b) m(a, b) -= qv[a] * pv[b];
-    put33(&A[0][0], 30, O_R, 3, -m);
+    put33(A, ld, O_R, 3, -m);
   }
-  put33(&A[0][0], 30, O_V, 3, skew(rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi)));
-  put33(&A[0][0], 30, O_P, 6, -RiT * sum_dt);
-  put33(&A[0][0], 30, O_P, 9, -dp_dba);
-  put33(&A[0][0], 30, O_P, 12, -dp_dbg);
-  put33(&A[0][0], 30, O_R, 12, -(left_tl(inverse(Qj) * Qi * corrected_delta_q) * dq_dbg));
-  put33(&A[0][0], 30, O_V, 6, -RiT);
-  put33(&A[0][0], 30, O_V, 9, -dv_dba);
-  put33(&A[0][0], 30, O_V, 12, -dv_dbg);
-  put33(&A[0][0], 30, O_BA, 9, -M3::I());
-  put33(&A[0][0], 30, O_BG, 12, -M3::I());
-  put33(&A[0][0], 30, O_P, 15, RiT);
-  put33(&A[0][0], 30, O_R, 18, left_tl(inverse(corrected_delta_q) * Qi_inv * Qj));
-  put33(&A[0][0], 30, O_V, 21, RiT);
-  put33(&A[0][0], 30, O_BA, 24, M3::I());
-  put33(&A[0][0], 30, O_BG, 27, M3::I());
+  put33(A, ld, O_V, 3, skew(rotate(Qi_inv, -1.0 * g_vec * sum_dt + Vj - Vi)));
+  put33(A, ld, O_P, 6, -RiT * sum_dt);
+  put33(A, ld, O_P, 9, -dp_dba);
+  put33(A, ld, O_P, 12, -dp_dbg);
+  put33(A, ld, O_R, 12, -(left_tl(inverse(Qj) * Qi * corrected_delta_q) * dq_dbg));
+  put33(A, ld, O_V, 6, -RiT);
+  put33(A, ld, O_V, 9, -dv_dba);
+  put33(A, ld, O_V, 12, -dv_dbg);
+  put33(A, ld, O_BA, 9, -M3::I());
+  put33(A, ld, O_BG, 12, -M3::I());
+  put33(A, ld, O_P, 15, RiT);
+  put33(A, ld, O_R, 18, left_tl(inverse(corrected_delta_q) * Qi_inv * Qj));
+  put33(A, ld, O_V, 21, RiT);
+  put33(A, ld, O_BA, 24, M3::I());
+  put33(A, ld, O_BG, 27, M3::I());
+}
+
+// whiten = false returns the raw residual and raw Jacobian blocks (the caller applies sqrt_info, e.g. in parallel)
+// Combined layout: J is 15 x 30 row-major over [pose_i(6) | sb_i(9) | pose_j(6) | sb_j(9)] tangent columns (or nullptr).
+LIO_HD inline void imu_factor_eval30(const PimData &pim, const double *pose_i, const double *sb_i, const double *pose_j, const double *sb_j,
+                                     double r[15], double (*J)[30], bool whiten = true) {
+  double raw[15];
+  double A[15][30];
+  if (J) for (int a = 0; a < 15; ++a) for (int c = 0; c < 30; ++c) A[a][c] = 0;
+  imu_factor_raw(pim, pose_i, sb_i, pose_j, sb_j, raw, J ? &A[0][0] : nullptr, 30);
+  if (whiten) { for (int i = 0; i < 15; ++i) { double s = 0; for (int j = i; j < 15; ++j) s += pim.sqrt_info[i][j] * raw[j]; r[i] = s; } }
+  else { for (int i = 0; i < 15; ++i) r[i] = raw[i]; }
+  if (!J) return;
   if (!whiten) {
     for (int i = 0; i < 15; ++i) for (int c = 0; c < 30; ++c) J[i][c] = A[i][c];
     return;

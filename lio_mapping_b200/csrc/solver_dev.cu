@@ -1,12 +1,25 @@
-// Device-resident Gauss-Newton / dogleg loop (stage C shell on the GPU).
+// Device-resident Gauss-Newton / dogleg loop (stage C shell on the GPU): ImuFactor, marginalisation prior, extrinsic
+// PriorFactor, the dense n = 15 (O + 1) + 6 normal equations and the Ceres-1.14 trust-region step all run on the device;
+// the host only enqueues kernels and reads the final state back.
 //
-// One CTA (1024 threads) per evaluation step turns the S blocks of the fused lidar kernel into the full normal
-// equations (lidar M^T S M blocks, ImuFactors, marginalisation prior, extrinsic PriorFactor), judges the last
-// candidate, and computes the next trust-region step — Ceres-1.14 TrustRegionMinimizer + TRADITIONAL_DOGLEG
-// semantics (reference configuration src/imu_processor/Estimator.cc:1909-1921), identical to solver_host.cc.
-// The dense Cholesky runs on the packed lower triangle in shared memory.  The host only enqueues
-// [asm_ppp, k_solver_step] pairs; there is no host synchronisation inside a solve.  A frozen extrinsic keeps its
-// 6 tangent slots with an identity block and zero gradient (its step is exactly zero), so n is fixed.
+// Per evaluation of a solve (reference: ceres::Solve at src/imu_processor/Estimator.cc:1989, options :1909-1921):
+//
+//   asm_ppp    (assemble.cu)  every PivotPointPlaneFactor at the state being evaluated -> O packed 7x7 blocks S_i
+//   k_factors  (O + 1 CTAs, beside asm_ppp on a second stream)  everything that depends on the state but not on the lidar
+//              features: ImuFactor::Evaluate (include/factor/ImuFactor.h:53-167) -> whitened J^T J (30 x 30), J^T r, cost;
+//              MarginalizationFactor::Evaluate (src/factor/MarginalizationFactor.cc:343-392) as Hp dx + bp and its cost;
+//              PriorFactor (src/factor/PriorFactor.cc:35-67); the 6 x 18 maps M_i of the lidar blocks
+//   k_step     (one CTA, 1024 threads)  judges the candidate (TrustRegionMinimizer), and for an accepted point gathers
+//              H = Hp + sum M_i^T S_i M_i + sum J^T J (+ PriorFactor) element-wise, Jacobi-scales it, factors
+//              H + mu D^2 with a tiled Cholesky in shared memory and takes the TRADITIONAL_DOGLEG step; writes the
+//              candidate and its frame terms (R, t) for the next asm_ppp launch.
+//
+// Cholesky: the lower triangle lives in shared memory as 8 x 8 tiles (XOR-swizzled so that the fp64 MMA fragment loads
+// are bank-conflict free).  Right-looking over 8-column panels: the diagonal tile is factored and inverted by warp 0
+// one panel ahead (look-ahead, overlapped with the trailing update), the panel solve X = A L^-T and the trailing update
+// C -= X X^T are fp64 tensor-core MMAs (mma.sync m8n8k4, DMMA) - the one piece of the solver that is a genuine GEMM.
+// The right-hand side rides along as an extra row, so the forward substitution is free; the back substitution walks the
+// tiles in reverse.  n <= 216 (O <= 13) fits one SM; larger windows keep the host controller.
 #include "solver_dev.cuh"
 #include <algorithm>
 
@@ -14,121 +27,53 @@ namespace lio {
 using namespace hm;
 
 constexpr int kDsThreads = 1024;
+constexpr int kDsWarps = kDsThreads / 32;
+constexpr int kFThreads = 256;
 
-__device__ __forceinline__ int d_off_pose(int k) { return 15 * k; }
+struct FPtrs { double *imu, *M, *prior, *ex, *G; };
+
 __device__ __forceinline__ const double *x_pose(const double *x, int k) { return x + 16 * k; }
 __device__ __forceinline__ const double *x_sb(const double *x, int k) { return x + 16 * k + 7; }
+// upper-triangle (row-major) index of (lo, hi), lo <= hi, in the packed 7 x 7 block of asm_ppp
+__device__ __forceinline__ int s_idx(int lo, int hi) { return lo * 7 - lo * (lo - 1) / 2 + (hi - lo); }
 
-__device__ double block_sum(double v, double *sred /*33*/) {
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __syncthreads();
-  if (lane_id() == 0) sred[warp_id()] = v;
-  __syncthreads();
-  if (warp_id() == 0) {
-    double w = (lane_id() < (blockDim.x >> 5)) ? sred[lane_id()] : 0.0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-    if (lane_id() == 0) sred[32] = w;
-  }
-  __syncthreads();
-  return sred[32];
+  return v;
 }
 
-// y = A x, A n x n row-major in global memory: one warp per row, coalesced.
-__device__ void matvec(const double *__restrict__ A, int n, const double *__restrict__ x, double *__restrict__ y) {
-  const int w = warp_id(), nw = blockDim.x >> 5, l = lane_id();
-  for (int r = w; r < n; r += nw) {
-    double s = 0;
-    for (int c = l; c < n; c += 32) s += A[(size_t)r * n + c] * x[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (l == 0) y[r] = s;
+// Sum of up to three values over the block; every thread gets the totals.  sred: 3 * 32 + 3 doubles.
+__device__ void block_sum3(double &a, double &b, double &c, double *sred) {
+  a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+  const int w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) { sred[w] = a; sred[32 + w] = b; sred[64 + w] = c; }
+  __syncthreads();
+  if (w == 0) {
+    double ta = l < nw ? sred[l] : 0.0, tb = l < nw ? sred[32 + l] : 0.0, tc = l < nw ? sred[64 + l] : 0.0;
+    ta = warp_sum(ta); tb = warp_sum(tb); tc = warp_sum(tc);
+    if (l == 0) { sred[96] = ta; sred[97] = tb; sred[98] = tc; }
   }
   __syncthreads();
+  a = sred[96]; b = sred[97]; c = sred[98];
 }
 
-__device__ __forceinline__ double &LP(double *L, int i, int j) { return L[(size_t)i * (i + 1) / 2 + j]; }
-
-// Cholesky of (H + mu D^2) on the packed lower triangle in shared memory, then solve for rhs (in/out, global).
-// Returns 1 on success (uniform).  s_flag[0] is scratch.
-__device__ int chol_solve_smem(const double *__restrict__ H, int n, double mu, const double *__restrict__ diagonal, double *L,
-                               double *rhs, int *s_flag) {
-  const int tid = threadIdx.x, T = blockDim.x;
-  for (int p = tid; p < n * (n + 1) / 2; p += T) {
-    int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-    while ((i + 1) * (i + 2) / 2 <= p) ++i;
-    while (i * (i + 1) / 2 > p) --i;
-    int j = p - i * (i + 1) / 2;
-    double v = H[(size_t)i * n + j];
-    if (i == j) v += mu * diagonal[i] * diagonal[i];
-    L[p] = v;
-  }
-  if (tid == 0) s_flag[0] = 1;
+__device__ double block_max(double v, double *sred) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int w = warp_id(), l = lane_id(), nw = blockDim.x >> 5;
   __syncthreads();
-  for (int k = 0; k < n; ++k) {
-    if (tid == 0) {
-      double d = LP(L, k, k);
-      if (!(d > 0.0) || !isfinite(d)) s_flag[0] = 0;
-      else LP(L, k, k) = sqrt(d);
-    }
-    __syncthreads();
-    if (!s_flag[0]) break;
-    const double lkk = LP(L, k, k);
-    for (int i = k + 1 + tid; i < n; i += T) LP(L, i, k) /= lkk;
-    __syncthreads();
-    // trailing update a(i,j) -= l_ik l_jk for k < j <= i: 16 threads share a row
-    for (int i = k + 1 + (tid >> 4); i < n; i += (T >> 4)) {
-      const double lik = LP(L, i, k);
-      double *row = L + (size_t)i * (i + 1) / 2;
-      for (int j = k + 1 + (tid & 15); j <= i; j += 16) row[j] -= lik * LP(L, j, k);
-    }
-    __syncthreads();
-  }
-  const int ok = s_flag[0];
+  if (l == 0) sred[w] = v;
   __syncthreads();
-  if (!ok) return 0;
-  // triangular solves by warp 0 (lane owns entries i == lane mod 32), values in registers
-  if (warp_id() == 0) {
-    const int l = lane_id();
-    double b[(kDsMaxN + 31) / 32];
+  if (w == 0) {
+    double t = l < nw ? sred[l] : 0.0;
 #pragma unroll
-    for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) { int i = l + 32 * q; b[q] = i < n ? rhs[i] : 0.0; }
-    for (int k = 0; k < n; ++k) {  // L y = b
-      double bk = 0.0;
-#pragma unroll
-      for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) if (q == (k >> 5)) bk = b[q];
-      double yk = bk / LP(L, k, k);
-      yk = __shfl_sync(0xffffffffu, yk, k & 31);
-#pragma unroll
-      for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) {
-        int i = l + 32 * q;
-        if (i == k) b[q] = yk;
-        else if (i > k && i < n) b[q] -= LP(L, i, k) * yk;
-      }
-    }
-    for (int k = n - 1; k >= 0; --k) {  // L^T x = y
-      double bk = 0.0;
-#pragma unroll
-      for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) if (q == (k >> 5)) bk = b[q];
-      double xk = bk / LP(L, k, k);
-      xk = __shfl_sync(0xffffffffu, xk, k & 31);
-#pragma unroll
-      for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) {
-        int i = l + 32 * q;
-        if (i == k) b[q] = xk;
-        else if (i < k) b[q] -= LP(L, k, i) * xk;
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < (kDsMaxN + 31) / 32; ++q) { int i = l + 32 * q; if (i < n) rhs[i] = b[q]; }
+    for (int o = 16; o > 0; o >>= 1) t = fmax(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (l == 0) sred[96] = t;
   }
   __syncthreads();
-  if (tid == 0) { int okv = 1; for (int i = 0; i < n; ++i) if (!isfinite(rhs[i])) okv = 0; s_flag[0] = okv; }
-  __syncthreads();
-  const int fin = s_flag[0];
-  __syncthreads();
-  return fin;
+  return sred[96];
 }
 
 __device__ void pose_dx_dev(const double *x, const double *x0, double *out) {  // MarginalizationFactor::Evaluate :347-372
@@ -140,289 +85,485 @@ __device__ void pose_dx_dev(const double *x, const double *x0, double *out) {  /
   out[3] = s * dn.x; out[4] = s * dn.y; out[5] = s * dn.z;
 }
 
-// Normal equations at state xe into (Hd, gd); cost components into s_cost[0..3] (ppp, pim, marg, ex prior).
-__device__ void build_normal(DevSolveState *S, const double *__restrict__ xe, const double *__restrict__ Sblk, const double *__restrict__ Hp,
-                             double *__restrict__ Hd, double *__restrict__ gd, double *sM, double *sSM, double *scratch, double *s_cost,
-                             double *sred) {
-  const int tid = threadIdx.x, T = blockDim.x;
-  const int O = S->O, n = S->n;
-  const int oe = 15 * (O + 1);
-  const bool ex_free = S->ex_free != 0;
-  for (int p = tid; p < n * n; p += T) Hd[p] = 0.0;
-  for (int p = tid; p < n; p += T) gd[p] = 0.0;
-  if (tid < 4) s_cost[tid] = 0.0;
-  // frame terms
-  if (tid < O) {
-    double R[9], t[3];
-    ppp_frame_terms_impl(x_pose(xe, 0), x_pose(xe, tid + 1), xe + 16 * (O + 1), R, t, sM + tid * 108);
-  }
-  __syncthreads();
-  if (S->point_distance_factor) {
-    // SM_i = Sgg_i * M_i (6 x 18)
-    for (int p = tid; p < O * 108; p += T) {
-      const int i = p / 108, q = p - i * 108, a = q / 18, c = q - a * 18;
-      const double *Sb = Sblk + i * kAsmStride;
-      double s = 0;
-      for (int b = 0; b < 6; ++b) {
-        const int lo = a < b ? a : b, hi = a < b ? b : a;
-        const int idx = lo * 7 - lo * (lo - 1) / 2 + (hi - lo);  // upper-triangle (row-major) index of (lo,hi) in 7x7
-        s += Sb[idx] * sM[i * 108 + b * 18 + c];
-      }
-      sSM[p] = s;
+// =====================================================================================================
+// k_factors: one CTA per ImuFactor (+ the frame terms M of the lidar block of frame b + 1), one CTA for the prior
+__global__ void __launch_bounds__(kFThreads)
+k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, int eval_index) {
+  __shared__ double sA[15 * 31];   // raw [J | r]
+  __shared__ double sJ[15 * 31];   // whitened
+  __shared__ double sdx[kDsMaxNp], sHdx[kDsMaxNp];
+  __shared__ double sred[kFThreads / 32];
+  if (S->done) return;
+  const int tid = threadIdx.x, O = S->O, b = blockIdx.x;
+  const double *xe = eval_index == 0 ? S->x : S->cand;
+  if (b < O) {
+    const bool imu = S->imu_factor && S->pim_valid[b];
+    for (int p = tid; p < 15 * 31; p += kFThreads) sA[p] = 0.0;
+    __syncthreads();
+    if (tid == 0 && imu) {
+      double raw[15];
+      imu_factor_raw(S->pim[b], x_pose(xe, b), x_sb(xe, b), x_pose(xe, b + 1), x_sb(xe, b + 1), raw, sA, 31);
+      for (int a = 0; a < 15; ++a) sA[a * 31 + 30] = raw[a];
+    }
+    if (tid == 32 && S->point_distance_factor) {
+      double R[9], t[3];
+      ppp_frame_terms_impl(x_pose(xe, 0), x_pose(xe, b + 1), xe + 16 * (O + 1), R, t, F.M + (size_t)b * kFMStride);
     }
     __syncthreads();
-    // shared blocks (pose_0 / ex rows and columns): sum over frames in frame order
-    for (int p = tid; p < 144; p += T) {
-      const int ra = p / 12, rb = p - ra * 12;
-      const int a = ra < 6 ? ra : ra + 6, b = rb < 6 ? rb : rb + 6;  // columns 0..5 (pose_0) or 12..17 (ex) of M
-      if ((!ex_free) && (ra >= 6 || rb >= 6)) continue;
+    if (!imu) return;
+    const PimData &pim = S->pim[b];
+    for (int p = tid; p < 15 * 31; p += kFThreads) {
+      const int a = p / 31, c = p - a * 31;
       double s = 0;
-      for (int i = 0; i < O; ++i) {
-        double v = 0;
-        for (int k = 0; k < 6; ++k) v += sM[i * 108 + k * 18 + a] * sSM[i * 108 + k * 18 + b];
-        s += v;
-      }
-      const int ia = ra < 6 ? ra : oe + (ra - 6), ib = rb < 6 ? rb : oe + (rb - 6);
-      Hd[(size_t)ia * n + ib] = s;
-    }
-    // frame-specific blocks
-    for (int p = tid; p < O * 324; p += T) {
-      const int i = p / 324, q = p - i * 324, a = q / 18, b = q - a * 18;
-      const int ba = a / 6, bb = b / 6;
-      if (ba != 1 && bb != 1) continue;
-      if (!ex_free && (ba == 2 || bb == 2)) continue;
-      double v = 0;
-      for (int k = 0; k < 6; ++k) v += sM[i * 108 + k * 18 + a] * sSM[i * 108 + k * 18 + b];
-      const int offs[3] = {0, d_off_pose(i + 1), oe};
-      Hd[(size_t)(offs[ba] + a % 6) * n + offs[bb] + b % 6] = v;
-    }
-    // gradient
-    for (int p = tid; p < 12 + O * 6; p += T) {
-      if (p < 12) {
-        if (!ex_free && p >= 6) continue;
-        const int a = p < 6 ? p : p + 6;
-        double s = 0;
-        for (int i = 0; i < O; ++i) {
-          const double *Sb = Sblk + i * kAsmStride;
-          double v = 0;
-          for (int k = 0; k < 6; ++k) v += sM[i * 108 + k * 18 + a] * Sb[k * 7 - k * (k - 1) / 2 + (6 - k)];
-          s += v;
-        }
-        gd[p < 6 ? p : oe + (p - 6)] = s;
-      } else {
-        const int i = (p - 12) / 6, a6 = (p - 12) % 6, a = 6 + a6;
-        const double *Sb = Sblk + i * kAsmStride;
-        double v = 0;
-        for (int k = 0; k < 6; ++k) v += sM[i * 108 + k * 18 + a] * Sb[k * 7 - k * (k - 1) / 2 + (6 - k)];
-        gd[d_off_pose(i + 1) + a6] = v;
-      }
-    }
-    if (tid == 0) { double c = 0; for (int i = 0; i < O; ++i) c += 0.5 * Sblk[i * kAsmStride + 28]; s_cost[0] = c; }
-  }
-  __syncthreads();
-  // ---- ImuFactors: one thread per factor builds the raw (sparse) Jacobian blocks and residual into shared scratch,
-  // all threads whiten with the upper-triangular sqrt_info in parallel, then J^T J / J^T r are accumulated in two
-  // phases (consecutive factors overlap on one pose/speed-bias block).
-  if (S->imu_factor) {
-    double *sA = scratch;                 // O x 15 x 31 raw [J | r]
-    double *sJ = scratch + O * 465;       // O x 15 x 31 whitened
-    if (tid < O && S->pim_valid[tid]) {
-      double r[15], Ji[15][6], Jsi[15][9], Jj[15][6], Jsj[15][9];
-      imu_factor_eval_impl(S->pim[tid], x_pose(xe, tid), x_sb(xe, tid), x_pose(xe, tid + 1), x_sb(xe, tid + 1), r, Ji, Jsi, Jj, Jsj, false);
-      double *A = sA + tid * 465;
-      for (int a = 0; a < 15; ++a) {
-        for (int c = 0; c < 6; ++c) { A[a * 31 + c] = Ji[a][c]; A[a * 31 + 15 + c] = Jj[a][c]; }
-        for (int c = 0; c < 9; ++c) { A[a * 31 + 6 + c] = Jsi[a][c]; A[a * 31 + 21 + c] = Jsj[a][c]; }
-        A[a * 31 + 30] = r[a];
-      }
-    }
-    __syncthreads();
-    for (int p = tid; p < O * 465; p += T) {
-      const int i = p / 465, q = p - i * 465, a = q / 31, c = q - a * 31;
-      if (!S->pim_valid[i]) continue;
-      double s = 0;
-      for (int k = a; k < 15; ++k) s += S->pim[i].sqrt_info[a][k] * sA[i * 465 + k * 31 + c];
+      for (int k = a; k < 15; ++k) s += pim.sqrt_info[a][k] * sA[k * 31 + c];
       sJ[p] = s;
     }
     __syncthreads();
-    for (int parity = 0; parity < 2; ++parity) {
-      for (int p = tid; p < O * 930; p += T) {
-        const int i = p / 930, q = p - i * 930;
-        if ((i & 1) != parity || !S->pim_valid[i]) continue;
-        const int base = 15 * i;
-        const double *J = sJ + i * 465;
-        if (q < 900) {
-          const int a = q / 30, b = q - a * 30;
-          double s = 0;
+    double *out = F.imu + (size_t)b * kFImuStride;
+    for (int p = tid; p < 931; p += kFThreads) {
+      double s = 0;
+      if (p < 900) {
+        const int a = p / 30, c = p - a * 30;
 #pragma unroll
-          for (int k = 0; k < 15; ++k) s += J[k * 31 + a] * J[k * 31 + b];
-          Hd[(size_t)(base + a) * n + base + b] += s;
-        } else {
-          const int a = q - 900;
-          double s = 0;
+        for (int k = 0; k < 15; ++k) s += sJ[k * 31 + a] * sJ[k * 31 + c];
+      } else if (p < 930) {
+        const int a = p - 900;
 #pragma unroll
-          for (int k = 0; k < 15; ++k) s += J[k * 31 + a] * J[k * 31 + 30];
-          gd[base + a] += s;
-        }
+        for (int k = 0; k < 15; ++k) s += sJ[k * 31 + a] * sJ[k * 31 + 30];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 15; ++k) s += sJ[k * 31 + 30] * sJ[k * 31 + 30];
+        s *= 0.5;
       }
-      __syncthreads();
+      out[p] = s;
     }
-    if (tid == 0) {
-      double c = 0;
-      for (int i = 0; i < O; ++i) if (S->pim_valid[i]) { double sq = 0; for (int k = 0; k < 15; ++k) sq += sJ[i * 465 + k * 31 + 30] * sJ[i * 465 + k * 31 + 30]; c += 0.5 * sq; }
-      s_cost[1] = c;
+    return;
+  }
+  // ---- prior CTA
+  const int np = 15 * O + 6;
+  if (tid == kFThreads - 1 && S->prior_factor) {   // extrinsic PriorFactor (applied only while the extrinsic is free)
+    double r[6], J[6][6];
+    prior_factor_impl(V3(S->ex0_pos), Q(S->ex0_quat[3], S->ex0_quat[0], S->ex0_quat[1], S->ex0_quat[2]), xe + 16 * (O + 1), r, J);
+    double c = 0;
+    for (int a = 0; a < 6; ++a) {
+      double gs = 0;
+      for (int k = 0; k < 6; ++k) gs += J[k][a] * r[k];
+      F.ex[36 + a] = gs;
+      for (int bb = 0; bb < 6; ++bb) { double s = 0; for (int k = 0; k < 6; ++k) s += J[k][a] * J[k][bb]; F.ex[a * 6 + bb] = s; }
+      c += 0.5 * r[a] * r[a];
+    }
+    F.ex[42] = c;
+  }
+  if (!(S->marginalization_factor && S->prior_valid)) return;
+  if (tid < O) {
+    pose_dx_dev(x_pose(xe, tid), S->x0_pose + 7 * tid, sdx + 15 * tid);
+    for (int a = 0; a < 9; ++a) sdx[15 * tid + 6 + a] = x_sb(xe, tid)[a] - S->x0_sb[9 * tid + a];
+  } else if (tid == O) {
+    pose_dx_dev(xe + 16 * (O + 1), S->x0_ex, sdx + 15 * O);
+  }
+  __syncthreads();
+  {
+    const int w = warp_id(), l = lane_id();
+    for (int r = w; r < np; r += kFThreads / 32) {
+      double s = 0;
+      for (int c = l; c < np; c += 32) s += Hp[(size_t)r * np + c] * sdx[c];
+      s = warp_sum(s);
+      if (l == 0) sHdx[r] = s;
     }
   }
   __syncthreads();
-  // ---- marginalisation prior
-  if (S->marginalization_factor && S->prior_valid) {
-    const int np = 15 * O + 6;
-    if (tid < O) {
-      pose_dx_dev(x_pose(xe, tid), S->x0_pose + 7 * tid, S->dx + 15 * tid);
-      for (int a = 0; a < 9; ++a) S->dx[15 * tid + 6 + a] = x_sb(xe, tid)[a] - S->x0_sb[9 * tid + a];
-    } else if (tid == O) {
-      pose_dx_dev(xe + 16 * (O + 1), S->x0_ex, S->dx + 15 * O);
+  double part = 0;
+  for (int a = tid; a < np; a += kFThreads) {
+    part += 2.0 * S->bp[a] * sdx[a] + sdx[a] * sHdx[a];
+    F.prior[a] = sHdx[a] + S->bp[a];
+  }
+  part = warp_sum(part);
+  if (lane_id() == 0) sred[warp_id()] = part;
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0;
+    for (int w = 0; w < kFThreads / 32; ++w) tot += sred[w];
+    F.prior[kDsMaxNp] = 0.5 * (S->c0 + tot);
+  }
+}
+
+// =====================================================================================================
+// tiled Cholesky in shared memory
+__device__ __forceinline__ int tile_off(int ib, int jb) { return (ib * (ib + 1) / 2 + jb) * 64; }
+__device__ __forceinline__ int swz(int r, int c) { return r * 8 + (c ^ ((r & 2) << 1)); }
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Warp 0: in-place Cholesky of the diagonal tile (lower triangle), then its inverse: on return the tile holds inv(L)
+// (lower) and zeros above.  Lane r < 8 keeps row r in registers; column k is scaled by rsqrt(a_kk) (broadcast by
+// shuffle) and the rank-1 update pulls l_jk from lane j.  Lanes 0-7 then each solve for one column of the inverse.
+__device__ void diag_factor(double *T, int *s_ok) {
+  const int l = lane_id();
+  double a[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) a[c] = (l < 8 && c <= l) ? T[swz(l & 7, c)] : 0.0;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double dk = __shfl_sync(0xffffffffu, a[k], k);
+    if (!(dk > 0.0) || !isfinite(dk)) ok = false;
+    const double lk = a[k] * rsqrt(dk);     // lane i >= k: l_ik (lane k: sqrt(a_kk))
+    a[k] = lk;
+#pragma unroll
+    for (int j = k + 1; j < 8; ++j) a[j] -= lk * __shfl_sync(0xffffffffu, lk, j);
+  }
+  if (!ok && l == 0) *s_ok = 0;
+  if (l < 8) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) if (c <= l) T[swz(l, c)] = a[c];
+  }
+  __syncwarp();
+  double x[8];
+  if (l < 8) {  // column l of inv(L): L x = e_l
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      double s = (i == l) ? 1.0 : 0.0;
+#pragma unroll
+      for (int k = 0; k < i; ++k) s -= (k >= l ? T[swz(i, k)] * x[k] : 0.0);
+      x[i] = (i >= l) ? s / T[swz(i, i)] : 0.0;
+    }
+  }
+  __syncwarp();
+  if (l < 8) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) T[swz(i, l)] = x[i];
+  }
+  __syncwarp();
+}
+
+// Factors the tiled matrix in place (strictly-lower tiles: L; diagonal tiles: inv(L_kk)) and overwrites y (padded to
+// 8 NB) with the solution of (L L^T) x = y.  Returns 1 on success; uniform.
+__device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
+  const int tid = threadIdx.x, w = warp_id(), l = lane_id();
+  const int fr = l >> 2, fq = l & 3;   // fragment row, fragment quad
+  if (tid == 0) *s_ok = 1;
+  __syncthreads();
+  if (w == 0) diag_factor(tiles + tile_off(0, 0), s_ok);
+  __syncthreads();
+  for (int kb = 0; kb < NB; ++kb) {
+    if (!*s_ok) break;
+    const double *Li = tiles + tile_off(kb, kb);   // inv(L_kk)
+    const int m = NB - 1 - kb;
+    // ---- panel solve: X = A inv(L)^T for the tiles below the diagonal; y_kb = inv(L) y_kb
+    const double b0 = Li[swz(fr, fq)], b1 = Li[swz(fr, fq + 4)];
+    for (int t = w; t < m; t += kDsWarps) {
+      double *A = tiles + tile_off(kb + 1 + t, kb);
+      const double a0 = A[swz(fr, fq)], a1 = A[swz(fr, fq + 4)];
+      double d0 = 0.0, d1 = 0.0;
+      dmma884(d0, d1, a0, b0);
+      dmma884(d0, d1, a1, b1);
+      *reinterpret_cast<double2 *>(A + swz(fr, 2 * fq)) = make_double2(d0, d1);
+    }
+    if (w == kDsWarps - 1) {
+      double v = 0.0;
+      if (l < 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v += (k <= l) ? Li[swz(l, k)] * y[8 * kb + k] : 0.0;
+      }
+      __syncwarp();
+      if (l < 8) y[8 * kb + l] = v;
     }
     __syncthreads();
-    matvec(Hp, np, S->dx, S->Hdx);
-    double part = 0;
-    for (int a = tid; a < np; a += T) part += 2.0 * S->bp[a] * S->dx[a] + S->dx[a] * S->Hdx[a];
-    const double tot = block_sum(part, sred);
-    if (tid == 0) s_cost[2] = 0.5 * (S->c0 + tot);
-    for (int p = tid; p < np * np; p += T) {
-      const int a = p / np, b = p - a * np;
-      const int ta = a < 15 * O ? a : (ex_free ? oe + (a - 15 * O) : -1);
-      const int tb = b < 15 * O ? b : (ex_free ? oe + (b - 15 * O) : -1);
-      if (ta >= 0 && tb >= 0) Hd[(size_t)ta * n + tb] += Hp[p];
-    }
-    for (int a = tid; a < np; a += T) {
-      const int ta = a < 15 * O ? a : (ex_free ? oe + (a - 15 * O) : -1);
-      if (ta >= 0) gd[ta] += S->Hdx[a] + S->bp[a];
-    }
-  }
-  __syncthreads();
-  // ---- extrinsic PriorFactor / frozen extrinsic
-  if (tid == 0) {
-    if (ex_free) {
-      if (S->prior_factor) {
-        double r[6], J[6][6];
-        prior_factor_impl(V3(S->ex0_pos), Q(S->ex0_quat[3], S->ex0_quat[0], S->ex0_quat[1], S->ex0_quat[2]), xe + 16 * (O + 1), r, J);
-        double c = 0;
-        for (int a = 0; a < 6; ++a) {
-          double gs = 0;
-          for (int k = 0; k < 6; ++k) gs += J[k][a] * r[k];
-          gd[oe + a] += gs;
-          for (int b = 0; b < 6; ++b) { double s = 0; for (int k = 0; k < 6; ++k) s += J[k][a] * J[k][b]; Hd[(size_t)(oe + a) * n + oe + b] += s; }
-          c += 0.5 * r[a] * r[a];
-        }
-        s_cost[3] = c;
-      }
+    if (m == 0) break;
+    // ---- trailing update C(i, j) -= X_i X_j^T, right-hand side rows, and the next diagonal tile one panel ahead
+    const int ntile = m * (m + 1) / 2;
+    if (w == 0) {
+      double *C = tiles + tile_off(kb + 1, kb + 1);
+      const double *X = tiles + tile_off(kb + 1, kb);
+      const double a0 = -X[swz(fr, fq)], a1 = -X[swz(fr, fq + 4)];
+      double2 c = *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq));
+      dmma884(c.x, c.y, a0, -a0);
+      dmma884(c.x, c.y, a1, -a1);
+      *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
+      __syncwarp();
+      diag_factor(C, s_ok);
     } else {
-      for (int a = 0; a < 6; ++a) { Hd[(size_t)(oe + a) * n + oe + a] = 1.0; gd[oe + a] = 0.0; }
+      for (int p = w; p < ntile + m; p += kDsWarps - 1) {   // p = 1 .. ntile - 1: tiles; ntile .. ntile + m - 1: rhs rows
+        if (p < ntile) {
+          int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+          while ((i + 1) * (i + 2) / 2 <= p) ++i;
+          while (i * (i + 1) / 2 > p) --i;
+          const int j = p - i * (i + 1) / 2;
+          double *C = tiles + tile_off(kb + 1 + i, kb + 1 + j);
+          const double *Xi = tiles + tile_off(kb + 1 + i, kb), *Xj = tiles + tile_off(kb + 1 + j, kb);
+          const double a0 = -Xi[swz(fr, fq)], a1 = -Xi[swz(fr, fq + 4)];
+          const double x0 = Xj[swz(fr, fq)], x1 = Xj[swz(fr, fq + 4)];
+          double2 c = *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq));
+          dmma884(c.x, c.y, a0, x0);
+          dmma884(c.x, c.y, a1, x1);
+          *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
+        } else if (l < 8) {
+          const int ib = kb + 1 + (p - ntile);
+          const double *X = tiles + tile_off(ib, kb);
+          double s = 0.0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s += X[swz(l, k)] * y[8 * kb + k];
+          y[8 * ib + l] -= s;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  const int ok = *s_ok;
+  if (!ok) return 0;
+  // ---- back substitution L^T x = y over the tiles in reverse
+  for (int jb = NB - 1; jb >= 0; --jb) {
+    if (w == 0) {
+      const double *Li = tiles + tile_off(jb, jb);
+      double v = 0.0;
+      if (l < 8) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) v += (r >= l) ? Li[swz(r, l)] * y[8 * jb + r] : 0.0;
+      }
+      __syncwarp();
+      if (l < 8) y[8 * jb + l] = v;
+    }
+    __syncthreads();
+    if (tid < 8 * jb) {
+      const int ib = tid >> 3, c = tid & 7;
+      const double *Lt = tiles + tile_off(jb, ib);
+      double s = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) s += Lt[swz(r, c)] * y[8 * jb + r];
+      y[tid] -= s;
+    }
+    __syncthreads();
+  }
+  return 1;
+}
+
+// =====================================================================================================
+// element-wise gather of the normal equations
+struct GatherCtx {
+  int O, n, oe, np;
+  bool ex_free, prior, lidar, imu, ex_prior;
+  const double *Hp, *Fimu, *Fprior, *Fex, *G, *G0;
+  const int *pim_valid;
+};
+
+__device__ __forceinline__ int prior_index(const GatherCtx &c, int a) {   // tangent -> prior canonical index, or -1
+  if (a < 15 * c.O) return a;
+  if (a >= c.oe) return c.ex_free ? 15 * c.O + (a - c.oe) : -1;
+  return -1;
+}
+// lidar block id: 0 pose_0, i (1..O) pose_i, O + 1 extrinsic, -1 none; sub = index inside the 6-block
+__device__ __forceinline__ int lidar_block(const GatherCtx &c, int a, int &sub) {
+  if (a >= c.oe) { sub = a - c.oe; return c.ex_free ? c.O + 1 : -1; }
+  const int k = a / 15, w = a - 15 * k;
+  if (w >= 6) return -1;
+  sub = w;
+  return k;
+}
+
+__device__ double h_elem(const GatherCtx &c, int a, int b) {   // a >= b, both < n
+  double v = 0.0;
+  if (!c.ex_free && a >= c.oe) return (a == b) ? 1.0 : 0.0;      // frozen extrinsic: identity block, zero gradient
+  if (c.prior) {
+    const int pa = prior_index(c, a), pb = prior_index(c, b);
+    if (pa >= 0 && pb >= 0) v += c.Hp[(size_t)pa * c.np + pb];
+  }
+  if (c.lidar) {
+    int sa, sb;
+    const int ba = lidar_block(c, a, sa), bb = lidar_block(c, b, sb);
+    if (ba >= 0 && bb >= 0) {
+      const bool sha = (ba == 0 || ba == c.O + 1), shb = (bb == 0 || bb == c.O + 1);
+      if (sha && shb) {
+        v += c.G0[((ba == 0 ? 0 : 6) + sa) * 12 + (bb == 0 ? 0 : 6) + sb];
+      } else if (!sha && !shb) {
+        if (ba == bb) v += c.G[(size_t)(ba - 1) * kFGStride + (6 + sa) * 18 + 6 + sb];
+      } else {
+        const int i = sha ? bb : ba;                              // the frame-specific one
+        const int ra = sha ? (ba == 0 ? 0 : 12) + sa : 6 + sa, rb = shb ? (bb == 0 ? 0 : 12) + sb : 6 + sb;
+        v += c.G[(size_t)(i - 1) * kFGStride + ra * 18 + rb];
+      }
     }
   }
-  __syncthreads();
+  if (c.imu && a < c.oe) {
+    const int ka = a / 15;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int k = ka - d;
+      if (k < 0 || k >= c.O || !c.pim_valid[k]) continue;
+      const int la = a - 15 * k, lb = b - 15 * k;
+      if (lb >= 0 && la < 30) v += c.Fimu[(size_t)k * kFImuStride + la * 30 + lb];
+    }
+  }
+  if (c.ex_prior && b >= c.oe) v += c.Fex[(a - c.oe) * 6 + (b - c.oe)];
+  return v;
 }
 
-__device__ void plus_state(const DevSolveState *S, const double *x, const double *delta, double *out) {
-  const int O = S->O;
-  if ((int)threadIdx.x <= O) {
-    const int k = threadIdx.x;
-    pose_plus_impl(x + 16 * k, delta + 15 * k, out + 16 * k);
-    for (int a = 0; a < 9; ++a) out[16 * k + 7 + a] = x[16 * k + 7 + a] + delta[15 * k + 6 + a];
-  } else if ((int)threadIdx.x == O + 1) {
-    if (S->ex_free) pose_plus_impl(x + 16 * (O + 1), delta + 15 * (O + 1), out + 16 * (O + 1));
-    else for (int a = 0; a < 7; ++a) out[16 * (O + 1) + a] = x[16 * (O + 1) + a];
+__device__ double g_elem(const GatherCtx &c, int a) {
+  if (!c.ex_free && a >= c.oe) return 0.0;
+  double v = 0.0;
+  if (c.prior) { const int pa = prior_index(c, a); if (pa >= 0) v += c.Fprior[pa]; }
+  if (c.lidar) {
+    int sa;
+    const int ba = lidar_block(c, a, sa);
+    if (ba == 0 || ba == c.O + 1) v += c.G0[144 + (ba == 0 ? 0 : 6) + sa];
+    else if (ba > 0) v += c.G[(size_t)(ba - 1) * kFGStride + 324 + 6 + sa];
+  }
+  if (c.imu && a < c.oe) {
+    const int ka = a / 15;
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+      const int k = ka - d;
+      if (k < 0 || k >= c.O || !c.pim_valid[k]) continue;
+      const int la = a - 15 * k;
+      if (la < 30) v += c.Fimu[(size_t)k * kFImuStride + 900 + la];
+    }
+  }
+  if (c.ex_prior && a >= c.oe) v += c.Fex[36 + (a - c.oe)];
+  return v;
+}
+
+// G_i = M_i^T S_gg M_i (18 x 18), M_i^T S_gr (18) per frame, and the blocks shared by all frames (pose_0 / extrinsic rows
+// and columns, 12 x 12 + 12) summed in frame order.  scratch: O * 108 doubles of shared memory.
+__device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const double *__restrict__ FM, double *G, double *G0, double *scratch) {
+  const int tid = threadIdx.x, T = blockDim.x;
+  for (int p = tid; p < O * 108; p += T) {     // SM_i = S_gg M_i (6 x 18)
+    const int i = p / 108, q = p - i * 108, a = q / 18, c = q - a * 18;
+    const double *Sb = Sblk + i * kAsmStride, *M = FM + (size_t)i * kFMStride;
+    double s = 0;
+#pragma unroll
+    for (int b = 0; b < 6; ++b) s += Sb[a < b ? s_idx(a, b) : s_idx(b, a)] * M[b * 18 + c];
+    scratch[p] = s;
+  }
+  __syncthreads();
+  for (int p = tid; p < O * 342; p += T) {
+    const int i = p / 342, q = p - i * 342;
+    const double *M = FM + (size_t)i * kFMStride;
+    double v = 0;
+    if (q < 324) {
+      const int a = q / 18, b = q - a * 18;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * scratch[i * 108 + k * 18 + b];
+    } else {
+      const int a = q - 324;
+      const double *Sb = Sblk + i * kAsmStride;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * Sb[s_idx(k, 6)];
+    }
+    G[(size_t)i * kFGStride + q] = v;
+  }
+  __syncthreads();
+  for (int p = tid; p < 156; p += T) {
+    double s = 0;
+    if (p < 144) {
+      const int ra = p / 12, rb = p - ra * 12;
+      const int a = ra < 6 ? ra : ra + 6, b = rb < 6 ? rb : rb + 6;
+      for (int i = 0; i < O; ++i) s += G[(size_t)i * kFGStride + a * 18 + b];
+    } else {
+      const int ra = p - 144, a = ra < 6 ? ra : ra + 6;
+      for (int i = 0; i < O; ++i) s += G[(size_t)i * kFGStride + 324 + a];
+    }
+    G0[p] = s;
   }
   __syncthreads();
 }
 
-__device__ void write_terms(const DevSolveState *S, const double *xe, double *Rt) {
-  if ((int)threadIdx.x < S->O) {
-    double M[108];
-    ppp_frame_terms_impl(x_pose(xe, 0), x_pose(xe, threadIdx.x + 1), xe + 16 * (S->O + 1), Rt + threadIdx.x * kAsmRtStride,
-                         Rt + threadIdx.x * kAsmRtStride + 9, M);
+// y = Hs v (row-major n x n in global memory, v in shared memory): one warp per row
+__device__ void matvec_g(const double *__restrict__ Hs, int n, const double *v, double *y) {
+  const int w = warp_id(), l = lane_id();
+  for (int r = w; r < n; r += kDsWarps) {
+    double s = 0;
+    for (int c = l; c < n; c += 32) s += Hs[(size_t)r * n + c] * v[c];
+    s = warp_sum(s);
+    if (l == 0) y[r] = s;
   }
+  __syncthreads();
 }
 
-__global__ void k_solver_terms(DevSolveState *S, double *Rt) { write_terms(S, S->x, Rt); }
+__device__ __noinline__ void write_terms(int O, const double *xe, double *Rt) {
+  double M[108];
+  ppp_frame_terms_impl(x_pose(xe, 0), x_pose(xe, threadIdx.x + 1), xe + 16 * (O + 1), Rt + threadIdx.x * kAsmRtStride,
+                       Rt + threadIdx.x * kAsmRtStride + 9, M);
+}
+
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define DS_MARK(k) do { if (tid == 0 && eval_index < 24) S->dbg[eval_index][k] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(kDsThreads, 1)
-k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict__ Hp, double *H0, double *g0,
-              const double *__restrict__ Sblk, double *Rt, int eval_index, size_t lsize) {
-  extern __shared__ double dsm[];
-  __shared__ double s_cost[4], sred[33];
-  __shared__ int s_flag[4];
+k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, double *g0, const double *__restrict__ Sblk,
+       FPtrs F, double *Rt, int eval_index) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ double sred[100];
+  __shared__ int s_flag[4], s_ok;
   if (S->done) return;
   const int tid = threadIdx.x, T = blockDim.x;
+  if (tid == 0 && eval_index < 24) { for (int k = 0; k < 12; ++k) S->dbg[eval_index][k] = 0; S->dbg[eval_index][0] = gtime_ns(); }
+  DS_MARK(1);
   const int O = S->O, n = S->n;
-  double *L = dsm;                                   // packed lower triangle, n(n+1)/2
-  double *sM = dsm + lsize;                          // O x 108
-  double *sSM = sM + O * 108;                        // O x 108
+  const int NB = (n + 7) / 8, NP = NB * 8;
+  double *tiles = dsm;
+  double *v_g = dsm + (size_t)(NB * (NB + 1) / 2) * 64;   // scaled gradient of the current x
+  double *v_scale = v_g + NP, *v_diag = v_scale + NP, *v_grad = v_diag + NP, *v_gn = v_grad + NP, *v_step = v_gn + NP;
+  double *v_tmp = v_step + NP, *v_y = v_tmp + NP;
   const double min_diagonal = 1e-6, max_diagonal = 1e32, min_mu = 1e-8, max_mu = 1.0, mu_factor = 10.0;
   const double initial_radius = 1e4, max_radius = 1e16, min_radius = 1e-32, min_relative_decrease = 1e-3;
   const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
   const int xdim = 16 * (O + 1) + 7;
+  const int oe = 15 * (O + 1), np = 15 * O + 6;
+  double *G = F.G, *G0 = F.G + (size_t)kMaxOpt * kFGStride;
 
-  // ---------------- evaluate ----------------
-  const double *xe = eval_index == 0 ? S->x : S->cand;
-  build_normal(S, xe, Sblk, Hp, Hc, S->gc, sM, sSM, L, s_cost, sred);
-  if (eval_index == 0) {
-    // residuals before optimisation + gates (Estimator.cc:1924-1985)
-    if (tid == 0) {
-      S->cost_ppp = s_cost[0]; S->cost_pim = s_cost[1]; S->cost_marg = s_cost[2];
+  // persistent vectors: global -> shared
+  for (int i = tid; i < NP; i += T) {
+    const bool in = i < n;
+    v_g[i] = in ? S->g[i] : 0.0; v_scale[i] = in ? S->scale[i] : 1.0; v_diag[i] = in ? S->diagonal[i] : 1.0;
+    v_grad[i] = in ? S->gradient[i] : 0.0; v_gn[i] = in ? S->gn[i] : 0.0;
+  }
+  __syncthreads();
+
+  // ---------------- cost of the evaluated state and the verdict ----------------
+  int build = 0;   // 1: (re)build H, g at the evaluated state and make it the current point
+  if (tid == 0) {
+    double c_ppp = 0, c_pim = 0;
+    if (S->point_distance_factor) for (int i = 0; i < O; ++i) c_ppp += 0.5 * Sblk[i * kAsmStride + 28];
+    if (S->imu_factor) for (int i = 0; i < O; ++i) if (S->pim_valid[i]) c_pim += F.imu[(size_t)i * kFImuStride + 930];
+    const double c_marg = (S->marginalization_factor && S->prior_valid) ? F.prior[kDsMaxNp] : 0.0;
+    sred[90] = c_ppp; sred[91] = c_pim; sred[92] = c_marg;
+    if (eval_index == 0) {
+      // residuals before optimisation + gates (Estimator.cc:1924-1985)
+      S->cost_ppp = c_ppp; S->cost_pim = c_pim; S->cost_marg = c_marg;
       int turn_off = 1;
-      if (S->imu_factor) turn_off = s_cost[1] > 1e3;
+      if (S->imu_factor) turn_off = c_pim > 1e3;
       S->turn_off = turn_off;
-      const double ratio = s_cost[2] / (s_cost[0] + s_cost[1]);
+      const double ratio = c_marg / (c_ppp + c_pim);
       if (!S->convergence_flag && !turn_off && ratio <= 2 && ratio != 0) S->convergence_flag = 1;
-      int changed = 0;
-      if (!S->convergence_flag) {
-        if (S->ex_free || S->prior_valid) changed = 1;
-        S->ex_free = 0; S->prior_valid = 0;
-      }
-      s_flag[1] = changed;
+      if (!S->convergence_flag) { S->ex_free = 0; S->prior_valid = 0; }
     }
-    __syncthreads();
-    if (s_flag[1]) build_normal(S, xe, Sblk, Hp, Hc, S->gc, sM, sSM, L, s_cost, sred);
-    // iteration zero
-    for (int p = tid; p < n * n; p += T) { const double v = Hc[p]; H[p] = v; H0[p] = v; }
-    for (int p = tid; p < n; p += T) { S->g[p] = S->gc[p]; g0[p] = S->gc[p]; }
-    __syncthreads();
-    if (tid == 0) {
-      const double c = s_cost[0] + s_cost[1] + s_cost[2] + s_cost[3];
-      S->x_cost = c; S->initial_cost = c; S->cost0 = c;
-      S->evaluations = 1;
-      S->radius = initial_radius; S->mu = min_mu; S->reuse = 0; S->invalid = 0; S->iteration = 0; S->successful = 0; S->termination = 0;
-      double gm = 0;
-      for (int i = 0; i < n; ++i) { S->scale[i] = 1.0 / (1.0 + sqrt(H[(size_t)i * n + i])); gm = fmax(gm, fabs(S->g[i])); }
-      double xn = 0;
-      const int xd = S->ex_free ? xdim : xdim - 7;
-      for (int i = 0; i < xd; ++i) xn += S->x[i] * S->x[i];
-      S->x_norm = sqrt(xn);
-      s_flag[2] = (gm <= gradient_tolerance) || !isfinite(c);
-      if (!isfinite(c)) S->termination = 2;
-      else if (gm <= gradient_tolerance) S->termination = 1;
-    }
-    __syncthreads();
-    if (s_flag[2]) { if (tid == 0) { S->done = 1; } return; }
-    for (int p = tid; p < n * n; p += T) { const int i = p / n, j = p - i * n; H[p] *= S->scale[i] * S->scale[j]; }
-    for (int p = tid; p < n; p += T) S->g[p] *= S->scale[p];
-    __syncthreads();
+  }
+  __syncthreads();
+  const bool ex_free = S->ex_free != 0;
+  const bool use_prior = S->marginalization_factor && S->prior_valid;
+  const bool ex_prior = ex_free && S->prior_factor;
+  const double cost_eval = sred[90] + sred[91] + (use_prior ? sred[92] : 0.0) + (ex_prior ? F.ex[42] : 0.0);
+  const int xd = ex_free ? xdim : xdim - 7;
+  if (eval_index == 0) {
+    build = 1;
   } else {
-    // ---------------- judge the candidate ----------------
+    double sn = 0, dummy1 = 0, dummy2 = 0;
+    for (int i = tid; i < xd; i += T) { const double d = S->x[i] - S->cand[i]; sn += d * d; }
+    block_sum3(sn, dummy1, dummy2, sred);
     if (tid == 0) {
-      double cand_cost = s_cost[0] + s_cost[1] + s_cost[2] + s_cost[3];
+      double cand_cost = cost_eval;
       if (!isfinite(cand_cost)) cand_cost = 1e300;
       S->cand_cost = cand_cost;
       S->evaluations += 1;
-      double sn = 0;
-      const int xd = S->ex_free ? xdim : xdim - 7;
-      for (int i = 0; i < xd; ++i) { const double d = S->x[i] - S->cand[i]; sn += d * d; }
-      sn = sqrt(sn);
       int verdict = 0;  // 0 reject, 1 accept, 2 terminate (converged)
       const double cost_change = S->x_cost - cand_cost;
-      if (sn <= parameter_tolerance * (S->x_norm + parameter_tolerance)) { verdict = 2; S->termination = 1; }
+      if (sqrt(sn) <= parameter_tolerance * (S->x_norm + parameter_tolerance)) { verdict = 2; S->termination = 1; }
       else if (fabs(cost_change) <= function_tolerance * S->x_cost) { verdict = 2; S->termination = 1; }
       else {
         const double rd = cost_change / S->model_cost_change;
@@ -444,26 +585,74 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
     __syncthreads();
     const int verdict = s_flag[1];
     if (verdict == 2) { if (tid == 0) S->done = 1; return; }
-    if (verdict == 1) {
+    build = verdict == 1;
+    if (build) {
       for (int p = tid; p < xdim; p += T) S->x[p] = S->cand[p];
-      for (int p = tid; p < n * n; p += T) { const int i = p / n, j = p - i * n; H[p] = Hc[p] * S->scale[i] * S->scale[j]; }
-      double gm = 0;
-      for (int p = tid; p < n; p += T) { gm = fmax(gm, fabs(S->gc[p])); S->g[p] = S->gc[p] * S->scale[p]; }
       __syncthreads();
-      // max-norm of the unscaled gradient and the new |x|
-      if (tid == 0) {
-        double m = 0;
-        for (int i = 0; i < n; ++i) m = fmax(m, fabs(S->gc[i]));
-        double xn = 0;
-        const int xd = S->ex_free ? xdim : xdim - 7;
-        for (int i = 0; i < xd; ++i) xn += S->x[i] * S->x[i];
-        S->x_norm = sqrt(xn);
-        s_flag[2] = m <= gradient_tolerance;
-        if (s_flag[2]) { S->termination = 1; S->done = 1; }
-      }
-      __syncthreads();
-      if (s_flag[2]) return;
     }
+  }
+
+  DS_MARK(2);
+  GatherCtx gc;
+  gc.O = O; gc.n = n; gc.oe = oe; gc.np = np;
+  gc.ex_free = ex_free; gc.prior = use_prior; gc.lidar = S->point_distance_factor != 0; gc.imu = S->imu_factor != 0; gc.ex_prior = ex_prior;
+  gc.Hp = Hp; gc.Fimu = F.imu; gc.Fprior = F.prior; gc.Fex = F.ex; gc.G = G; gc.G0 = G0; gc.pim_valid = S->pim_valid;
+
+  if (build) {
+    // ---------------- normal equations at the new current point ----------------
+    if (gc.lidar) lidar_blocks(O, Sblk, F.M, G, G0, tiles);
+    DS_MARK(3);
+    // unscaled diagonal, gradient; Jacobi scaling is fixed at iteration zero
+    double gm = 0, xn = 0;
+    for (int a = tid; a < n; a += T) {
+      const double ga = g_elem(gc, a);
+      gm = fmax(gm, fabs(ga));
+      if (eval_index == 0) {
+        const double sc = 1.0 / (1.0 + sqrt(h_elem(gc, a, a)));
+        v_scale[a] = sc; S->scale[a] = sc;
+        g0[a] = ga;
+      }
+      v_g[a] = ga;   // unscaled for the moment
+    }
+    for (int i = tid; i < xd; i += T) xn += S->x[i] * S->x[i];
+    gm = block_max(gm, sred);
+    { double d1 = 0, d2 = 0; block_sum3(xn, d1, d2, sred); }
+    for (int a = tid; a < n; a += T) { v_g[a] *= v_scale[a]; S->g[a] = v_g[a]; }
+    if (tid == 0) {
+      S->x_norm = sqrt(xn);
+      int stop = 0;
+      if (eval_index == 0) {
+        S->x_cost = cost_eval; S->initial_cost = cost_eval; S->cost0 = cost_eval;
+        S->evaluations = 1;
+        S->radius = initial_radius; S->mu = min_mu; S->reuse = 0; S->invalid = 0; S->iteration = 0; S->successful = 0; S->termination = 0;
+        if (!isfinite(cost_eval)) { S->termination = 2; stop = 1; }
+        else if (gm <= gradient_tolerance) { S->termination = 1; stop = 1; }
+      } else if (gm <= gradient_tolerance) { S->termination = 1; stop = 1; }
+      if (stop) S->done = 1;
+      s_flag[2] = stop;
+    }
+    __syncthreads();
+    if (s_flag[2]) return;
+    DS_MARK(4);
+    // scaled H of the current point -> global (both triangles); diagonal D of the trust region
+    for (int p = tid; p < n * (n + 1) / 2; p += T) {
+      int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
+      while ((a + 1) * (a + 2) / 2 <= p) ++a;
+      while (a * (a + 1) / 2 > p) --a;
+      const int b = p - a * (a + 1) / 2;
+      const double h = h_elem(gc, a, b);
+      if (eval_index == 0) { H0[(size_t)a * n + b] = h; H0[(size_t)b * n + a] = h; }
+      const double hs = h * v_scale[a] * v_scale[b];
+      Hs[(size_t)a * n + b] = hs; Hs[(size_t)b * n + a] = hs;
+      if (a == b) {
+        const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
+        v_diag[a] = d; S->diagonal[a] = d;
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += T) { v_grad[i] = v_g[i] / v_diag[i]; S->gradient[i] = v_grad[i]; }
+    __syncthreads();
+    DS_MARK(5);
   }
 
   // ---------------- next step (loops over invalid steps without a new evaluation) ----------------
@@ -474,47 +663,62 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
       else if (S->radius < min_radius) { S->termination = 1; stop = 1; }
       else S->iteration += 1;
       s_flag[1] = stop;
+      s_flag[3] = S->reuse;
     }
     __syncthreads();
     if (s_flag[1]) { if (tid == 0) S->done = 1; return; }
     int linear_ok = 1;
-    if (!S->reuse) {
+    if (!s_flag[3]) {
+      // Cauchy point scale: alpha = |gradient|^2 / (sg^T H sg), sg = gradient / D
+      for (int i = tid; i < n; i += T) v_tmp[i] = v_g[i] / (v_diag[i] * v_diag[i]);
       __syncthreads();
-      if (tid == 0) S->reuse = 1;
-      for (int i = tid; i < n; i += T) {
-        const double d = sqrt(fmin(fmax(H[(size_t)i * n + i], min_diagonal), max_diagonal));
-        S->diagonal[i] = d;
-        S->gradient[i] = S->g[i] / d;
-        S->tmp[i] = S->g[i] / (d * d);  // sg
-      }
-      __syncthreads();
-      matvec(H, n, S->tmp, S->tmp2);
-      double pa = 0, pb = 0;
-      for (int i = tid; i < n; i += T) { pa += S->gradient[i] * S->gradient[i]; pb += S->tmp[i] * S->tmp2[i]; }
-      const double ga = block_sum(pa, sred);
-      const double gb = block_sum(pb, sred);
-      if (tid == 0) S->alpha = ga / gb;
+      matvec_g(Hs, n, v_tmp, v_y);
+      double pa = 0, pb = 0, pc = 0;
+      for (int i = tid; i < n; i += T) { pa += v_grad[i] * v_grad[i]; pb += v_tmp[i] * v_y[i]; }
+      block_sum3(pa, pb, pc, sred);
+      double mu = S->mu;
+      if (tid == 0) { S->alpha = pa / pb; S->reuse = 1; }
+      DS_MARK(6);
       linear_ok = 0;
-      while (true) {
+      while (mu < max_mu) {
+        // tiles of H + mu D^2 (lower triangle; identity on the padding), right-hand side g
+        for (int p = tid; p < (NB * (NB + 1) / 2) * 64; p += T) {
+          const int t = p >> 6, e = p & 63, r = e >> 3, cs = e & 7, c = cs ^ ((r & 2) << 1);
+          int ib = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+          while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
+          while (ib * (ib + 1) / 2 > t) --ib;
+          const int jb = t - ib * (ib + 1) / 2;
+          const int a = 8 * ib + r, b = 8 * jb + c;
+          double v;
+          if (a < n && b < n) { v = Hs[(size_t)a * n + b]; if (a == b) v += mu * v_diag[a] * v_diag[a]; }
+          else v = (a == b) ? 1.0 : 0.0;
+          tiles[p] = v;
+        }
+        for (int i = tid; i < NP; i += T) v_y[i] = i < n ? v_g[i] : 0.0;
         __syncthreads();
-        if (!(S->mu < max_mu)) break;
-        for (int i = tid; i < n; i += T) S->tmp[i] = S->g[i];
-        __syncthreads();
-        const int ok = chol_solve_smem(H, n, S->mu, S->diagonal, L, S->tmp, s_flag);
-        if (!ok) { __syncthreads(); if (tid == 0) S->mu *= mu_factor; continue; }
-        for (int i = tid; i < n; i += T) S->gn[i] = -S->diagonal[i] * S->tmp[i];
+        DS_MARK(7);
+        int ok = chol_solve_tiles(tiles, NB, v_y, &s_ok);
+        DS_MARK(8);
+        if (ok) {
+          double bad = 0;
+          for (int i = tid; i < n; i += T) if (!isfinite(v_y[i])) bad = 1.0;
+          bad = block_max(bad, sred);
+          ok = bad == 0.0;
+        }
+        if (!ok) { mu *= mu_factor; __syncthreads(); continue; }
+        for (int i = tid; i < n; i += T) { v_gn[i] = -v_diag[i] * v_y[i]; S->gn[i] = v_gn[i]; }
         linear_ok = 1;
         break;
       }
+      if (tid == 0) S->mu = mu;
       __syncthreads();
     }
     int step_valid = linear_ok;
     if (linear_ok) {
       double p1 = 0, p2 = 0, p3 = 0;
-      for (int i = tid; i < n; i += T) { p1 += S->gradient[i] * S->gradient[i]; p2 += S->gn[i] * S->gn[i]; p3 += S->gradient[i] * S->gn[i]; }
-      const double gradient_norm = sqrt(block_sum(p1, sred));
-      const double gn_norm = sqrt(block_sum(p2, sred));
-      const double g_dot_gn = block_sum(p3, sred);
+      for (int i = tid; i < n; i += T) { p1 += v_grad[i] * v_grad[i]; p2 += v_gn[i] * v_gn[i]; p3 += v_grad[i] * v_gn[i]; }
+      block_sum3(p1, p2, p3, sred);
+      const double gradient_norm = sqrt(p1), gn_norm = sqrt(p2), g_dot_gn = p3;
       const double radius = S->radius, alpha = S->alpha;
       double c_grad, c_gn, dsn;
       if (gn_norm <= radius) { c_grad = 0.0; c_gn = 1.0; dsn = gn_norm; }
@@ -528,19 +732,19 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
         const double beta = (c <= 0) ? (d - c) / bma2 : (radius * radius - a2) / (d + c);
         c_grad = -alpha * (1.0 - beta); c_gn = beta; dsn = -1.0;
       }
-      double pn = 0;
+      double pn = 0, z1 = 0, z2 = 0;
       for (int i = tid; i < n; i += T) {
-        const double sv = c_grad * S->gradient[i] + c_gn * S->gn[i];
+        const double sv = c_grad * v_grad[i] + c_gn * v_gn[i];
         pn += sv * sv;
-        S->step[i] = sv / S->diagonal[i];
+        v_step[i] = sv / v_diag[i];
       }
-      const double sn2 = block_sum(pn, sred);
-      if (dsn < 0) dsn = sqrt(sn2);
-      matvec(H, n, S->step, S->tmp2);
-      double q1 = 0, q2 = 0;
-      for (int i = tid; i < n; i += T) { q1 += S->step[i] * S->g[i]; q2 += S->step[i] * S->tmp2[i]; }
-      const double sg = block_sum(q1, sred), shs = block_sum(q2, sred);
-      const double mcc = -sg - 0.5 * shs;
+      block_sum3(pn, z1, z2, sred);
+      if (dsn < 0) dsn = sqrt(pn);
+      matvec_g(Hs, n, v_step, v_y);
+      double q1 = 0, q2 = 0, q3 = 0;
+      for (int i = tid; i < n; i += T) { q1 += v_step[i] * v_g[i]; q2 += v_step[i] * v_y[i]; }
+      block_sum3(q1, q2, q3, sred);
+      const double mcc = -q1 - 0.5 * q2;
       step_valid = mcc > 0.0;
       if (tid == 0) { S->model_cost_change = mcc; S->dogleg_step_norm = dsn; }
     }
@@ -560,57 +764,144 @@ k_solver_step(DevSolveState *S, double *H, double *Hc, const double *__restrict_
     if (tid == 0) S->invalid = 0;
     break;
   }
+  DS_MARK(9);
   // candidate = Plus(x, step .* scale); frame terms of the candidate for the next asm_ppp launch
-  for (int i = tid; i < n; i += T) S->tmp[i] = S->step[i] * S->scale[i];
+  for (int i = tid; i < n; i += T) v_tmp[i] = v_step[i] * v_scale[i];
   __syncthreads();
-  plus_state(S, S->x, S->tmp, S->cand);
-  write_terms(S, S->cand, Rt);
+  if (tid <= O) {
+    const int k = tid;
+    pose_plus_impl(S->x + 16 * k, v_tmp + 15 * k, S->cand + 16 * k);
+    for (int a = 0; a < 9; ++a) S->cand[16 * k + 7 + a] = S->x[16 * k + 7 + a] + v_tmp[15 * k + 6 + a];
+  } else if (tid == O + 1) {
+    if (ex_free) pose_plus_impl(S->x + 16 * (O + 1), v_tmp + 15 * (O + 1), S->cand + 16 * (O + 1));
+    else for (int a = 0; a < 7; ++a) S->cand[16 * (O + 1) + a] = S->x[16 * (O + 1) + a];
+  }
+  __syncthreads();
+  if (tid < O) write_terms(O, S->cand, Rt);
+  __syncthreads();
+  DS_MARK(10);
+  if (tid == 0 && eval_index < 24) S->dbg[eval_index][11] = gtime_ns();
 }
 
-bool DevSolver::supports(int O) const {
-  const int n = 15 * (O + 1) + 6;
-  const size_t lsz = std::max((size_t)n * (n + 1) / 2, (size_t)O * 930);
-  const size_t need = sizeof(double) * (lsz + (size_t)O * 216);
-  return O <= kMaxOpt && need <= 200 * 1024;
+// =====================================================================================================
+static size_t step_smem_bytes(int O) {
+  const int n = 15 * (O + 1) + 6, NB = (n + 7) / 8;
+  return sizeof(double) * ((size_t)(NB * (NB + 1) / 2) * 64 + 8 * (size_t)NB * 8);
 }
 
-int DevSolver::init(int O) {
+bool DevSolver::supports(int O_) const { return O_ >= 1 && O_ <= kDsMaxOpt && step_smem_bytes(O_) <= 225 * 1024; }
+
+int DevSolver::init(int O_) {
+  O = O_;
   const int n = 15 * (O + 1) + 6, np = 15 * O + 6;
-  lsize = std::max((size_t)n * (n + 1) / 2, (size_t)O * 930);  // Cholesky area, also the IMU scratch
-  smem_bytes = sizeof(double) * (lsize + (size_t)O * 216);
+  smem_bytes = step_smem_bytes(O);
   if (cudaMalloc(&st, sizeof(DevSolveState)) != cudaSuccess) return -1;
-  if (cudaMalloc(&H, sizeof(double) * n * n) != cudaSuccess) return -1;
-  if (cudaMalloc(&Hc, sizeof(double) * n * n) != cudaSuccess) return -1;
+  if (cudaMalloc(&Hs, sizeof(double) * n * n) != cudaSuccess) return -1;
   if (cudaMalloc(&H0, sizeof(double) * n * n) != cudaSuccess) return -1;
   if (cudaMalloc(&g0, sizeof(double) * n) != cudaSuccess) return -1;
   if (cudaMalloc(&Hp, sizeof(double) * np * np) != cudaSuccess) return -1;
+  if (cudaMalloc(&F, sizeof(double) * f_doubles()) != cudaSuccess) return -1;
   if (cudaMallocHost((void **)&h_st, sizeof(DevSolveState)) != cudaSuccess) return -1;
   if (cudaMemset(st, 0, sizeof(DevSolveState)) != cudaSuccess) return -1;
-  if (cudaFuncSetAttribute(k_solver_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
+  if (cudaMemset(F, 0, sizeof(double) * f_doubles()) != cudaSuccess) return -1;
+  if (cudaFuncSetAttribute(k_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes) != cudaSuccess) return -1;
+  if (cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking) != cudaSuccess) return -1;
+  if (cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming) != cudaSuccess) return -1;
+  if (cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming) != cudaSuccess) return -1;
   return 0;
 }
 
 void DevSolver::destroy() {
-  void *p[] = {st, H, Hc, H0, g0, Hp};
+  void *p[] = {st, Hs, H0, g0, Hp, F};
   for (void *q : p) if (q) cudaFree(q);
   if (h_st) cudaFreeHost(h_st);
-  st = nullptr; H = Hc = H0 = g0 = Hp = nullptr; h_st = nullptr;
+  if (aux) cudaStreamDestroy(aux);
+  if (ev_fork) cudaEventDestroy(ev_fork);
+  if (ev_join) cudaEventDestroy(ev_join);
+  st = nullptr; Hs = Hp = H0 = g0 = F = nullptr; h_st = nullptr; aux = nullptr; ev_fork = ev_join = nullptr;
 }
 
-int dev_solver_terms(DevSolver &ds, double *Rt_dev, cudaStream_t st, int *launches) {
-  k_solver_terms<<<1, 32, 0, st>>>(ds.st, Rt_dev);
+static FPtrs fptrs(const DevSolver &ds) {
+  FPtrs f;
+  f.imu = ds.F + ds.off_imu(); f.M = ds.F + ds.off_M(); f.prior = ds.F + ds.off_prior(); f.ex = ds.F + ds.off_ex(); f.G = ds.F + ds.off_G();
+  return f;
+}
+
+int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *launches) {
+  cudaError_t e = cudaEventRecord(ds.ev_fork, st);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(ds.aux, ds.ev_fork, 0);
+  if (e == cudaSuccess) {
+    k_factors<<<ds.O + 1, kFThreads, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), eval_index);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(ds.ev_join, ds.aux);
   if (launches) *launches += 1;
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
   return LIO_OK;
 }
 
 int dev_solver_step(DevSolver &ds, const double *S_dev, double *Rt_dev, int eval_index, cudaStream_t st, int *launches) {
-  k_solver_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.H, ds.Hc, ds.Hp, ds.H0, ds.g0, S_dev, Rt_dev, eval_index, ds.lsize);
+  cudaError_t e = cudaStreamWaitEvent(st, ds.ev_join, 0);
+  if (e == cudaSuccess) {
+    k_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.Hs, ds.Hp, ds.H0, ds.g0, S_dev, fptrs(ds), Rt_dev, eval_index);
+    e = cudaGetLastError();
+  }
   if (launches) *launches += 1;
-  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
   return LIO_OK;
 }
 
 }  // namespace lio
+
+// ---- test seam: the tiled shared-memory Cholesky alone, on an explicit host system ------------------------------------
+namespace lio {
+__global__ void __launch_bounds__(kDsThreads, 1)
+k_chol_test(const double *__restrict__ A, const double *__restrict__ b, int n, double *__restrict__ x, int *__restrict__ ok_out) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ int s_ok;
+  const int tid = threadIdx.x, T = blockDim.x;
+  const int NB = (n + 7) / 8, NP = NB * 8;
+  double *tiles = dsm, *y = dsm + (size_t)(NB * (NB + 1) / 2) * 64;
+  for (int p = tid; p < (NB * (NB + 1) / 2) * 64; p += T) {
+    const int t = p >> 6, e = p & 63, r = e >> 3, cs = e & 7, c = cs ^ ((r & 2) << 1);
+    int ib = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
+    while (ib * (ib + 1) / 2 > t) --ib;
+    const int jb = t - ib * (ib + 1) / 2;
+    const int a = 8 * ib + r, bb = 8 * jb + c;
+    tiles[p] = (a < n && bb < n) ? A[(size_t)a * n + bb] : (a == bb ? 1.0 : 0.0);
+  }
+  for (int i = tid; i < NP; i += T) y[i] = i < n ? b[i] : 0.0;
+  __syncthreads();
+  const int ok = chol_solve_tiles(tiles, NB, y, &s_ok);
+  for (int i = tid; i < n; i += T) x[i] = y[i];
+  if (tid == 0) *ok_out = ok;
+}
+}  // namespace lio
+
+// Solves A x = b (A symmetric positive definite, n x n row-major, n <= 216) with the device solver's tiled Cholesky.
+extern "C" int lio_dev_cholesky_solve_host(const double *A, const double *b, int n, double *x, int *ok, int device) {
+  using namespace lio;
+  if (!A || !b || !x || !ok || n < 1 || n > 15 * (kDsMaxOpt + 1) + 6) return LIO_ERR_INVALID;
+  if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
+  LIO_CUDA_OK(cudaSetDevice(device));
+  const int NB = (n + 7) / 8;
+  const size_t smem = sizeof(double) * ((size_t)(NB * (NB + 1) / 2) * 64 + (size_t)NB * 8);
+  double *dA = nullptr, *db = nullptr, *dx = nullptr;
+  int *dok = nullptr;
+  int rc = LIO_OK;
+  if (cudaMalloc(&dA, sizeof(double) * n * n) != cudaSuccess || cudaMalloc(&db, sizeof(double) * n) != cudaSuccess ||
+      cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dok, sizeof(int)) != cudaSuccess) rc = LIO_ERR_CUDA;
+  if (rc == LIO_OK) {
+    cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice);
+    cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice);
+    cudaFuncSetAttribute(k_chol_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_chol_test<<<1, kDsThreads, smem>>>(dA, db, n, dx, dok);
+    cudaError_t e = cudaMemcpy(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); rc = LIO_ERR_CUDA; }
+  } else lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+  void *fr[] = {dA, db, dx, dok};
+  for (void *q : fr) if (q) cudaFree(q);
+  return rc;
+}

@@ -8,6 +8,7 @@ namespace lio {
 constexpr int kDsMaxN = 15 * (kMaxOpt + 1) + 6;  // 261
 constexpr int kDsMaxNp = 15 * kMaxOpt + 6;       // 246
 constexpr int kDsXDim = 16 * (kMaxOpt + 1) + 7;
+constexpr int kDsMaxOpt = 13;                    // largest opt window whose Cholesky tiles fit one SM's shared memory
 
 struct DevSolveState {
   // parameters: [pose_k(7) sb_k(9)] k = 0..O, then extrinsic pose(7)
@@ -21,36 +22,58 @@ struct DevSolveState {
   double radius, mu, alpha, x_cost, cand_cost, model_cost_change, dogleg_step_norm, x_norm;
   double initial_cost, cost_pim, cost_ppp, cost_marg;
   double ex0_pos[3], ex0_quat[4];  // PriorFactor target (transform_lb_ at problem build), quat x y z w
-  double scale[kDsMaxN], diagonal[kDsMaxN], gradient[kDsMaxN], gn[kDsMaxN], step[kDsMaxN], g[kDsMaxN], gc[kDsMaxN], tmp[kDsMaxN], tmp2[kDsMaxN];
+  // first linearisation (parity / debugging)
+  double cost0;
+  // ---- everything above is read back after a solve (offsetof(scale) bytes) ----
+  double scale[kDsMaxN], diagonal[kDsMaxN], gradient[kDsMaxN], gn[kDsMaxN], g[kDsMaxN];
   // marginalisation prior (canonical order [pose_0,sb_0,...,pose_{O-1},sb_{O-1},ex])
-  double bp[kDsMaxNp], dx[kDsMaxNp], Hdx[kDsMaxNp], c0;
+  double bp[kDsMaxNp], c0;
   double x0_pose[7 * kMaxOpt], x0_sb[9 * kMaxOpt], x0_ex[7];
   // IMU factors i -> i+1
   PimData pim[kMaxOpt];
   int pim_valid[kMaxOpt];
-  double imu_J[kMaxOpt][15][30];
-  double imu_r[kMaxOpt][15];
-  // first linearisation (parity / debugging)
-  double cost0;
+  // phase timestamps of k_step per evaluation (thread 0): [0] %globaltimer at entry, [1..9] clock64 at phase boundaries
+  // (entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit), [11] %globaltimer at exit
+  long long dbg[24][12];
 };
+
+// Scratch written by k_factors (state-dependent, lidar-independent terms at the state being evaluated) and read by
+// k_step.  Strides in doubles.
+constexpr int kFImuStride = 936;   // J^T J (30 x 30) | J^T r (30) | cost | pad
+constexpr int kFMStride = 108;     // M_i (6 x 18) of the PivotPointPlane frame terms
+constexpr int kFGStride = 344;     // G_i = M_i^T S_gg M_i (18 x 18) | M_i^T S_gr (18) | pad   (written by k_step itself)
 
 struct DevSolver {
   DevSolveState *st = nullptr;     // device
-  double *H = nullptr, *Hc = nullptr, *Hp = nullptr, *H0 = nullptr;  // device n x n (row-major), prior np x np
-  double *g0 = nullptr;
-  DevSolveState *h_st = nullptr;   // pinned staging copy (only the scalar / vector part is moved each scan)
-  size_t smem_bytes = 0, lsize = 0;
+  double *Hs = nullptr;            // n x n, Jacobi-scaled normal matrix of the current x (row-major)
+  double *Hp = nullptr;            // prior np x np
+  double *H0 = nullptr, *g0 = nullptr;   // first linearisation, unscaled (parity getter)
+  double *F = nullptr;             // factor scratch: imu | M | prior vec | ex prior | G
+  DevSolveState *h_st = nullptr;   // pinned staging copy
+  size_t smem_bytes = 0;
+  int O = 0;
+  cudaStream_t aux = nullptr;      // k_factors runs beside asm_ppp
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int init(int O);
   void destroy();
   bool supports(int O) const;
+  // scratch offsets (doubles)
+  size_t off_imu() const { return 0; }
+  size_t off_M() const { return (size_t)kMaxOpt * kFImuStride; }
+  size_t off_prior() const { return off_M() + (size_t)kMaxOpt * kFMStride; }                    // np gradient terms | cost
+  size_t off_ex() const { return off_prior() + kDsMaxNp + 8; }                                   // 36 J^T J | 6 J^T r | cost
+  size_t off_G() const { return off_ex() + 48; }                                                 // O x kFGStride | 144 + 12 shared
+  size_t f_doubles() const { return off_G() + (size_t)kMaxOpt * kFGStride + 160; }
 };
 
+// Enqueues the lidar-independent factor evaluation (ImuFactors, marginalisation prior, extrinsic PriorFactor, frame
+// terms M_i) at the state the coming asm_ppp launch evaluates: x for eval_index 0, the candidate afterwards.
+// Runs on ds.aux, ordered after everything enqueued so far on `st`; dev_solver_step joins it.
+int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *launches);
 // Enqueues one evaluation step of the solver on `st` (no host synchronisation):
 //   eval_index 0: build the normal equations at x from S_dev, run the convergence gates, take the first step;
 //   eval_index k > 0: judge the candidate evaluated by the preceding asm_ppp launch, then take the next step.
 // After each call Rt_dev holds the frame terms of the next state to evaluate.
 int dev_solver_step(DevSolver &ds, const double *S_dev, double *Rt_dev, int eval_index, cudaStream_t st, int *launches);
-// Frame terms of the CURRENT x into Rt_dev (before the first asm_ppp launch of a solve).
-int dev_solver_terms(DevSolver &ds, double *Rt_dev, cudaStream_t st, int *launches);
 
 }  // namespace lio

@@ -213,6 +213,12 @@ class Estimator:
         return dict(asm_ms=o[0], asm_launches=int(o[1]), asm_features=int(o[2]), bytes_per_feature=o[3],
                     knn_ms=o[4], knn_launches=int(o[5]), knn_queries=int(o[6]), bytes_per_query=o[7])
 
+    def solver_trace(self):
+        """Phase timestamps of the device solver's step kernel, (24, 12) int64 (see lio_est_solver_trace)."""
+        out = np.zeros((24, 12), np.int64)
+        _lib.check(_lib.lib().lio_est_solver_trace(self.h, out, out.size), "lio_est_solver_trace")
+        return out
+
     def states(self):
         out = np.zeros((self.W + 1, 16))
         _lib.check(_lib.lib().lio_est_get_states(self.h, out), "lio_est_get_states")
