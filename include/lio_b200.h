@@ -285,9 +285,10 @@ int lio_est_last_normal_equations(lio_est *est, double *H, double *g, double *co
 /* Kernels launched by the last process_scan call. */
 int lio_est_last_launches(lio_est *est);
 /* Diagnostic: phase timestamps of the device-resident solver's step kernel for the evaluations of the last solve:
- * out[24][12] (row = evaluation; [0] / [11] = GPU wall clock in ns at kernel entry / exit, [1..10] = SM clock at the phase
- * boundaries entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit).  Zeros when the
- * host controller is in use. */
+ * out[24][16] (row = evaluation; [0] / [11] = GPU wall clock in ns at kernel entry / exit, [1..10] = SM clock at the phase
+ * boundaries entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit; [12..15] = cycles
+ * inside the Cholesky: diagonal-tile factorisation, panel solve, trailing update, back substitution).  Zeros when the host
+ * controller is in use. */
 int lio_est_solver_trace(lio_est *est, long long *out, int cap);
 /* CUDA-event timing of the fused residual+Jacobian kernel accumulated since the last reset (events recorded
  * on the estimator's stream around every launch): out[0..3] = {sum ms, launches, features processed, bytes/feature};

@@ -607,7 +607,7 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
   c->acc_n = 0.2; c->gyr_n = 0.02; c->acc_w = 2e-4; c->gyr_w = 2e-5; c->g_norm = 9.805;
   c->max_num_iterations = 10; c->odom_max_iterations = 10;
   c->max_frame_points = 1 << 16; c->max_scan_points = 1 << 18;
-  c->device_solver = 0;
+  c->device_solver = 1;   // GPU-resident dogleg loop (solver_dev.cu); 0 keeps the host controller (also used when O > 13)
   c->overlap_marginalization = 1;
 }
 
@@ -1499,26 +1499,26 @@ static int solve_optimization_dev(lio_est *e) {
   e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
   vector_to_double(e);
   DevSolveState &S = *e->ds.h_st;
-  S.O = O; S.n = 15 * (O + 1) + 6; S.max_it = e->cfg.max_num_iterations;
-  S.imu_factor = e->cfg.imu_factor; S.point_distance_factor = e->cfg.point_distance_factor;
-  S.prior_factor = e->cfg.prior_factor; S.marginalization_factor = e->cfg.marginalization_factor;
-  S.ex_free = e->ex_constant ? 0 : 1;
-  S.prior_valid = (e->cfg.marginalization_factor && e->prior.valid) ? 1 : 0;
-  S.convergence_flag = e->convergence_flag ? 1 : 0;
-  S.turn_off = 1; S.done = 0; S.iteration = 0; S.successful = 0; S.evaluations = 0; S.termination = 0; S.reuse = 0; S.invalid = 0;
+  S.sc.O = O; S.sc.n = 15 * (O + 1) + 6; S.sc.max_it = e->cfg.max_num_iterations;
+  S.sc.imu_factor = e->cfg.imu_factor; S.sc.point_distance_factor = e->cfg.point_distance_factor;
+  S.sc.prior_factor = e->cfg.prior_factor; S.sc.marginalization_factor = e->cfg.marginalization_factor;
+  S.sc.ex_free = e->ex_constant ? 0 : 1;
+  S.sc.prior_valid = (e->cfg.marginalization_factor && e->prior.valid) ? 1 : 0;
+  S.sc.convergence_flag = e->convergence_flag ? 1 : 0;
+  S.sc.turn_off = 1; S.sc.done = 0; S.sc.iteration = 0; S.sc.successful = 0; S.sc.evaluations = 0; S.sc.termination = 0; S.sc.reuse = 0; S.sc.invalid = 0;
   for (int k = 0; k <= O; ++k) { std::memcpy(S.x + 16 * k, e->para_pose[k].data(), 7 * sizeof(double)); std::memcpy(S.x + 16 * k + 7, e->para_sb[k].data(), 9 * sizeof(double)); }
   std::memcpy(S.x + 16 * (O + 1), e->para_ex, 7 * sizeof(double));
   {
     const Tw tt = tlb_double(e);
-    S.ex0_pos[0] = tt.pos.x; S.ex0_pos[1] = tt.pos.y; S.ex0_pos[2] = tt.pos.z;
-    S.ex0_quat[0] = tt.rot.x; S.ex0_quat[1] = tt.rot.y; S.ex0_quat[2] = tt.rot.z; S.ex0_quat[3] = tt.rot.w;
+    S.sc.ex0_pos[0] = tt.pos.x; S.sc.ex0_pos[1] = tt.pos.y; S.sc.ex0_pos[2] = tt.pos.z;
+    S.sc.ex0_quat[0] = tt.rot.x; S.sc.ex0_quat[1] = tt.rot.y; S.sc.ex0_quat[2] = tt.rot.z; S.sc.ex0_quat[3] = tt.rot.w;
   }
   for (int i = 0; i < O; ++i) {
     Preintegration &pim = *e->pre[pivot + i + 1];
     S.pim_valid[i] = pim.sum_dt > 10.0 ? 0 : 1;
     S.pim[i] = pim.data();
   }
-  if (S.prior_valid) {
+  if (S.sc.prior_valid) {
     const MargPrior &pr = e->prior;
     std::memcpy(S.bp, pr.bp.data(), sizeof(double) * pr.n);
     S.c0 = pr.c0;
@@ -1547,7 +1547,7 @@ static int solve_optimization_dev(lio_est *e) {
   }
   EST_CUDA(cudaMemcpyAsync(e->d_Rt, e->h_Rt, sizeof(double) * O * kAsmRtStride, cudaMemcpyHostToDevice, st));
   asm_plan(ap, e->sm_count);
-  ap.skip_flag = &e->ds.st->done;
+  ap.skip_flag = &e->ds.st->sc.done;
   const bool peers = e->world > 1 && e->npeers == e->world;
   if (e->world > 1 && !peers && !e->allreduce) {
     lio_set_last_error(__FILE__, __LINE__, "sharded context without an exchange: call lio_est_set_peers or pass an allreduce callback");
@@ -1577,7 +1577,7 @@ static int solve_optimization_dev(lio_est *e) {
     cudaEventRecord(e->evp[2 * ev + 1], st);
     if (peers) {
       k_xwait<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
-                                reinterpret_cast<int *>(e->xbuf + kXErrOff), &e->ds.st->done);
+                                reinterpret_cast<int *>(e->xbuf + kXErrOff), &e->ds.st->sc.done);
       ++e->launches;
     } else if (e->world > 1 && e->allreduce) {
       if (e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride) != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
@@ -1594,7 +1594,7 @@ static int solve_optimization_dev(lio_est *e) {
     lio_set_last_error(__FILE__, __LINE__, "peer exchange timed out (a rank did not publish its rows)");
     return LIO_ERR_CUDA;
   }
-  for (int ev = 0; ev < std::min(nevals, S.evaluations); ++ev) {
+  for (int ev = 0; ev < std::min(nevals, S.sc.evaluations); ++ev) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
   }
@@ -1602,15 +1602,15 @@ static int solve_optimization_dev(lio_est *e) {
   std::memcpy(e->para_ex, S.x + 16 * (O + 1), 7 * sizeof(double));
   e->S_valid = false;
   e->summary = DoglegSummary();
-  e->summary.iterations = S.iteration; e->summary.successful_steps = S.successful; e->summary.evaluations = S.evaluations;
-  e->summary.termination = S.termination; e->summary.initial_cost = S.initial_cost; e->summary.final_cost = S.x_cost;
-  e->cost_pim = S.cost_pim; e->cost_ppp = S.cost_ppp; e->cost_marg = S.cost_marg;
-  e->turn_off = S.turn_off != 0;
-  e->convergence_flag = S.convergence_flag != 0;
-  e->ex_constant = S.ex_free == 0;
-  if (!S.prior_valid) e->prior.valid = false;
-  e->have_H0 = true; e->H0 = Mat(); e->cost0 = S.initial_cost;
-  if (S.termination == 2 && !std::isfinite(S.x_cost)) { lio_set_last_error(__FILE__, __LINE__, "solver breakdown"); return LIO_ERR_NUMERIC; }
+  e->summary.iterations = S.sc.iteration; e->summary.successful_steps = S.sc.successful; e->summary.evaluations = S.sc.evaluations;
+  e->summary.termination = S.sc.termination; e->summary.initial_cost = S.sc.initial_cost; e->summary.final_cost = S.sc.x_cost;
+  e->cost_pim = S.sc.cost_pim; e->cost_ppp = S.sc.cost_ppp; e->cost_marg = S.sc.cost_marg;
+  e->turn_off = S.sc.turn_off != 0;
+  e->convergence_flag = S.sc.convergence_flag != 0;
+  e->ex_constant = S.sc.ex_free == 0;
+  if (!S.sc.prior_valid) e->prior.valid = false;
+  e->have_H0 = true; e->H0 = Mat(); e->cost0 = S.sc.initial_cost;
+  if (S.sc.termination == 2 && !std::isfinite(S.sc.x_cost)) { lio_set_last_error(__FILE__, __LINE__, "solver breakdown"); return LIO_ERR_NUMERIC; }
   e->t_solve = now_s() - t0;
   double_to_vector(e);
   const double t1 = now_s();
@@ -1925,10 +1925,10 @@ extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, d
 extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
 
 extern "C" int lio_est_solver_trace(lio_est *e, long long *out, int cap) {
-  if (!e || !out || cap < 24 * 12) return LIO_ERR_INVALID;
-  if (!e->use_dev_solver) { std::memset(out, 0, sizeof(long long) * 24 * 12); return LIO_OK; }
+  if (!e || !out || cap < 24 * 16) return LIO_ERR_INVALID;
+  if (!e->use_dev_solver) { std::memset(out, 0, sizeof(long long) * 24 * 16); return LIO_OK; }
   LIO_CUDA_OK(cudaSetDevice(e->device));
-  LIO_CUDA_OK(cudaMemcpy(out, reinterpret_cast<const char *>(e->ds.st) + offsetof(DevSolveState, dbg), sizeof(long long) * 24 * 12, cudaMemcpyDeviceToHost));
+  LIO_CUDA_OK(cudaMemcpy(out, reinterpret_cast<const char *>(e->ds.st) + offsetof(DevSolveState, dbg), sizeof(long long) * 24 * 16, cudaMemcpyDeviceToHost));
   return LIO_OK;
 }
 

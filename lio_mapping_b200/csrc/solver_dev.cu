@@ -93,11 +93,11 @@ k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FP
   __shared__ double sJ[15 * 31];   // whitened
   __shared__ double sdx[kDsMaxNp], sHdx[kDsMaxNp];
   __shared__ double sred[kFThreads / 32];
-  if (S->done) return;
-  const int tid = threadIdx.x, O = S->O, b = blockIdx.x;
+  if (S->sc.done) return;
+  const int tid = threadIdx.x, O = S->sc.O, b = blockIdx.x;
   const double *xe = eval_index == 0 ? S->x : S->cand;
   if (b < O) {
-    const bool imu = S->imu_factor && S->pim_valid[b];
+    const bool imu = S->sc.imu_factor && S->pim_valid[b];
     for (int p = tid; p < 15 * 31; p += kFThreads) sA[p] = 0.0;
     __syncthreads();
     if (tid == 0 && imu) {
@@ -105,7 +105,7 @@ k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FP
       imu_factor_raw(S->pim[b], x_pose(xe, b), x_sb(xe, b), x_pose(xe, b + 1), x_sb(xe, b + 1), raw, sA, 31);
       for (int a = 0; a < 15; ++a) sA[a * 31 + 30] = raw[a];
     }
-    if (tid == 32 && S->point_distance_factor) {
+    if (tid == 32 && S->sc.point_distance_factor) {
       double R[9], t[3];
       ppp_frame_terms_impl(x_pose(xe, 0), x_pose(xe, b + 1), xe + 16 * (O + 1), R, t, F.M + (size_t)b * kFMStride);
     }
@@ -141,9 +141,9 @@ k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FP
   }
   // ---- prior CTA
   const int np = 15 * O + 6;
-  if (tid == kFThreads - 1 && S->prior_factor) {   // extrinsic PriorFactor (applied only while the extrinsic is free)
+  if (tid == kFThreads - 1 && S->sc.prior_factor) {   // extrinsic PriorFactor (applied only while the extrinsic is free)
     double r[6], J[6][6];
-    prior_factor_impl(V3(S->ex0_pos), Q(S->ex0_quat[3], S->ex0_quat[0], S->ex0_quat[1], S->ex0_quat[2]), xe + 16 * (O + 1), r, J);
+    prior_factor_impl(V3(S->sc.ex0_pos), Q(S->sc.ex0_quat[3], S->sc.ex0_quat[0], S->sc.ex0_quat[1], S->sc.ex0_quat[2]), xe + 16 * (O + 1), r, J);
     double c = 0;
     for (int a = 0; a < 6; ++a) {
       double gs = 0;
@@ -154,7 +154,7 @@ k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FP
     }
     F.ex[42] = c;
   }
-  if (!(S->marginalization_factor && S->prior_valid)) return;
+  if (!(S->sc.marginalization_factor && S->sc.prior_valid)) return;
   if (tid < O) {
     pose_dx_dev(x_pose(xe, tid), S->x0_pose + 7 * tid, sdx + 15 * tid);
     for (int a = 0; a < 9; ++a) sdx[15 * tid + 6 + a] = x_sb(xe, tid)[a] - S->x0_sb[9 * tid + a];
@@ -198,10 +198,12 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
 
 // Warp 0: in-place Cholesky of the diagonal tile (lower triangle), then its inverse: on return the tile holds inv(L)
 // (lower) and zeros above.  Lane r < 8 keeps row r in registers; column k is scaled by rsqrt(a_kk) (broadcast by
-// shuffle) and the rank-1 update pulls l_jk from lane j.  Lanes 0-7 then each solve for one column of the inverse.
+// shuffle) and the rank-1 update pulls l_jk from lane j.  The reciprocal diagonal 1 / l_kk = rsqrt(a_kk) stays in
+// registers, so the inverse (lane l solves L x = e_l by right-looking substitution) needs no division: fp64 division and
+// rsqrt are ~200-cycle dependent chains on this part and sit on the critical path of the whole factorisation.
 __device__ void diag_factor(double *T, int *s_ok) {
   const int l = lane_id();
-  double a[8];
+  double a[8], dinv[8];
 #pragma unroll
   for (int c = 0; c < 8; ++c) a[c] = (l < 8 && c <= l) ? T[swz(l & 7, c)] : 0.0;
   bool ok = true;
@@ -209,7 +211,9 @@ __device__ void diag_factor(double *T, int *s_ok) {
   for (int k = 0; k < 8; ++k) {
     const double dk = __shfl_sync(0xffffffffu, a[k], k);
     if (!(dk > 0.0) || !isfinite(dk)) ok = false;
-    const double lk = a[k] * rsqrt(dk);     // lane i >= k: l_ik (lane k: sqrt(a_kk))
+    const double inv = rsqrt(dk);
+    dinv[k] = inv;
+    const double lk = a[k] * inv;     // lane i >= k: l_ik (lane k: sqrt(a_kk))
     a[k] = lk;
 #pragma unroll
     for (int j = k + 1; j < 8; ++j) a[j] -= lk * __shfl_sync(0xffffffffu, lk, j);
@@ -220,14 +224,15 @@ __device__ void diag_factor(double *T, int *s_ok) {
     for (int c = 0; c < 8; ++c) if (c <= l) T[swz(l, c)] = a[c];
   }
   __syncwarp();
-  double x[8];
-  if (l < 8) {  // column l of inv(L): L x = e_l
+  double x[8], sacc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      double s = (i == l) ? 1.0 : 0.0;
+  for (int i = 0; i < 8; ++i) { sacc[i] = (i == l) ? 1.0 : 0.0; x[i] = 0.0; }
+  if (l < 8) {  // column l of inv(L)
 #pragma unroll
-      for (int k = 0; k < i; ++k) s -= (k >= l ? T[swz(i, k)] * x[k] : 0.0);
-      x[i] = (i >= l) ? s / T[swz(i, i)] : 0.0;
+    for (int k = 0; k < 8; ++k) {
+      x[k] = sacc[k] * dinv[k];       // zero for k < l
+#pragma unroll
+      for (int i = k + 1; i < 8; ++i) sacc[i] -= T[swz(i, k)] * x[k];
     }
   }
   __syncwarp();
@@ -240,7 +245,7 @@ __device__ void diag_factor(double *T, int *s_ok) {
 
 // Factors the tiled matrix in place (strictly-lower tiles: L; diagonal tiles: inv(L_kk)) and overwrites y (padded to
 // 8 NB) with the solution of (L L^T) x = y.  Returns 1 on success; uniform.
-__device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
+__device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, long long *prof = nullptr) {
   const int tid = threadIdx.x, w = warp_id(), l = lane_id();
   const int fr = l >> 2, fq = l & 3;   // fragment row, fragment quad
   if (tid == 0) *s_ok = 1;
@@ -249,6 +254,7 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
   __syncthreads();
   for (int kb = 0; kb < NB; ++kb) {
     if (!*s_ok) break;
+    const long long tp0 = clock64();
     const double *Li = tiles + tile_off(kb, kb);   // inv(L_kk)
     const int m = NB - 1 - kb;
     // ---- panel solve: X = A inv(L)^T for the tiles below the diagonal; y_kb = inv(L) y_kb
@@ -271,6 +277,8 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
       if (l < 8) y[8 * kb + l] = v;
     }
     __syncthreads();
+    const long long tp1 = clock64();
+    if (prof && kb == 0 && tid == 0) prof[1] = tp1 - tp0;
     if (m == 0) break;
     // ---- trailing update C(i, j) -= X_i X_j^T, right-hand side rows, and the next diagonal tile one panel ahead
     const int ntile = m * (m + 1) / 2;
@@ -283,14 +291,15 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
       dmma884(c.x, c.y, a1, -a1);
       *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
       __syncwarp();
+      const long long td0 = clock64();
       diag_factor(C, s_ok);
+      if (prof && kb == 0 && tid == 0) prof[0] = clock64() - td0;
     } else {
-      for (int p = w; p < ntile + m; p += kDsWarps - 1) {   // p = 1 .. ntile - 1: tiles; ntile .. ntile + m - 1: rhs rows
+      // tasks p = 1 .. ntile - 1: tile (i, j) with p = i (i + 1) / 2 + j;  p = ntile .. ntile + m - 1: rhs rows of tile-row p - ntile
+      int i = 0, j = w;                                   // (i, j) of p = w, advanced incrementally (no sqrt on the hot path)
+      while (j > i) { j -= i + 1; ++i; }
+      for (int p = w; p < ntile + m; p += kDsWarps - 1) {
         if (p < ntile) {
-          int i = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-          while ((i + 1) * (i + 2) / 2 <= p) ++i;
-          while (i * (i + 1) / 2 > p) --i;
-          const int j = p - i * (i + 1) / 2;
           double *C = tiles + tile_off(kb + 1 + i, kb + 1 + j);
           const double *Xi = tiles + tile_off(kb + 1 + i, kb), *Xj = tiles + tile_off(kb + 1 + j, kb);
           const double a0 = -Xi[swz(fr, fq)], a1 = -Xi[swz(fr, fq + 4)];
@@ -299,6 +308,8 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
           dmma884(c.x, c.y, a0, x0);
           dmma884(c.x, c.y, a1, x1);
           *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
+          j += kDsWarps - 1;
+          while (j > i) { j -= i + 1; ++i; }
         } else if (l < 8) {
           const int ib = kb + 1 + (p - ntile);
           const double *X = tiles + tile_off(ib, kb);
@@ -310,10 +321,12 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
       }
     }
     __syncthreads();
+    if (prof && kb == 0 && tid == 0) prof[2] = clock64() - tp1;
   }
   __syncthreads();
   const int ok = *s_ok;
   if (!ok) return 0;
+  const long long tb0 = clock64();
   // ---- back substitution L^T x = y over the tiles in reverse
   for (int jb = NB - 1; jb >= 0; --jb) {
     if (w == 0) {
@@ -337,6 +350,7 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok) {
     }
     __syncthreads();
   }
+  if (prof && tid == 0) prof[3] = clock64() - tb0;
   return 1;
 }
 
@@ -346,7 +360,8 @@ struct GatherCtx {
   int O, n, oe, np;
   bool ex_free, prior, lidar, imu, ex_prior;
   const double *Hp, *Fimu, *Fprior, *Fex, *G, *G0;
-  const int *pim_valid;
+  const double *zero;     // a 0.0 in shared memory: the target of absent terms
+  const int *pim_valid;   // shared-memory copy
 };
 
 __device__ __forceinline__ int prior_index(const GatherCtx &c, int a) {   // tangent -> prior canonical index, or -1
@@ -363,12 +378,14 @@ __device__ __forceinline__ int lidar_block(const GatherCtx &c, int a, int &sub) 
   return k;
 }
 
-__device__ double h_elem(const GatherCtx &c, int a, int b) {   // a >= b, both < n
-  double v = 0.0;
+// All contributions are looked up first and loaded together (one memory round trip per element instead of a chain of
+// conditional loads); absent terms read a zero, so the summation order prior + lidar + imu + imu + extrinsic prior is fixed.
+__device__ __forceinline__ double h_elem(const GatherCtx &c, int a, int b) {   // a >= b, both < n
   if (!c.ex_free && a >= c.oe) return (a == b) ? 1.0 : 0.0;      // frozen extrinsic: identity block, zero gradient
+  const double *p0 = c.zero, *p1 = c.zero, *p2 = c.zero, *p3 = c.zero, *p4 = c.zero;
   if (c.prior) {
     const int pa = prior_index(c, a), pb = prior_index(c, b);
-    if (pa >= 0 && pb >= 0) v += c.Hp[(size_t)pa * c.np + pb];
+    if (pa >= 0 && pb >= 0) p0 = c.Hp + (size_t)pa * c.np + pb;
   }
   if (c.lidar) {
     int sa, sb;
@@ -376,52 +393,50 @@ __device__ double h_elem(const GatherCtx &c, int a, int b) {   // a >= b, both <
     if (ba >= 0 && bb >= 0) {
       const bool sha = (ba == 0 || ba == c.O + 1), shb = (bb == 0 || bb == c.O + 1);
       if (sha && shb) {
-        v += c.G0[((ba == 0 ? 0 : 6) + sa) * 12 + (bb == 0 ? 0 : 6) + sb];
+        p1 = c.G0 + ((ba == 0 ? 0 : 6) + sa) * 12 + (bb == 0 ? 0 : 6) + sb;
       } else if (!sha && !shb) {
-        if (ba == bb) v += c.G[(size_t)(ba - 1) * kFGStride + (6 + sa) * 18 + 6 + sb];
+        if (ba == bb) p1 = c.G + (size_t)(ba - 1) * kFGStride + (6 + sa) * 18 + 6 + sb;
       } else {
         const int i = sha ? bb : ba;                              // the frame-specific one
         const int ra = sha ? (ba == 0 ? 0 : 12) + sa : 6 + sa, rb = shb ? (bb == 0 ? 0 : 12) + sb : 6 + sb;
-        v += c.G[(size_t)(i - 1) * kFGStride + ra * 18 + rb];
+        p1 = c.G + (size_t)(i - 1) * kFGStride + ra * 18 + rb;
       }
     }
   }
   if (c.imu && a < c.oe) {
     const int ka = a / 15;
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const int k = ka - d;
-      if (k < 0 || k >= c.O || !c.pim_valid[k]) continue;
-      const int la = a - 15 * k, lb = b - 15 * k;
-      if (lb >= 0 && la < 30) v += c.Fimu[(size_t)k * kFImuStride + la * 30 + lb];
+    {
+      const int k = ka, lb = b - 15 * k;
+      if (k < c.O && c.pim_valid[k] && lb >= 0) p2 = c.Fimu + (size_t)k * kFImuStride + (a - 15 * k) * 30 + lb;
+    }
+    {
+      const int k = ka - 1, lb = b - 15 * k;
+      if (k >= 0 && k < c.O && c.pim_valid[k] && lb >= 0) p3 = c.Fimu + (size_t)k * kFImuStride + (a - 15 * k) * 30 + lb;
     }
   }
-  if (c.ex_prior && b >= c.oe) v += c.Fex[(a - c.oe) * 6 + (b - c.oe)];
-  return v;
+  if (c.ex_prior && b >= c.oe) p4 = c.Fex + (a - c.oe) * 6 + (b - c.oe);
+  const double v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3, v4 = *p4;
+  return (((v0 + v1) + v2) + v3) + v4;
 }
 
-__device__ double g_elem(const GatherCtx &c, int a) {
+__device__ __forceinline__ double g_elem(const GatherCtx &c, int a) {
   if (!c.ex_free && a >= c.oe) return 0.0;
-  double v = 0.0;
-  if (c.prior) { const int pa = prior_index(c, a); if (pa >= 0) v += c.Fprior[pa]; }
+  const double *p0 = c.zero, *p1 = c.zero, *p2 = c.zero, *p3 = c.zero, *p4 = c.zero;
+  if (c.prior) { const int pa = prior_index(c, a); if (pa >= 0) p0 = c.Fprior + pa; }
   if (c.lidar) {
     int sa;
     const int ba = lidar_block(c, a, sa);
-    if (ba == 0 || ba == c.O + 1) v += c.G0[144 + (ba == 0 ? 0 : 6) + sa];
-    else if (ba > 0) v += c.G[(size_t)(ba - 1) * kFGStride + 324 + 6 + sa];
+    if (ba == 0 || ba == c.O + 1) p1 = c.G0 + 144 + (ba == 0 ? 0 : 6) + sa;
+    else if (ba > 0) p1 = c.G + (size_t)(ba - 1) * kFGStride + 324 + 6 + sa;
   }
   if (c.imu && a < c.oe) {
     const int ka = a / 15;
-#pragma unroll
-    for (int d = 0; d < 2; ++d) {
-      const int k = ka - d;
-      if (k < 0 || k >= c.O || !c.pim_valid[k]) continue;
-      const int la = a - 15 * k;
-      if (la < 30) v += c.Fimu[(size_t)k * kFImuStride + 900 + la];
-    }
+    if (ka < c.O && c.pim_valid[ka]) p2 = c.Fimu + (size_t)ka * kFImuStride + 900 + (a - 15 * ka);
+    if (ka >= 1 && ka - 1 < c.O && c.pim_valid[ka - 1]) p3 = c.Fimu + (size_t)(ka - 1) * kFImuStride + 900 + (a - 15 * (ka - 1));
   }
-  if (c.ex_prior && a >= c.oe) v += c.Fex[36 + (a - c.oe)];
-  return v;
+  if (c.ex_prior && a >= c.oe) p4 = c.Fex + 36 + (a - c.oe);
+  const double v0 = *p0, v1 = *p1, v2 = *p2, v3 = *p3, v4 = *p4;
+  return (((v0 + v1) + v2) + v3) + v4;
 }
 
 // G_i = M_i^T S_gg M_i (18 x 18), M_i^T S_gr (18) per frame, and the blocks shared by all frames (pose_0 / extrinsic rows
@@ -469,14 +484,29 @@ __device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const doubl
   __syncthreads();
 }
 
-// y = Hs v (row-major n x n in global memory, v in shared memory): one warp per row
+// y = Hs v (row-major n x n in global memory, v in shared memory): one warp per row, two rows and all their columns in
+// flight per warp (n <= 224: seven 32-column slices)
 __device__ void matvec_g(const double *__restrict__ Hs, int n, const double *v, double *y) {
   const int w = warp_id(), l = lane_id();
-  for (int r = w; r < n; r += kDsWarps) {
-    double s = 0;
-    for (int c = l; c < n; c += 32) s += Hs[(size_t)r * n + c] * v[c];
-    s = warp_sum(s);
-    if (l == 0) y[r] = s;
+  for (int r0 = w; r0 < n; r0 += 2 * kDsWarps) {
+    const int r1 = r0 + kDsWarps;
+    const bool has1 = r1 < n;
+    double a0[7], a1[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const int c = l + 32 * q;
+      a0[q] = c < n ? Hs[(size_t)r0 * n + c] : 0.0;
+      a1[q] = (c < n && has1) ? Hs[(size_t)r1 * n + c] : 0.0;
+    }
+    double s0 = 0, s1 = 0;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+      const int c = l + 32 * q;
+      const double vc = c < n ? v[c] : 0.0;
+      s0 += a0[q] * vc; s1 += a1[q] * vc;
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (l == 0) { y[r0] = s0; if (has1) y[r1] = s1; }
   }
   __syncthreads();
 }
@@ -494,17 +524,23 @@ __device__ __forceinline__ long long gtime_ns() {
 }
 #define DS_MARK(k) do { if (tid == 0 && eval_index < 24) S->dbg[eval_index][k] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(kDsThreads, 1)
-k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, double *g0, const double *__restrict__ Sblk,
-       FPtrs F, double *Rt, int eval_index) {
-  extern __shared__ __align__(16) double dsm[];
-  __shared__ double sred[100];
-  __shared__ int s_flag[4], s_ok;
-  if (S->done) return;
+struct StepShared {
+  double sred[100];
+  double zero;
+  DevScalars sc;
+  int flag[4], ok, pim_valid[kMaxOpt];
+};
+
+__device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double *Hs, const double *__restrict__ Hp, double *H0, double *g0,
+                          const double *__restrict__ Sblk, FPtrs F, double *Rt, int eval_index) {
+  DevScalars &sc = sh.sc;
+  double *sred = sh.sred;
+  int *s_flag = sh.flag;
+  int &s_ok = sh.ok;
   const int tid = threadIdx.x, T = blockDim.x;
-  if (tid == 0 && eval_index < 24) { for (int k = 0; k < 12; ++k) S->dbg[eval_index][k] = 0; S->dbg[eval_index][0] = gtime_ns(); }
+  if (tid == 0 && eval_index < 24) { for (int k = 0; k < 16; ++k) S->dbg[eval_index][k] = 0; S->dbg[eval_index][0] = gtime_ns(); }
   DS_MARK(1);
-  const int O = S->O, n = S->n;
+  const int O = sc.O, n = sc.n;
   const int NB = (n + 7) / 8, NP = NB * 8;
   double *tiles = dsm;
   double *v_g = dsm + (size_t)(NB * (NB + 1) / 2) * 64;   // scaled gradient of the current x
@@ -527,27 +563,33 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
 
   // ---------------- cost of the evaluated state and the verdict ----------------
   int build = 0;   // 1: (re)build H, g at the evaluated state and make it the current point
-  if (tid == 0) {
+  int tiles_ready = 0;      // the gather below leaves H + mu_tiles D^2 in the Cholesky tiles
+  double mu_tiles = 0.0;
+  if (warp_id() == 0) {   // cost components: lane i fetches frame i's terms, summed in frame order by lane 0
+    const int l = lane_id();
+    double cp = (l < O && sc.point_distance_factor) ? 0.5 * Sblk[l * kAsmStride + 28] : 0.0;
+    double ci = (l < O && sc.imu_factor && sh.pim_valid[l]) ? F.imu[(size_t)l * kFImuStride + 930] : 0.0;
     double c_ppp = 0, c_pim = 0;
-    if (S->point_distance_factor) for (int i = 0; i < O; ++i) c_ppp += 0.5 * Sblk[i * kAsmStride + 28];
-    if (S->imu_factor) for (int i = 0; i < O; ++i) if (S->pim_valid[i]) c_pim += F.imu[(size_t)i * kFImuStride + 930];
-    const double c_marg = (S->marginalization_factor && S->prior_valid) ? F.prior[kDsMaxNp] : 0.0;
+    for (int i = 0; i < O; ++i) { c_ppp += __shfl_sync(0xffffffffu, cp, i); c_pim += __shfl_sync(0xffffffffu, ci, i); }
+    if (l == 0) {
+    const double c_marg = (sc.marginalization_factor && sc.prior_valid) ? F.prior[kDsMaxNp] : 0.0;
     sred[90] = c_ppp; sred[91] = c_pim; sred[92] = c_marg;
     if (eval_index == 0) {
       // residuals before optimisation + gates (Estimator.cc:1924-1985)
-      S->cost_ppp = c_ppp; S->cost_pim = c_pim; S->cost_marg = c_marg;
+      sc.cost_ppp = c_ppp; sc.cost_pim = c_pim; sc.cost_marg = c_marg;
       int turn_off = 1;
-      if (S->imu_factor) turn_off = c_pim > 1e3;
-      S->turn_off = turn_off;
+      if (sc.imu_factor) turn_off = c_pim > 1e3;
+      sc.turn_off = turn_off;
       const double ratio = c_marg / (c_ppp + c_pim);
-      if (!S->convergence_flag && !turn_off && ratio <= 2 && ratio != 0) S->convergence_flag = 1;
-      if (!S->convergence_flag) { S->ex_free = 0; S->prior_valid = 0; }
+      if (!sc.convergence_flag && !turn_off && ratio <= 2 && ratio != 0) sc.convergence_flag = 1;
+      if (!sc.convergence_flag) { sc.ex_free = 0; sc.prior_valid = 0; }
+    }
     }
   }
   __syncthreads();
-  const bool ex_free = S->ex_free != 0;
-  const bool use_prior = S->marginalization_factor && S->prior_valid;
-  const bool ex_prior = ex_free && S->prior_factor;
+  const bool ex_free = sc.ex_free != 0;
+  const bool use_prior = sc.marginalization_factor && sc.prior_valid;
+  const bool ex_prior = ex_free && sc.prior_factor;
   const double cost_eval = sred[90] + sred[91] + (use_prior ? sred[92] : 0.0) + (ex_prior ? F.ex[42] : 0.0);
   const int xd = ex_free ? xdim : xdim - 7;
   if (eval_index == 0) {
@@ -559,32 +601,32 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
     if (tid == 0) {
       double cand_cost = cost_eval;
       if (!isfinite(cand_cost)) cand_cost = 1e300;
-      S->cand_cost = cand_cost;
-      S->evaluations += 1;
+      sc.cand_cost = cand_cost;
+      sc.evaluations += 1;
       int verdict = 0;  // 0 reject, 1 accept, 2 terminate (converged)
-      const double cost_change = S->x_cost - cand_cost;
-      if (sqrt(sn) <= parameter_tolerance * (S->x_norm + parameter_tolerance)) { verdict = 2; S->termination = 1; }
-      else if (fabs(cost_change) <= function_tolerance * S->x_cost) { verdict = 2; S->termination = 1; }
+      const double cost_change = sc.x_cost - cand_cost;
+      if (sqrt(sn) <= parameter_tolerance * (sc.x_norm + parameter_tolerance)) { verdict = 2; sc.termination = 1; }
+      else if (fabs(cost_change) <= function_tolerance * sc.x_cost) { verdict = 2; sc.termination = 1; }
       else {
-        const double rd = cost_change / S->model_cost_change;
+        const double rd = cost_change / sc.model_cost_change;
         if (rd > min_relative_decrease) {
           verdict = 1;
-          S->x_cost = cand_cost;
-          S->successful += 1;
-          if (rd < 0.25) S->radius *= 0.5;
-          if (rd > 0.75) S->radius = fmin(max_radius, fmax(S->radius, 3.0 * S->dogleg_step_norm));
-          S->mu = fmax(min_mu, 2.0 * S->mu / mu_factor);
-          S->reuse = 0;
+          sc.x_cost = cand_cost;
+          sc.successful += 1;
+          if (rd < 0.25) sc.radius *= 0.5;
+          if (rd > 0.75) sc.radius = fmin(max_radius, fmax(sc.radius, 3.0 * sc.dogleg_step_norm));
+          sc.mu = fmax(min_mu, 2.0 * sc.mu / mu_factor);
+          sc.reuse = 0;
         } else {
-          S->radius *= 0.5;
-          S->reuse = 1;
+          sc.radius *= 0.5;
+          sc.reuse = 1;
         }
       }
       s_flag[1] = verdict;
     }
     __syncthreads();
     const int verdict = s_flag[1];
-    if (verdict == 2) { if (tid == 0) S->done = 1; return; }
+    if (verdict == 2) { if (tid == 0) sc.done = 1; return; }
     build = verdict == 1;
     if (build) {
       for (int p = tid; p < xdim; p += T) S->x[p] = S->cand[p];
@@ -595,8 +637,8 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
   DS_MARK(2);
   GatherCtx gc;
   gc.O = O; gc.n = n; gc.oe = oe; gc.np = np;
-  gc.ex_free = ex_free; gc.prior = use_prior; gc.lidar = S->point_distance_factor != 0; gc.imu = S->imu_factor != 0; gc.ex_prior = ex_prior;
-  gc.Hp = Hp; gc.Fimu = F.imu; gc.Fprior = F.prior; gc.Fex = F.ex; gc.G = G; gc.G0 = G0; gc.pim_valid = S->pim_valid;
+  gc.ex_free = ex_free; gc.prior = use_prior; gc.lidar = sc.point_distance_factor != 0; gc.imu = sc.imu_factor != 0; gc.ex_prior = ex_prior;
+  gc.Hp = Hp; gc.Fimu = F.imu; gc.Fprior = F.prior; gc.Fex = F.ex; gc.G = G; gc.G0 = G0; gc.pim_valid = sh.pim_valid; gc.zero = &sh.zero;
 
   if (build) {
     // ---------------- normal equations at the new current point ----------------
@@ -619,36 +661,91 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
     { double d1 = 0, d2 = 0; block_sum3(xn, d1, d2, sred); }
     for (int a = tid; a < n; a += T) { v_g[a] *= v_scale[a]; S->g[a] = v_g[a]; }
     if (tid == 0) {
-      S->x_norm = sqrt(xn);
+      sc.x_norm = sqrt(xn);
       int stop = 0;
       if (eval_index == 0) {
-        S->x_cost = cost_eval; S->initial_cost = cost_eval; S->cost0 = cost_eval;
-        S->evaluations = 1;
-        S->radius = initial_radius; S->mu = min_mu; S->reuse = 0; S->invalid = 0; S->iteration = 0; S->successful = 0; S->termination = 0;
-        if (!isfinite(cost_eval)) { S->termination = 2; stop = 1; }
-        else if (gm <= gradient_tolerance) { S->termination = 1; stop = 1; }
-      } else if (gm <= gradient_tolerance) { S->termination = 1; stop = 1; }
-      if (stop) S->done = 1;
+        sc.x_cost = cost_eval; sc.initial_cost = cost_eval; sc.cost0 = cost_eval;
+        sc.evaluations = 1;
+        sc.radius = initial_radius; sc.mu = min_mu; sc.reuse = 0; sc.invalid = 0; sc.iteration = 0; sc.successful = 0; sc.termination = 0;
+        if (!isfinite(cost_eval)) { sc.termination = 2; stop = 1; }
+        else if (gm <= gradient_tolerance) { sc.termination = 1; stop = 1; }
+      } else if (gm <= gradient_tolerance) { sc.termination = 1; stop = 1; }
+      if (stop) sc.done = 1;
       s_flag[2] = stop;
     }
     __syncthreads();
     if (s_flag[2]) return;
     DS_MARK(4);
-    // scaled H of the current point -> global (both triangles); diagonal D of the trust region
-    for (int p = tid; p < n * (n + 1) / 2; p += T) {
-      int a = (int)((sqrt(8.0 * p + 1.0) - 1.0) * 0.5);
-      while ((a + 1) * (a + 2) / 2 <= p) ++a;
-      while (a * (a + 1) / 2 > p) --a;
-      const int b = p - a * (a + 1) / 2;
-      const double h = h_elem(gc, a, b);
-      if (eval_index == 0) { H0[(size_t)a * n + b] = h; H0[(size_t)b * n + a] = h; }
-      const double hs = h * v_scale[a] * v_scale[b];
-      Hs[(size_t)a * n + b] = hs; Hs[(size_t)b * n + a] = hs;
-      if (a == b) {
-        const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
-        v_diag[a] = d; S->diagonal[a] = d;
+    // scaled H of the current point -> global (both triangles) and, with mu D^2 on the diagonal, straight into the
+    // Cholesky tiles.  One warp per 15 x 15 parameter block pair (K >= L; block O + 1 = extrinsic, 6 wide): inside a block
+    // every contribution is a plain sub-matrix (prior rows, the 6 x 6 pose part of a lidar G, ImuFactor quadrants), so
+    // the per-element work is five pointer offsets, their loads and the stores.
+    mu_tiles = sc.mu;
+    {
+      const int l = lane_id();
+      const int nblk = O + 2, npair = nblk * (nblk + 1) / 2;
+      for (int pp = warp_id(); pp < npair; pp += kDsWarps) {
+        int K = 0, L = pp;
+        while (L > K) { L -= K + 1; ++K; }
+        const int szK = K == O + 1 ? 6 : 15, szL = L == O + 1 ? 6 : 15;
+        const int baseK = K == O + 1 ? oe : 15 * K, baseL = L == O + 1 ? oe : 15 * L;
+        const bool exK = K == O + 1, exL = L == O + 1;
+        const bool frozen = exK && !ex_free;          // identity rows, nothing else
+        // prior: rows/cols of frames < O and of a free extrinsic
+        const int pK = K < O ? 15 * K : (exK && ex_free ? 15 * O : -1), pL = L < O ? 15 * L : (exL && ex_free ? 15 * O : -1);
+        const double *q0 = (!frozen && use_prior && pK >= 0 && pL >= 0) ? Hp + (size_t)pK * np + pL : nullptr;
+        // lidar: 6 x 6 pose sub-block (rows r < 6, cols c < 6) of G0 or of one frame's G
+        const double *q1 = nullptr;
+        int ld1 = 18;
+        if (!frozen && gc.lidar) {
+          const bool shK = K == 0 || exK, shL = L == 0 || exL;
+          if (shK && shL) { q1 = G0 + (exK ? 6 : 0) * 12 + (exL ? 6 : 0); ld1 = 12; }
+          else if (!shK && !shL) { if (K == L) q1 = G + (size_t)(K - 1) * kFGStride + 6 * 18 + 6; }
+          else if (shK) q1 = G + (size_t)(L - 1) * kFGStride + 12 * 18 + 6;              // K = extrinsic, L = frame
+          else q1 = G + (size_t)(K - 1) * kFGStride + 6 * 18 + (exL ? 12 : 0);             // K = frame, L = pose_0
+        }
+        // ImuFactors: factor k covers blocks k and k + 1
+        const double *q2 = nullptr, *q3 = nullptr;
+        if (!frozen && gc.imu && !exK) {
+          if (K == L) {
+            if (K < O && sh.pim_valid[K]) q2 = F.imu + (size_t)K * kFImuStride;
+            if (K >= 1 && sh.pim_valid[K - 1]) q3 = F.imu + (size_t)(K - 1) * kFImuStride + 15 * 30 + 15;
+          } else if (L == K - 1 && sh.pim_valid[L]) {
+            q3 = F.imu + (size_t)L * kFImuStride + 15 * 30;
+          }
+        }
+        const double *q4 = (!frozen && ex_prior && exK && exL) ? F.ex : nullptr;
+        for (int e = l; e < szK * szL; e += 32) {
+          const int r = e / szL, c = e - r * szL;
+          if (K == L && c > r) continue;
+          const int ga = baseK + r, gb = baseL + c;
+          double h;
+          if (frozen) h = (ga == gb) ? 1.0 : 0.0;
+          else {
+            const bool pose = r < 6 && c < 6;
+            const double v0 = q0 ? q0[(size_t)r * np + c] : 0.0;
+            const double v1 = (q1 && pose) ? q1[r * ld1 + c] : 0.0;
+            const double v2 = q2 ? q2[r * 30 + c] : 0.0;
+            const double v3 = q3 ? q3[r * 30 + c] : 0.0;
+            const double v4 = q4 ? q4[r * 6 + c] : 0.0;
+            h = (((v0 + v1) + v2) + v3) + v4;
+          }
+          if (eval_index == 0) { H0[(size_t)ga * n + gb] = h; H0[(size_t)gb * n + ga] = h; }
+          const double hs = h * v_scale[ga] * v_scale[gb];
+          Hs[(size_t)ga * n + gb] = hs; Hs[(size_t)gb * n + ga] = hs;
+          double tv = hs;
+          if (ga == gb) {
+            const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
+            v_diag[ga] = d; S->diagonal[ga] = d;
+            tv = hs + mu_tiles * d * d;
+          }
+          tiles[tile_off(ga >> 3, gb >> 3) + swz(ga & 7, gb & 7)] = tv;
+        }
       }
+      for (int a2 = n + warp_id(); a2 < NP; a2 += kDsWarps)   // padding rows: identity
+        for (int b2 = l; b2 <= a2; b2 += 32) tiles[tile_off(a2 >> 3, b2 >> 3) + swz(a2 & 7, b2 & 7)] = (a2 == b2) ? 1.0 : 0.0;
     }
+    tiles_ready = 1;
     __syncthreads();
     for (int i = tid; i < n; i += T) { v_grad[i] = v_g[i] / v_diag[i]; S->gradient[i] = v_grad[i]; }
     __syncthreads();
@@ -659,14 +756,14 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
   while (true) {
     if (tid == 0) {
       int stop = 0;
-      if (S->iteration >= S->max_it) { S->termination = 0; stop = 1; }
-      else if (S->radius < min_radius) { S->termination = 1; stop = 1; }
-      else S->iteration += 1;
+      if (sc.iteration >= sc.max_it) { sc.termination = 0; stop = 1; }
+      else if (sc.radius < min_radius) { sc.termination = 1; stop = 1; }
+      else sc.iteration += 1;
       s_flag[1] = stop;
-      s_flag[3] = S->reuse;
+      s_flag[3] = sc.reuse;
     }
     __syncthreads();
-    if (s_flag[1]) { if (tid == 0) S->done = 1; return; }
+    if (s_flag[1]) { if (tid == 0) sc.done = 1; return; }
     int linear_ok = 1;
     if (!s_flag[3]) {
       // Cauchy point scale: alpha = |gradient|^2 / (sg^T H sg), sg = gradient / D
@@ -676,28 +773,27 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
       double pa = 0, pb = 0, pc = 0;
       for (int i = tid; i < n; i += T) { pa += v_grad[i] * v_grad[i]; pb += v_tmp[i] * v_y[i]; }
       block_sum3(pa, pb, pc, sred);
-      double mu = S->mu;
-      if (tid == 0) { S->alpha = pa / pb; S->reuse = 1; }
+      double mu = sc.mu;
+      if (tid == 0) { sc.alpha = pa / pb; sc.reuse = 1; }
       DS_MARK(6);
       linear_ok = 0;
       while (mu < max_mu) {
         // tiles of H + mu D^2 (lower triangle; identity on the padding), right-hand side g
-        for (int p = tid; p < (NB * (NB + 1) / 2) * 64; p += T) {
-          const int t = p >> 6, e = p & 63, r = e >> 3, cs = e & 7, c = cs ^ ((r & 2) << 1);
-          int ib = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-          while ((ib + 1) * (ib + 2) / 2 <= t) ++ib;
-          while (ib * (ib + 1) / 2 > t) --ib;
-          const int jb = t - ib * (ib + 1) / 2;
-          const int a = 8 * ib + r, b = 8 * jb + c;
-          double v;
-          if (a < n && b < n) { v = Hs[(size_t)a * n + b]; if (a == b) v += mu * v_diag[a] * v_diag[a]; }
-          else v = (a == b) ? 1.0 : 0.0;
-          tiles[p] = v;
+        if (!(tiles_ready && mu == mu_tiles)) {
+          for (int a = warp_id(); a < NP; a += kDsWarps) {
+            for (int b = lane_id(); b <= a; b += 32) {
+              double v;
+              if (a < n) { v = Hs[(size_t)a * n + b]; if (a == b) v += mu * v_diag[a] * v_diag[a]; }
+              else v = (a == b) ? 1.0 : 0.0;
+              tiles[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = v;
+            }
+          }
         }
+        tiles_ready = 0;
         for (int i = tid; i < NP; i += T) v_y[i] = i < n ? v_g[i] : 0.0;
         __syncthreads();
         DS_MARK(7);
-        int ok = chol_solve_tiles(tiles, NB, v_y, &s_ok);
+        int ok = chol_solve_tiles(tiles, NB, v_y, &s_ok, eval_index < 24 ? &S->dbg[eval_index][12] : nullptr);
         DS_MARK(8);
         if (ok) {
           double bad = 0;
@@ -710,7 +806,7 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
         linear_ok = 1;
         break;
       }
-      if (tid == 0) S->mu = mu;
+      if (tid == 0) sc.mu = mu;
       __syncthreads();
     }
     int step_valid = linear_ok;
@@ -719,7 +815,7 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
       for (int i = tid; i < n; i += T) { p1 += v_grad[i] * v_grad[i]; p2 += v_gn[i] * v_gn[i]; p3 += v_grad[i] * v_gn[i]; }
       block_sum3(p1, p2, p3, sred);
       const double gradient_norm = sqrt(p1), gn_norm = sqrt(p2), g_dot_gn = p3;
-      const double radius = S->radius, alpha = S->alpha;
+      const double radius = sc.radius, alpha = sc.alpha;
       double c_grad, c_gn, dsn;
       if (gn_norm <= radius) { c_grad = 0.0; c_gn = 1.0; dsn = gn_norm; }
       else if (gradient_norm * alpha >= radius) { c_grad = -(radius / gradient_norm); c_gn = 0.0; dsn = radius; }
@@ -746,22 +842,22 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
       block_sum3(q1, q2, q3, sred);
       const double mcc = -q1 - 0.5 * q2;
       step_valid = mcc > 0.0;
-      if (tid == 0) { S->model_cost_change = mcc; S->dogleg_step_norm = dsn; }
+      if (tid == 0) { sc.model_cost_change = mcc; sc.dogleg_step_norm = dsn; }
     }
     __syncthreads();
     if (!step_valid) {
       if (tid == 0) {
-        S->invalid += 1;
-        s_flag[1] = S->invalid >= 5;
-        if (s_flag[1]) { S->termination = 2; S->done = 1; }
-        S->mu *= mu_factor;
-        S->reuse = 0;
+        sc.invalid += 1;
+        s_flag[1] = sc.invalid >= 5;
+        if (s_flag[1]) { sc.termination = 2; sc.done = 1; }
+        sc.mu *= mu_factor;
+        sc.reuse = 0;
       }
       __syncthreads();
       if (s_flag[1]) return;
       continue;
     }
-    if (tid == 0) S->invalid = 0;
+    if (tid == 0) sc.invalid = 0;
     break;
   }
   DS_MARK(9);
@@ -781,6 +877,23 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
   __syncthreads();
   DS_MARK(10);
   if (tid == 0 && eval_index < 24) S->dbg[eval_index][11] = gtime_ns();
+}
+
+__global__ void __launch_bounds__(kDsThreads, 1)
+k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, double *g0, const double *__restrict__ Sblk,
+       FPtrs F, double *Rt, int eval_index) {
+  extern __shared__ __align__(16) double dsm[];
+  __shared__ StepShared sh;
+  static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is copied as 8-byte words");
+  if (S->sc.done) return;
+  const int tid = threadIdx.x;
+  if (tid < (int)(sizeof(DevScalars) / 8)) reinterpret_cast<long long *>(&sh.sc)[tid] = reinterpret_cast<const long long *>(&S->sc)[tid];
+  if (tid >= 64 && tid < 64 + kMaxOpt) sh.pim_valid[tid - 64] = S->pim_valid[tid - 64];
+  if (tid == 128) sh.zero = 0.0;
+  __syncthreads();
+  step_body(S, sh, dsm, Hs, Hp, H0, g0, Sblk, F, Rt, eval_index);
+  __syncthreads();
+  if (tid < (int)(sizeof(DevScalars) / 8)) reinterpret_cast<long long *>(&S->sc)[tid] = reinterpret_cast<const long long *>(&sh.sc)[tid];
 }
 
 // =====================================================================================================

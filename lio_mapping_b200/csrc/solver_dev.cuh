@@ -10,10 +10,9 @@ constexpr int kDsMaxNp = 15 * kMaxOpt + 6;       // 246
 constexpr int kDsXDim = 16 * (kMaxOpt + 1) + 7;
 constexpr int kDsMaxOpt = 13;                    // largest opt window whose Cholesky tiles fit one SM's shared memory
 
-struct DevSolveState {
-  // parameters: [pose_k(7) sb_k(9)] k = 0..O, then extrinsic pose(7)
-  double x[kDsXDim], cand[kDsXDim];
-  // flags
+// Scalar part of the solver state.  k_step keeps a copy in shared memory for the duration of a launch (thread 0 runs the
+// trust-region bookkeeping on it without global round trips) and writes it back on exit.
+struct DevScalars {
   int O, n, max_it;
   int imu_factor, point_distance_factor, prior_factor, marginalization_factor;
   int ex_free, prior_valid, convergence_flag, turn_off;
@@ -22,8 +21,13 @@ struct DevSolveState {
   double radius, mu, alpha, x_cost, cand_cost, model_cost_change, dogleg_step_norm, x_norm;
   double initial_cost, cost_pim, cost_ppp, cost_marg;
   double ex0_pos[3], ex0_quat[4];  // PriorFactor target (transform_lb_ at problem build), quat x y z w
-  // first linearisation (parity / debugging)
-  double cost0;
+  double cost0;                    // first linearisation (parity / debugging)
+};
+
+struct DevSolveState {
+  // parameters: [pose_k(7) sb_k(9)] k = 0..O, then extrinsic pose(7)
+  double x[kDsXDim], cand[kDsXDim];
+  DevScalars sc;
   // ---- everything above is read back after a solve (offsetof(scale) bytes) ----
   double scale[kDsMaxN], diagonal[kDsMaxN], gradient[kDsMaxN], gn[kDsMaxN], g[kDsMaxN];
   // marginalisation prior (canonical order [pose_0,sb_0,...,pose_{O-1},sb_{O-1},ex])
@@ -34,7 +38,9 @@ struct DevSolveState {
   int pim_valid[kMaxOpt];
   // phase timestamps of k_step per evaluation (thread 0): [0] %globaltimer at entry, [1..9] clock64 at phase boundaries
   // (entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit), [11] %globaltimer at exit
-  long long dbg[24][12];
+  // [12..15] inside the Cholesky (cycles): look-ahead diag_factor of panel 1, panel solve of panel 0, trailing update of
+  // panel 0 (incl. barrier), back substitution
+  long long dbg[24][16];
 };
 
 // Scratch written by k_factors (state-dependent, lidar-independent terms at the state being evaluated) and read by

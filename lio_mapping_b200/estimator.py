@@ -214,8 +214,8 @@ class Estimator:
                     knn_ms=o[4], knn_launches=int(o[5]), knn_queries=int(o[6]), bytes_per_query=o[7])
 
     def solver_trace(self):
-        """Phase timestamps of the device solver's step kernel, (24, 12) int64 (see lio_est_solver_trace)."""
-        out = np.zeros((24, 12), np.int64)
+        """Phase timestamps of the device solver's step kernel, (24, 16) int64 (see lio_est_solver_trace)."""
+        out = np.zeros((24, 16), np.int64)
         _lib.check(_lib.lib().lio_est_solver_trace(self.h, out, out.size), "lio_est_solver_trace")
         return out
 

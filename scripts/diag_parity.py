@@ -50,5 +50,6 @@ if tr.any():
             if c[k] > 0:
                 ph.append("%s %.1f" % (names[k - 1], (c[k] - last) / 1965.0)); last = c[k]
         gap = (tr[ev, 0] - prev_end) / 1e3 if prev_end else 0.0
-        print("  ev %2d  kernel %.1f us  gap %.1f us | %s" % (ev, (tr[ev, 11] - tr[ev, 0]) / 1e3, gap, "  ".join(ph)))
+        print("  ev %2d  kernel %.1f us  gap %.1f us | %s | chol cycles: diag %d panel %d update %d backsub %d" % (
+            ev, (tr[ev, 11] - tr[ev, 0]) / 1e3, gap, "  ".join(ph), tr[ev, 12], tr[ev, 13], tr[ev, 14], tr[ev, 15]))
         prev_end = tr[ev, 11]
