@@ -184,8 +184,10 @@ int lio_asm_set_fold_chunks(int chunks);
 
 /* Test seam of the device-resident solver: solves A x = b (A symmetric positive definite, n x n row-major, n <= 216) with
  * the tiled shared-memory Cholesky (fp64 tensor-core MMA trailing update) that the dogleg step of the device solver uses
- * in place of Ceres' dense factorisation (Estimator.cc:1911 DENSE_SCHUR).  *ok = 0 when a pivot is not positive. */
-int lio_dev_cholesky_solve_host(const double *A, const double *b, int n, double *x, int *ok, int device);
+ * in place of Ceres' dense factorisation (Estimator.cc:1911 DENSE_SCHUR).  *ok = 0 when a pivot is not positive.
+ * prof (optional, 4 * ceil(n / 8) + 1 entries): SM cycles per 8-column panel {panel solve, own tile update, diagonal-tile
+ * factorisation, trailing update incl. barrier} as seen by the warp that runs the serial chain, then the back substitution. */
+int lio_dev_cholesky_solve_host(const double *A, const double *b, int n, double *x, int *ok, long long *prof, int device);
 
 /* IntegrationBase (include/imu_processor/IntegrationBase.h:72-388) */
 typedef struct lio_pim lio_pim;
@@ -287,8 +289,8 @@ int lio_est_last_launches(lio_est *est);
 /* Diagnostic: phase timestamps of the device-resident solver's step kernel for the evaluations of the last solve:
  * out[24][16] (row = evaluation; [0] / [11] = GPU wall clock in ns at kernel entry / exit, [1..10] = SM clock at the phase
  * boundaries entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit; [12..15] = cycles
- * inside the Cholesky: diagonal-tile factorisation, panel solve, trailing update, back substitution).  Zeros when the host
- * controller is in use. */
+ * reserved), followed by 4 * 28 + 4 entries: the per-panel cycle profile of evaluation 1's Cholesky in the layout of
+ * lio_dev_cholesky_solve_host's prof.  cap >= 24 * 16 + 116.  Zeros when the host controller is in use. */
 int lio_est_solver_trace(lio_est *est, long long *out, int cap);
 /* CUDA-event timing of the fused residual+Jacobian kernel accumulated since the last reset (events recorded
  * on the estimator's stream around every launch): out[0..3] = {sum ms, launches, features processed, bytes/feature};

@@ -101,7 +101,7 @@ def lib():
     L.lio_asm_ppp_host.argtypes = [f32p, f32p, ip, f64p, f64p, f64p, ip]
     L.lio_asm_set_fold_chunks.argtypes = [ip]
     L.lio_asm_stream_bench.argtypes = [C.c_longlong, ip, ip, f64p]
-    L.lio_dev_cholesky_solve_host.argtypes = [f64p, f64p, ip, f64p, C.POINTER(ip), ip]
+    L.lio_dev_cholesky_solve_host.argtypes = [f64p, f64p, ip, f64p, C.POINTER(ip), vp, ip]
     L.lio_pim_create.argtypes = [f64p, f64p, f64p, f64p, f64p, C.POINTER(vp)]
     L.lio_pim_destroy.argtypes = [vp]
     L.lio_pim_push_back.argtypes = [vp, C.c_double, f64p, f64p]

@@ -1925,10 +1925,10 @@ extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, d
 extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
 
 extern "C" int lio_est_solver_trace(lio_est *e, long long *out, int cap) {
-  if (!e || !out || cap < 24 * 16) return LIO_ERR_INVALID;
-  if (!e->use_dev_solver) { std::memset(out, 0, sizeof(long long) * 24 * 16); return LIO_OK; }
+  if (!e || !out || cap < 24 * 16 + 4 * 28 + 4) return LIO_ERR_INVALID;
+  if (!e->use_dev_solver) { std::memset(out, 0, sizeof(long long) * (24 * 16 + 4 * 28 + 4)); return LIO_OK; }
   LIO_CUDA_OK(cudaSetDevice(e->device));
-  LIO_CUDA_OK(cudaMemcpy(out, reinterpret_cast<const char *>(e->ds.st) + offsetof(DevSolveState, dbg), sizeof(long long) * 24 * 16, cudaMemcpyDeviceToHost));
+  LIO_CUDA_OK(cudaMemcpy(out, reinterpret_cast<const char *>(e->ds.st) + offsetof(DevSolveState, dbg), sizeof(long long) * (24 * 16 + 4 * 28 + 4), cudaMemcpyDeviceToHost));
   return LIO_OK;
 }
 

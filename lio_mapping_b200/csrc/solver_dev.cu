@@ -243,6 +243,14 @@ __device__ void diag_factor(double *T, int *s_ok) {
   __syncwarp();
 }
 
+// clock64 ordered after a shared-memory value has arrived: a plain clock read right behind __syncthreads() captures the
+// barrier's ISSUE time (BAR.SYNC.DEFER_BLOCKING), not its release
+__device__ __forceinline__ long long clock_after(double v) {
+  long long t;
+  asm volatile("{\n\t.reg .b64 tmp;\n\tmov.b64 tmp, %1;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(t) : "d"(v) : "memory");
+  return t;
+}
+
 // Factors the tiled matrix in place (strictly-lower tiles: L; diagonal tiles: inv(L_kk)) and overwrites y (padded to
 // 8 NB) with the solution of (L L^T) x = y.  Returns 1 on success; uniform.
 __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, long long *prof = nullptr) {
@@ -250,24 +258,47 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
   const int fr = l >> 2, fq = l & 3;   // fragment row, fragment quad
   if (tid == 0) *s_ok = 1;
   __syncthreads();
-  if (w == 0) diag_factor(tiles + tile_off(0, 0), s_ok);
+  // The serial chain (diagonal tiles) runs on the LAST warp: the issue arbiter favours the highest warp id of a
+  // scheduler, so the chain is never starved by the seven update warps it shares its scheduler with.
+  constexpr int kChainWarp = kDsWarps - 1;
+  if (w == kChainWarp) diag_factor(tiles + tile_off(0, 0), s_ok);
   __syncthreads();
   for (int kb = 0; kb < NB; ++kb) {
     if (!*s_ok) break;
-    const long long tp0 = clock64();
+    const long long tp0 = clock_after(y[0]);
     const double *Li = tiles + tile_off(kb, kb);   // inv(L_kk)
     const int m = NB - 1 - kb;
-    // ---- panel solve: X = A inv(L)^T for the tiles below the diagonal; y_kb = inv(L) y_kb
+    // ---- panel solve: X = A inv(L)^T for the tiles below the diagonal; y_kb = inv(L) y_kb.  The chain warp takes the first
+    // tile and at once applies it to the next diagonal tile, so that after the barrier it can start factoring immediately
+    // (behind the barrier the same update would queue behind everybody else's shared-memory traffic: 850 cycles measured).
     const double b0 = Li[swz(fr, fq)], b1 = Li[swz(fr, fq + 4)];
-    for (int t = w; t < m; t += kDsWarps) {
-      double *A = tiles + tile_off(kb + 1 + t, kb);
-      const double a0 = A[swz(fr, fq)], a1 = A[swz(fr, fq + 4)];
-      double d0 = 0.0, d1 = 0.0;
-      dmma884(d0, d1, a0, b0);
-      dmma884(d0, d1, a1, b1);
-      *reinterpret_cast<double2 *>(A + swz(fr, 2 * fq)) = make_double2(d0, d1);
+    if (w == kChainWarp) {
+      if (m > 0) {
+        double *A = tiles + tile_off(kb + 1, kb);
+        const double a0 = A[swz(fr, fq)], a1 = A[swz(fr, fq + 4)];
+        double d0 = 0.0, d1 = 0.0;
+        dmma884(d0, d1, a0, b0);
+        dmma884(d0, d1, a1, b1);
+        *reinterpret_cast<double2 *>(A + swz(fr, 2 * fq)) = make_double2(d0, d1);
+        __syncwarp();
+        double *C = tiles + tile_off(kb + 1, kb + 1);
+        const double x0 = A[swz(fr, fq)], x1 = A[swz(fr, fq + 4)];
+        double2 c = *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq));
+        dmma884(c.x, c.y, -x0, x0);
+        dmma884(c.x, c.y, -x1, x1);
+        *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
+      }
+    } else {
+      for (int t = 1 + w; t < m; t += kDsWarps - 1) {
+        double *A = tiles + tile_off(kb + 1 + t, kb);
+        const double a0 = A[swz(fr, fq)], a1 = A[swz(fr, fq + 4)];
+        double d0 = 0.0, d1 = 0.0;
+        dmma884(d0, d1, a0, b0);
+        dmma884(d0, d1, a1, b1);
+        *reinterpret_cast<double2 *>(A + swz(fr, 2 * fq)) = make_double2(d0, d1);
+      }
     }
-    if (w == kDsWarps - 1) {
+    if (w == 0) {
       double v = 0.0;
       if (l < 8) {
 #pragma unroll
@@ -277,28 +308,25 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
       if (l < 8) y[8 * kb + l] = v;
     }
     __syncthreads();
-    const long long tp1 = clock64();
-    if (prof && kb == 0 && tid == 0) prof[1] = tp1 - tp0;
+    const long long tp1 = clock_after(y[8 * kb]);      // y_kb was written by warp 0 before the barrier: really after release
+    if (prof && w == kChainWarp && l == 0) prof[4 * kb + 0] = tp1 - tp0;
     if (m == 0) break;
     // ---- trailing update C(i, j) -= X_i X_j^T, right-hand side rows, and the next diagonal tile one panel ahead
     const int ntile = m * (m + 1) / 2;
-    if (w == 0) {
+    if (w == kChainWarp) {
       double *C = tiles + tile_off(kb + 1, kb + 1);
-      const double *X = tiles + tile_off(kb + 1, kb);
-      const double a0 = -X[swz(fr, fq)], a1 = -X[swz(fr, fq + 4)];
-      double2 c = *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq));
-      dmma884(c.x, c.y, a0, -a0);
-      dmma884(c.x, c.y, a1, -a1);
-      *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
-      __syncwarp();
       const long long td0 = clock64();
       diag_factor(C, s_ok);
-      if (prof && kb == 0 && tid == 0) prof[0] = clock64() - td0;
-    } else {
-      // tasks p = 1 .. ntile - 1: tile (i, j) with p = i (i + 1) / 2 + j;  p = ntile .. ntile + m - 1: rhs rows of tile-row p - ntile
-      int i = 0, j = w;                                   // (i, j) of p = w, advanced incrementally (no sqrt on the hot path)
+      if (prof && l == 0) { prof[4 * kb + 1] = td0 - tp1; prof[4 * kb + 2] = clock64() - td0; }
+    } else if ((w & 3) != (kChainWarp & 3)) {
+      // tasks p = 1 .. ntile - 1: tile (i, j) with p = i (i + 1) / 2 + j;  p = ntile .. ntile + m - 1: rhs rows of tile-row p - ntile.
+      // The warps that share the chain warp's scheduler (w % 4 == 3) take no tasks: their fp64 MMAs would queue in front of
+      // every dependent fp64 operation of the chain (measured: the diagonal tile takes 4.9k cycles beside them, 2.0k alone).
+      constexpr int kWorkers = kDsWarps - kDsWarps / 4;          // 24
+      const int wi = w - (w >> 2);                               // dense index of this worker: 0 .. 23
+      int i = 0, j = wi + 1;                                      // (i, j) of p = wi + 1, advanced incrementally (no sqrt on the hot path)
       while (j > i) { j -= i + 1; ++i; }
-      for (int p = w; p < ntile + m; p += kDsWarps - 1) {
+      for (int p = wi + 1; p < ntile + m; p += kWorkers) {
         if (p < ntile) {
           double *C = tiles + tile_off(kb + 1 + i, kb + 1 + j);
           const double *Xi = tiles + tile_off(kb + 1 + i, kb), *Xj = tiles + tile_off(kb + 1 + j, kb);
@@ -308,7 +336,7 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
           dmma884(c.x, c.y, a0, x0);
           dmma884(c.x, c.y, a1, x1);
           *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
-          j += kDsWarps - 1;
+          j += kWorkers;
           while (j > i) { j -= i + 1; ++i; }
         } else if (l < 8) {
           const int ib = kb + 1 + (p - ntile);
@@ -321,36 +349,47 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
       }
     }
     __syncthreads();
-    if (prof && kb == 0 && tid == 0) prof[2] = clock64() - tp1;
+    if (prof && w == kChainWarp && l == 0) prof[4 * kb + 3] = clock_after(y[8 * (kb + 1)]) - tp1;
   }
   __syncthreads();
   const int ok = *s_ok;
   if (!ok) return 0;
   const long long tb0 = clock64();
-  // ---- back substitution L^T x = y over the tiles in reverse
-  for (int jb = NB - 1; jb >= 0; --jb) {
-    if (w == 0) {
-      const double *Li = tiles + tile_off(jb, jb);
-      double v = 0.0;
-      if (l < 8) {
+  // ---- back substitution L^T x = y over the tiles in reverse.  Only the first 8 warps take part (8 NB <= 256 rows): the
+  // 8 threads of tile-row jb turn their finished y into x = inv(L_jj)^T y (they share a warp), one named barrier
+  // publishes x, then every thread of the rows above subtracts its tile's contribution.
+  if (w < 8) {
+    for (int jb = NB - 1; jb >= 0; --jb) {
+      if ((tid >> 3) == jb) {
+        const double *Li = tiles + tile_off(jb, jb);
+        const int c = tid & 7;
+        __syncwarp(0xffu << (l & 24));
+        double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-        for (int r = 0; r < 8; ++r) v += (r >= l) ? Li[swz(r, l)] * y[8 * jb + r] : 0.0;
+        for (int r = 0; r < 8; r += 2) {
+          v0 += (r >= c) ? Li[swz(r, c)] * y[8 * jb + r] : 0.0;
+          v1 += (r + 1 >= c) ? Li[swz(r + 1, c)] * y[8 * jb + r + 1] : 0.0;
+        }
+        __syncwarp(0xffu << (l & 24));
+        y[8 * jb + c] = v0 + v1;
       }
-      __syncwarp();
-      if (l < 8) y[8 * jb + l] = v;
-    }
-    __syncthreads();
-    if (tid < 8 * jb) {
-      const int ib = tid >> 3, c = tid & 7;
-      const double *Lt = tiles + tile_off(jb, ib);
-      double s = 0.0;
+      double lt[8];   // this thread's column of tile (jb, ib): independent of x, fetched before the barrier
+      if (tid < 8 * jb) {
+        const double *Lt = tiles + tile_off(jb, tid >> 3);
 #pragma unroll
-      for (int r = 0; r < 8; ++r) s += Lt[swz(r, c)] * y[8 * jb + r];
-      y[tid] -= s;
+        for (int r = 0; r < 8; ++r) lt[r] = Lt[swz(r, tid & 7)];
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < 8 * jb) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) { s0 += lt[r] * y[8 * jb + r]; s1 += lt[r + 1] * y[8 * jb + r + 1]; }
+        y[tid] -= s0 + s1;
+      }
     }
-    __syncthreads();
   }
-  if (prof && tid == 0) prof[3] = clock64() - tb0;
+  __syncthreads();
+  if (prof && tid == 0) prof[4 * NB] = clock_after(y[0]) - tb0;
   return 1;
 }
 
@@ -484,30 +523,29 @@ __device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const doubl
   __syncthreads();
 }
 
-// y = Hs v (row-major n x n in global memory, v in shared memory): one warp per row, two rows and all their columns in
-// flight per warp (n <= 224: seven 32-column slices)
-__device__ void matvec_g(const double *__restrict__ Hs, int n, const double *v, double *y) {
-  const int w = warp_id(), l = lane_id();
-  for (int r0 = w; r0 < n; r0 += 2 * kDsWarps) {
-    const int r1 = r0 + kDsWarps;
-    const bool has1 = r1 < n;
-    double a0[7], a1[7];
-#pragma unroll
-    for (int q = 0; q < 7; ++q) {
-      const int c = l + 32 * q;
-      a0[q] = c < n ? Hs[(size_t)r0 * n + c] : 0.0;
-      a1[q] = (c < n && has1) ? Hs[(size_t)r1 * n + c] : 0.0;
+// y = H v with H the symmetric matrix whose lower triangle sits in the (unfactored) tiles; v, y in shared memory.
+// Four threads per row, each over a quarter of the columns (needs n <= blockDim.x / 4).
+__device__ void symv_tiles(const double *tiles, int n, const double *v, double *y) {
+  const int a = threadIdx.x >> 2, q = threadIdx.x & 3;
+  double s = 0.0;
+  if (a < n) {
+    const int ta = a >> 3, ra = a & 7;
+    for (int b = q; b < n; b += 4) {
+      const double h = (b <= a) ? tiles[tile_off(ta, b >> 3) + swz(ra, b & 7)] : tiles[tile_off(b >> 3, ta) + swz(b & 7, ra)];
+      s += h * v[b];
     }
-    double s0 = 0, s1 = 0;
-#pragma unroll
-    for (int q = 0; q < 7; ++q) {
-      const int c = l + 32 * q;
-      const double vc = c < n ? v[c] : 0.0;
-      s0 += a0[q] * vc; s1 += a1[q] * vc;
-    }
-    s0 = warp_sum(s0); s1 = warp_sum(s1);
-    if (l == 0) { y[r0] = s0; if (has1) y[r1] = s1; }
   }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  if (a < n && q == 0) y[a] = s;
+  __syncthreads();
+}
+
+// (re)load the pure scaled H (lower triangle, identity on the padding) from global memory into the tiles
+__device__ void refill_tiles(double *tiles, const double *__restrict__ Hs, int n, int NP) {
+  for (int a = warp_id(); a < NP; a += kDsWarps)
+    for (int b = lane_id(); b <= a; b += 32)
+      tiles[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = (a < n) ? Hs[(size_t)a * n + b] : ((a == b) ? 1.0 : 0.0);
   __syncthreads();
 }
 
@@ -545,7 +583,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
   double *tiles = dsm;
   double *v_g = dsm + (size_t)(NB * (NB + 1) / 2) * 64;   // scaled gradient of the current x
   double *v_scale = v_g + NP, *v_diag = v_scale + NP, *v_grad = v_diag + NP, *v_gn = v_grad + NP, *v_step = v_gn + NP;
-  double *v_tmp = v_step + NP, *v_y = v_tmp + NP;
+  double *v_tmp = v_step + NP, *v_y = v_tmp + NP, *v_hsg = v_y + NP;
   const double min_diagonal = 1e-6, max_diagonal = 1e32, min_mu = 1e-8, max_mu = 1.0, mu_factor = 10.0;
   const double initial_radius = 1e4, max_radius = 1e16, min_radius = 1e-32, min_relative_decrease = 1e-3;
   const double function_tolerance = 1e-6, gradient_tolerance = 1e-10, parameter_tolerance = 1e-8;
@@ -557,14 +595,13 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
   for (int i = tid; i < NP; i += T) {
     const bool in = i < n;
     v_g[i] = in ? S->g[i] : 0.0; v_scale[i] = in ? S->scale[i] : 1.0; v_diag[i] = in ? S->diagonal[i] : 1.0;
-    v_grad[i] = in ? S->gradient[i] : 0.0; v_gn[i] = in ? S->gn[i] : 0.0;
+    v_grad[i] = in ? S->gradient[i] : 0.0; v_gn[i] = in ? S->gn[i] : 0.0; v_hsg[i] = in ? S->hsg[i] : 0.0;
   }
   __syncthreads();
 
   // ---------------- cost of the evaluated state and the verdict ----------------
   int build = 0;   // 1: (re)build H, g at the evaluated state and make it the current point
-  int tiles_ready = 0;      // the gather below leaves H + mu_tiles D^2 in the Cholesky tiles
-  double mu_tiles = 0.0;
+  int tiles_ready = 0;      // the gather below leaves the pure scaled H in the Cholesky tiles
   if (warp_id() == 0) {   // cost components: lane i fetches frame i's terms, summed in frame order by lane 0
     const int l = lane_id();
     double cp = (l < O && sc.point_distance_factor) ? 0.5 * Sblk[l * kAsmStride + 28] : 0.0;
@@ -676,11 +713,9 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     __syncthreads();
     if (s_flag[2]) return;
     DS_MARK(4);
-    // scaled H of the current point -> global (both triangles) and, with mu D^2 on the diagonal, straight into the
-    // Cholesky tiles.  One warp per 15 x 15 parameter block pair (K >= L; block O + 1 = extrinsic, 6 wide): inside a block
+    // scaled H of the current point (lower triangle) -> global and straight into the Cholesky tiles.  One warp per 15 x 15 parameter block pair (K >= L; block O + 1 = extrinsic, 6 wide): inside a block
     // every contribution is a plain sub-matrix (prior rows, the 6 x 6 pose part of a lidar G, ImuFactor quadrants), so
     // the per-element work is five pointer offsets, their loads and the stores.
-    mu_tiles = sc.mu;
     {
       const int l = lane_id();
       const int nblk = O + 2, npair = nblk * (nblk + 1) / 2;
@@ -732,14 +767,12 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
           }
           if (eval_index == 0) { H0[(size_t)ga * n + gb] = h; H0[(size_t)gb * n + ga] = h; }
           const double hs = h * v_scale[ga] * v_scale[gb];
-          Hs[(size_t)ga * n + gb] = hs; Hs[(size_t)gb * n + ga] = hs;
-          double tv = hs;
+          Hs[(size_t)ga * n + gb] = hs;
           if (ga == gb) {
             const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
             v_diag[ga] = d; S->diagonal[ga] = d;
-            tv = hs + mu_tiles * d * d;
           }
-          tiles[tile_off(ga >> 3, gb >> 3) + swz(ga & 7, gb & 7)] = tv;
+          tiles[tile_off(ga >> 3, gb >> 3) + swz(ga & 7, gb & 7)] = hs;
         }
       }
       for (int a2 = n + warp_id(); a2 < NP; a2 += kDsWarps)   // padding rows: identity
@@ -766,34 +799,29 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     if (s_flag[1]) { if (tid == 0) sc.done = 1; return; }
     int linear_ok = 1;
     if (!s_flag[3]) {
-      // Cauchy point scale: alpha = |gradient|^2 / (sg^T H sg), sg = gradient / D
-      for (int i = tid; i < n; i += T) v_tmp[i] = v_g[i] / (v_diag[i] * v_diag[i]);
+      // Cauchy point scale: alpha = |gradient|^2 / (sg^T H sg), sg = gradient / D; H sg is kept (model cost change)
+      if (!tiles_ready) refill_tiles(tiles, Hs, n, NP);
+      for (int i = tid; i < NP; i += T) v_tmp[i] = i < n ? v_g[i] / (v_diag[i] * v_diag[i]) : 0.0;
       __syncthreads();
-      matvec_g(Hs, n, v_tmp, v_y);
+      symv_tiles(tiles, n, v_tmp, v_hsg);
       double pa = 0, pb = 0, pc = 0;
-      for (int i = tid; i < n; i += T) { pa += v_grad[i] * v_grad[i]; pb += v_tmp[i] * v_y[i]; }
+      for (int i = tid; i < n; i += T) { pa += v_grad[i] * v_grad[i]; pb += v_tmp[i] * v_hsg[i]; S->hsg[i] = v_hsg[i]; }
       block_sum3(pa, pb, pc, sred);
       double mu = sc.mu;
       if (tid == 0) { sc.alpha = pa / pb; sc.reuse = 1; }
       DS_MARK(6);
       linear_ok = 0;
+      bool pure = true;   // the tiles hold the pure H
       while (mu < max_mu) {
         // tiles of H + mu D^2 (lower triangle; identity on the padding), right-hand side g
-        if (!(tiles_ready && mu == mu_tiles)) {
-          for (int a = warp_id(); a < NP; a += kDsWarps) {
-            for (int b = lane_id(); b <= a; b += 32) {
-              double v;
-              if (a < n) { v = Hs[(size_t)a * n + b]; if (a == b) v += mu * v_diag[a] * v_diag[a]; }
-              else v = (a == b) ? 1.0 : 0.0;
-              tiles[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = v;
-            }
-          }
-        }
+        if (!pure) refill_tiles(tiles, Hs, n, NP);
+        for (int i = tid; i < n; i += T) tiles[tile_off(i >> 3, i >> 3) + swz(i & 7, i & 7)] += mu * v_diag[i] * v_diag[i];
+        pure = false;
         tiles_ready = 0;
         for (int i = tid; i < NP; i += T) v_y[i] = i < n ? v_g[i] : 0.0;
         __syncthreads();
         DS_MARK(7);
-        int ok = chol_solve_tiles(tiles, NB, v_y, &s_ok, eval_index < 24 ? &S->dbg[eval_index][12] : nullptr);
+        int ok = chol_solve_tiles(tiles, NB, v_y, &s_ok, eval_index == 1 ? S->chol_prof : nullptr);
         DS_MARK(8);
         if (ok) {
           double bad = 0;
@@ -806,7 +834,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
         linear_ok = 1;
         break;
       }
-      if (tid == 0) sc.mu = mu;
+      if (tid == 0) { sc.mu = mu; sc.mu_fact = mu; }
       __syncthreads();
     }
     int step_valid = linear_ok;
@@ -836,9 +864,14 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
       }
       block_sum3(pn, z1, z2, sred);
       if (dsn < 0) dsn = sqrt(pn);
-      matvec_g(Hs, n, v_step, v_y);
+      // H step without a matrix pass: step = c_grad sg - c_gn y with (H + mu D^2) y = g and gn = -D y, hence
+      // H step = c_grad (H sg) - c_gn (g + mu D gn)
+      const double mu_f = sc.mu_fact;
       double q1 = 0, q2 = 0, q3 = 0;
-      for (int i = tid; i < n; i += T) { q1 += v_step[i] * v_g[i]; q2 += v_step[i] * v_y[i]; }
+      for (int i = tid; i < n; i += T) {
+        const double hstep = c_grad * v_hsg[i] - c_gn * (v_g[i] + mu_f * v_diag[i] * v_gn[i]);
+        q1 += v_step[i] * v_g[i]; q2 += v_step[i] * hstep;
+      }
       block_sum3(q1, q2, q3, sred);
       const double mcc = -q1 - 0.5 * q2;
       step_valid = mcc > 0.0;
@@ -899,7 +932,7 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
 // =====================================================================================================
 static size_t step_smem_bytes(int O) {
   const int n = 15 * (O + 1) + 6, NB = (n + 7) / 8;
-  return sizeof(double) * ((size_t)(NB * (NB + 1) / 2) * 64 + 8 * (size_t)NB * 8);
+  return sizeof(double) * ((size_t)(NB * (NB + 1) / 2) * 64 + 9 * (size_t)NB * 8);
 }
 
 bool DevSolver::supports(int O_) const { return O_ >= 1 && O_ <= kDsMaxOpt && step_smem_bytes(O_) <= 225 * 1024; }
@@ -969,7 +1002,8 @@ int dev_solver_step(DevSolver &ds, const double *S_dev, double *Rt_dev, int eval
 // ---- test seam: the tiled shared-memory Cholesky alone, on an explicit host system ------------------------------------
 namespace lio {
 __global__ void __launch_bounds__(kDsThreads, 1)
-k_chol_test(const double *__restrict__ A, const double *__restrict__ b, int n, double *__restrict__ x, int *__restrict__ ok_out) {
+k_chol_test(const double *__restrict__ A, const double *__restrict__ b, int n, double *__restrict__ x, int *__restrict__ ok_out,
+            long long *__restrict__ prof) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ int s_ok;
   const int tid = threadIdx.x, T = blockDim.x;
@@ -986,14 +1020,14 @@ k_chol_test(const double *__restrict__ A, const double *__restrict__ b, int n, d
   }
   for (int i = tid; i < NP; i += T) y[i] = i < n ? b[i] : 0.0;
   __syncthreads();
-  const int ok = chol_solve_tiles(tiles, NB, y, &s_ok);
+  const int ok = chol_solve_tiles(tiles, NB, y, &s_ok, prof);
   for (int i = tid; i < n; i += T) x[i] = y[i];
   if (tid == 0) *ok_out = ok;
 }
 }  // namespace lio
 
 // Solves A x = b (A symmetric positive definite, n x n row-major, n <= 216) with the device solver's tiled Cholesky.
-extern "C" int lio_dev_cholesky_solve_host(const double *A, const double *b, int n, double *x, int *ok, int device) {
+extern "C" int lio_dev_cholesky_solve_host(const double *A, const double *b, int n, double *x, int *ok, long long *prof, int device) {
   using namespace lio;
   if (!A || !b || !x || !ok || n < 1 || n > 15 * (kDsMaxOpt + 1) + 6) return LIO_ERR_INVALID;
   if (lio_device_count() <= 0) return LIO_ERR_NO_DEVICE;
@@ -1002,19 +1036,24 @@ extern "C" int lio_dev_cholesky_solve_host(const double *A, const double *b, int
   const size_t smem = sizeof(double) * ((size_t)(NB * (NB + 1) / 2) * 64 + (size_t)NB * 8);
   double *dA = nullptr, *db = nullptr, *dx = nullptr;
   int *dok = nullptr;
+  long long *dprof = nullptr;
+  const size_t nprof = 4 * (size_t)NB + 1;
   int rc = LIO_OK;
   if (cudaMalloc(&dA, sizeof(double) * n * n) != cudaSuccess || cudaMalloc(&db, sizeof(double) * n) != cudaSuccess ||
-      cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dok, sizeof(int)) != cudaSuccess) rc = LIO_ERR_CUDA;
+      cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dok, sizeof(int)) != cudaSuccess ||
+      cudaMalloc(&dprof, sizeof(long long) * nprof) != cudaSuccess) rc = LIO_ERR_CUDA;
   if (rc == LIO_OK) {
     cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice);
     cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(k_chol_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_chol_test<<<1, kDsThreads, smem>>>(dA, db, n, dx, dok);
+    cudaMemset(dprof, 0, sizeof(long long) * nprof);
+    k_chol_test<<<1, kDsThreads, smem>>>(dA, db, n, dx, dok, prof ? dprof : nullptr);
     cudaError_t e = cudaMemcpy(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && prof) e = cudaMemcpy(prof, dprof, sizeof(long long) * nprof, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) e = cudaMemcpy(ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); rc = LIO_ERR_CUDA; }
   } else lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
-  void *fr[] = {dA, db, dx, dok};
+  void *fr[] = {dA, db, dx, dok, dprof};
   for (void *q : fr) if (q) cudaFree(q);
   return rc;
 }

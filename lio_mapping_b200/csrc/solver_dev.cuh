@@ -22,6 +22,7 @@ struct DevScalars {
   double initial_cost, cost_pim, cost_ppp, cost_marg;
   double ex0_pos[3], ex0_quat[4];  // PriorFactor target (transform_lb_ at problem build), quat x y z w
   double cost0;                    // first linearisation (parity / debugging)
+  double mu_fact;                  // the mu the current Gauss-Newton step was factored with
 };
 
 struct DevSolveState {
@@ -30,6 +31,7 @@ struct DevSolveState {
   DevScalars sc;
   // ---- everything above is read back after a solve (offsetof(scale) bytes) ----
   double scale[kDsMaxN], diagonal[kDsMaxN], gradient[kDsMaxN], gn[kDsMaxN], g[kDsMaxN];
+  double hsg[kDsMaxN];   // H (g / D^2) of the current linearisation: Cauchy-point scale and the model cost change need it
   // marginalisation prior (canonical order [pose_0,sb_0,...,pose_{O-1},sb_{O-1},ex])
   double bp[kDsMaxNp], c0;
   double x0_pose[7 * kMaxOpt], x0_sb[9 * kMaxOpt], x0_ex[7];
@@ -41,6 +43,7 @@ struct DevSolveState {
   // [12..15] inside the Cholesky (cycles): look-ahead diag_factor of panel 1, panel solve of panel 0, trailing update of
   // panel 0 (incl. barrier), back substitution
   long long dbg[24][16];
+  long long chol_prof[4 * 28 + 4];   // per-panel cycles of the Cholesky of evaluation 1 (see lio_dev_cholesky_solve_host)
 };
 
 // Scratch written by k_factors (state-dependent, lidar-independent terms at the state being evaluated) and read by
@@ -51,7 +54,8 @@ constexpr int kFGStride = 344;     // G_i = M_i^T S_gg M_i (18 x 18) | M_i^T S_g
 
 struct DevSolver {
   DevSolveState *st = nullptr;     // device
-  double *Hs = nullptr;            // n x n, Jacobi-scaled normal matrix of the current x (row-major)
+  double *Hs = nullptr;            // n x n row-major, LOWER triangle of the Jacobi-scaled normal matrix of the current x
+                                   // (only re-read when a factorisation has to be repeated with a larger mu)
   double *Hp = nullptr;            // prior np x np
   double *H0 = nullptr, *g0 = nullptr;   // first linearisation, unscaled (parity getter)
   double *F = nullptr;             // factor scratch: imu | M | prior vec | ex prior | G

@@ -215,9 +215,10 @@ class Estimator:
 
     def solver_trace(self):
         """Phase timestamps of the device solver's step kernel, (24, 16) int64 (see lio_est_solver_trace)."""
-        out = np.zeros((24, 16), np.int64)
+        out = np.zeros(24 * 16 + 4 * 28 + 4, np.int64)
         _lib.check(_lib.lib().lio_est_solver_trace(self.h, out, out.size), "lio_est_solver_trace")
-        return out
+        self.chol_profile = out[24 * 16:]
+        return out[:24 * 16].reshape(24, 16)
 
     def states(self):
         out = np.zeros((self.W + 1, 16))

@@ -50,6 +50,10 @@ if tr.any():
             if c[k] > 0:
                 ph.append("%s %.1f" % (names[k - 1], (c[k] - last) / 1965.0)); last = c[k]
         gap = (tr[ev, 0] - prev_end) / 1e3 if prev_end else 0.0
-        print("  ev %2d  kernel %.1f us  gap %.1f us | %s | chol cycles: diag %d panel %d update %d backsub %d" % (
-            ev, (tr[ev, 11] - tr[ev, 0]) / 1e3, gap, "  ".join(ph), tr[ev, 12], tr[ev, 13], tr[ev, 14], tr[ev, 15]))
+        print("  ev %2d  kernel %.1f us  gap %.1f us | %s" % (ev, (tr[ev, 11] - tr[ev, 0]) / 1e3, gap, "  ".join(ph)))
         prev_end = tr[ev, 11]
+    cp = eg.chol_profile
+    NB = (15 * (Oo + 1) + 6 + 7) // 8
+    pp = cp[:4 * NB].reshape(NB, 4)
+    print("  Cholesky of evaluation 1 inside k_step, cycles per panel [solve, own, diag, update_total]:", pp[:3].tolist(), "...", pp[-3:].tolist())
+    print("  sums", pp.sum(0).tolist(), "backsub", int(cp[4 * NB]), "total %.1f us" % ((pp[:, 0].sum() + pp[:, 3].sum() + cp[4 * NB]) / 1965.0))

@@ -13,7 +13,7 @@ def _solve(A, b):
     n = A.shape[0]
     x = np.zeros(n)
     ok = C.c_int()
-    _lib.check(_lib.lib().lio_dev_cholesky_solve_host(np.ascontiguousarray(A), np.ascontiguousarray(b), n, x, C.byref(ok), 0), "chol")
+    _lib.check(_lib.lib().lio_dev_cholesky_solve_host(np.ascontiguousarray(A), np.ascontiguousarray(b), n, x, C.byref(ok), None, 0), "chol")
     return x, ok.value
 
 
