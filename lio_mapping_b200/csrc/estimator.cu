@@ -17,6 +17,7 @@
 #include "factors_host.h"
 #include "factors_impl.h"
 #include "knn.cuh"
+#include "odom.cuh"
 #include "qr.cuh"
 #include "solver_dev.cuh"
 #include "solver_host.h"
@@ -126,17 +127,6 @@ k_deskew(float4 *__restrict__ cloud, const int *__restrict__ n_dev, TransformF e
   cloud[i] = make_float4(bx + es.px, by + es.py, bz + es.pz, p.w);
 }
 
-// ---- device LaserOdom (Estimator::CalculateLaserOdom, Estimator.cc:1242-1359) -------------------
-struct OdomState {
-  double AtA[36];
-  double AtB[6];
-  float matP[36];
-  int degenerate;
-  int done;
-  int iter;
-  unsigned counter;
-};
-
 constexpr int kOdomThreads = 256;
 
 __global__ void __launch_bounds__(kOdomThreads)
@@ -241,98 +231,66 @@ k_odom_reduce(const float4 *__restrict__ pts, const float4 *__restrict__ coef, c
   if (threadIdx.x == 0) st->counter = 0u;
 }
 
-// cyclic Jacobi eigen-decomposition of a symmetric 6x6 (float), ascending eigenvalues, vectors in columns
-__device__ void sym_eigen6(const float *Ain, float *evals, float *V) {
-  float A[36];
-  for (int i = 0; i < 36; ++i) { A[i] = Ain[i]; V[i] = (i % 7 == 0) ? 1.f : 0.f; }
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    float off = 0.f, diag = 0.f;
-    for (int i = 0; i < 6; ++i) { diag += A[i * 6 + i] * A[i * 6 + i]; for (int j = i + 1; j < 6; ++j) off += A[i * 6 + j] * A[i * 6 + j]; }
-    if (off <= FLT_EPSILON * FLT_EPSILON * diag || off == 0.f) break;
-    for (int p = 0; p < 5; ++p)
-      for (int q = p + 1; q < 6; ++q) {
-        float apq = A[p * 6 + q];
-        if (apq == 0.f) continue;
-        float theta = (A[q * 6 + q] - A[p * 6 + p]) / (2.f * apq);
-        float t = (theta >= 0.f ? 1.f : -1.f) / (fabsf(theta) + sqrtf(theta * theta + 1.f));
-        float c = 1.f / sqrtf(t * t + 1.f), s = t * c;
-        for (int k = 0; k < 6; ++k) { float a = A[k * 6 + p], b = A[k * 6 + q]; A[k * 6 + p] = c * a - s * b; A[k * 6 + q] = s * a + c * b; }
-        for (int k = 0; k < 6; ++k) { float a = A[p * 6 + k], b = A[q * 6 + k]; A[p * 6 + k] = c * a - s * b; A[q * 6 + k] = s * a + c * b; }
-        for (int k = 0; k < 6; ++k) { float a = V[k * 6 + p], b = V[k * 6 + q]; V[k * 6 + p] = c * a - s * b; V[k * 6 + q] = s * a + c * b; }
-      }
-  }
-  int idx[6] = {0, 1, 2, 3, 4, 5};
-  for (int i = 0; i < 5; ++i) for (int j = i + 1; j < 6; ++j) if (A[idx[j] * 6 + idx[j]] < A[idx[i] * 6 + idx[i]]) { int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
-  float Vc[36];
-  for (int i = 0; i < 36; ++i) Vc[i] = V[i];
-  for (int j = 0; j < 6; ++j) { evals[j] = A[idx[j] * 6 + idx[j]]; for (int k = 0; k < 6; ++k) V[k * 6 + j] = Vc[k * 6 + idx[j]]; }
-}
-
-// round < 0: CalculateLaserOdom (the first executed round carries the degeneracy analysis);  round >= 0: scan-to-map loop
-// index of PointMapping::OptimizeTransformTobeMapped, where a round with fewer than min_features matches is skipped
-// entirely (`continue`, PointMapping.cc:609-611) and the degeneracy analysis belongs to loop index 0 only.
 __global__ void k_odom_solve(OdomState *__restrict__ st, TransformF *__restrict__ tf_dev, double delta_r_abort, double delta_t_abort,
                              int round = -1, const int *__restrict__ n_dev = nullptr, int min_features = 0, int left_update = 0) {
   if (threadIdx.x != 0 || st->done) return;
-  if (n_dev && *n_dev < min_features) { st->iter += 1; return; }
-  const bool first_round = round < 0 ? (st->iter == 0) : (round == 0);
-  float A[6][6], B[6], X[6], AtA[36];
-  for (int a = 0; a < 6; ++a) { for (int b = 0; b < 6; ++b) { A[a][b] = (float)st->AtA[a * 6 + b]; AtA[a * 6 + b] = A[a][b]; } B[a] = (float)st->AtB[a]; }
-  colpiv_qr_solve<6, 6>(A, B, X);
-  if (first_round) {
-    float E[6], V[36], V2[36];
-    sym_eigen6(AtA, E, V);
-    for (int k = 0; k < 36; ++k) V2[k] = V[k];
-    int degenerate = 0;
-    for (int i = 0; i < 6; ++i) {
-      if (E[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; degenerate = 1; }
-      else break;
+  odom_solve_step(st, tf_dev, delta_r_abort, delta_t_abort, round, n_dev, min_features, left_update);
+}
+
+// One CalculateLaserOdom round after the k-NN launch, as a single CTA: reduce the round's features (float products
+// accumulated in double, fixed thread -> feature mapping and a fixed reduction tree: deterministic), solve, and zero the
+// k-NN launch state (tile status words, ticket) so that the next round's k-NN launch needs no memset.
+constexpr int kOdomRoundThreads = 512;
+__global__ void __launch_bounds__(kOdomRoundThreads)
+k_odom_round(const float4 *__restrict__ pts, const float4 *__restrict__ coef, const int *__restrict__ n_dev, TransformF *__restrict__ tf_dev,
+             OdomState *__restrict__ st, double delta_r_abort, double delta_t_abort, unsigned long long *__restrict__ knn_status, int knn_ntiles,
+             int *__restrict__ knn_ticket) {
+  __shared__ double sred[kOdomRoundThreads / 32][27];
+  if (st->done) return;   // the k-NN launch of a finished chain was a no-op: nothing to clean
+  const int n = *n_dev;
+  const TransformF tf = *tf_dev;
+  float R[9];
+  odom_rotation(tf, R);
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0.0;
+  for (int i = threadIdx.x; i < n; i += kOdomRoundThreads) {
+    float row[6], d2;
+    odom_row(tf, R, __ldg(pts + i), __ldg(coef + i), row, d2);
+    int k = 0;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+#pragma unroll
+      for (int b = a; b < 6; ++b) acc[k++] += (double)(row[a] * row[b]);
     }
-    for (int a = 0; a < 6; ++a)
-      for (int c = 0; c < 6; ++c) { float s = 0.f; for (int k = 0; k < 6; ++k) s += V2[a * 6 + k] * V[c * 6 + k]; st->matP[a * 6 + c] = s; }
-    st->degenerate = degenerate;
+#pragma unroll
+    for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(row[a] * (-d2));
   }
-  if (st->degenerate) {
-    float X2[6];
-    for (int a = 0; a < 6; ++a) { float s = 0.f; for (int c = 0; c < 6; ++c) s += st->matP[a * 6 + c] * X[c]; X2[a] = s; }
-    for (int a = 0; a < 6; ++a) X[a] = X2[a];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane_id() == 0) sred[warp_id()][k] = v;
   }
-  TransformF tf = *tf_dev;
-  // R_SO3(local_transform.rot): normalised copy of the rotation before the update
-  float n0 = sqrtf(tf.qx * tf.qx + tf.qy * tf.qy + tf.qz * tf.qz + tf.qw * tf.qw);
-  float ox = tf.qx / n0, oy = tf.qy / n0, oz = tf.qz / n0, ow = tf.qw / n0;
-  tf.px += X[3]; tf.py += X[4]; tf.pz += X[5];
-  {  // rot = rot * DeltaQ(X[0..2])  (Hamilton product, not normalised)
-    float dx = X[0] / 2.f, dy = X[1] / 2.f, dz = X[2] / 2.f, dw = 1.f;
-    float nw, nx, ny, nz;
-    if (left_update) {  // rot = DeltaQ(x) * rot  (MapBuilder.cc:984-985)
-      nw = dw * tf.qw - dx * tf.qx - dy * tf.qy - dz * tf.qz;
-      nx = dw * tf.qx + dx * tf.qw + dy * tf.qz - dz * tf.qy;
-      ny = dw * tf.qy + dy * tf.qw + dz * tf.qx - dx * tf.qz;
-      nz = dw * tf.qz + dz * tf.qw + dx * tf.qy - dy * tf.qx;
+  for (int t = threadIdx.x; t < knn_ntiles; t += kOdomRoundThreads) knn_status[t] = 0ull;
+  if (threadIdx.x == 0) *knn_ticket = 0;
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    double v = 0;
+#pragma unroll
+    for (int w = 0; w < kOdomRoundThreads / 32; ++w) v += sred[w][threadIdx.x];
+    if (threadIdx.x < 21) {
+      int k = threadIdx.x, a = 0;
+      while (k >= 6 - a) { k -= 6 - a; ++a; }
+      const int b = a + k;
+      st->AtA[a * 6 + b] = v; st->AtA[b * 6 + a] = v;
     } else {
-      nw = tf.qw * dw - tf.qx * dx - tf.qy * dy - tf.qz * dz;
-      nx = tf.qw * dx + tf.qx * dw + tf.qy * dz - tf.qz * dy;
-      ny = tf.qw * dy + tf.qy * dw + tf.qz * dx - tf.qx * dz;
-      nz = tf.qw * dz + tf.qz * dw + tf.qx * dy - tf.qy * dx;
+      st->AtB[threadIdx.x - 21] = v;
     }
-    tf.qx = nx; tf.qy = ny; tf.qz = nz; tf.qw = nw;
   }
-  if (!isfinite(tf.px)) tf.px = 0.f;
-  if (!isfinite(tf.py)) tf.py = 0.f;
-  if (!isfinite(tf.pz)) tf.pz = 0.f;
-  *tf_dev = tf;
-  // angularDistance: d = a * b.conjugate(); 2*atan2(|d.vec|, |d.w|)
-  float cw = ow * tf.qw + ox * tf.qx + oy * tf.qy + oz * tf.qz;
-  float cx = -ow * tf.qx + ox * tf.qw - oy * tf.qz + oz * tf.qy;
-  float cy = -ow * tf.qy + oy * tf.qw - oz * tf.qx + ox * tf.qz;
-  float cz = -ow * tf.qz + oz * tf.qw - ox * tf.qy + oy * tf.qx;
-  float ad = 2.f * atan2f(sqrtf(cx * cx + cy * cy + cz * cz), fabsf(cw));
-  float delta_r = (float)((double)ad * 180.0 / M_PI);
-  double tx = (double)(X[3] * 100.f), ty = (double)(X[4] * 100.f), tz = (double)(X[5] * 100.f);
-  float delta_t = (float)sqrt(tx * tx + ty * ty + tz * tz);
-  st->iter += 1;
-  if ((double)delta_r < delta_r_abort && (double)delta_t < delta_t_abort) st->done = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) odom_solve_step(st, tf_dev, delta_r_abort, delta_t_abort);
 }
 
 }  // namespace lio
@@ -903,10 +861,16 @@ static int build_local_map(lio_est *e) {
   EST_CUDA(cudaMemcpyAsync(e->d_tf, e->h_tf, sizeof(TransformF) * (W + 1), cudaMemcpyHostToDevice, st));
   k_concat<<<std::max(1, std::min(e->sm_count * 4, (e->local_cap + 255) / 256)), 256, 0, st>>>(cp, e->d_local, e->d_counts + 1, e->local_cap);
   ++e->launches;
-  int rc = e->vg.run(e->d_local, e->d_counts + 1, e->local_cap, e->cfg.surf_filter_size, e->d_map, e->local_cap, e->d_counts + 2, nullptr, st, &e->launches);
+  // Host-side bound of the concatenated cloud: the frames' own sizes are mirrored on the host (the merged pivot cloud is
+  // at most the sum of the frames merged into it), so the voxel grid, its sort and the hash build are sized for the data,
+  // not for the worst-case capacity.
+  long long bound = 64;
+  for (int i = 0; i < W; ++i) bound += e->size_surf_stack[i] > 0 ? e->size_surf_stack[i] : e->cfg.max_frame_points;
+  const int n_bound = (int)std::min<long long>(e->local_cap, bound);
+  int rc = e->vg.run(e->d_local, e->d_counts + 1, n_bound, e->cfg.surf_filter_size, e->d_map, e->local_cap, e->d_counts + 2, nullptr, st, &e->launches);
   if (rc != LIO_OK) return rc;
   const float cell = std::sqrt(e->cfg.min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
-  rc = e->hash.build(e->d_map, e->d_counts + 2, e->local_cap, cell, st, &e->launches);
+  rc = e->hash.build(e->d_map, e->d_counts + 2, n_bound, cell, st, &e->launches);
   if (rc != LIO_OK) return rc;
   e->t_build = now_s() - t0;
   const double t1 = now_s();
@@ -935,15 +899,36 @@ static int build_local_map(lio_est *e) {
   if (e->cfg.imu_factor && owns_frame(e, W)) {
     const int idx = W, slot = e->slot_of[W];
     EST_CUDA(cudaMemsetAsync(e->d_odom, 0, sizeof(OdomState), st));
-    const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
-    for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
-      rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
-                                  e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], e->cfg.keep_features ? 1 : 0,
-                                  &e->d_odom->done, e->knn, st, &e->launches);
-      if (rc != LIO_OK) return rc;
-      k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
-      k_odom_solve<<<1, 32, 0, st>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
-      e->launches += 2;
+    if (!e->cfg.keep_features) {
+      // two launches per round and no memset: the k-NN + plane fit of the newest frame, then ONE CTA that reduces the
+      // round's features to A^T A / A^T b, takes the 6 x 6 Gauss-Newton step and re-arms the k-NN launch state
+      KnnBatch b;
+      b.nframes = 1;
+      KnnFrame &f = b.f[0];
+      f.surf = e->slot_ptr[slot]; f.n_dev = e->d_slot_n + slot; f.n_bound = e->cfg.max_frame_points; f.tf = e->d_tf + idx;
+      f.out_p = e->feats[idx].pts; f.out_c = e->feats[idx].coef; f.out_src = e->feats[idx].src; f.out_count = e->feats[idx].count;
+      f.append = 0; f.tile0 = 0;
+      for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
+        rc = calculate_features_batch(e->hash, b, e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, &e->d_odom->done, e->knn, st, &e->launches,
+                                      0, it > 0);
+        if (rc != LIO_OK) return rc;
+        k_odom_round<<<1, kOdomRoundThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, 0.05, 0.05,
+                                                      e->knn.status, b.ntiles, e->knn.ticket);
+        ++e->launches;
+      }
+    } else {
+      // keep_features: every round re-evaluates ALL kept features at the current transform (Estimator.cc:978-980), so the
+      // reduction is a pass of its own
+      const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
+      for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
+        rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
+                                    e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], 1,
+                                    &e->d_odom->done, e->knn, st, &e->launches);
+        if (rc != LIO_OK) return rc;
+        k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
+        k_odom_solve<<<1, 32, 0, st>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
+        e->launches += 2;
+      }
     }
   }
   // one synchronisation: feature counts, map size, odom iterations
@@ -980,6 +965,7 @@ static int build_local_map(lio_est *e) {
   for (int k = pivot + 1; k <= W; ++k)
     if (e->h_feat_n[k] > e->feats[k].cap) { lio_set_last_error(__FILE__, __LINE__, "feature buffer overflow"); return LIO_ERR_CAPACITY; }
   if (e->h_counts[W + 1 + 1] >= e->local_cap) { lio_set_last_error(__FILE__, __LINE__, "local map capacity exceeded"); return LIO_ERR_CAPACITY; }
+  if (e->h_counts[W + 1 + 1] > n_bound) { lio_set_last_error(__FILE__, __LINE__, "internal: host bound of the local cloud below its device count"); return LIO_ERR_CAPACITY; }
   e->t_feat = now_s() - t1;
   return LIO_OK;
 }

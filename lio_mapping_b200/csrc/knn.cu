@@ -90,6 +90,7 @@ int CellHash::init(int cap) {
   cap_points = cap;
   table_size = 1024;
   while (table_size < 2 * cap) table_size <<= 1;
+  eff_size = table_size;
   int ntiles = table_size / (kHashThreads * kScanPer) + 1;
   if (cudaMalloc(&keys, sizeof(unsigned long long) * table_size) != cudaSuccess) return -1;
   if (cudaMalloc(&count, sizeof(int) * table_size) != cudaSuccess) return -1;
@@ -111,6 +112,10 @@ int CellHash::build(const float4 *map, const int *n_dev, int n_max, float cell_s
   if (n_max > cap_points) return LIO_ERR_CAPACITY;
   cell = cell_size;
   inv_cell = 1.0f / cell_size;
+  eff_size = 1024;
+  while (eff_size < 2 * n_max) eff_size <<= 1;
+  if (eff_size > table_size) eff_size = table_size;
+  const int table_size = eff_size;   // everything below works on the slots in use
   int ntiles = (table_size + kHashThreads * kScanPer - 1) / (kHashThreads * kScanPer);
   cudaMemsetAsync(keys, 0xff, sizeof(unsigned long long) * table_size, st);
   cudaMemsetAsync(count, 0, sizeof(int) * table_size, st);
@@ -462,23 +467,25 @@ void knn_plan(KnnBatch &b) {
 }
 
 int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
-                             KnnWork &work, cudaStream_t st, int *launches, int fit) {
+                             KnnWork &work, cudaStream_t st, int *launches, int fit, bool state_clean) {
   if (b.nframes <= 0) return LIO_OK;
   knn_plan(b);
   if (b.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
-  cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * b.ntiles, st);
-  cudaMemsetAsync(work.ticket, 0, sizeof(int), st);
+  if (!state_clean) {
+    cudaMemsetAsync(work.status, 0, sizeof(unsigned long long) * b.ntiles, st);
+    cudaMemsetAsync(work.ticket, 0, sizeof(int), st);
+  }
   if (fit == 2)
-    knn_plane<2><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+    knn_plane<2><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.eff_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
                                                    min_plane_dis, done_flag, work.status, work.ticket);
   else if (fit == 3)
-    knn_plane<3><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+    knn_plane<3><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.eff_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
                                                    min_plane_dis, done_flag, work.status, work.ticket);
   else if (fit == 1)
-    knn_plane<1><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+    knn_plane<1><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.eff_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
                                                    min_plane_dis, done_flag, work.status, work.ticket);
   else
-    knn_plane<0><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.table_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
+    knn_plane<0><<<b.ntiles, kKnnThreads, 0, st>>>(b, h.keys, h.count, h.start, h.eff_size - 1, h.inv_cell, h.cellpts, min_match_sq_dis,
                                                    min_plane_dis, done_flag, work.status, work.ticket);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();

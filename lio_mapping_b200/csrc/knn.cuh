@@ -9,7 +9,8 @@ struct TransformF {  // Twist<float>: rot (x,y,z,w) + pos
 };
 
 struct CellHash {
-  int table_size = 0;  // power of two
+  int table_size = 0;  // allocated slots, power of two
+  int eff_size = 0;    // slots in use by the current build: the power of two >= 2 x its point bound (<= table_size)
   int cap_points = 0;
   float cell = 1.0f, inv_cell = 1.0f;
   unsigned long long *keys = nullptr;  // [table_size], ~0 = empty
@@ -21,7 +22,8 @@ struct CellHash {
   int *ticket = nullptr;
   int init(int cap_points);
   void destroy();
-  // Builds the hash over map[0..*n_dev): cells of edge `cell` (>= search radius).
+  // Builds the hash over map[0..*n_dev): cells of edge `cell` (>= search radius).  n_max bounds *n_dev; the table, its
+  // memsets and the scan are sized from n_max, so a tight bound (the caller usually knows one) keeps the build cheap.
   int build(const float4 *map, const int *n_dev, int n_max, float cell_size, cudaStream_t st, int *launches);
 };
 
@@ -63,8 +65,9 @@ struct KnnWork {
 
 // CalculateFeatures for several frames against the same map in ONE launch (tiles are dealt frame-major so each
 // frame's accepted features are compacted in query order).
+// state_clean: work.status[0 .. ntiles) and work.ticket are already zero (a previous k_odom_round re-armed them): no memsets.
 int calculate_features_batch(const CellHash &h, KnnBatch &b, float min_match_sq_dis, float min_plane_dis, const int *done_flag,
-                             KnnWork &work, cudaStream_t st, int *launches, int fit = 0);
+                             KnnWork &work, cudaStream_t st, int *launches, int fit = 0, bool state_clean = false);
 
 // fit = 2 / 3: the scan-to-map flavours of PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:514-606 surf with the
 // sign-normalised coefficient and intensity = s |pd2|; :381-512 corner with ONE feature per line, intensity = s ld2).

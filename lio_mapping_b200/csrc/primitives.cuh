@@ -63,14 +63,17 @@ constexpr int kRsBits = 8;
 constexpr int kRsBins = 1 << kRsBits;
 
 struct RadixSortTemp {
-  int *tile_hist = nullptr;  // [ntiles_max][256]
+  unsigned *buf = nullptr;   // digit histograms [4][256] | tickets [8] | look-back status [4][ntiles_max][256]
+  size_t words = 0;
   int ntiles_max = 0;
+  int init(int max_keys);
+  void destroy();
 };
 
 // Sorts n pairs by the low `key_bits` bits (rounded up to a multiple of 8).  n is read from the
 // device (n_dev) so that data-dependent sizes need no host round trip; n_max bounds the grid.
 // Result ends in (keys_a, vals_a) if the number of passes is even, else in (keys_b, vals_b):
-// the function returns which (0 = a, 1 = b).
+// the function returns which (0 = a, 1 = b), or -1 when n_max exceeds the workspace.
 int radix_sort_pairs(unsigned *keys_a, unsigned *vals_a, unsigned *keys_b, unsigned *vals_b, const int *n_dev, int n_max,
                      int key_bits, RadixSortTemp &tmp, cudaStream_t st, int *launches);
 

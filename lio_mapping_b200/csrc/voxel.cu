@@ -129,13 +129,11 @@ vg_emit(const float4 *__restrict__ in, const int *__restrict__ n_dev, const unsi
 
 int VoxelGrid::init(int cap_) {
   cap = cap_;
-  int ntiles = (cap + kRsTile - 1) / kRsTile + 1;
   if (cudaMalloc(&keys_a, sizeof(unsigned) * cap) != cudaSuccess) return -1;
   if (cudaMalloc(&vals_a, sizeof(unsigned) * cap) != cudaSuccess) return -1;
   if (cudaMalloc(&keys_b, sizeof(unsigned) * cap) != cudaSuccess) return -1;
   if (cudaMalloc(&vals_b, sizeof(unsigned) * cap) != cudaSuccess) return -1;
-  if (cudaMalloc(&rs.tile_hist, sizeof(int) * (size_t)ntiles * kRsBins) != cudaSuccess) return -1;
-  rs.ntiles_max = ntiles;
+  if (rs.init(cap) != 0) return -1;
   nstatus = (cap + kEmitThreads - 1) / kEmitThreads + 1;
   if (cudaMalloc(&status, sizeof(unsigned long long) * nstatus) != cudaSuccess) return -1;
   if (cudaMalloc(&bbox, sizeof(unsigned) * 8) != cudaSuccess) return -1;
@@ -145,9 +143,10 @@ int VoxelGrid::init(int cap_) {
 }
 
 void VoxelGrid::destroy() {
-  void *p[] = {keys_a, vals_a, keys_b, vals_b, rs.tile_hist, status, bbox, ticket};
+  void *p[] = {keys_a, vals_a, keys_b, vals_b, status, bbox, ticket};
   for (void *q : p) if (q) cudaFree(q);
-  keys_a = vals_a = keys_b = vals_b = nullptr; rs.tile_hist = nullptr; status = nullptr; bbox = nullptr; ticket = nullptr;
+  rs.destroy();
+  keys_a = vals_a = keys_b = vals_b = nullptr; status = nullptr; bbox = nullptr; ticket = nullptr;
 }
 
 int VoxelGrid::run(const float4 *in, const int *n_dev_in, int n_max, float leaf, float4 *out, int out_cap, int *nout_dev,
@@ -163,6 +162,7 @@ int VoxelGrid::run(const float4 *in, const int *n_dev_in, int n_max, float leaf,
   vg_keys<<<nblk, 256, 0, st>>>(in, n_dev, bbox, leaf, keys_a, vals_a, overflow);
   if (launches) *launches += 3;
   int which = radix_sort_pairs(keys_a, vals_a, keys_b, vals_b, n_dev, n_max, 32, rs, st, launches);
+  if (which < 0) return LIO_ERR_CAPACITY;
   const unsigned *k = which ? keys_b : keys_a, *v = which ? vals_b : vals_a;
   int etiles = (n_max + kEmitThreads - 1) / kEmitThreads;
   cudaMemsetAsync(status, 0, sizeof(unsigned long long) * (size_t)(etiles + 1), st);
