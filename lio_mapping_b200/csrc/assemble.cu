@@ -125,42 +125,63 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   const int begin = (tile - F.tile0) * P.tile_feats;
   const int end = min(begin + P.tile_feats, F.n);
   const int nchunks = (end > begin) ? (end - begin + kAsmChunk - 1) / kAsmChunk : 0;
-  if (threadIdx.x == 0) {
+  if (nchunks == 1) {
+    // A tile of one chunk (every tile of a window solve: 512 features) gains nothing from the TMA ring - arming a barrier,
+    // the bulk copy and the phase wait only add latency - so each thread fetches its two features directly (16 B streaming
+    // loads, all four in flight) and computes from registers.
+    double u[kAsmPerThread][7], sv[kAsmPerThread];
+    float4 pf[kAsmPerThread], cf[kAsmPerThread];
 #pragma unroll
-    for (int s = 0; s < kAsmStages; ++s) mbar_init(&full_bar[s], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  auto issue = [&](int k) {  // elected thread: arm the barrier, start both bulk copies of chunk k
-    const int s = k % kAsmStages;
-    const int c0 = begin + k * kAsmChunk;
-    const unsigned bytes = (unsigned)(min(kAsmChunk, end - c0) * (int)sizeof(float4));
-    mbar_expect_tx(&full_bar[s], 2u * bytes);
-    tma_load_1d(&s_pts[s][0], F.pts + c0, bytes, &full_bar[s]);
-    tma_load_1d(&s_coef[s][0], F.coef + c0, bytes, &full_bar[s]);
-  };
-  if (threadIdx.x == 0) for (int k = 0; k < min(kAsmStages, nchunks); ++k) issue(k);
-  for (int k = 0; k < nchunks; ++k) {
-    const int s = k % kAsmStages;
-    mbar_wait(&full_bar[s], (unsigned)((k / kAsmStages) & 1));
-    {
-      double u[kAsmPerThread][7], sv[kAsmPerThread];
-#pragma unroll
-      for (int j = 0; j < kAsmPerThread; ++j) {
-        const int li = j * kAsmThreads + threadIdx.x;
-        const bool ok = begin + k * kAsmChunk + li < end;   // past the end: all-zero feature (u = 0, s = 1) contributes nothing
-        float4 pf = s_pts[s][li], cf = s_coef[s][li];
-        if (!ok) { pf = make_float4(0.f, 0.f, 0.f, 0.f); cf = pf; }
-        feature_terms(R, t, pf, cf, u[j], sv[j]);
-      }
-#pragma unroll
-      for (int j = 0; j < kAsmPerThread; ++j) accumulate_outer(acc, u[j], sv[j]);
-#pragma unroll
-      for (int j = 0; j < kAsmPerThread; ++j) accumulate_rho(acc, prod, sv[j]);
+    for (int j = 0; j < kAsmPerThread; ++j) {
+      const int idx = begin + j * kAsmThreads + threadIdx.x;
+      const bool ok = idx < end;
+      pf[j] = ok ? ld_stream(F.pts + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      cf[j] = ok ? ld_stream(F.coef + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if ((k + 1) % P.fold_chunks == 0) { acc[28] += log(prod); prod = 1.0; }
-    __syncthreads();  // stage s fully consumed
-    if (threadIdx.x == 0 && k + kAsmStages < nchunks) issue(k + kAsmStages);
+#pragma unroll
+    for (int j = 0; j < kAsmPerThread; ++j) feature_terms(R, t, pf[j], cf[j], u[j], sv[j]);
+#pragma unroll
+    for (int j = 0; j < kAsmPerThread; ++j) accumulate_outer(acc, u[j], sv[j]);
+#pragma unroll
+    for (int j = 0; j < kAsmPerThread; ++j) accumulate_rho(acc, prod, sv[j]);
+  } else {
+    if (threadIdx.x == 0) {
+  #pragma unroll
+      for (int s = 0; s < kAsmStages; ++s) mbar_init(&full_bar[s], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](int k) {  // elected thread: arm the barrier, start both bulk copies of chunk k
+      const int s = k % kAsmStages;
+      const int c0 = begin + k * kAsmChunk;
+      const unsigned bytes = (unsigned)(min(kAsmChunk, end - c0) * (int)sizeof(float4));
+      mbar_expect_tx(&full_bar[s], 2u * bytes);
+      tma_load_1d(&s_pts[s][0], F.pts + c0, bytes, &full_bar[s]);
+      tma_load_1d(&s_coef[s][0], F.coef + c0, bytes, &full_bar[s]);
+    };
+    if (threadIdx.x == 0) for (int k = 0; k < min(kAsmStages, nchunks); ++k) issue(k);
+    for (int k = 0; k < nchunks; ++k) {
+      const int s = k % kAsmStages;
+      mbar_wait(&full_bar[s], (unsigned)((k / kAsmStages) & 1));
+      {
+        double u[kAsmPerThread][7], sv[kAsmPerThread];
+  #pragma unroll
+        for (int j = 0; j < kAsmPerThread; ++j) {
+          const int li = j * kAsmThreads + threadIdx.x;
+          const bool ok = begin + k * kAsmChunk + li < end;   // past the end: all-zero feature (u = 0, s = 1) contributes nothing
+          float4 pf = s_pts[s][li], cf = s_coef[s][li];
+          if (!ok) { pf = make_float4(0.f, 0.f, 0.f, 0.f); cf = pf; }
+          feature_terms(R, t, pf, cf, u[j], sv[j]);
+        }
+  #pragma unroll
+        for (int j = 0; j < kAsmPerThread; ++j) accumulate_outer(acc, u[j], sv[j]);
+  #pragma unroll
+        for (int j = 0; j < kAsmPerThread; ++j) accumulate_rho(acc, prod, sv[j]);
+      }
+      if ((k + 1) % P.fold_chunks == 0) { acc[28] += log(prod); prod = 1.0; }
+      __syncthreads();  // stage s fully consumed
+      if (threadIdx.x == 0 && k + kAsmStages < nchunks) issue(k + kAsmStages);
+    }
   }
   acc[28] += log(prod);
   // warp reduce-scatter: each level halves the values a lane owns (30 shuffles instead of 29 x 5)
@@ -204,15 +225,17 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // last CTA: one thread per (frame, component) sums that frame's per-tile partials in tile order
-  // (independent L2 loads, so the chain pipelines); deterministic and no second launch.
-  for (int q = threadIdx.x; q < P.nframes * 29; q += kAsmThreads) {
-    const int f = q / 29, k = q - f * 29;
+  // last CTA: one warp per frame, one lane per component, sums that frame's per-tile partials in tile order (four
+  // interleaved accumulators, loads issued sixteen at a time so the L2 round trips overlap); deterministic, no second launch.
+  for (int f = warp_id(); f < P.nframes; f += kAsmThreads / 32) {
+    const int k = lane_id();
+    if (k >= 29) continue;
     if (P.npeers > 0 && !((P.owned_mask >> f) & 1u)) continue;   // a peer reduces this frame and writes the row here
     const int t0 = P.f[f].tile0;
     const int t1 = (f + 1 < P.nframes) ? P.f[f + 1].tile0 : P.ntiles;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;
     int tt = t0;
+#pragma unroll 4
     for (; tt + 3 < t1; tt += 4) {
       v0 += __ldcg(partial + (size_t)tt * kAsmStride + k);
       v1 += __ldcg(partial + (size_t)(tt + 1) * kAsmStride + k);

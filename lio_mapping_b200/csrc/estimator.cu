@@ -1353,9 +1353,28 @@ static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, 
     for (int k = 0; k < m; ++k) s += Tm(r, k) * b[k];
     b2[r] = b[m + r] - s;
   }
+  // Eigen square root of the Schur complement (MarginalizationFactor.cc:276-311).  Only the factors that touch the dropped
+  // blocks enter A, so the speed-bias blocks sb_2 .. sb_O (and pose_O's sb) have exactly-zero rows and columns in A2: its
+  // spectrum is that of the non-zero principal sub-matrix plus zeros, which the eps test drops.  The decomposition is
+  // therefore taken on the compressed matrix (75 of 156 rows for O = 10: ~9x fewer flops) and scattered back; the
+  // reference decomposes the padded matrix and arrives at the same kept eigenpairs.
+  std::vector<int> nz;
+  for (int r = 0; r < nr; ++r) {
+    bool any = b2[r] != 0.0;
+    const double *row = &A2.d[(size_t)r * nr];
+    for (int c = 0; c < nr && !any; ++c) any = row[c] != 0.0 || A2.d[(size_t)c * nr + r] != 0.0;
+    if (any) nz.push_back(r);
+  }
+  const int nc = (int)nz.size();
+  Mat Ac(nc, nc);
+  Vec bc(nc);
+  for (int r = 0; r < nc; ++r) {
+    bc[r] = b2[nz[r]];
+    for (int c = 0; c < nc; ++c) Ac(r, c) = A2(nz[r], nz[c]);
+  }
   Vec ev2;
   Mat V2;
-  sym_eigen(A2, ev2, V2, 1);  // threads > 1 measured slower on the bench host (thread start-up ~0.1 ms each)
+  if (nc > 0) sym_eigen(Ac, ev2, V2, 1);
   MargPrior np;
   np.valid = true;
   np.n = nr;
@@ -1364,14 +1383,16 @@ static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, 
   np.c0 = 0;
   // Hp = V S V^T, bp = V_kept V_kept^T b, c0 = sum (v^T b)^2 / lambda over kept eigenpairs
   std::vector<int> kept;
-  for (int k = 0; k < nr; ++k) if (ev2[k] > eps) kept.push_back(k);
-  Vec vb(nr, 0.0);
-  for (int k : kept) { double s = 0; for (int r = 0; r < nr; ++r) s += V2(r, k) * b2[r]; vb[k] = s; np.c0 += s * s / ev2[k]; }
-  weighted_gram(V2, ev2, kept, np.Hp);
-  for (int r = 0; r < nr; ++r) {
+  for (int k = 0; k < nc; ++k) if (ev2[k] > eps) kept.push_back(k);
+  Vec vb(nc, 0.0);
+  for (int k : kept) { double s = 0; for (int r = 0; r < nc; ++r) s += V2(r, k) * bc[r]; vb[k] = s; np.c0 += s * s / ev2[k]; }
+  Mat Hc(nc, nc);
+  if (nc > 0) weighted_gram(V2, ev2, kept, Hc);
+  for (int r = 0; r < nc; ++r) {
     double sb = 0;
     for (int k : kept) sb += V2(r, k) * vb[k];
-    np.bp[r] = sb;
+    np.bp[nz[r]] = sb;
+    for (int c = 0; c < nc; ++c) np.Hp(nz[r], nz[c]) = Hc(r, c);
   }
   np.x0_pose = std::move(x0_pose);
   np.x0_sb = std::move(x0_sb);

