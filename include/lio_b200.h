@@ -226,11 +226,14 @@ typedef struct lio_est_config {   /* EstimatorConfig (Estimator.h:77-108), lidar
   int odom_max_iterations;       /* PointMapping num_max_iterations_, PointMapping.h:171 */
   int max_frame_points;          /* capacity of one down-sampled frame cloud (surf_stack_ entry) */
   int max_scan_points;           /* capacity of the incoming laser_cloud_surf_last_ */
-  int device_solver;             /* 1: dogleg loop + dense Cholesky resident on the GPU (no host sync inside a solve);
-                                    0 (default, faster at n <= 171 in round 1): host controller around the fused kernel */
+  int device_solver;             /* 1 (default): ImuFactor / marginalisation prior / PriorFactor evaluation, the dense normal
+                                    equations, the tiled Cholesky and the dogleg controller all resident on the GPU (no host
+                                    sync inside a solve; opt windows up to 13); 0: host controller around the fused kernel */
   int overlap_marginalization;   /* 1 (default): the Schur-complement / eigen algebra of scan k's marginalisation runs on a
                                     worker thread beside scan k+1's device front end (started at that call's entry, joined
                                     before its solve); 0: inline at the end of scan k, the reference's order.  Same result. */
+  int solver_graph;              /* 1 (default): the device solver's launches of one solve are captured once as a CUDA graph
+                                    and replayed per scan (single-GPU contexts); 0: plain stream launches.  Same result. */
 } lio_est_config;
 
 typedef struct lio_est lio_est;

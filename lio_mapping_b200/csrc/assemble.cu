@@ -14,6 +14,7 @@
 // shuffles -> shared memory -> per-tile partials; the last CTA to finish sums the partials of each
 // frame in tile order, so the result is deterministic and needs no second launch.
 #include "assemble.cuh"
+#include <cstring>
 
 namespace lio {
 
@@ -299,17 +300,51 @@ void asm_plan(AsmParams &p, int sm_count) {
   p.ntiles = t;
 }
 
-int asm_launch(const AsmParams &p, const double *Rt_dev, AsmWork &work, cudaStream_t st, int *launches) {
-  if (p.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
-  if (p.nframes <= 0) return LIO_OK;
-  constexpr size_t kSmem = 2 * sizeof(float4) * kAsmStages * kAsmChunk;
+constexpr size_t kAsmSmem = 2 * sizeof(float4) * kAsmStages * kAsmChunk;
+
+void asm_prepare() {
   static bool attr_set[64] = {};  // per device: the opt-in above 48 KB is a per-context function attribute
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaFuncSetAttribute(asm_ppp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem);
+    cudaFuncSetAttribute(asm_ppp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsmSmem);
     attr_set[dev & 63] = true;
   }
+}
+
+bool asm_is_graph_node(cudaGraphNode_t node) {
+  cudaGraphNodeType ty;
+  if (cudaGraphNodeGetType(node, &ty) != cudaSuccess || ty != cudaGraphNodeTypeKernel) return false;
+  cudaKernelNodeParams kp;
+  if (cudaGraphKernelNodeGetParams(node, &kp) != cudaSuccess) return false;
+  return kp.func == reinterpret_cast<void *>(asm_ppp);
+}
+
+int asm_graph_update(cudaGraphExec_t exec, cudaGraphNode_t node, const AsmParams &p, const double *Rt_dev, AsmWork &work) {
+  if (p.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
+  AsmParams pc = p;
+  const double *rt = Rt_dev;
+  double *partial = work.partial, *out = work.out;
+  unsigned *counter = work.counter;
+  void *args[] = {&pc, &rt, &partial, &out, &counter};
+  cudaKernelNodeParams kp;
+  std::memset(&kp, 0, sizeof(kp));
+  kp.func = reinterpret_cast<void *>(asm_ppp);
+  kp.gridDim = dim3((unsigned)(p.ntiles > 0 ? p.ntiles : 1));
+  kp.blockDim = dim3(kAsmThreads);
+  kp.sharedMemBytes = (unsigned)kAsmSmem;
+  kp.kernelParams = args;
+  kp.extra = nullptr;
+  cudaError_t e = cudaGraphExecKernelNodeSetParams(exec, node, &kp);
+  if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); return LIO_ERR_CUDA; }
+  return LIO_OK;
+}
+
+int asm_launch(const AsmParams &p, const double *Rt_dev, AsmWork &work, cudaStream_t st, int *launches) {
+  if (p.ntiles > work.ntiles_max) return LIO_ERR_CAPACITY;
+  if (p.nframes <= 0) return LIO_OK;
+  constexpr size_t kSmem = kAsmSmem;
+  asm_prepare();
   asm_ppp<<<p.ntiles, kAsmThreads, kSmem, st>>>(p, Rt_dev, work.partial, work.out, work.counter);
   if (launches) *launches += 1;
   cudaError_t e = cudaGetLastError();

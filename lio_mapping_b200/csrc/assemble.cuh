@@ -51,5 +51,11 @@ void asm_plan(AsmParams &p, int sm_count);
 //   [0..27] upper triangle (row-major) of S = sum rho'(r^2) [g;r][g;r]^T,  [28] sum rho(r^2).
 // Rt_dev: device buffer of nframes x kAsmRtStride doubles (written by the host shell or by the device solver).
 int asm_launch(const AsmParams &p, const double *Rt_dev, AsmWork &work, cudaStream_t st, int *launches);
+// CUDA-graph support (the device solver replays one captured graph per solve): is `node` a launch of the fused kernel, and
+// re-parameterise such a node of an instantiated graph for this solve's feature counts / tile plan.
+bool asm_is_graph_node(cudaGraphNode_t node);
+int asm_graph_update(cudaGraphExec_t exec, cudaGraphNode_t node, const AsmParams &p, const double *Rt_dev, AsmWork &work);
+// One-time per-device set-up (the dynamic shared memory opt-in); asm_launch does it lazily, graph capture wants it done before.
+void asm_prepare();
 
 }  // namespace lio

@@ -487,6 +487,13 @@ struct lio_est {
   // device-resident solver
   DevSolver ds;
   bool use_dev_solver = false;
+  // the device solver's launches of one solve, captured once and replayed (single-GPU contexts)
+  cudaStream_t gstream = nullptr;
+  cudaGraph_t sgraph = nullptr;
+  cudaGraphExec_t sexec = nullptr;
+  std::vector<cudaGraphNode_t> asm_nodes;
+  cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
+  int graph_launches = 0;
   bool prior_uploaded = false;
   cudaEvent_t evp[2 * 24] = {};
   // cached lidar reduction for the current parameter values
@@ -567,6 +574,7 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
   c->max_frame_points = 1 << 16; c->max_scan_points = 1 << 18;
   c->device_solver = 1;   // GPU-resident dogleg loop (solver_dev.cu); 0 keeps the host controller (also used when O > 13)
   c->overlap_marginalization = 1;
+  c->solver_graph = 1;
 }
 
 extern "C" int lio_est_destroy(lio_est *e) {
@@ -579,6 +587,11 @@ extern "C" int lio_est_destroy(lio_est *e) {
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 48; ++k) if (e->evp[k]) cudaEventDestroy(e->evp[k]);
   e->ds.destroy();
+  if (e->sexec) cudaGraphExecDestroy(e->sexec);
+  if (e->sgraph) cudaGraphDestroy(e->sgraph);
+  if (e->gstream) cudaStreamDestroy(e->gstream);
+  if (e->ev_gin) cudaEventDestroy(e->ev_gin);
+  if (e->ev_gout) cudaEventDestroy(e->ev_gout);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->evk0) cudaEventDestroy(e->evk0);
@@ -676,6 +689,11 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   for (int k = 0; k < 48 && ok; ++k) ok = ok && cudaEventCreate(&e->evp[k]) == cudaSuccess;
   e->use_dev_solver = cfg->device_solver != 0 && e->ds.supports(O) && cfg->max_num_iterations <= 22;
   if (e->use_dev_solver) ok = ok && e->ds.init(O) == 0;
+  if (e->use_dev_solver && cfg->solver_graph) {
+    ok = ok && cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->ev_gin, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&e->ev_gout, cudaEventDisableTiming) == cudaSuccess;
+  }
   if (!ok) {
     lio_set_last_error(__FILE__, __LINE__, "lio_est_create: device allocation failed");
     lio_est_destroy(e);
@@ -1565,31 +1583,75 @@ static int solve_optimization_dev(lio_est *e) {
     for (int i = 1; i <= O; ++i) if (owns_frame(e, pivot + i)) ap.owned_mask |= 1u << (i - 1);
   }
   const int nevals = e->cfg.max_num_iterations + 1;
-  for (int ev = 0; ev < nevals; ++ev) {
-    rc = dev_solver_factors(e->ds, ev, st, &e->launches);   // ImuFactors / prior / M_i on the second stream, beside asm_ppp
-    if (rc != LIO_OK) return rc;
-    const double *result = e->asmw.out;
-    if (peers) {
-      ap.epoch = ++e->xepoch;
-      const size_t par = (size_t)(ap.epoch & 1u) * kXRowBytes;
-      for (int r = 0; r < e->npeers; ++r) {
-        ap.peer_out[r] = reinterpret_cast<double *>(e->peer_base[r] + par);
-        ap.peer_flag[r] = reinterpret_cast<unsigned *>(e->peer_base[r] + kXFlagOff);
+  auto enqueue = [&](cudaStream_t q, bool capturing) -> int {
+    // timing events inside a capture must be EXTERNAL event nodes to stay usable with cudaEventElapsedTime
+    const unsigned evflag = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+    for (int ev = 0; ev < nevals; ++ev) {
+      int r2 = dev_solver_factors(e->ds, ev, q, &e->launches);   // ImuFactors / prior / M_i on the second stream, beside asm_ppp
+      if (r2 != LIO_OK) return r2;
+      const double *result = e->asmw.out;
+      if (peers) {
+        ap.epoch = ++e->xepoch;
+        const size_t par = (size_t)(ap.epoch & 1u) * kXRowBytes;
+        for (int r = 0; r < e->npeers; ++r) {
+          ap.peer_out[r] = reinterpret_cast<double *>(e->peer_base[r] + par);
+          ap.peer_flag[r] = reinterpret_cast<unsigned *>(e->peer_base[r] + kXFlagOff);
+        }
+        result = reinterpret_cast<const double *>(e->xbuf + par);
       }
-      result = reinterpret_cast<const double *>(e->xbuf + par);
+      cudaEventRecordWithFlags(e->evp[2 * ev], q, evflag);
+      r2 = asm_launch(ap, e->d_Rt, e->asmw, q, &e->launches);
+      if (r2 != LIO_OK) return r2;
+      cudaEventRecordWithFlags(e->evp[2 * ev + 1], q, evflag);
+      if (peers) {
+        k_xwait<<<1, 32, 0, q>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
+                                 reinterpret_cast<int *>(e->xbuf + kXErrOff), &e->ds.st->sc.done);
+        ++e->launches;
+      } else if (e->world > 1 && e->allreduce) {
+        if (e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride) != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
+      }
+      r2 = dev_solver_step(e->ds, result, e->d_Rt, ev, q, &e->launches);
+      if (r2 != LIO_OK) return r2;
     }
-    cudaEventRecord(e->evp[2 * ev], st);
-    rc = asm_launch(ap, e->d_Rt, e->asmw, st, &e->launches);
-    if (rc != LIO_OK) return rc;
-    cudaEventRecord(e->evp[2 * ev + 1], st);
-    if (peers) {
-      k_xwait<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
-                                reinterpret_cast<int *>(e->xbuf + kXErrOff), &e->ds.st->sc.done);
-      ++e->launches;
-    } else if (e->world > 1 && e->allreduce) {
-      if (e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride) != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
+    return LIO_OK;
+  };
+  if (e->gstream && e->world == 1) {
+    // One graph per solve: the launch sequence (and the fork / join with the factor stream) is captured the first time and
+    // replayed afterwards; only the asm_ppp nodes are re-parameterised with this scan's feature counts and tile plan.
+    cudaStream_t gs = e->gstream;
+    EST_CUDA(cudaEventRecord(e->ev_gin, st));
+    EST_CUDA(cudaStreamWaitEvent(gs, e->ev_gin, 0));
+    if (!e->sexec) {
+      asm_prepare();
+      const int l0 = e->launches;
+      EST_CUDA(cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal));
+      rc = enqueue(gs, true);
+      cudaGraph_t g = nullptr;
+      const cudaError_t ce = cudaStreamEndCapture(gs, &g);
+      if (rc != LIO_OK) { if (g) cudaGraphDestroy(g); return rc; }
+      if (ce != cudaSuccess || !g) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); return LIO_ERR_CUDA; }
+      e->sgraph = g;
+      e->graph_launches = e->launches - l0;
+      e->launches = l0;
+      EST_CUDA(cudaGraphInstantiate(&e->sexec, g, 0));
+      size_t nn = 0;
+      EST_CUDA(cudaGraphGetNodes(g, nullptr, &nn));
+      std::vector<cudaGraphNode_t> nodes(nn);
+      EST_CUDA(cudaGraphGetNodes(g, nodes.data(), &nn));
+      e->asm_nodes.clear();
+      for (cudaGraphNode_t nd : nodes) if (asm_is_graph_node(nd)) e->asm_nodes.push_back(nd);
+      if ((int)e->asm_nodes.size() != nevals) { lio_set_last_error(__FILE__, __LINE__, "solver graph: unexpected node count"); return LIO_ERR_CUDA; }
     }
-    rc = dev_solver_step(e->ds, result, e->d_Rt, ev, st, &e->launches);
+    for (cudaGraphNode_t nd : e->asm_nodes) {
+      rc = asm_graph_update(e->sexec, nd, ap, e->d_Rt, e->asmw);
+      if (rc != LIO_OK) return rc;
+    }
+    EST_CUDA(cudaGraphLaunch(e->sexec, gs));
+    e->launches += e->graph_launches;
+    EST_CUDA(cudaEventRecord(e->ev_gout, gs));
+    EST_CUDA(cudaStreamWaitEvent(st, e->ev_gout, 0));
+  } else {
+    rc = enqueue(st, false);
     if (rc != LIO_OK) return rc;
   }
   if (peers) EST_CUDA(cudaMemcpyAsync(e->h_S + kMaxOpt * kAsmStride, e->xbuf + kXErrOff, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -1604,6 +1666,7 @@ static int solve_optimization_dev(lio_est *e) {
   for (int ev = 0; ev < std::min(nevals, S.sc.evaluations); ++ev) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
+    else (void)cudaGetLastError();   // a failed timing query must not surface as the next launch's error
   }
   for (int k = 0; k <= O; ++k) { std::memcpy(e->para_pose[k].data(), S.x + 16 * k, 7 * sizeof(double)); std::memcpy(e->para_sb[k].data(), S.x + 16 * k + 7, 9 * sizeof(double)); }
   std::memcpy(e->para_ex, S.x + 16 * (O + 1), 7 * sizeof(double));
