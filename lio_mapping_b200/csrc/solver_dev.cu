@@ -26,7 +26,7 @@
 namespace lio {
 using namespace hm;
 
-constexpr int kDsThreads = 1024;
+constexpr int kDsThreads = 512;   // 128 registers per thread: the serial diagonal-tile chain lives entirely in one lane's registers
 constexpr int kDsWarps = kDsThreads / 32;
 constexpr int kFThreads = 256;
 
@@ -196,33 +196,44 @@ __device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
 }
 
-// Warp 0: in-place Cholesky of the diagonal tile (lower triangle), then its inverse: on return the tile holds inv(L)
-// (lower) and zeros above.  Lane r < 8 keeps row r in registers; column k is scaled by rsqrt(a_kk) (broadcast by
-// shuffle) and the rank-1 update pulls l_jk from lane j.  The reciprocal diagonal 1 / l_kk = rsqrt(a_kk) stays in
-// registers, so the inverse (lane l solves L x = e_l by right-looking substitution) needs no division: fp64 division and
-// rsqrt are ~200-cycle dependent chains on this part and sit on the critical path of the whole factorisation.
+// Chain warp: in-place Cholesky of the diagonal tile (lower triangle), then its inverse: on return the tile holds inv(L)
+// (lower) and zeros above.  ONE lane factors the 8 x 8 tile entirely in registers: per column the dependent chain is
+// rsqrt -> multiply -> fused multiply-add (about 85 cycles), with no shuffle or shared-memory access on it - those go
+// through the SM's memory pipe, which the update warps keep saturated (the row-per-lane variant with two shuffles per
+// column takes 1.4k cycles alone but 2.6k beside them).  rsqrt(a_kk) = 1 / l_kk stays in registers, so the inverse needs no
+// division; lanes 0-7 each solve L x = e_l for one column by right-looking substitution.
 __device__ void diag_factor(double *T, int *s_ok) {
   const int l = lane_id();
-  double a[8], dinv[8];
+  double dinv[8];
+  if (l == 0) {
+    double a[8][8];
 #pragma unroll
-  for (int c = 0; c < 8; ++c) a[c] = (l < 8 && c <= l) ? T[swz(l & 7, c)] : 0.0;
-  bool ok = true;
+    for (int r = 0; r < 8; ++r)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const double dk = __shfl_sync(0xffffffffu, a[k], k);
-    if (!(dk > 0.0) || !isfinite(dk)) ok = false;
-    const double inv = rsqrt(dk);
-    dinv[k] = inv;
-    const double lk = a[k] * inv;     // lane i >= k: l_ik (lane k: sqrt(a_kk))
-    a[k] = lk;
+      for (int c = 0; c <= r; ++c) a[r][c] = T[swz(r, c)];
+    bool ok = true;
 #pragma unroll
-    for (int j = k + 1; j < 8; ++j) a[j] -= lk * __shfl_sync(0xffffffffu, lk, j);
+    for (int k = 0; k < 8; ++k) {
+      const double d = a[k][k];
+      if (!(d > 0.0) || !isfinite(d)) ok = false;
+      const double inv = rsqrt(d);
+      dinv[k] = inv;
+      a[k][k] = d * inv;
+#pragma unroll
+      for (int i = k + 1; i < 8; ++i) a[i][k] *= inv;
+#pragma unroll
+      for (int i = k + 1; i < 8; ++i)
+#pragma unroll
+        for (int j = k + 1; j <= i; ++j) a[i][j] -= a[i][k] * a[j][k];
+    }
+    if (!ok) *s_ok = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) T[swz(r, c)] = a[r][c];
   }
-  if (!ok && l == 0) *s_ok = 0;
-  if (l < 8) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) if (c <= l) T[swz(l, c)] = a[c];
-  }
+  for (int k = 0; k < 8; ++k) dinv[k] = __shfl_sync(0xffffffffu, dinv[k], 0);
   __syncwarp();
   double x[8], sacc[8];
 #pragma unroll
@@ -322,8 +333,8 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
       // tasks p = 1 .. ntile - 1: tile (i, j) with p = i (i + 1) / 2 + j;  p = ntile .. ntile + m - 1: rhs rows of tile-row p - ntile.
       // The warps that share the chain warp's scheduler (w % 4 == 3) take no tasks: their fp64 MMAs would queue in front of
       // every dependent fp64 operation of the chain (measured: the diagonal tile takes 4.9k cycles beside them, 2.0k alone).
-      constexpr int kWorkers = kDsWarps - kDsWarps / 4;          // 24
-      const int wi = w - (w >> 2);                               // dense index of this worker: 0 .. 23
+      constexpr int kWorkers = kDsWarps - kDsWarps / 4;          // 12
+      const int wi = w - (w >> 2);                               // dense index of this worker: 0 .. 11
       int i = 0, j = wi + 1;                                      // (i, j) of p = wi + 1, advanced incrementally (no sqrt on the hot path)
       while (j > i) { j -= i + 1; ++i; }
       for (int p = wi + 1; p < ntile + m; p += kWorkers) {
@@ -571,19 +582,35 @@ __device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const doubl
 }
 
 // y = H v with H the symmetric matrix whose lower triangle sits in the (unfactored) tiles; v, y in shared memory.
-// Four threads per row, each over a quarter of the columns (needs n <= blockDim.x / 4).
+// Two threads per row, each over every other column (needs n <= blockDim.x / 2); the tile address advances
+// incrementally along the row / down the column.
 __device__ void symv_tiles(const double *tiles, int n, const double *v, double *y) {
-  const int a = threadIdx.x >> 2, q = threadIdx.x & 3;
-  double s = 0.0;
+  const int a = threadIdx.x >> 1, q = threadIdx.x & 1;
+  double s0 = 0.0, s1 = 0.0;
   if (a < n) {
     const int ta = a >> 3, ra = a & 7;
-    for (int b = q; b < n; b += 4) {
-      const double h = (b <= a) ? tiles[tile_off(ta, b >> 3) + swz(ra, b & 7)] : tiles[tile_off(b >> 3, ta) + swz(b & 7, ra)];
-      s += h * v[b];
+    const double *row = tiles + tile_off(ta, 0);            // tiles (ta, jb), jb = 0 .. ta: contiguous, 64 doubles apart
+    for (int jb = 0; jb < ta; ++jb, row += 64) {
+#pragma unroll
+      for (int c = 0; c < 8; c += 4) {
+        s0 += row[swz(ra, c + q)] * v[8 * jb + c + q];
+        s1 += row[swz(ra, c + 2 + q)] * v[8 * jb + c + 2 + q];
+      }
+    }
+    for (int c = q; c <= ra; c += 2) s0 += row[swz(ra, c)] * v[8 * ta + c];               // diagonal tile, lower part
+    for (int r = ra + 1 + q; r < 8 && 8 * ta + r < n; r += 2) s1 += row[swz(r, ra)] * v[8 * ta + r];   // its mirror
+    const int NB = (n + 7) >> 3;
+    for (int ib = ta + 1; ib < NB; ++ib) {                                                  // column ra of the tiles below
+      const double *col = tiles + tile_off(ib, ta);
+#pragma unroll
+      for (int r = 0; r < 8; r += 4) {
+        s0 += col[swz(r + q, ra)] * v[8 * ib + r + q];
+        s1 += col[swz(r + 2 + q, ra)] * v[8 * ib + r + 2 + q];
+      }
     }
   }
+  double s = s0 + s1;
   s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
   if (a < n && q == 0) y[a] = s;
   __syncthreads();
 }
