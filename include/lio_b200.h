@@ -260,6 +260,35 @@ int lio_est_process_imu_batch(lio_est *est, int n, const double *dt, const doubl
  * feature buffers full, voxel index overflow; LIO_ERR_NUMERIC; LIO_ERR_CUDA) the context is POISONED: every later
  * lio_est_process_scan_* call returns LIO_ERR_INVALID until the context is destroyed and re-created. */
 int lio_est_process_scan_host(lio_est *est, const float *surf_last, int n);
+/* ---- The same scan, phase by phase - for callers that keep the reference's control flow (Estimator::ProcessLaserOdom ->
+ * SolveOptimization, Estimator.cc:618-774, 1648-2438) and only swap the heavy parts:
+ *
+ *   lio_est_open_scan_host / _dev   push the sweep (TransformToEnd :62-103, VoxelGrid :678-693), BuildLocalMap (:1361-1646:
+ *                                   local map, k-NN + plane fit of every window frame, CalculateLaserOdom), VectorToDouble
+ *                                   (:2440-2478).  The window stays "open" until lio_est_close_scan.
+ *   lio_est_get_parameters          the ceres parameter blocks para_pose_ (O + 1 x 7: px py pz qx qy qz qw), para_speed_bias_
+ *                                   (O + 1 x 9: v ba bg), para_ex_pose_ (7) of the open window (Estimator.h:282-284)
+ *   lio_est_assemble                what ceres::Problem would evaluate at the given blocks (NULL = the estimator's own): the
+ *                                   normal equations H = J^T J (n x n row-major), g = J^T r and the cost 1/2 sum rho, over
+ *                                   every residual block added at :1747-1904 (ImuFactors, PivotPointPlaneFactors with
+ *                                   CauchyLoss, MarginalizationFactor, PriorFactor).  n = 15 (O + 1) + 6, or 6 less while the
+ *                                   extrinsic block is constant.  No gates, no step; nothing of the estimator changes.
+ *   lio_est_solve                   ceres::Solve (:1989-1990) from the given blocks (in/out; NULL = the estimator's own) with
+ *                                   at most max_iter iterations (<= 22 with the device solver); gates :1924-1985 included.
+ *                                   summary[8] = iterations, successful steps, termination (0 no convergence / 1 convergence /
+ *                                   2 failure), initial cost, final cost, evaluations, convergence_flag, extrinsic held constant.
+ *   lio_est_close_scan              DoubleToVector (:2479-2568) from the given blocks (NULL = the estimator's own),
+ *                                   marginalisation of the oldest frame (:2040-2275), SlideWindow (:2570-2666).
+ *
+ * lio_est_process_scan_* == open + solve(max_num_iterations) + close.  Errors poison the context as described above;
+ * LIO_ERR_INVALID when the calls come out of order. */
+int lio_est_open_scan_host(lio_est *est, const float *surf_last, int n);
+int lio_est_open_scan_dev(lio_est *est, const float *surf_last_dev, const int *n_dev, int n_max);
+int lio_est_get_parameters(lio_est *est, double *pose, double *speed_bias, double *ex);
+int lio_est_assemble(lio_est *est, const double *pose, const double *speed_bias, const double *ex, double *H, double *g,
+                     double *cost, int *n);
+int lio_est_solve(lio_est *est, double *pose, double *speed_bias, double *ex, int max_iter, double summary[8]);
+int lio_est_close_scan(lio_est *est, const double *pose, const double *speed_bias, const double *ex);
 /* Optional: announce that the next sweep has arrived (call before stage A / lio_pp_process_*).  Starts the background
  * marginalisation algebra of the previous scan now instead of at the lio_est_process_scan_* entry, so it also overlaps
  * the feature extraction of the new sweep.  No effect with overlap_marginalization = 0. */
@@ -289,6 +318,9 @@ int lio_est_get_prior(lio_est *est, double *Hp, double *bp);
 int lio_est_last_normal_equations(lio_est *est, double *H, double *g, double *cost, int *n);
 /* Kernels launched by the last process_scan call. */
 int lio_est_last_launches(lio_est *est);
+/* Text of the last failed scan-level call on THIS context (lio_last_error() is per calling thread; a process that drives
+ * several estimators from one thread reads the per-handle copy). */
+const char *lio_est_last_error(lio_est *est);
 /* Diagnostic: phase timestamps of the device-resident solver's step kernel for the evaluations of the last solve:
  * out[24][16] (row = evaluation; [0] / [11] = GPU wall clock in ns at kernel entry / exit, [1..10] = SM clock at the phase
  * boundaries entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit; [12..15] = cycles

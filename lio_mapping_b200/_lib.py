@@ -117,6 +117,12 @@ def lib():
     L.lio_est_process_imu.argtypes = [vp, C.c_double, f64p, f64p, C.c_double]
     L.lio_est_process_scan_host.argtypes = [vp, f32p, ip]
     L.lio_est_begin_scan.argtypes = [vp]
+    L.lio_est_open_scan_host.argtypes = [vp, f32p, ip]
+    L.lio_est_open_scan_dev.argtypes = [vp, vp, vp, ip]
+    L.lio_est_get_parameters.argtypes = [vp, f64p, f64p, f64p]
+    L.lio_est_assemble.argtypes = [vp, vp, vp, vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(ip)]
+    L.lio_est_solve.argtypes = [vp, f64p, f64p, f64p, ip, f64p]
+    L.lio_est_close_scan.argtypes = [vp, vp, vp, vp]
     L.lio_est_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.lio_est_set_peers.argtypes = [vp, ip, C.POINTER(vp)]
     L.lio_ipc_export.argtypes = [vp, u8p]
@@ -137,6 +143,8 @@ def lib():
     L.lio_est_get_prior.argtypes = [vp, f64p, f64p]
     L.lio_est_last_normal_equations.argtypes = [vp, f64p, f64p, C.POINTER(C.c_double), C.POINTER(ip)]
     L.lio_est_last_launches.argtypes = [vp]
+    L.lio_est_last_error.argtypes = [vp]
+    L.lio_est_last_error.restype = C.c_char_p
     L.lio_est_solver_trace.argtypes = [vp, np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS"), ip]
     L.lio_est_frame_owner.argtypes = [ip, ip]
     L.lio_est_kernel_profile.argtypes = [vp, f64p, ip]

@@ -419,6 +419,8 @@ struct lio_est {
   struct ImuBlockStore { double JtJ[30 * 30], Jtr[30], cost; bool used; } imu_blocks_store[kMaxOpt];
   std::atomic<int> imu_next{0}, imu_done{0};  // shared pool of ImuFactor indices of one linearisation (caller + helper)
   double t_marg_wait = 0;
+  char err[512] = "";         // text of the last failed call on THIS handle (lio_est_last_error)
+  bool window_open = false;   // between lio_est_open_scan_* and lio_est_close_scan (stepwise API)
   bool poisoned = false;   // a scan failed half-way: the window bookkeeping is inconsistent, every later call fails fast
   int W = 0, O = 0, device = 0;
   cudaStream_t stream = 0;
@@ -1286,6 +1288,7 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
 }
 
 static void prior_join(lio_est *e);
+static int slide_window(lio_est *e);
 static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, std::vector<double> x0_sb, const double *x0_ex);
 // ---- marginalisation (MarginalizationInfo::PreMarginalize / Marginalize, MarginalizationFactor.cc:132-311)
 static int marginalize(lio_est *e) {
@@ -1441,15 +1444,25 @@ static void prior_join(lio_est *e) {
   e->t_marg_wait += now_s() - t0;
 }
 
-static int solve_optimization(lio_est *e) {
-  const int O = e->O;
+// SolveOptimization (Estimator.cc:1648-2438) in three phases, also exported one by one (lio_est_open_scan_* / lio_est_solve /
+// lio_est_close_scan) for callers that keep the reference's control flow:
+//   scan_open   BuildLocalMap, join the previous marginalisation, VectorToDouble                       (:1361-1646, :2440-2478)
+//   scan_solve  problem build + gates + ceres::Solve from the para_* blocks                            (:1747-1990)
+//   scan_close  DoubleToVector, marginalisation of the oldest frame, SlideWindow                        (:2479-2568, :2040-2275, :2570-2666)
+static int scan_open_window(lio_est *e) {
   e->turn_off = true;
   int rc = build_local_map(e);
   if (rc != LIO_OK) return rc;
   prior_join(e);  // the previous scan's marginalisation algebra ran beside the front end above
-  const double t0 = now_s();
   e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
   vector_to_double(e);
+  e->window_open = true;
+  return LIO_OK;
+}
+
+static int solve_host(lio_est *e, int max_it) {
+  const int O = e->O;
+  const double t0 = now_s();
   // residuals before optimisation + gates (:1924-1985)
   Mat H;
   Vec g;
@@ -1497,34 +1510,38 @@ static int solve_optimization(lio_est *e) {
     if (ex_free) pose_plus(&x[16 * (O + 1)], &d[15 * (O + 1)], &out[16 * (O + 1)]);
   };
   DoglegOptions opt;
-  opt.max_num_iterations = e->cfg.max_num_iterations;
+  opt.max_num_iterations = max_it;
   dogleg_solve(opt, P, &e->summary);
   if (e->summary.termination == 2 && !std::isfinite(e->summary.final_cost)) { lio_set_last_error(__FILE__, __LINE__, "solver breakdown"); return LIO_ERR_NUMERIC; }
   e->t_solve = now_s() - t0;
+  return LIO_OK;
+}
+
+static int scan_close_window(lio_est *e) {
   double_to_vector(e);
   const double t1 = now_s();
   if (e->cfg.marginalization_factor && !e->turn_off) {
     vector_to_double(e);
-    rc = marginalize(e);
+    const int rc = marginalize(e);
     if (rc != LIO_OK) return rc;
+    e->prior_uploaded = false;
   }
   e->t_marg = now_s() - t1;
-  return LIO_OK;
+  e->window_open = false;
+  return slide_window(e);
 }
 
 // ---- SolveOptimization with the device-resident dogleg loop --------------------------------------
-static int solve_optimization_dev(lio_est *e) {
+// The solve from the current para_* blocks on the device.  assemble_only: one evaluation without gates or steps, nothing of
+// the estimator's own state is touched (lio_est_assemble); the first linearisation stays readable in ds.H0 / ds.g0.
+static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
   const int O = e->O, pivot = e->W - O;
   cudaStream_t st = e->stream;
-  e->turn_off = true;
-  int rc = build_local_map(e);
-  if (rc != LIO_OK) return rc;
-  prior_join(e);  // the previous scan's marginalisation algebra ran beside the front end above
+  int rc = LIO_OK;
   const double t0 = now_s();
-  e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
-  vector_to_double(e);
   DevSolveState &S = *e->ds.h_st;
-  S.sc.O = O; S.sc.n = 15 * (O + 1) + 6; S.sc.max_it = e->cfg.max_num_iterations;
+  S.sc.O = O; S.sc.n = 15 * (O + 1) + 6; S.sc.max_it = assemble_only ? 0 : max_it;
+  S.sc.skip_gates = assemble_only ? 1 : 0; S.sc.pad_ = 0;
   S.sc.imu_factor = e->cfg.imu_factor; S.sc.point_distance_factor = e->cfg.point_distance_factor;
   S.sc.prior_factor = e->cfg.prior_factor; S.sc.marginalization_factor = e->cfg.marginalization_factor;
   S.sc.ex_free = e->ex_constant ? 0 : 1;
@@ -1582,7 +1599,7 @@ static int solve_optimization_dev(lio_est *e) {
     ap.npeers = e->npeers; ap.self = e->rank;
     for (int i = 1; i <= O; ++i) if (owns_frame(e, pivot + i)) ap.owned_mask |= 1u << (i - 1);
   }
-  const int nevals = e->cfg.max_num_iterations + 1;
+  const int nevals = (assemble_only ? 0 : max_it) + 1;
   auto enqueue = [&](cudaStream_t q, bool capturing) -> int {
     // timing events inside a capture must be EXTERNAL event nodes to stay usable with cudaEventElapsedTime
     const unsigned evflag = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
@@ -1615,7 +1632,7 @@ static int solve_optimization_dev(lio_est *e) {
     }
     return LIO_OK;
   };
-  if (e->gstream && e->world == 1) {
+  if (e->gstream && e->world == 1 && !assemble_only && max_it == e->cfg.max_num_iterations) {
     // One graph per solve: the launch sequence (and the fork / join with the factor stream) is captured the first time and
     // replayed afterwards; only the asm_ppp nodes are re-parameterised with this scan's feature counts and tile plan.
     cudaStream_t gs = e->gstream;
@@ -1668,6 +1685,8 @@ static int solve_optimization_dev(lio_est *e) {
     if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
     else (void)cudaGetLastError();   // a failed timing query must not surface as the next launch's error
   }
+  e->have_H0 = true; e->H0 = Mat(); e->cost0 = S.sc.initial_cost;
+  if (assemble_only) return LIO_OK;
   for (int k = 0; k <= O; ++k) { std::memcpy(e->para_pose[k].data(), S.x + 16 * k, 7 * sizeof(double)); std::memcpy(e->para_sb[k].data(), S.x + 16 * k + 7, 9 * sizeof(double)); }
   std::memcpy(e->para_ex, S.x + 16 * (O + 1), 7 * sizeof(double));
   e->S_valid = false;
@@ -1679,20 +1698,12 @@ static int solve_optimization_dev(lio_est *e) {
   e->convergence_flag = S.sc.convergence_flag != 0;
   e->ex_constant = S.sc.ex_free == 0;
   if (!S.sc.prior_valid) e->prior.valid = false;
-  e->have_H0 = true; e->H0 = Mat(); e->cost0 = S.sc.initial_cost;
   if (S.sc.termination == 2 && !std::isfinite(S.sc.x_cost)) { lio_set_last_error(__FILE__, __LINE__, "solver breakdown"); return LIO_ERR_NUMERIC; }
   e->t_solve = now_s() - t0;
-  double_to_vector(e);
-  const double t1 = now_s();
-  if (e->cfg.marginalization_factor && !e->turn_off) {
-    vector_to_double(e);
-    rc = marginalize(e);
-    if (rc != LIO_OK) return rc;
-    e->prior_uploaded = false;
-  }
-  e->t_marg = now_s() - t1;
   return LIO_OK;
 }
+
+static int scan_solve(lio_est *e, int max_it) { return e->use_dev_solver ? solve_dev(e, max_it, false) : solve_host(e, max_it); }
 
 static int slide_window(lio_est *e) {  // Estimator.cc:2570-2666
   const int W = e->W, O = e->O, pivot = W - O;
@@ -1720,22 +1731,23 @@ static int slide_window(lio_est *e) {  // Estimator.cc:2570-2666
   return LIO_OK;
 }
 
-static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max);
+static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max, bool open_only);
 // The pre-integration buffer, the slot rotation and size_surf_stack advance before the fallible device work.  A failure
 // after that point leaves the window half-slid, so the context is poisoned: later calls return LIO_ERR_INVALID instead of
 // running on inconsistent state (documented in lio_b200.h).
-static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max) {
+static int process_scan_common(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max, bool open_only = false) {
+  if (e->window_open) { lio_set_last_error(__FILE__, __LINE__, "a scan is open: finish it with lio_est_close_scan first"); return LIO_ERR_INVALID; }
   if (e->poisoned) {
     lio_set_last_error(__FILE__, __LINE__, "estimator context poisoned by an earlier failed scan: destroy and re-create it");
     return LIO_ERR_INVALID;
   }
   if (!e->tmp_pre) { lio_set_last_error(__FILE__, __LINE__, "process_scan before finish_init"); return LIO_ERR_INVALID; }
-  const int rc = process_scan_body(e, scan_dev, n_dev, n_max);
-  if (rc != LIO_OK) e->poisoned = true;
+  const int rc = process_scan_body(e, scan_dev, n_dev, n_max, open_only);
+  if (rc != LIO_OK) { e->poisoned = true; std::snprintf(e->err, sizeof(e->err), "%s", lio_last_error()); }
   return rc;
 }
 
-static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max) {
+static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_dev, int n_max, bool open_only) {
   const int W = e->W;
   cudaStream_t st = e->stream;
   marg_start(e);
@@ -1789,9 +1801,11 @@ static int process_scan_body(lio_est *e, const float4 *scan_dev, const int *n_de
   if (rc != LIO_OK) return rc;
   EST_CUDA(cudaMemcpyAsync(e->d_own_n + slot, e->d_slot_n + slot, sizeof(int), cudaMemcpyDeviceToDevice, st));
   push_shift(e->size_surf_stack, 0);
-  rc = e->use_dev_solver ? solve_optimization_dev(e) : solve_optimization(e);
+  rc = scan_open_window(e);
+  if (rc != LIO_OK || open_only) return rc;
+  rc = scan_solve(e, e->cfg.max_num_iterations);
   if (rc != LIO_OK) return rc;
-  rc = slide_window(e);
+  rc = scan_close_window(e);
   if (rc != LIO_OK) return rc;
   e->t_total = now_s() - t0;
   return LIO_OK;
@@ -1818,6 +1832,117 @@ extern "C" int lio_est_process_scan_dev(lio_est *e, const float *surf_last_dev, 
   if (n_max > e->cfg.max_scan_points) n_max = e->cfg.max_scan_points;   // the voxel filter clamps *n_dev to n_max on the device
   LIO_CUDA_OK(cudaSetDevice(e->device));
   return process_scan_common(e, reinterpret_cast<const float4 *>(surf_last_dev), n_dev, n_max);
+}
+
+// ---- stepwise API: the phases of ProcessLaserOdom / SolveOptimization one by one ----------------------------------------
+extern "C" int lio_est_open_scan_host(lio_est *e, const float *surf_last, int n) {
+  if (!e || n < 0 || (n > 0 && !surf_last)) return LIO_ERR_INVALID;
+  if (n > e->cfg.max_scan_points) return LIO_ERR_CAPACITY;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  if (n > 0) LIO_CUDA_OK(cudaMemcpyAsync(e->d_scan, surf_last, sizeof(float4) * n, cudaMemcpyHostToDevice, e->stream));
+  e->h_counts[e->W + 8] = n;
+  LIO_CUDA_OK(cudaMemcpyAsync(e->d_counts, e->h_counts + e->W + 8, sizeof(int), cudaMemcpyHostToDevice, e->stream));
+  return process_scan_common(e, e->d_scan, e->d_counts, n > 0 ? n : 1, true);
+}
+
+extern "C" int lio_est_open_scan_dev(lio_est *e, const float *surf_last_dev, const int *n_dev, int n_max) {
+  if (!e || !surf_last_dev || !n_dev || n_max <= 0) return LIO_ERR_INVALID;
+  if (n_max > e->cfg.max_scan_points) n_max = e->cfg.max_scan_points;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  return process_scan_common(e, reinterpret_cast<const float4 *>(surf_last_dev), n_dev, n_max, true);
+}
+
+static int need_open(lio_est *e) {
+  int rc = LIO_OK;
+  if (e->poisoned) { lio_set_last_error(__FILE__, __LINE__, "estimator context poisoned by an earlier failed scan: destroy and re-create it"); rc = LIO_ERR_INVALID; }
+  else if (!e->window_open) { lio_set_last_error(__FILE__, __LINE__, "no open scan: call lio_est_open_scan_host / _dev first"); rc = LIO_ERR_INVALID; }
+  if (rc != LIO_OK) std::snprintf(e->err, sizeof(e->err), "%s", lio_last_error());
+  return rc;
+}
+
+static void load_parameters(lio_est *e, const double *pose, const double *sb, const double *ex) {
+  for (int k = 0; k <= e->O; ++k) {
+    if (pose) std::memcpy(e->para_pose[k].data(), pose + 7 * k, 7 * sizeof(double));
+    if (sb) std::memcpy(e->para_sb[k].data(), sb + 9 * k, 9 * sizeof(double));
+  }
+  if (ex) std::memcpy(e->para_ex, ex, 7 * sizeof(double));
+  e->S_valid = false;
+}
+static void store_parameters(const lio_est *e, double *pose, double *sb, double *ex) {
+  for (int k = 0; k <= e->O; ++k) {
+    if (pose) std::memcpy(pose + 7 * k, e->para_pose[k].data(), 7 * sizeof(double));
+    if (sb) std::memcpy(sb + 9 * k, e->para_sb[k].data(), 9 * sizeof(double));
+  }
+  if (ex) std::memcpy(ex, e->para_ex, 7 * sizeof(double));
+}
+
+extern "C" int lio_est_get_parameters(lio_est *e, double *pose, double *speed_bias, double *ex) {
+  if (!e) return LIO_ERR_INVALID;
+  int rc = need_open(e);
+  if (rc != LIO_OK) return rc;
+  store_parameters(e, pose, speed_bias, ex);
+  return LIO_OK;
+}
+
+extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, double *cost, int *n);
+
+extern "C" int lio_est_assemble(lio_est *e, const double *pose, const double *speed_bias, const double *ex, double *H, double *g,
+                                double *cost, int *n) {
+  if (!e || !n) return LIO_ERR_INVALID;
+  int rc = need_open(e);
+  if (rc != LIO_OK) return rc;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  // evaluate at the caller's blocks, then put the estimator's own blocks back
+  std::vector<double> kp(7 * (e->O + 1)), ks(9 * (e->O + 1));
+  double kx[7];
+  store_parameters(e, kp.data(), ks.data(), kx);
+  load_parameters(e, pose, speed_bias, ex);
+  if (e->use_dev_solver) {
+    rc = solve_dev(e, 0, true);
+    if (rc == LIO_OK) rc = lio_est_last_normal_equations(e, H, g, cost, n);
+  } else {
+    Mat Hh;
+    Vec gg;
+    double c = 0;
+    if (!linearize(e, Hh, gg, c, nullptr, nullptr, nullptr)) { lio_set_last_error(__FILE__, __LINE__, "non-finite cost"); rc = LIO_ERR_NUMERIC; }
+    else {
+      *n = Hh.r;
+      if (H) std::memcpy(H, Hh.d.data(), sizeof(double) * Hh.r * Hh.r);
+      if (g) std::memcpy(g, gg.data(), sizeof(double) * Hh.r);
+      if (cost) *cost = c;
+    }
+  }
+  load_parameters(e, kp.data(), ks.data(), kx);
+  return rc;
+}
+
+extern "C" int lio_est_solve(lio_est *e, double *pose, double *speed_bias, double *ex, int max_iter, double summary[8]) {
+  if (!e || max_iter < 0) return LIO_ERR_INVALID;
+  int rc = need_open(e);
+  if (rc != LIO_OK) return rc;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  if (e->use_dev_solver && max_iter > 22) return LIO_ERR_INVALID;
+  load_parameters(e, pose, speed_bias, ex);
+  rc = scan_solve(e, max_iter);
+  if (rc != LIO_OK) { e->poisoned = true; std::snprintf(e->err, sizeof(e->err), "%s", lio_last_error()); return rc; }
+  store_parameters(e, pose, speed_bias, ex);
+  if (summary) {
+    summary[0] = e->summary.iterations; summary[1] = e->summary.successful_steps; summary[2] = e->summary.termination;
+    summary[3] = e->summary.initial_cost; summary[4] = e->summary.final_cost; summary[5] = e->summary.evaluations;
+    summary[6] = e->convergence_flag ? 1 : 0; summary[7] = e->ex_constant ? 1 : 0;
+  }
+  return LIO_OK;
+}
+
+extern "C" int lio_est_close_scan(lio_est *e, const double *pose, const double *speed_bias, const double *ex) {
+  if (!e) return LIO_ERR_INVALID;
+  int rc = need_open(e);
+  if (rc != LIO_OK) return rc;
+  LIO_CUDA_OK(cudaSetDevice(e->device));
+  load_parameters(e, pose, speed_bias, ex);
+  rc = scan_close_window(e);
+  if (rc != LIO_OK) { e->poisoned = true; std::snprintf(e->err, sizeof(e->err), "%s", lio_last_error()); }
+  return rc;
 }
 
 extern "C" int lio_est_frame_owner(int frame_rel, int world) {  // frame_rel in 1..O (relative to the pivot)
@@ -1993,6 +2118,7 @@ extern "C" int lio_est_last_normal_equations(lio_est *e, double *H, double *g, d
   return LIO_OK;
 }
 extern "C" int lio_est_last_launches(lio_est *e) { return e ? e->launches : 0; }
+extern "C" const char *lio_est_last_error(lio_est *e) { return e ? e->err : "null handle"; }
 
 extern "C" int lio_est_solver_trace(lio_est *e, long long *out, int cap) {
   if (!e || !out || cap < 24 * 16 + 4 * 28 + 4) return LIO_ERR_INVALID;

@@ -685,7 +685,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     if (l == 0) {
     const double c_marg = (sc.marginalization_factor && sc.prior_valid) ? F.prior[kDsMaxNp] : 0.0;
     sred[90] = c_ppp; sred[91] = c_pim; sred[92] = c_marg;
-    if (eval_index == 0) {
+    if (eval_index == 0 && !sc.skip_gates) {
       // residuals before optimisation + gates (Estimator.cc:1924-1985)
       sc.cost_ppp = c_ppp; sc.cost_pim = c_pim; sc.cost_marg = c_marg;
       int turn_off = 1;

@@ -17,6 +17,7 @@ struct DevScalars {
   int imu_factor, point_distance_factor, prior_factor, marginalization_factor;
   int ex_free, prior_valid, convergence_flag, turn_off;
   int iteration, successful, evaluations, termination, done, reuse, invalid;
+  int skip_gates, pad_;   // skip_gates: pure assembly (lio_est_assemble): the convergence gates of Estimator.cc:1924-1985 are not applied
   // trust region
   double radius, mu, alpha, x_cost, cand_cost, model_cost_change, dogleg_step_norm, x_norm;
   double initial_cost, cost_pim, cost_ppp, cost_marg;

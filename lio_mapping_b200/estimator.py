@@ -160,6 +160,41 @@ class Estimator:
         s = np.ascontiguousarray(surf_last, np.float32).reshape(-1, 4)
         _lib.check(_lib.lib().lio_est_process_scan_host(self.h, s, s.shape[0]), "lio_est_process_scan_host")
 
+    # ---- stepwise API (Estimator::ProcessLaserOdom / SolveOptimization phase by phase)
+    def open_scan(self, surf_last):
+        s = np.ascontiguousarray(surf_last, np.float32).reshape(-1, 4)
+        _lib.check(_lib.lib().lio_est_open_scan_host(self.h, s, s.shape[0]), "lio_est_open_scan_host")
+
+    def parameters(self):
+        O = self.c.opt_window_size
+        pose = np.zeros((O + 1, 7)); sb = np.zeros((O + 1, 9)); ex = np.zeros(7)
+        _lib.check(_lib.lib().lio_est_get_parameters(self.h, pose, sb, ex), "lio_est_get_parameters")
+        return pose, sb, ex
+
+    def assemble(self, pose=None, sb=None, ex=None):
+        """(H, g, cost) of the open window's ceres problem at the given parameter blocks (None: the estimator's own)."""
+        nmax = 15 * (self.c.opt_window_size + 1) + 6
+        H = np.zeros((nmax, nmax)); g = np.zeros(nmax); cost = C.c_double(); n = C.c_int()
+        keep = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (pose, sb, ex)]
+        ptr = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]
+        _lib.check(_lib.lib().lio_est_assemble(self.h, ptr[0], ptr[1], ptr[2], H, g, C.byref(cost), C.byref(n)), "lio_est_assemble")
+        n = n.value
+        return H.reshape(-1)[:n * n].reshape(n, n).copy(), g[:n].copy(), cost.value
+
+    def solve(self, pose, sb, ex, max_iter=None):
+        pose = np.ascontiguousarray(pose, np.float64).copy(); sb = np.ascontiguousarray(sb, np.float64).copy()
+        ex = np.ascontiguousarray(ex, np.float64).copy()
+        summ = np.zeros(8)
+        _lib.check(_lib.lib().lio_est_solve(self.h, pose, sb, ex, self.c.max_num_iterations if max_iter is None else int(max_iter), summ),
+                   "lio_est_solve")
+        keys = ["iterations", "successful", "termination", "initial_cost", "final_cost", "evaluations", "convergence_flag", "ex_constant"]
+        return pose, sb, ex, dict(zip(keys, summ.tolist()))
+
+    def close_scan(self, pose=None, sb=None, ex=None):
+        keep = [None if a is None else np.ascontiguousarray(a, np.float64) for a in (pose, sb, ex)]
+        ptr = [None if a is None else a.ctypes.data_as(C.c_void_p) for a in keep]
+        _lib.check(_lib.lib().lio_est_close_scan(self.h, ptr[0], ptr[1], ptr[2]), "lio_est_close_scan")
+
     def begin_scan(self):
         """Announce the next sweep (starts the previous scan's background marginalisation algebra)."""
         _lib.check(_lib.lib().lio_est_begin_scan(self.h), "lio_est_begin_scan")

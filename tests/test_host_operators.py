@@ -92,3 +92,28 @@ def test_header_is_plain_c99_and_c_client_links(tmp_path):
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
     assert run.returncode == 0, (run.stdout, run.stderr)
     assert "liblio_b200 version" in run.stdout
+
+
+def _build_shim(tmp_path):
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = tmp_path / "estimator_shim"
+    cmd = ["g++", "-std=c++14", "-Wall", "-Wextra", "-Werror", "-I" + os.path.join(root, "include"),
+           os.path.join(root, "examples", "estimator_shim.cc"), "-L" + os.path.join(root, "lio_mapping_b200"), "-llio_b200",
+           "-Wl,-rpath," + os.path.join(root, "lio_mapping_b200"), "-o", str(exe)]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    return exe
+
+
+def test_cxx_estimator_shim_compiles_and_links(tmp_path):
+    """The C++ shim that keeps the reference's Estimator member names / control flow (examples/estimator_shim.cc) compiles
+    with -Wall -Wextra -Werror against the C header and links against the library; without a device it reports that the
+    estimator cannot be created (there is no CPU fallback) and exits cleanly."""
+    import subprocess
+    exe = _build_shim(tmp_path)
+    if _lib.lib().lio_device_count() > 0:
+        return
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, (run.stdout, run.stderr)
+    assert "no CPU fallback" in run.stdout
