@@ -141,6 +141,25 @@ int lio_laser_odom_host(const float *map, int K, const float *surf, int M, float
                         float min_plane_dis, int keep_features, int max_iter, float *pts4, float *coef4, int32_t *src,
                         int *n_out, int *iters, int device);
 
+/* ---- lio::PointMapping with its rolling cube map resident in HBM (src/point_processor/PointMapping.cc) -------------------
+ * The 21 x 21 x 11 cubes of 50 m (:77-82, :121-122) hold their corner / surf clouds as HBM segments; the cube directory
+ * (pointer, count, capacity) is host state.  lio_pm_process_host is PointMapping::Process (:765-1052, imu_inited_ == false,
+ * num_stack_frames_ == 1): associate the odometry increment (:753-756), bring the last features to the map frame and back
+ * (:782-800, :1013-1016), re-centre the cube array (:809-931), select the cubes in the field of view (:944-1003), pull
+ * laser_cloud_{corner,surf}_from_map_ (:1005-1011), VoxelGrid the stacks (:1016-1022), OptimizeTransformTobeMapped
+ * (:325-753) and UpdateMapDatabase (:1112-1208: order-preserving insert + VoxelGrid of every valid cube).
+ * transform_sum7 = transform_sum_ from the odometry (qx qy qz qw px py pz); out: transform_tobe_mapped_ and
+ * info3 = {iterations, corner_from_map size, surf_from_map size}.  Cube index = i + 21 j + 441 k (PointMapping.h:150-153). */
+typedef struct lio_pm lio_pm;
+int lio_pm_create(int max_points, float corner_filter_size, float surf_filter_size, float min_match_sq_dis, float min_plane_dis,
+                  int max_iterations, int device, void *cuda_stream, lio_pm **out);
+int lio_pm_destroy(lio_pm *pm);
+int lio_pm_process_host(lio_pm *pm, const float *corner_last, int nc, const float *surf_last, int ns, const float transform_sum7[7],
+                        float transform_tobe_mapped7[7], int info3[3]);
+int lio_pm_map_centre(lio_pm *pm, int centre3[3]);                 /* laser_cloud_cen_length_ / width_ / height_ */
+int lio_pm_cube_size(lio_pm *pm, int cube_index, int which, int *n);  /* which: 0 corner, 1 surf */
+int lio_pm_cube_download(lio_pm *pm, int cube_index, int which, float *out_xyzi, int cap);
+
 /* PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:325-753): scan-to-map 6-DoF float Gauss-Newton of
  * transform_tobe_mapped_ (tf7, in/out) against explicit corner / surf maps (laser_cloud_corner_from_map_ /
  * laser_cloud_surf_from_map_; the cube-map store that selects them is outside this operator).  Per round: corner matching

@@ -92,6 +92,12 @@ def lib():
     L.lio_pcl32_to_xyzi.argtypes = [u8p, ip, f32p]
     L.lio_scan_to_map_host.argtypes = [f32p, ip, f32p, ip, f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, C.c_double, C.c_double,
                                        ip, f32p, f32p, i32p, C.POINTER(ip), C.POINTER(ip), ip]
+    L.lio_pm_create.argtypes = [ip, C.c_float, C.c_float, C.c_float, C.c_float, ip, ip, vp, C.POINTER(vp)]
+    L.lio_pm_destroy.argtypes = [vp]
+    L.lio_pm_process_host.argtypes = [vp, f32p, ip, f32p, ip, f32p, f32p, i32p]
+    L.lio_pm_map_centre.argtypes = [vp, i32p]
+    L.lio_pm_cube_size.argtypes = [vp, ip, ip, C.POINTER(ip)]
+    L.lio_pm_cube_download.argtypes = [vp, ip, ip, f32p, ip]
     L.lio_transform_to_end_host.argtypes = [f32p, ip, f32p, C.c_float, ip]
     L.lio_laser_odom_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, ip, f32p, f32p, i32p,
                                       C.POINTER(ip), C.POINTER(ip), ip]

@@ -2274,6 +2274,86 @@ extern "C" int lio_transform_to_end_host(float *cloud, int n, const float *tf7_e
   return LIO_OK;
 }
 
+// ---- PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:325-753) on device-resident clouds -----------------------
+namespace lio {
+
+int ScanToMapWork::init(int cap_corner_map, int cap_surf_map, int cap_queries) {
+  cap_feat = cap_queries > 0 ? cap_queries : 1;
+  if (hc.init(cap_corner_map > 0 ? cap_corner_map : 1) != 0 || hs.init(cap_surf_map > 0 ? cap_surf_map : 1) != 0 || w.init(cap_feat + 1) != 0) return -1;
+  auto alloc = [](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
+  if (!(alloc((void **)&fo.pts, sizeof(float4) * cap_feat) && alloc((void **)&fo.coef, sizeof(float4) * cap_feat) &&
+        alloc((void **)&fo.src, sizeof(int) * cap_feat) && alloc((void **)&d_n, sizeof(int) * 8) && alloc((void **)&d_tf, sizeof(TransformF)) &&
+        alloc((void **)&d_odom, sizeof(OdomState)) && alloc((void **)&d_partial, sizeof(double) * 32 * 1024) && alloc((void **)&d_z, sizeof(float) * 4)))
+    return -1;
+  fo.cap = cap_feat;
+  fo.count = d_n + 4;
+  return 0;
+}
+
+void ScanToMapWork::destroy() {
+  void *fr[] = {fo.pts, fo.coef, fo.src, d_n, d_tf, d_odom, d_partial, d_z};
+  for (void *q : fr) if (q) cudaFree(q);
+  hc.destroy(); hs.destroy(); w.destroy();
+  fo = FeatureOut(); d_n = nullptr; d_tf = nullptr; d_odom = nullptr; d_partial = nullptr; d_z = nullptr;
+}
+
+// Maps and stacks are device arrays; Kc / Ks are known on the host (the caller assembled the maps), the stack sizes are
+// device counts bounded by Mc_max / Ms_max.  tf7 (host, in/out).  No synchronisation before the final read-back.
+int scan_to_map_run(ScanToMapWork &W, const float4 *d_cmap, int Kc, const float4 *d_smap, int Ks, const float4 *d_corner, const int *d_nc,
+                    int Mc_max, const float4 *d_surf, const int *d_ns, int Ms_max, float *tf7, float min_match_sq_dis, float min_plane_dis,
+                    int max_iter, double delta_r_abort, double delta_t_abort, int variant, int *n_out, int *iters, int sm, cudaStream_t st) {
+  if (n_out) *n_out = 0;
+  if (iters) *iters = 0;
+  if (Kc <= 10 || Ks <= 100 || max_iter == 0) return LIO_OK;  // PointMapping.cc:327-329: nothing to optimise against
+  if (Mc_max + Ms_max > W.cap_feat) { lio_set_last_error(__FILE__, __LINE__, "scan-to-map: stacks exceed the feature capacity"); return LIO_ERR_CAPACITY; }
+  const int hn[2] = {Kc, Ks};
+  LIO_CUDA_OK(cudaMemcpyAsync(W.d_n, hn, sizeof(hn), cudaMemcpyHostToDevice, st));
+  LIO_CUDA_OK(cudaMemsetAsync(W.d_n + 4, 0, sizeof(int), st));
+  LIO_CUDA_OK(cudaMemcpyAsync(W.d_tf, tf7, sizeof(TransformF), cudaMemcpyHostToDevice, st));
+  LIO_CUDA_OK(cudaMemsetAsync(W.d_odom, 0, sizeof(OdomState), st));
+  {  // point_on_z_axis_ = T0 * (0, 0, 10), fixed for the whole optimisation (PointMapping.cc:803-806); float, no FMA
+    const float qx = tf7[0], qy = tf7[1], qz = tf7[2], qw = tf7[3], vx = 0.0f, vy = 0.0f, vz = 10.0f;
+    volatile float ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
+    volatile float ux2 = ux + ux, uy2 = uy + uy, uz2 = uz + uz;
+    volatile float cx = qy * uz2 - qz * uy2, cy = qz * ux2 - qx * uz2, cz = qx * uy2 - qy * ux2;
+    volatile float ax = ux2 * qw, ay = uy2 * qw, az = uz2 * qw;
+    volatile float rx = vx + ax, ry = vy + ay, rz = vz + az;
+    volatile float sx = rx + cx, sy = ry + cy, sz = rz + cz;
+    const float hz[4] = {sx + tf7[4], sy + tf7[5], sz + tf7[6], 0.f};
+    LIO_CUDA_OK(cudaMemcpyAsync(W.d_z, hz, sizeof(hz), cudaMemcpyHostToDevice, st));
+    LIO_CUDA_OK(cudaStreamSynchronize(st));   // hn / hz are stack variables
+  }
+  const float cell = sqrtf(min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
+  int rc = W.hc.build(d_cmap, W.d_n, Kc, cell, st, nullptr);
+  if (rc == LIO_OK) rc = W.hs.build(d_smap, W.d_n + 1, Ks, cell, st, nullptr);
+  const int cap = std::max(1, Mc_max + Ms_max);
+  const int nb = std::max(1, std::min(sm, (cap + kOdomThreads - 1) / kOdomThreads));
+  for (int it = 0; it < max_iter && rc == LIO_OK; ++it) {
+    rc = calculate_features_dev(W.hc, d_cmap, d_corner, d_nc, std::max(Mc_max, 1), W.d_tf, min_match_sq_dis, min_plane_dis, W.fo, 0,
+                                &W.d_odom->done, W.w, st, nullptr, 3, W.d_z);
+    if (rc == LIO_OK)
+      rc = calculate_features_dev(W.hs, d_smap, d_surf, d_ns, std::max(Ms_max, 1), W.d_tf, min_match_sq_dis, min_plane_dis, W.fo, 1,
+                                  &W.d_odom->done, W.w, st, nullptr, 2, W.d_z);
+    if (rc != LIO_OK) break;
+    k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(W.fo.pts, W.fo.coef, W.fo.count, W.d_tf, W.d_odom, W.d_partial, variant == 1 ? 2 : 1);
+    k_odom_solve<<<1, 32, 0, st>>>(W.d_odom, W.d_tf, delta_r_abort, delta_t_abort, it, W.fo.count, 50, variant == 1 ? 1 : 0);
+  }
+  if (rc != LIO_OK) return rc;
+  int m = 0;
+  OdomState hs2;
+  cudaError_t ce = cudaMemcpyAsync(&m, W.d_n + 4, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(&hs2, W.d_odom, sizeof(OdomState), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(tf7, W.d_tf, sizeof(TransformF), cudaMemcpyDeviceToHost, st);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); return LIO_ERR_CUDA; }
+  if (m > cap) { lio_set_last_error(__FILE__, __LINE__, "feature buffer overflow"); return LIO_ERR_CAPACITY; }
+  if (n_out) *n_out = m;
+  if (iters) *iters = hs2.iter;
+  return LIO_OK;
+}
+
+}  // namespace lio
+
 // ---- C-ABI: PointMapping::OptimizeTransformTobeMapped on explicit host arrays (parity entry) ------------------------
 extern "C" int lio_scan_to_map_host(const float *corner_map, int Kc, const float *surf_map, int Ks, const float *corner, int Mc,
                                     const float *surf, int Ms, float *tf7, float min_match_sq_dis, float min_plane_dis, int max_iter,
@@ -2286,86 +2366,40 @@ extern "C" int lio_scan_to_map_host(const float *corner_map, int Kc, const float
   if (n_out) *n_out = 0;
   if (iters) *iters = 0;
   if (Kc <= 10 || Ks <= 100 || max_iter == 0) return LIO_OK;  // PointMapping.cc:327-329: nothing to optimise against
-  const int cap = std::max(1, Mc + Ms);
-  CellHash hc, hs;
-  KnnWork w;
+  ScanToMapWork W;
   float4 *d_cmap = nullptr, *d_smap = nullptr, *d_corner = nullptr, *d_surf = nullptr;
-  FeatureOut fo;
-  int *d_n = nullptr;
-  TransformF *d_tf = nullptr;
-  OdomState *d_odom = nullptr;
-  double *d_partial = nullptr;
-  float *d_z = nullptr;
+  int *d_cnt = nullptr;
   int rc = LIO_OK, sm = 148;
   cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
-  if (hc.init(Kc) != 0 || hs.init(Ks) != 0 || w.init(std::max(Mc, Ms) + 1) != 0) rc = LIO_ERR_CUDA;
   auto alloc = [&](void **p, size_t bytes) { return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess; };
-  if (rc == LIO_OK && !(alloc((void **)&d_cmap, sizeof(float4) * Kc) && alloc((void **)&d_smap, sizeof(float4) * Ks) &&
-                        alloc((void **)&d_corner, sizeof(float4) * Mc) && alloc((void **)&d_surf, sizeof(float4) * Ms) &&
-                        alloc((void **)&fo.pts, sizeof(float4) * cap) && alloc((void **)&fo.coef, sizeof(float4) * cap) &&
-                        alloc((void **)&fo.src, sizeof(int) * cap) && alloc((void **)&d_n, sizeof(int) * 8) &&
-                        alloc((void **)&d_tf, sizeof(TransformF)) && alloc((void **)&d_odom, sizeof(OdomState)) &&
-                        alloc((void **)&d_partial, sizeof(double) * 32 * 1024) && alloc((void **)&d_z, sizeof(float) * 4)))
+  if (W.init(Kc, Ks, Mc + Ms) != 0 || !(alloc((void **)&d_cmap, sizeof(float4) * Kc) && alloc((void **)&d_smap, sizeof(float4) * Ks) &&
+                                         alloc((void **)&d_corner, sizeof(float4) * Mc) && alloc((void **)&d_surf, sizeof(float4) * Ms) &&
+                                         alloc((void **)&d_cnt, sizeof(int) * 2))) {
+    lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
     rc = LIO_ERR_CUDA;
-  if (rc != LIO_OK) lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
+  }
   if (rc == LIO_OK) {
-    const int hn[5] = {Kc, Ks, Mc, Ms, 0};
+    const int hn[2] = {Mc, Ms};
     cudaMemcpy(d_cmap, corner_map, sizeof(float4) * Kc, cudaMemcpyHostToDevice);
     cudaMemcpy(d_smap, surf_map, sizeof(float4) * Ks, cudaMemcpyHostToDevice);
     if (Mc) cudaMemcpy(d_corner, corner, sizeof(float4) * Mc, cudaMemcpyHostToDevice);
     if (Ms) cudaMemcpy(d_surf, surf, sizeof(float4) * Ms, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_n, hn, sizeof(hn), cudaMemcpyHostToDevice);
-    cudaMemcpy(d_tf, tf7, sizeof(TransformF), cudaMemcpyHostToDevice);
-    cudaMemset(d_odom, 0, sizeof(OdomState));
-    {  // point_on_z_axis_ = T0 * (0, 0, 10), fixed for the whole optimisation (PointMapping.cc:803-806); float, no FMA
-      const float qx = tf7[0], qy = tf7[1], qz = tf7[2], qw = tf7[3], vx = 0.0f, vy = 0.0f, vz = 10.0f;
-      volatile float ux = qy * vz - qz * vy, uy = qz * vx - qx * vz, uz = qx * vy - qy * vx;
-      volatile float ux2 = ux + ux, uy2 = uy + uy, uz2 = uz + uz;
-      volatile float cx = qy * uz2 - qz * uy2, cy = qz * ux2 - qx * uz2, cz = qx * uy2 - qy * ux2;
-      volatile float ax = ux2 * qw, ay = uy2 * qw, az = uz2 * qw;
-      volatile float rx = vx + ax, ry = vy + ay, rz = vz + az;
-      volatile float sx = rx + cx, sy = ry + cy, sz = rz + cz;
-      const float hz[4] = {sx + tf7[4], sy + tf7[5], sz + tf7[6], 0.f};
-      cudaMemcpy(d_z, hz, sizeof(hz), cudaMemcpyHostToDevice);
-    }
-    fo.count = d_n + 4; fo.cap = cap;
-    const float cell = sqrtf(min_match_sq_dis) * (1.0f + 1.0f / 1024.0f);
-    rc = hc.build(d_cmap, d_n, Kc, cell, 0, nullptr);
-    if (rc == LIO_OK) rc = hs.build(d_smap, d_n + 1, Ks, cell, 0, nullptr);
-    const int nb = std::max(1, std::min(sm, (cap + kOdomThreads - 1) / kOdomThreads));
-    for (int it = 0; it < max_iter && rc == LIO_OK; ++it) {
-      rc = calculate_features_dev(hc, d_cmap, d_corner, d_n + 2, std::max(Mc, 1), d_tf, min_match_sq_dis, min_plane_dis, fo, 0,
-                                  &d_odom->done, w, 0, nullptr, 3, d_z);
-      if (rc == LIO_OK)
-        rc = calculate_features_dev(hs, d_smap, d_surf, d_n + 3, std::max(Ms, 1), d_tf, min_match_sq_dis, min_plane_dis, fo, 1,
-                                    &d_odom->done, w, 0, nullptr, 2, d_z);
-      if (rc != LIO_OK) break;
-      k_odom_reduce<<<nb, kOdomThreads>>>(fo.pts, fo.coef, fo.count, d_tf, d_odom, d_partial, variant == 1 ? 2 : 1);
-      k_odom_solve<<<1, 32>>>(d_odom, d_tf, delta_r_abort, delta_t_abort, it, fo.count, 50, variant == 1 ? 1 : 0);
-    }
+    cudaMemcpy(d_cnt, hn, sizeof(hn), cudaMemcpyHostToDevice);
+    int m = 0;
+    rc = scan_to_map_run(W, d_cmap, Kc, d_smap, Ks, d_corner, d_cnt, Mc, d_surf, d_cnt + 1, Ms, tf7, min_match_sq_dis, min_plane_dis, max_iter,
+                         delta_r_abort, delta_t_abort, variant, &m, iters, sm, 0);
     if (rc == LIO_OK) {
-      int m = 0;
-      OdomState hs2;
-      cudaError_t ce = cudaMemcpy(&m, d_n + 4, sizeof(int), cudaMemcpyDeviceToHost);
-      if (ce == cudaSuccess) ce = cudaMemcpy(&hs2, d_odom, sizeof(OdomState), cudaMemcpyDeviceToHost);
-      if (ce == cudaSuccess) ce = cudaMemcpy(tf7, d_tf, sizeof(TransformF), cudaMemcpyDeviceToHost);
-      if (ce != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(ce)); rc = LIO_ERR_CUDA; }
-      else if (m > cap) { lio_set_last_error(__FILE__, __LINE__, "feature buffer overflow"); rc = LIO_ERR_CAPACITY; }
-      else {
-        if (n_out) *n_out = m;
-        if (iters) *iters = hs2.iter;
-        if (m > 0) {
-          if (pts4) cudaMemcpy(pts4, fo.pts, sizeof(float4) * m, cudaMemcpyDeviceToHost);
-          if (coef4) cudaMemcpy(coef4, fo.coef, sizeof(float4) * m, cudaMemcpyDeviceToHost);
-          if (src) cudaMemcpy(src, fo.src, sizeof(int) * m, cudaMemcpyDeviceToHost);
-        }
+      if (n_out) *n_out = m;
+      if (m > 0) {
+        if (pts4) cudaMemcpy(pts4, W.fo.pts, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+        if (coef4) cudaMemcpy(coef4, W.fo.coef, sizeof(float4) * m, cudaMemcpyDeviceToHost);
+        if (src) cudaMemcpy(src, W.fo.src, sizeof(int) * m, cudaMemcpyDeviceToHost);
       }
     }
   }
-  void *fr[] = {d_cmap, d_smap, d_corner, d_surf, fo.pts, fo.coef, fo.src, d_n, d_tf, d_odom, d_partial, d_z};
+  void *fr[] = {d_cmap, d_smap, d_corner, d_surf, d_cnt};
   for (void *q : fr) if (q) cudaFree(q);
-  hc.destroy(); hs.destroy();
-  w.destroy();
+  W.destroy();
   return rc;
 }
 

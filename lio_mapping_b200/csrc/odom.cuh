@@ -17,6 +17,25 @@ struct OdomState {
   unsigned counter;
 };
 
+// Workspace + driver of the scan-to-map optimisation on device-resident clouds (estimator.cu); shared by the host-array
+// parity entry lio_scan_to_map_host and by the cube-map context (cubemap.cu).
+struct ScanToMapWork {
+  CellHash hc, hs;
+  KnnWork w;
+  FeatureOut fo;
+  int *d_n = nullptr;          // [0] Kc [1] Ks [4] feature count
+  TransformF *d_tf = nullptr;
+  OdomState *d_odom = nullptr;
+  double *d_partial = nullptr;
+  float *d_z = nullptr;
+  int cap_feat = 0;
+  int init(int cap_corner_map, int cap_surf_map, int cap_queries);
+  void destroy();
+};
+int scan_to_map_run(ScanToMapWork &W, const float4 *d_cmap, int Kc, const float4 *d_smap, int Ks, const float4 *d_corner, const int *d_nc,
+                    int Mc_max, const float4 *d_surf, const int *d_ns, int Ms_max, float *tf7, float min_match_sq_dis, float min_plane_dis,
+                    int max_iter, double delta_r_abort, double delta_t_abort, int variant, int *n_out, int *iters, int sm, cudaStream_t st);
+
 // rot.toRotationMatrix() of the (possibly un-normalised) float quaternion
 __device__ __forceinline__ void odom_rotation(const TransformF &tf, float (&R)[9]) {
   const float tx = 2.f * tf.qx, ty = 2.f * tf.qy, tz = 2.f * tf.qz;

@@ -9,7 +9,7 @@
 //   map extraction          PointMapping.cc:1005-1011 (concatenate the valid cubes, corner and surf separately)
 //   UpdateMapDatabase       PointMapping.cc:1112-1208 (insert the down-sampled stacks, re-filter the touched valid cubes)
 //   PointMapping::Process   PointMapping.cc:765-1052  (imu_inited_ == false path, num_stack_frames_ == 1)
-// No device counterpart exists yet: this file is groundwork for it and is pinned by invariants only.
+// Device counterpart: lio_mapping_b200/csrc/cubemap.cu (lio_pm_*), compared cube by cube in tests/test_point_mapping_gpu.py.
 #include "o_api.h"
 #include <cmath>
 
@@ -194,6 +194,19 @@ void orc_pm_process(void *h, const float *corner, int nc, const float *surf, int
   tobe7[0] = m->tobe.rot.x; tobe7[1] = m->tobe.rot.y; tobe7[2] = m->tobe.rot.z; tobe7[3] = m->tobe.rot.w;
   tobe7[4] = m->tobe.pos.x; tobe7[5] = m->tobe.pos.y; tobe7[6] = m->tobe.pos.z;
   info3[0] = m->last_iters; info3[1] = (int)m->last_corner_from_map; info3[2] = (int)m->last_surf_from_map;
+}
+int orc_pm_cube_size(void *h, long long index, int which) {
+  PointMappingOracle *m = (PointMappingOracle *)h;
+  return (int)(which == 0 ? m->map.corner[(size_t)index] : m->map.surf[(size_t)index]).size();
+}
+void orc_pm_cube_copy(void *h, long long index, int which, float *out) {
+  PointMappingOracle *m = (PointMappingOracle *)h;
+  const Cloud &c = which == 0 ? m->map.corner[(size_t)index] : m->map.surf[(size_t)index];
+  std::memcpy(out, c.data(), sizeof(PointXYZI) * c.size());
+}
+void orc_pm_centre(void *h, int *out3) {
+  PointMappingOracle *m = (PointMappingOracle *)h;
+  out3[0] = m->map.cen_l; out3[1] = m->map.cen_w; out3[2] = m->map.cen_h;
 }
 void *orc_cm_create() { return new CubeMap(); }
 void orc_cm_destroy(void *h) { delete (CubeMap *)h; }

@@ -530,6 +530,9 @@ class PointMappingOracle:
         self.L.orc_pm_create.restype = C.c_void_p
         self.L.orc_pm_destroy.argtypes = [C.c_void_p]
         self.L.orc_pm_process.argtypes = [C.c_void_p, f32p, C.c_int, f32p, C.c_int, f32p, f32p, i32p]
+        self.L.orc_pm_cube_size.argtypes = [C.c_void_p, C.c_longlong, C.c_int]
+        self.L.orc_pm_cube_copy.argtypes = [C.c_void_p, C.c_longlong, C.c_int, f32p]
+        self.L.orc_pm_centre.argtypes = [C.c_void_p, i32p]
         self.h = self.L.orc_pm_create()
 
     def __del__(self):
@@ -545,3 +548,20 @@ class PointMappingOracle:
                               s if s.shape[0] else np.zeros((1, 4), np.float32), s.shape[0],
                               np.ascontiguousarray(transform_sum7, np.float32), tobe, info)
         return tobe, dict(iterations=int(info[0]), corner_from_map=int(info[1]), surf_from_map=int(info[2]))
+
+    def centre(self):
+        out = np.zeros(3, np.int32)
+        self.L.orc_pm_centre(self.h, out)
+        return tuple(out.tolist())
+
+    def cube(self, index, which):
+        w = 0 if which == "corner" else 1
+        n = self.L.orc_pm_cube_size(self.h, int(index), w)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        if n:
+            self.L.orc_pm_cube_copy(self.h, int(index), w, out)
+        return out[:n]
+
+    def cube_sizes(self, which):
+        w = 0 if which == "corner" else 1
+        return np.array([self.L.orc_pm_cube_size(self.h, i, w) for i in range(21 * 21 * 11)], np.int64)
