@@ -243,32 +243,74 @@ knn_plane(const KnnBatch B, const unsigned long long *__restrict__ hkeys, const 
   int bp[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) { bk[k] = kInfKey; bp[k] = -1; }
+  // Balanced scan.  The 27 cells of a query hold very different numbers of points, so a lane that owns whole cells idles
+  // while its neighbours work (14.9 of 32 lanes active in round 1).  Instead: each lane looks up its <= 4 cells (the four
+  // first probes in flight together), the group lays the cell ranges end to end (lane-major order; an exclusive scan of the
+  // lane totals by shuffles), and lane g takes candidates g, g + 8, ... of that list, four loads in flight at a time.
+  // The top-5 by (d^2, map index) does not depend on the order candidates are seen in.
+  __shared__ int s_cst[kQueriesPerBlock][32];    // first cellpts index of every range
+  __shared__ int s_cpre[kQueriesPerBlock][33];   // exclusive prefix of the range sizes, [32] = total
+  const int ql = threadIdx.x / kGroup;
   if (active) {
     p = __ldg(F.surf + q);
     assoc_to_map(tf, p.x, p.y, p.z, sx, sy, sz);
     const int cx = (int)floorf(sx * inv_cell), cy = (int)floorf(sy * inv_cell), cz = (int)floorf(sz * inv_cell);
-    for (int c = g; c < 27; c += kGroup) {
+    unsigned long long key4[4], got4[4];
+    unsigned s4[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = g + kGroup * k;
       const int dz = c / 9 - 1, dy = (c / 3) % 3 - 1, dx = c % 3 - 1;
-      const unsigned long long key = pack_cell(cx + dx, cy + dy, cz + dz);
-      unsigned s = hash_cell(key) & hmask;
-      int slot = -1;
-      while (true) {
-        unsigned long long k = hkeys[s];
-        if (k == key) { slot = (int)s; break; }
-        if (k == kEmptyKey) break;
-        s = (s + 1) & hmask;
+      key4[k] = pack_cell(cx + dx, cy + dy, cz + dz);
+      s4[k] = hash_cell(key4[k]) & hmask;
+      got4[k] = (c < 27) ? hkeys[s4[k]] : kEmptyKey;
+    }
+    int st4[4], cn4[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      while (got4[k] != key4[k] && got4[k] != kEmptyKey) { s4[k] = (s4[k] + 1) & hmask; got4[k] = hkeys[s4[k]]; }
+      const bool found = got4[k] == key4[k];
+      st4[k] = found ? hstart[s4[k]] : 0;
+      cn4[k] = found ? hcount[s4[k]] : 0;
+      tot += cn4[k];
+    }
+    int incl = tot;
+#pragma unroll
+    for (int o = 1; o < kGroup; o <<= 1) {
+      const int t = __shfl_up_sync(gmask, incl, o, kGroup);
+      if (g >= o) incl += t;
+    }
+    const int T = __shfl_sync(gmask, incl, kGroup - 1, kGroup);
+    int run = incl - tot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_cst[ql][4 * g + k] = st4[k]; s_cpre[ql][4 * g + k] = run; run += cn4[k]; }
+    if (g == kGroup - 1) s_cpre[ql][32] = run;
+    __syncwarp(gmask);
+    int r = 0;
+    for (int f0 = g; f0 < T; f0 += kGroup * 4) {
+      int addr[4];
+      float4 m4[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int f = f0 + kGroup * u;
+        addr[u] = -1;
+        if (f < T) {
+          while (f >= s_cpre[ql][r + 1]) ++r;
+          addr[u] = s_cst[ql][r] + (f - s_cpre[ql][r]);
+          m4[u] = __ldg(cellpts + addr[u]);
+        }
       }
-      if (slot < 0) continue;
-      const int st = hstart[slot], cnt = hcount[slot];
-      for (int j = st; j < st + cnt; ++j) {
-        const float4 m = __ldg(cellpts + j);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (addr[u] < 0) continue;
+        const float4 m = m4[u];
         // flann::L2_Simple<float>: sequential diff*diff accumulation over x, y, z
         const float d0 = sx - m.x, d1 = sy - m.y, d2 = sz - m.z;
         float d = 0.f;
         d += d0 * d0; d += d1 * d1; d += d2 * d2;
         const unsigned long long kk = pack_key(d, __float_as_int(m.w));
         if (kk < bk[4]) {
-          bk[4] = kk; bp[4] = j;
+          bk[4] = kk; bp[4] = addr[u];
 #pragma unroll
           for (int t = 4; t > 0; --t) {
             if (bk[t] < bk[t - 1]) {
