@@ -160,6 +160,36 @@ int lio_pm_map_centre(lio_pm *pm, int centre3[3]);                 /* laser_clou
 int lio_pm_cube_size(lio_pm *pm, int cube_index, int which, int *n);  /* which: 0 corner, 1 surf */
 int lio_pm_cube_download(lio_pm *pm, int cube_index, int which, float *out_xyzi, int cap);
 
+/* ---- lio::PointOdometry: scan-to-scan odometry of the pre-initialisation phase + the /compact_data pass-through ---------
+ * (src/point_processor/PointOdometry.cc; include/point_processor/PointOdometry.h).  lio_po_create mirrors the constructor
+ * PointOdometry(scan_period, io_ratio, num_max_iterations) (:66-86; defaults 0.1, 2, 25); the capacities bound the four feature
+ * clouds and the full-resolution cloud of one sweep.  lio_po_process_host is Process() + PublishResults() (:294-766) for one
+ * synchronised set of the five /laser_cloud_* topics (what HasNewData() :227-235 gates): the first sweep only becomes the
+ * "last" clouds (:302-310); afterwards, while odometry is enabled, up to num_max_iterations rounds of corner (:338-441) and
+ * surf (:443-549) matching against the last sweep + the damped 6 x 6 float Gauss-Newton (:551-664) refine transform_es_
+ * (sweep end -> start), transform_sum_ accumulates its inverse (:667-669) and the less-sharp / less-flat clouds are de-skewed
+ * to the sweep end (:673-674) before they replace the last clouds.  After lio_po_set_enable_odom(po, 0) - the /enable_odom
+ * service the estimator calls once the IMU is initialised (:126-131) - the call is the pure pass-through: clouds swapped in,
+ * transform_sum_ untouched.  Outputs (any may be NULL): transform_sum_ and transform_es_ as (qx qy qz qw px py pz),
+ * info4 = {iterations executed, published (io_ratio gate :726), frame_count_, matches of the last round}.
+ * lio_po_compact_data writes the /compact_data payload of the sweep just processed (:732-762, 3 + corner + surf + full points of
+ * 4 floats; LIO_ERR_INVALID when the io_ratio gate did not publish it) - feed it to lio_xyzi_to_pcl32 for the PointCloud2 bytes or
+ * to lio_compact_decode / lio_pm_process_host on the receiving side.  which: 0 last_corner_cloud_, 1 last_surf_cloud_,
+ * 2 full_cloud_ (de-skewed when published while odometry is enabled, :728-730). */
+typedef struct lio_po lio_po;
+int lio_po_create(float scan_period, int io_ratio, int num_max_iterations, int max_feature_points, int max_full_points, int device,
+                  void *cuda_stream, lio_po **out);
+int lio_po_destroy(lio_po *po);
+int lio_po_set_enable_odom(lio_po *po, int enable);
+int lio_po_process_host(lio_po *po, const float *corner_points_sharp, int n_sharp, const float *corner_points_less_sharp, int n_less_sharp,
+                        const float *surf_points_flat, int n_flat, const float *surf_points_less_flat, int n_less_flat,
+                        const float *full_cloud, int n_full, float transform_sum7[7], float transform_es7[7], int info4[4]);
+int lio_po_cloud_size(lio_po *po, int which, int *n);
+int lio_po_cloud_download(lio_po *po, int which, float *out_xyzi, int cap);
+int lio_po_compact_data(lio_po *po, float *out_xyzi, int cap_points, int *n_points);
+int lio_po_last_launches(lio_po *po);
+int lio_po_matches(lio_po *po, int kind, int32_t *out, int cap_queries);   /* test aid: indices of the last search, 2 (corner) / 3 (surf) per query */
+
 /* PointMapping::OptimizeTransformTobeMapped (PointMapping.cc:325-753): scan-to-map 6-DoF float Gauss-Newton of
  * transform_tobe_mapped_ (tf7, in/out) against explicit corner / surf maps (laser_cloud_corner_from_map_ /
  * laser_cloud_surf_from_map_; the cube-map store that selects them is outside this operator).  Per round: corner matching

@@ -98,6 +98,15 @@ def lib():
     L.lio_pm_map_centre.argtypes = [vp, i32p]
     L.lio_pm_cube_size.argtypes = [vp, ip, ip, C.POINTER(ip)]
     L.lio_pm_cube_download.argtypes = [vp, ip, ip, f32p, ip]
+    L.lio_po_create.argtypes = [C.c_float, ip, ip, ip, ip, ip, vp, C.POINTER(vp)]
+    L.lio_po_destroy.argtypes = [vp]
+    L.lio_po_set_enable_odom.argtypes = [vp, ip]
+    L.lio_po_process_host.argtypes = [vp] + [f32p, ip] * 5 + [f32p, f32p, i32p]
+    L.lio_po_cloud_size.argtypes = [vp, ip, C.POINTER(ip)]
+    L.lio_po_cloud_download.argtypes = [vp, ip, f32p, ip]
+    L.lio_po_compact_data.argtypes = [vp, f32p, ip, C.POINTER(ip)]
+    L.lio_po_last_launches.argtypes = [vp]
+    L.lio_po_matches.argtypes = [vp, ip, i32p, ip]
     L.lio_transform_to_end_host.argtypes = [f32p, ip, f32p, C.c_float, ip]
     L.lio_laser_odom_host.argtypes = [f32p, ip, f32p, ip, f32p, C.c_float, C.c_float, ip, ip, f32p, f32p, i32p,
                                       C.POINTER(ip), C.POINTER(ip), ip]

@@ -136,7 +136,8 @@ __device__ __forceinline__ void sym_eigen6(const float *Ain, float *evals, float
 // index of PointMapping::OptimizeTransformTobeMapped, where a round with fewer than min_features matches is skipped
 // entirely (`continue`, PointMapping.cc:609-611) and the degeneracy analysis belongs to loop index 0 only.
 __device__ inline void odom_solve_step(OdomState *__restrict__ st, TransformF *__restrict__ tf_dev, double delta_r_abort, double delta_t_abort,
-                                int round = -1, const int *__restrict__ n_dev = nullptr, int min_features = 0, int left_update = 0) {
+                                int round = -1, const int *__restrict__ n_dev = nullptr, int min_features = 0, int left_update = 0,
+                                float eig_thre = 100.f) {
   if (n_dev && *n_dev < min_features) { st->iter += 1; return; }
   const bool first_round = round < 0 ? (st->iter == 0) : (round == 0);
   float A[6][6], B[6], X[6], AtA[36];
@@ -148,7 +149,7 @@ __device__ inline void odom_solve_step(OdomState *__restrict__ st, TransformF *_
     for (int k = 0; k < 36; ++k) V2[k] = V[k];
     int degenerate = 0;
     for (int i = 0; i < 6; ++i) {
-      if (E[i] < 100.f) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; degenerate = 1; }
+      if (E[i] < eig_thre) { for (int j = 0; j < 6; ++j) V2[i * 6 + j] = 0.f; degenerate = 1; }
       else break;
     }
     for (int a = 0; a < 6; ++a)

@@ -565,3 +565,51 @@ class PointMappingOracle:
     def cube_sizes(self, which):
         w = 0 if which == "corner" else 1
         return np.array([self.L.orc_pm_cube_size(self.h, i, w) for i in range(21 * 21 * 11)], np.int64)
+
+
+class PointOdometryOracle:
+    """lio::PointOdometry (src/point_processor/PointOdometry.cc:294-766): scan-to-scan odometry + the /compact_data payload (oracle only)."""
+
+    def __init__(self, scan_period=0.1, io_ratio=2, num_max_iterations=25):
+        self.L = lib()
+        self.L.orc_po_create.restype = C.c_void_p
+        self.L.orc_po_create.argtypes = [C.c_float, C.c_int, C.c_int]
+        self.L.orc_po_destroy.argtypes = [C.c_void_p]
+        self.L.orc_po_set_enable_odom.argtypes = [C.c_void_p, C.c_int]
+        self.L.orc_po_process.argtypes = [C.c_void_p] + [f32p, C.c_int] * 5 + [f32p, f32p, i32p]
+        self.L.orc_po_cloud_size.argtypes = [C.c_void_p, C.c_int]
+        self.L.orc_po_cloud_copy.argtypes = [C.c_void_p, C.c_int, f32p]
+        self.L.orc_po_matches.argtypes = [C.c_void_p, C.c_int, i32p]
+        self.h = self.L.orc_po_create(scan_period, io_ratio, num_max_iterations)
+
+    def __del__(self):
+        try:
+            self.L.orc_po_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_enable_odom(self, enable):
+        self.L.orc_po_set_enable_odom(self.h, int(bool(enable)))
+
+    def process(self, sharp, less_sharp, flat, less_flat, full):
+        args = []
+        for c in (sharp, less_sharp, flat, less_flat, full):
+            c = np.ascontiguousarray(c, np.float32).reshape(-1, 4)
+            args += [c if c.shape[0] else np.zeros((1, 4), np.float32), c.shape[0]]
+        ts = np.zeros(7, np.float32); te = np.zeros(7, np.float32); info = np.zeros(4, np.int32)
+        self.L.orc_po_process(self.h, *args, ts, te, info)
+        return ts, te, dict(iterations=int(info[0]), published=int(info[1]), frame_count=int(info[2]), matches=int(info[3]))
+
+    def cloud(self, which):
+        w = {"last_corner": 0, "last_surf": 1, "full": 2, "compact": 3}[which]
+        n = self.L.orc_po_cloud_size(self.h, w)
+        out = np.zeros((max(n, 1), 4), np.float32)
+        if n:
+            self.L.orc_po_cloud_copy(self.h, w, out)
+        return out[:n]
+
+    def matches(self, kind, n):
+        k = 0 if kind == "corner" else 1
+        out = np.zeros((max(n, 1), 2 + k), np.int32)
+        m = self.L.orc_po_matches(self.h, k, out)
+        return out[:m]
