@@ -401,3 +401,59 @@ extern "C" int orc_toy_solve(int n, int m, const double *A, const double *B, con
   summary[3] = sum.initial_cost; summary[4] = sum.final_cost; summary[5] = sum.num_linearizations;
   return 0;
 }
+
+// ---- toy marginalisation through the oracle's MarginalizationInfo (pins the Schur / eigen square-root algebra against numpy) ----
+// nb Euclidean parameter blocks of size bs in one contiguous array x; factor k: r = Wi x_i + Wj x_j - y (nr rows) between blocks
+// (bi[k], bj[k]); every factor that touches block 0 is added with block 0 in its drop set (all others are left out, like the
+// reference's marginalisation step which only takes the factors of the dropped states).  Outputs: m, n, the order of the kept
+// blocks, linearized_jacobians (n x n), linearized_residuals (n), and the assembled A (pos x pos), b (pos).
+namespace {
+struct ToyLinear2 : orc::CostFunction {
+  const double *wi, *wj, *y;
+  int nr, bs;
+  ToyLinear2(const double *wi_, const double *wj_, const double *y_, int nr_, int bs_) : wi(wi_), wj(wj_), y(y_), nr(nr_), bs(bs_) {
+    num_residuals = nr_;
+    block_sizes = {bs_, bs_};
+  }
+  bool Evaluate(double const *const *parameters, double *residuals, double **jacobians) const override {
+    for (int r = 0; r < nr; ++r) {
+      double s = -y[r];
+      for (int c = 0; c < bs; ++c) s += wi[r * bs + c] * parameters[0][c] + wj[r * bs + c] * parameters[1][c];
+      residuals[r] = s;
+    }
+    if (jacobians) {
+      if (jacobians[0]) std::memcpy(jacobians[0], wi, sizeof(double) * nr * bs);
+      if (jacobians[1]) std::memcpy(jacobians[1], wj, sizeof(double) * nr * bs);
+    }
+    return true;
+  }
+};
+}  // namespace
+
+extern "C" int orc_toy_marginalize(int nb, int bs, int nf, int nr, const int *bi, const int *bj, const double *W /*nf x 2 x nr x bs*/,
+                                   const double *y /*nf x nr*/, double *x /*nb x bs*/, int use_cauchy, int *mn /*2*/, int *kept_blocks /*nb*/,
+                                   double *lin_J, double *lin_r, double *A_out, double *b_out) {
+  orc::MarginalizationInfo mi;
+  orc::CauchyLoss loss(1.0);
+  for (int k = 0; k < nf; ++k) {
+    if (bi[k] != 0 && bj[k] != 0) continue;
+    std::vector<int> drop;
+    if (bi[k] == 0) drop.push_back(0);
+    if (bj[k] == 0) drop.push_back(1);
+    auto cost = std::make_shared<ToyLinear2>(W + (size_t)k * 2 * nr * bs, W + (size_t)k * 2 * nr * bs + nr * bs, y + (size_t)k * nr, nr, bs);
+    mi.AddResidualBlockInfo(std::make_shared<orc::ResidualBlockInfo>(cost, use_cauchy ? &loss : nullptr,
+                                                                     std::vector<double *>{x + (size_t)bi[k] * bs, x + (size_t)bj[k] * bs}, drop));
+  }
+  mi.PreMarginalize();
+  mi.Marginalize();
+  mn[0] = mi.m; mn[1] = mi.n;
+  int nk = 0;
+  for (const auto &it : mi.parameter_block_idx)
+    if (it.second >= mi.m) kept_blocks[(it.second - mi.m) / bs] = (int)((reinterpret_cast<double *>(it.first) - x) / bs), ++nk;
+  std::memcpy(lin_J, mi.linearized_jacobians.d.data(), sizeof(double) * mi.n * mi.n);
+  std::memcpy(lin_r, mi.linearized_residuals.data(), sizeof(double) * mi.n);
+  const int pos = mi.m + mi.n;
+  std::memcpy(A_out, mi.A_dbg.d.data(), sizeof(double) * pos * pos);
+  std::memcpy(b_out, mi.b_dbg.data(), sizeof(double) * pos);
+  return nk;
+}

@@ -613,3 +613,20 @@ class PointOdometryOracle:
         out = np.zeros((max(n, 1), 2 + k), np.int32)
         m = self.L.orc_po_matches(self.h, k, out)
         return out[:m]
+
+
+def toy_marginalize(nb, bs, bi, bj, W, y, x, use_cauchy=False):
+    """Linear two-block factors over nb Euclidean blocks; block 0 is marginalised through the oracle's MarginalizationInfo.
+    Returns dict(m, n, kept (block ids in prior order), J, r, A, b)."""
+    L = lib()
+    W = np.ascontiguousarray(W, np.float64); y = np.ascontiguousarray(y, np.float64); x = np.ascontiguousarray(x, np.float64).copy()
+    bi = np.ascontiguousarray(bi, np.int32); bj = np.ascontiguousarray(bj, np.int32)
+    nf, _, nr, _ = W.shape
+    pos = nb * bs
+    mn = np.zeros(2, np.int32); kept = np.full(nb, -1, np.int32)
+    J = np.zeros(pos * pos); r = np.zeros(pos); A = np.zeros(pos * pos); b = np.zeros(pos)
+    L.orc_toy_marginalize.argtypes = [C.c_int] * 4 + [i32p, i32p, f64p, f64p, f64p, C.c_int, i32p, i32p, f64p, f64p, f64p, f64p]
+    nk = L.orc_toy_marginalize(nb, bs, nf, nr, bi, bj, W, y, x, int(use_cauchy), mn, kept, J, r, A, b)
+    m, n = int(mn[0]), int(mn[1])
+    return dict(m=m, n=n, kept=kept[:nk].copy(), J=J[:n * n].reshape(n, n).copy(), r=r[:n].copy(),
+                A=A[:(m + n) ** 2].reshape(m + n, m + n).copy(), b=b[:m + n].copy())
