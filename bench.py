@@ -309,6 +309,17 @@ def main():
     if profiling:
         torch.cuda.cudart().cudaProfilerStop()
     clocks = sampler.stop() if rank == 0 else None
+    if os.environ.get("LIO_BENCH_TRACE") == "1" and rank == 0:
+        # device-side timeline of the last solve (%globaltimer stamps, ns): per evaluation the gap kernels between two k_step launches
+        tr = est.solver_trace()
+        n_ev = int((tr[:12, 0] > 0).sum())
+        print("[trace] eval: k_step in..out | gap to next k_step | asm in/out, k_factors in/out, k_hpart out (all relative to the previous k_step's exit)", file=sys.stderr)
+        for e_ in range(1, n_ev):
+            t0 = int(tr[e_ - 1, 11])
+            rel = lambda v: (int(v) - t0) / 1000.0 if v else float("nan")
+            print("[trace] ev %2d  k_step %6.1f us | gap %5.1f | asm %5.1f..%5.1f  k_factors %5.1f..%5.1f  k_hpart ..%5.1f | phases(cyc) %s" % (
+                e_, (int(tr[e_, 11]) - int(tr[e_, 0])) / 1000.0, rel(tr[e_, 0]), rel(tr[13, e_]), rel(tr[14, e_]), rel(tr[e_, 12]), rel(tr[e_, 13]),
+                rel(tr[e_, 14]), np.diff(tr[e_, 1:11]).tolist()), file=sys.stderr)
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(np.sum(ms))
     if world > 1:

@@ -109,6 +109,12 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
   __shared__ double sred[kAsmThreads / 32][29];
   __shared__ bool is_last;
   if (P.skip_flag && *P.skip_flag) return;
+  if (P.stamps && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long i = P.stamps[1]++;
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (i < 16) P.stamps[16 + i] = t;
+  }
   const int tile = blockIdx.x;
   int fi = 0;
 #pragma unroll 1
@@ -260,7 +266,15 @@ asm_ppp(const AsmParams P, const double *__restrict__ Rt, double *__restrict__ p
       asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl), "r"(P.epoch) : "memory");
     }
   }
-  if (threadIdx.x == 0) *counter = 0u;
+  if (threadIdx.x == 0) {
+    *counter = 0u;
+    if (P.stamps) {
+      const long long i = P.stamps[0]++;
+      long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (i < 16) P.stamps[32 + i] = t;
+    }
+  }
 }
 
 int AsmWork::init(int max_features_total) {

@@ -24,6 +24,7 @@ struct AsmParams {
   int ntiles;
   int fold_chunks; // stages between folds of the per-thread (1 + r^2) product into the cost (set by asm_plan)
   const int *skip_flag;  // optional device flag: non-zero -> the launch returns at once (device solver already terminated)
+  long long *stamps;     // optional trace area (3 x 16 words: counters, %globaltimer at the first CTA's entry, at the tail's exit)
   // Fused exchange over peer memory (multi-GPU, frames sharded by rank): the last CTA writes the S blocks of the frames
   // this rank owns into its own AND every peer's result buffer (P2P stores over NVLink), then publishes `epoch` in each
   // peer's flag slot with system-scope release.  npeers == 0: single-GPU behaviour (all rows written locally).

@@ -87,15 +87,27 @@ __device__ void pose_dx_dev(const double *x, const double *x0, double *out) {  /
 
 // =====================================================================================================
 // k_factors: one CTA per ImuFactor (+ the frame terms M of the lidar block of frame b + 1), one CTA for the prior
+__device__ __forceinline__ long long gtime_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// %globaltimer stamps of the kernels between two k_step launches (dbg[eval][12..15], zeroed with the state upload):
+// [12] first k_factors CTA in, [13] last k_factors CTA out, [14] last k_hpart CTA out, [15] asm_ppp tail out (assemble.cu)
+__device__ __forceinline__ void stamp_max(DevSolveState *S, int ev, int slot) {
+  if (ev < 24) atomicMax(reinterpret_cast<unsigned long long *>(&S->dbg[ev][slot]), (unsigned long long)gtime_ns());
+}
+
 __global__ void __launch_bounds__(kFThreads, 2)   // <= 128 registers: a CTA must fit beside an asm_ppp CTA on the same SM
-k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, int eval_index) {
+k_factors(DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, int eval_index) {
   __shared__ double sA[15 * 31];   // raw [J | r]
   __shared__ double sJ[15 * 31];   // whitened
-  __shared__ double sdx[kDsMaxNp], sHdx[kDsMaxNp];
+  __shared__ double sdx[kDsMaxNp];
   __shared__ double sred[kFThreads / 32];
   if (S->sc.done) return;
   const int tid = threadIdx.x, O = S->sc.O, b = blockIdx.x;
   const double *xe = eval_index == 0 ? S->x : S->cand;
+  if (b == 0 && tid == 0 && eval_index < 24) S->dbg[eval_index][12] = gtime_ns();
   if (b < O) {
     const bool imu = S->sc.imu_factor && S->pim_valid[b];
     for (int p = tid; p < 15 * 31; p += kFThreads) sA[p] = 0.0;
@@ -137,24 +149,33 @@ k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FP
       }
       out[p] = s;
     }
+    __syncthreads();
+    if (tid == 0) stamp_max(S, eval_index, 13);
     return;
   }
-  // ---- prior CTA
+  // ---- extrinsic PriorFactor CTA (applied only while the extrinsic is free)
   const int np = 15 * O + 6;
-  if (tid == kFThreads - 1 && S->sc.prior_factor) {   // extrinsic PriorFactor (applied only while the extrinsic is free)
-    double r[6], J[6][6];
-    prior_factor_impl(V3(S->sc.ex0_pos), Q(S->sc.ex0_quat[3], S->sc.ex0_quat[0], S->sc.ex0_quat[1], S->sc.ex0_quat[2]), xe + 16 * (O + 1), r, J);
-    double c = 0;
-    for (int a = 0; a < 6; ++a) {
-      double gs = 0;
-      for (int k = 0; k < 6; ++k) gs += J[k][a] * r[k];
-      F.ex[36 + a] = gs;
-      for (int bb = 0; bb < 6; ++bb) { double s = 0; for (int k = 0; k < 6; ++k) s += J[k][a] * J[k][bb]; F.ex[a * 6 + bb] = s; }
-      c += 0.5 * r[a] * r[a];
+  if (b == O) {
+    if (tid == 0 && S->sc.prior_factor) {
+      double r[6], J[6][6];
+      prior_factor_impl(V3(S->sc.ex0_pos), Q(S->sc.ex0_quat[3], S->sc.ex0_quat[0], S->sc.ex0_quat[1], S->sc.ex0_quat[2]), xe + 16 * (O + 1), r, J);
+      double c = 0;
+      for (int a = 0; a < 6; ++a) {
+        double gs = 0;
+        for (int k = 0; k < 6; ++k) gs += J[k][a] * r[k];
+        F.ex[36 + a] = gs;
+        for (int bb = 0; bb < 6; ++bb) { double s = 0; for (int k = 0; k < 6; ++k) s += J[k][a] * J[k][bb]; F.ex[a * 6 + bb] = s; }
+        c += 0.5 * r[a] * r[a];
+      }
+      F.ex[42] = c;
+      stamp_max(S, eval_index, 13);
     }
-    F.ex[42] = c;
+    return;
   }
+  // ---- marginalisation prior, slice p of kFPriorCtas: rows r = p, p + kFPriorCtas, ... of Hp dx + bp and their share of the cost
+  // (a single CTA needed 11 us for the 156 x 156 matrix-vector product: 20 dependent row passes per warp)
   if (!(S->sc.marginalization_factor && S->sc.prior_valid)) return;
+  const int p = b - O - 1;
   if (tid < O) {
     pose_dx_dev(x_pose(xe, tid), S->x0_pose + 7 * tid, sdx + 15 * tid);
     for (int a = 0; a < 9; ++a) sdx[15 * tid + 6 + a] = x_sb(xe, tid)[a] - S->x0_sb[9 * tid + a];
@@ -162,28 +183,27 @@ k_factors(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FP
     pose_dx_dev(xe + 16 * (O + 1), S->x0_ex, sdx + 15 * O);
   }
   __syncthreads();
+  double part = 0;
   {
     const int w = warp_id(), l = lane_id();
-    for (int r = w; r < np; r += kFThreads / 32) {
+    for (int r = p + kFPriorCtas * w; r < np; r += kFPriorCtas * (kFThreads / 32)) {
       double s = 0;
       for (int c = l; c < np; c += 32) s += Hp[(size_t)r * np + c] * sdx[c];
       s = warp_sum(s);
-      if (l == 0) sHdx[r] = s;
+      if (l == 0) {
+        const double bpr = S->bp[r];
+        F.prior[r] = s + bpr;
+        part += 2.0 * bpr * sdx[r] + sdx[r] * s;
+      }
     }
   }
-  __syncthreads();
-  double part = 0;
-  for (int a = tid; a < np; a += kFThreads) {
-    part += 2.0 * S->bp[a] * sdx[a] + sdx[a] * sHdx[a];
-    F.prior[a] = sHdx[a] + S->bp[a];
-  }
-  part = warp_sum(part);
   if (lane_id() == 0) sred[warp_id()] = part;
   __syncthreads();
   if (tid == 0) {
     double tot = 0;
     for (int w = 0; w < kFThreads / 32; ++w) tot += sred[w];
-    F.prior[kDsMaxNp] = 0.5 * (S->c0 + tot);
+    F.prior[kDsMaxNp + 1 + p] = tot;   // k_hpart adds the slices in order: F.prior[kDsMaxNp] = (c0 + sum) / 2
+    stamp_max(S, eval_index, 13);
   }
 }
 
@@ -495,7 +515,7 @@ __device__ __forceinline__ double g_elem(const GatherCtx &c, int a) {
 // hflags records the structure (free extrinsic, prior in use) the gather assumed: the convergence gates of evaluation 0
 // can still change it, in which case k_step falls back to its own full gather.
 __global__ void __launch_bounds__(256)
-k_hpart(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, double *__restrict__ Hpart) {
+k_hpart(DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, double *__restrict__ Hpart, int eval_index) {
   __shared__ double s_zero;
   __shared__ int s_pimv[kMaxOpt];
   if (S->sc.done) return;
@@ -516,7 +536,14 @@ k_hpart(const DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtr
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     gpart[n] = gc.ex_free ? 1.0 : 0.0;
     gpart[n + 1] = gc.prior ? 1.0 : 0.0;
+    if (gc.prior) {   // cost of the marginalisation prior from the slices of k_factors, in slice order
+      double tot = 0;
+      for (int p = 0; p < kFPriorCtas; ++p) tot += F.prior[kDsMaxNp + 1 + p];
+      F.prior[kDsMaxNp] = 0.5 * (S->c0 + tot);
+    }
   }
+  __syncthreads();
+  if (threadIdx.x == 0) stamp_max(S, eval_index, 14);
 }
 
 // lidar share of H(a, b), a >= b (zero when either index is not a pose / free-extrinsic entry)
@@ -629,11 +656,6 @@ __device__ __noinline__ void write_terms(int O, const double *xe, double *Rt) {
                        Rt + threadIdx.x * kAsmRtStride + 9, M);
 }
 
-__device__ __forceinline__ long long gtime_ns() {
-  long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
 #define DS_MARK(k) do { if (tid == 0 && eval_index < 24) S->dbg[eval_index][k] = clock64(); } while (0)
 
 struct StepShared {
@@ -650,7 +672,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
   int *s_flag = sh.flag;
   int &s_ok = sh.ok;
   const int tid = threadIdx.x, T = blockDim.x;
-  if (tid == 0 && eval_index < 24) { for (int k = 0; k < 16; ++k) S->dbg[eval_index][k] = 0; S->dbg[eval_index][0] = gtime_ns(); }
+  if (tid == 0 && eval_index < 24) { for (int k = 0; k < 12; ++k) S->dbg[eval_index][k] = 0; S->dbg[eval_index][0] = gtime_ns(); }
   DS_MARK(1);
   const int O = sc.O, n = sc.n;
   const int NB = (n + 7) / 8, NP = NB * 8;
@@ -1088,8 +1110,8 @@ int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *laun
   cudaError_t e = cudaEventRecord(ds.ev_fork, st);
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ds.aux, ds.ev_fork, 0);
   if (e == cudaSuccess) {
-    k_factors<<<ds.O + 1, kFThreads, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), eval_index);
-    k_hpart<<<64, 256, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), ds.Hpart);
+    k_factors<<<ds.O + 1 + kFPriorCtas, kFThreads, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), eval_index);
+    k_hpart<<<64, 256, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), ds.Hpart, eval_index);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(ds.ev_join, ds.aux);

@@ -7,6 +7,7 @@ namespace lio {
 
 constexpr int kDsMaxN = 15 * (kMaxOpt + 1) + 6;  // 261
 constexpr int kDsMaxNp = 15 * kMaxOpt + 6;       // 246
+constexpr int kFPriorCtas = 13;                  // CTAs of k_factors that share the prior's matrix-vector product
 constexpr int kDsXDim = 16 * (kMaxOpt + 1) + 7;
 constexpr int kDsMaxOpt = 13;                    // largest opt window whose Cholesky tiles fit one SM's shared memory
 
@@ -75,7 +76,7 @@ struct DevSolver {
   size_t off_imu() const { return 0; }
   size_t off_M() const { return (size_t)kMaxOpt * kFImuStride; }
   size_t off_prior() const { return off_M() + (size_t)kMaxOpt * kFMStride; }                    // np gradient terms | cost
-  size_t off_ex() const { return off_prior() + kDsMaxNp + 8; }                                   // 36 J^T J | 6 J^T r | cost
+  size_t off_ex() const { return off_prior() + kDsMaxNp + 8 + 16; }                                   // 36 J^T J | 6 J^T r | cost
   size_t off_G() const { return off_ex() + 48; }                                                 // O x kFGStride | 144 + 12 shared
   size_t f_doubles() const { return off_G() + (size_t)kMaxOpt * kFGStride + 160; }
 };
