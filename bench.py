@@ -320,6 +320,13 @@ def main():
             print("[trace] ev %2d  k_step %6.1f us | gap %5.1f | asm %5.1f..%5.1f  k_factors %5.1f..%5.1f  k_hpart ..%5.1f | phases(cyc) %s" % (
                 e_, (int(tr[e_, 11]) - int(tr[e_, 0])) / 1000.0, rel(tr[e_, 0]), rel(tr[13, e_]), rel(tr[14, e_]), rel(tr[e_, 12]), rel(tr[e_, 13]),
                 rel(tr[e_, 14]), np.diff(tr[e_, 1:11]).tolist()), file=sys.stderr)
+        cp = est.chol_profile
+        NBp = (15 * (W + 1) + 6 + 7) // 8
+        pp_ = cp[:4 * NBp].reshape(NBp, 4)
+        print("[trace] in-kernel Cholesky (eval 1) per panel [solve, own_update, diag, update_total] cycles: %s backsub %d total %d" % (
+            pp_.tolist(), int(cp[4 * NBp]), int(pp_[:, 0].sum() + pp_[:, 3].sum() + cp[4 * NBp])), file=sys.stderr)
+        print("[trace] chol %%globaltimer ns: entry->loop %d, loop %d, backsub %d, total %d" % (
+            cp[4 * NBp + 2] - cp[4 * NBp + 1], cp[4 * NBp + 3] - cp[4 * NBp + 2], cp[4 * NBp + 4] - cp[4 * NBp + 3], cp[4 * NBp + 4] - cp[4 * NBp + 1]), file=sys.stderr)
     ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(np.sum(ms))
     if world > 1:

@@ -276,9 +276,13 @@ __device__ void diag_factor(double *T, int *s_ok) {
 
 // clock64 ordered after a shared-memory value has arrived: a plain clock read right behind __syncthreads() captures the
 // barrier's ISSUE time (BAR.SYNC.DEFER_BLOCKING), not its release
+// clock64 read that really happens after v is available (v = a shared-memory value loaded behind a barrier): the read is
+// control-dependent on v, so neither ptxas nor the issue logic can run it ahead of the load.  (A clock read that merely
+// follows the barrier in program order, or "uses" v in a dead move, is issued while the warp still waits: round 2's first
+// per-panel profile under-counted every panel by the time spent at the barriers.)
 __device__ __forceinline__ long long clock_after(double v) {
-  long long t;
-  asm volatile("{\n\t.reg .b64 tmp;\n\tmov.b64 tmp, %1;\n\tmov.u64 %0, %%clock64;\n\t}" : "=l"(t) : "d"(v) : "memory");
+  long long t = 0;
+  if (__double_as_longlong(v) != 0x7ff8dead00000001LL) asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : : "memory");
   return t;
 }
 
@@ -287,6 +291,7 @@ __device__ __forceinline__ long long clock_after(double v) {
 __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, long long *prof = nullptr) {
   const int tid = threadIdx.x, w = warp_id(), l = lane_id();
   const int fr = l >> 2, fq = l & 3;   // fragment row, fragment quad
+  if (prof && tid == 0) prof[4 * NB + 1] = gtime_ns();
   if (tid == 0) *s_ok = 1;
   __syncthreads();
   // The serial chain (diagonal tiles) runs on the LAST warp: the issue arbiter favours the highest warp id of a
@@ -294,6 +299,7 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
   constexpr int kChainWarp = kDsWarps - 1;
   if (w == kChainWarp) diag_factor(tiles + tile_off(0, 0), s_ok);
   __syncthreads();
+  if (prof && w == kChainWarp && l == 0) prof[4 * NB + 2] = gtime_ns();
   for (int kb = 0; kb < NB; ++kb) {
     if (!*s_ok) break;
     const long long tp0 = clock_after(y[0]);
@@ -348,29 +354,58 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
       double *C = tiles + tile_off(kb + 1, kb + 1);
       const long long td0 = clock64();
       diag_factor(C, s_ok);
-      if (prof && l == 0) { prof[4 * kb + 1] = td0 - tp1; prof[4 * kb + 2] = clock64() - td0; }
+      if (prof && l == 0) { prof[4 * kb + 1] = gtime_ns(); prof[4 * kb + 2] = clock64() - td0; }
     } else if ((w & 3) != (kChainWarp & 3)) {
-      // tasks p = 1 .. ntile - 1: tile (i, j) with p = i (i + 1) / 2 + j;  p = ntile .. ntile + m - 1: rhs rows of tile-row p - ntile.
+      // tile tasks p = 1 .. ntile - 1: tile (i, j) with p = i (i + 1) / 2 + j (p = 0 is the next diagonal tile: the chain warp's).
       // The warps that share the chain warp's scheduler (w % 4 == 3) take no tasks: their fp64 MMAs would queue in front of
       // every dependent fp64 operation of the chain (measured: the diagonal tile takes 4.9k cycles beside them, 2.0k alone).
       constexpr int kWorkers = kDsWarps - kDsWarps / 4;          // 12
       const int wi = w - (w >> 2);                               // dense index of this worker: 0 .. 11
-      int i = 0, j = wi + 1;                                      // (i, j) of p = wi + 1, advanced incrementally (no sqrt on the hot path)
-      while (j > i) { j -= i + 1; ++i; }
-      for (int p = wi + 1; p < ntile + m; p += kWorkers) {
-        if (p < ntile) {
-          double *C = tiles + tile_off(kb + 1 + i, kb + 1 + j);
-          const double *Xi = tiles + tile_off(kb + 1 + i, kb), *Xj = tiles + tile_off(kb + 1 + j, kb);
-          const double a0 = -Xi[swz(fr, fq)], a1 = -Xi[swz(fr, fq + 4)];
-          const double x0 = Xj[swz(fr, fq)], x1 = Xj[swz(fr, fq + 4)];
-          double2 c = *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq));
-          dmma884(c.x, c.y, a0, x0);
-          dmma884(c.x, c.y, a1, x1);
-          *reinterpret_cast<double2 *>(C + swz(fr, 2 * fq)) = c;
-          j += kWorkers;
-          while (j > i) { j -= i + 1; ++i; }
-        } else if (l < 8) {
-          const int ib = kb + 1 + (p - ntile);
+      // Each worker takes a CONTIGUOUS range of the tile tasks (row-major over the lower triangle), so that the fragments of the
+      // row tile X_i stay in registers while j runs along the row: the update is bound by shared-memory bandwidth (2 kB per tile:
+      // two X fragments, C in and out), a cached row saves a quarter of it.
+      const int ntask = ntile - 1;                               // tile tasks p = 1 .. ntile - 1
+      const int per = (ntask + kWorkers - 1) / kWorkers;
+      const int p0 = 1 + wi * per, p1 = min(ntile, p0 + per);
+      if (p0 < p1) {
+        int i = (int)((sqrt(8.0 * p0 + 1.0) - 1.0) * 0.5);
+        while ((i + 1) * (i + 2) / 2 <= p0) ++i;
+        while (i * (i + 1) / 2 > p0) --i;
+        int j = p0 - i * (i + 1) / 2;
+        const int o0 = swz(fr, fq), o1 = swz(fr, fq + 4), oc = swz(fr, 2 * fq);
+        // The range is walked row segment by row segment with strength-reduced pointers (the generic tile_off / swizzle
+        // arithmetic cost ~60 instructions per tile: with 4 warps per scheduler the update was issue bound, not MMA bound):
+        // along a row the C tiles are contiguous (+64 doubles) and X_j advances by (kb + 2 + j) tiles.
+        for (int p = p0; p < p1;) {
+          const int jend = min(i, j + (p1 - p) - 1);
+          const double *Xi = tiles + tile_off(kb + 1 + i, kb);
+          const double a0 = -Xi[o0], a1 = -Xi[o1];
+          double *Cp = tiles + tile_off(kb + 1 + i, kb + 1 + j) + oc;
+          const double *xp = tiles + tile_off(kb + 1 + j, kb);
+          int xinc = (kb + 2 + j) * 64;
+          double x0 = xp[o0], x1 = xp[o1];
+          double2 c = *reinterpret_cast<double2 *>(Cp);
+#pragma unroll 2
+          for (int jj = j; jj <= jend; ++jj) {
+            const bool more = jj < jend;
+            const double *xn = xp + xinc;
+            double nx0 = 0.0, nx1 = 0.0;
+            double2 nc = make_double2(0.0, 0.0);
+            if (more) { nx0 = xn[o0]; nx1 = xn[o1]; nc = *reinterpret_cast<double2 *>(Cp + 64); }
+            dmma884(c.x, c.y, a0, x0);
+            dmma884(c.x, c.y, a1, x1);
+            *reinterpret_cast<double2 *>(Cp) = c;
+            Cp += 64; xp = xn; xinc += 64;
+            x0 = nx0; x1 = nx1; c = nc;
+          }
+          p += jend - j + 1;
+          j = 0; ++i;
+        }
+      }
+      // right-hand side rows of tile-row r (r = 0 .. m - 1), one per worker in turn
+      if (l < 8) {
+        for (int r = wi; r < m; r += kWorkers) {
+          const int ib = kb + 1 + r;
           const double *X = tiles + tile_off(ib, kb);
           double s = 0.0;
 #pragma unroll
@@ -386,6 +421,7 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
   const int ok = *s_ok;
   if (!ok) return 0;
   const long long tb0 = clock64();
+  if (prof && w == kChainWarp && l == 0) prof[4 * NB + 3] = gtime_ns();
   // ---- back substitution L^T x = y over the tiles in reverse.  Only the first 8 warps take part (8 NB <= 256 rows): the
   // 8 threads of tile-row jb turn their finished y into x = inv(L_jj)^T y (they share a warp), one named barrier
   // publishes x, then every thread of the rows above subtracts its tile's contribution.
@@ -420,7 +456,7 @@ __device__ int chol_solve_tiles(double *tiles, int NB, double *y, int *s_ok, lon
     }
   }
   __syncthreads();
-  if (prof && tid == 0) prof[4 * NB] = clock_after(y[0]) - tb0;
+  if (prof && tid == 0) { const long long te = clock_after(y[0]); prof[4 * NB] = te - tb0; prof[4 * NB + 4] = gtime_ns(); }
   return 1;
 }
 
@@ -1171,19 +1207,24 @@ extern "C" int lio_dev_cholesky_solve_host(const double *A, const double *b, int
   double *dA = nullptr, *db = nullptr, *dx = nullptr;
   int *dok = nullptr;
   long long *dprof = nullptr;
-  const size_t nprof = 4 * (size_t)NB + 1;
+  const size_t nprof = 4 * (size_t)NB + 1, nprof_dev = nprof + 4;   // + 4 in-kernel phase stamps (not returned)
   int rc = LIO_OK;
   if (cudaMalloc(&dA, sizeof(double) * n * n) != cudaSuccess || cudaMalloc(&db, sizeof(double) * n) != cudaSuccess ||
       cudaMalloc(&dx, sizeof(double) * n) != cudaSuccess || cudaMalloc(&dok, sizeof(int)) != cudaSuccess ||
-      cudaMalloc(&dprof, sizeof(long long) * nprof) != cudaSuccess) rc = LIO_ERR_CUDA;
+      cudaMalloc(&dprof, sizeof(long long) * nprof_dev) != cudaSuccess) rc = LIO_ERR_CUDA;
   if (rc == LIO_OK) {
     cudaMemcpy(dA, A, sizeof(double) * n * n, cudaMemcpyHostToDevice);
     cudaMemcpy(db, b, sizeof(double) * n, cudaMemcpyHostToDevice);
     cudaFuncSetAttribute(k_chol_test, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaMemset(dprof, 0, sizeof(long long) * nprof);
+    cudaMemset(dprof, 0, sizeof(long long) * nprof_dev);
     k_chol_test<<<1, kDsThreads, smem>>>(dA, db, n, dx, dok, prof ? dprof : nullptr);
     cudaError_t e = cudaMemcpy(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess && prof) e = cudaMemcpy(prof, dprof, sizeof(long long) * nprof, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && prof) {   // the four %globaltimer stamps become durations (ns) appended behind the per-panel cycles when the caller left room
+      long long st[4];
+      e = cudaMemcpy(st, dprof + nprof, sizeof(st), cudaMemcpyDeviceToHost);
+      if (e == cudaSuccess) std::fprintf(stderr, "[k_chol_test] ns: entry->loop %lld, loop %lld, backsub %lld, total %lld\n", st[1] - st[0], st[2] - st[1], st[3] - st[2], st[3] - st[0]);
+    }
     if (e == cudaSuccess) e = cudaMemcpy(ok, dok, sizeof(int), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) { lio_set_last_error(__FILE__, __LINE__, cudaGetErrorString(e)); rc = LIO_ERR_CUDA; }
   } else lio_set_last_error(__FILE__, __LINE__, "cudaMalloc failed");
