@@ -551,7 +551,7 @@ __device__ __forceinline__ double g_elem(const GatherCtx &c, int a) {
 // hflags records the structure (free extrinsic, prior in use) the gather assumed: the convergence gates of evaluation 0
 // can still change it, in which case k_step falls back to its own full gather.
 __global__ void __launch_bounds__(256)
-k_hpart(DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, double *__restrict__ Hpart, int eval_index) {
+k_hpart(DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, double *__restrict__ Hpart, double *__restrict__ HpartT, int eval_index) {
   __shared__ double s_zero;
   __shared__ int s_pimv[kMaxOpt];
   if (S->sc.done) return;
@@ -565,13 +565,30 @@ k_hpart(DevSolveState *__restrict__ S, const double *__restrict__ Hp, FPtrs F, d
   gc.imu = S->sc.imu_factor != 0; gc.ex_prior = gc.ex_free && S->sc.prior_factor;
   gc.Hp = Hp; gc.Fimu = F.imu; gc.Fprior = F.prior; gc.Fex = F.ex; gc.G = nullptr; gc.G0 = nullptr; gc.pim_valid = s_pimv; gc.zero = &s_zero;
   double *gpart = Hpart + (size_t)n * n;
-  for (int a = blockIdx.x; a < n; a += gridDim.x) {
-    for (int b = threadIdx.x; b <= a; b += blockDim.x) Hpart[(size_t)a * n + b] = h_elem(gc, a, b);
-    if (threadIdx.x == blockDim.x - 1) gpart[a] = g_elem(gc, a);
+  if (eval_index == 0) {
+    for (int a = blockIdx.x; a < n; a += gridDim.x) {
+      for (int b = threadIdx.x; b <= a; b += blockDim.x) Hpart[(size_t)a * n + b] = h_elem(gc, a, b);
+      if (threadIdx.x == blockDim.x - 1) gpart[a] = g_elem(gc, a);
+    }
+  } else {
+    // the Jacobi scaling is fixed since evaluation 0: write the scaled entries straight in the step kernel's swizzled tile
+    // layout (identity on the padding rows), so that k_step fetches its Cholesky tiles with one coalesced copy
+    const int NP = ((n + 7) / 8) * 8;
+    for (int a = blockIdx.x; a < NP; a += gridDim.x) {
+      if (a < n) {
+        const double sa = S->scale[a];
+        for (int b = threadIdx.x; b <= a; b += blockDim.x)
+          HpartT[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = h_elem(gc, a, b) * sa * S->scale[b];
+        if (threadIdx.x == blockDim.x - 1) gpart[a] = g_elem(gc, a);
+      } else {
+        for (int b = threadIdx.x; b <= a; b += blockDim.x) HpartT[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = (a == b) ? 1.0 : 0.0;
+      }
+    }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     gpart[n] = gc.ex_free ? 1.0 : 0.0;
     gpart[n + 1] = gc.prior ? 1.0 : 0.0;
+    gpart[n + 2] = eval_index == 0 ? 0.0 : 1.0;   // which of Hpart / HpartT this launch wrote
     if (gc.prior) {   // cost of the marginalisation prior from the slices of k_factors, in slice order
       double tot = 0;
       for (int p = 0; p < kFPriorCtas; ++p) tot += F.prior[kDsMaxNp + 1 + p];
@@ -678,11 +695,24 @@ __device__ void symv_tiles(const double *tiles, int n, const double *v, double *
   __syncthreads();
 }
 
-// (re)load the pure scaled H (lower triangle, identity on the padding) from global memory into the tiles
-__device__ void refill_tiles(double *tiles, const double *__restrict__ Hs, int n, int NP) {
-  for (int a = warp_id(); a < NP; a += kDsWarps)
-    for (int b = lane_id(); b <= a; b += 32)
-      tiles[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] = (a < n) ? Hs[(size_t)a * n + b] : ((a == b) ? 1.0 : 0.0);
+// block-wide copy of a tile set (ndoubles = tiles x 64) between global and shared memory, 16 bytes per access, eight in flight
+__device__ __forceinline__ void copy_tiles(double *__restrict__ dst, const double *__restrict__ src, int ndoubles) {
+  const int n2 = ndoubles >> 1, T = blockDim.x;
+  const double2 *s2 = reinterpret_cast<const double2 *>(src);
+  double2 *d2 = reinterpret_cast<double2 *>(dst);
+  int k = threadIdx.x;
+  for (; k + 7 * T < n2; k += 8 * T) {
+    double2 v[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = s2[k + q * T];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) d2[k + q * T] = v[q];
+  }
+  for (; k < n2; k += T) d2[k] = s2[k];
+}
+// (re)load the pure scaled H of the current x (tile layout, saved by the evaluation that built it)
+__device__ void refill_tiles(double *tiles, const double *__restrict__ HsT, int ntd) {
+  copy_tiles(tiles, HsT, ntd);
   __syncthreads();
 }
 
@@ -702,7 +732,8 @@ struct StepShared {
 };
 
 __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double *Hs, const double *__restrict__ Hp, double *H0, double *g0,
-                          const double *__restrict__ Sblk, FPtrs F, const double *__restrict__ Hpart, double *Rt, int eval_index) {
+                          const double *__restrict__ Sblk, FPtrs F, const double *__restrict__ Hpart, const double *__restrict__ HpartT, double *Rt,
+                          int eval_index) {
   DevScalars &sc = sh.sc;
   double *sred = sh.sred;
   int *s_flag = sh.flag;
@@ -711,7 +742,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
   if (tid == 0 && eval_index < 24) { for (int k = 0; k < 12; ++k) S->dbg[eval_index][k] = 0; S->dbg[eval_index][0] = gtime_ns(); }
   DS_MARK(1);
   const int O = sc.O, n = sc.n;
-  const int NB = (n + 7) / 8, NP = NB * 8;
+  const int NB = (n + 7) / 8, NP = NB * 8, ntd = (NB * (NB + 1) / 2) * 64;
   double *tiles = dsm;
   double *v_g = dsm + (size_t)(NB * (NB + 1) / 2) * 64;   // scaled gradient of the current x
   double *v_scale = v_g + NP, *v_diag = v_scale + NP, *v_grad = v_diag + NP, *v_gn = v_grad + NP, *v_step = v_gn + NP;
@@ -854,7 +885,45 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     // scaled H of the current point (lower triangle) -> global and straight into the Cholesky tiles.  One warp per 15 x 15 parameter block pair (K >= L; block O + 1 = extrinsic, 6 wide): inside a block
     // every contribution is a plain sub-matrix (prior rows, the 6 x 6 pose part of a lidar G, ImuFactor quadrants), so
     // the per-element work is five pointer offsets, their loads and the stores.
-    if (fast) {
+    if (fast && eval_index >= 1 && gpart[n + 2] != 0.0) {
+      // k_hpart left the scaled lidar-independent share in tile layout: one coalesced copy, then the lidar entries (pose rows
+      // and the free extrinsic only: <= 72 x 72 / 2 candidates) are added in place
+      copy_tiles(tiles, HpartT, ntd);
+      __syncthreads();
+      if (gc.lidar) {
+        // the structurally non-zero lidar entries only: per frame the 6 pose_i rows against [pose_0 | pose_i | extrinsic]
+        // (108 candidates, lower part kept), then the 12 x 12 block shared by pose_0 and the extrinsic; <= 4 per thread, all
+        // their loads independent
+        const int total = O * 108 + 144;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {   // O <= 13: 1548 candidates <= 4 x 512
+          const int e = tid + k * kDsThreads;
+          if (e >= total) continue;
+          int a, b;
+          if (e < O * 108) {
+            const int f = e / 108, q = e - f * 108, r = q / 18, c = q - r * 18;
+            a = 15 * (f + 1) + r;
+            if (c < 6) b = c;                                                   // pose_i x pose_0
+            else if (c < 12) { if (c - 6 > r) continue; b = 15 * (f + 1) + (c - 6); }   // pose_i x pose_i, lower part
+            else { if (!ex_free) continue; b = a; a = oe + (c - 12); }          // extrinsic x pose_i (the extrinsic rows are the last)
+          } else {
+            const int q = e - O * 108, r = q / 12, c = q - r * 12;
+            a = r < 6 ? r : oe + (r - 6);
+            b = c < 6 ? c : oe + (c - 6);
+            if (b > a || (!ex_free && a >= oe)) continue;
+          }
+          int sa = 0;
+          const int ba = lidar_block(gc, a, sa);
+          const double lh = lidar_h(gc, ba, sa, b);
+          if (lh != 0.0) tiles[tile_off(a >> 3, b >> 3) + swz(a & 7, b & 7)] += lh * v_scale[a] * v_scale[b];
+        }
+        __syncthreads();
+      }
+      for (int a = tid; a < n; a += T) {
+        const double d = sqrt(fmin(fmax(tiles[tile_off(a >> 3, a >> 3) + swz(a & 7, a & 7)], min_diagonal), max_diagonal));
+        v_diag[a] = d; S->diagonal[a] = d;
+      }
+    } else if (fast) {
       // one warp per row: the row of Hpart is streamed (all its 32-column slices in flight), the lidar block entry is added
       const int l = lane_id();
       for (int a = warp_id(); a < NP; a += kDsWarps) {
@@ -875,7 +944,6 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
           const double h = hq[q] + (ba >= 0 ? lidar_h(gc, ba, sa, b) : 0.0);
           if (eval_index == 0) { H0[(size_t)a * n + b] = h; H0[(size_t)b * n + a] = h; }
           const double hs = h * sca * v_scale[b];
-          Hs[(size_t)a * n + b] = hs;
           if (a == b) {
             const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
             v_diag[a] = d; S->diagonal[a] = d;
@@ -934,7 +1002,6 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
           }
           if (eval_index == 0) { H0[(size_t)ga * n + gb] = h; H0[(size_t)gb * n + ga] = h; }
           const double hs = h * v_scale[ga] * v_scale[gb];
-          Hs[(size_t)ga * n + gb] = hs;
           if (ga == gb) {
             const double d = sqrt(fmin(fmax(hs, min_diagonal), max_diagonal));
             v_diag[ga] = d; S->diagonal[ga] = d;
@@ -947,6 +1014,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     }
     tiles_ready = 1;
     __syncthreads();
+    copy_tiles(Hs, tiles, ntd);   // kept for a mu retry / an invalid step of a later evaluation (plain stores, nobody waits for them)
     for (int i = tid; i < n; i += T) { v_grad[i] = v_g[i] / v_diag[i]; S->gradient[i] = v_grad[i]; }
     __syncthreads();
     DS_MARK(5);
@@ -967,7 +1035,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
     int linear_ok = 1;
     if (!s_flag[3]) {
       // Cauchy point scale: alpha = |gradient|^2 / (sg^T H sg), sg = gradient / D; H sg is kept (model cost change)
-      if (!tiles_ready) refill_tiles(tiles, Hs, n, NP);
+      if (!tiles_ready) refill_tiles(tiles, Hs, ntd);
       for (int i = tid; i < NP; i += T) v_tmp[i] = i < n ? v_g[i] / (v_diag[i] * v_diag[i]) : 0.0;
       __syncthreads();
       symv_tiles(tiles, n, v_tmp, v_hsg);
@@ -981,7 +1049,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
       bool pure = true;   // the tiles hold the pure H
       while (mu < max_mu) {
         // tiles of H + mu D^2 (lower triangle; identity on the padding), right-hand side g
-        if (!pure) refill_tiles(tiles, Hs, n, NP);
+        if (!pure) refill_tiles(tiles, Hs, ntd);
         for (int i = tid; i < n; i += T) tiles[tile_off(i >> 3, i >> 3) + swz(i & 7, i & 7)] += mu * v_diag[i] * v_diag[i];
         pure = false;
         tiles_ready = 0;
@@ -1081,7 +1149,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
 
 __global__ void __launch_bounds__(kDsThreads, 1)
 k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, double *g0, const double *__restrict__ Sblk,
-       FPtrs F, const double *__restrict__ Hpart, double *Rt, int eval_index) {
+       FPtrs F, const double *__restrict__ Hpart, const double *__restrict__ HpartT, double *Rt, int eval_index) {
   extern __shared__ __align__(16) double dsm[];
   __shared__ StepShared sh;
   static_assert(sizeof(DevScalars) % 8 == 0, "DevScalars is copied as 8-byte words");
@@ -1091,7 +1159,7 @@ k_step(DevSolveState *S, double *Hs, const double *__restrict__ Hp, double *H0, 
   if (tid >= 64 && tid < 64 + kMaxOpt) sh.pim_valid[tid - 64] = S->pim_valid[tid - 64];
   if (tid == 128) sh.zero = 0.0;
   __syncthreads();
-  step_body(S, sh, dsm, Hs, Hp, H0, g0, Sblk, F, Hpart, Rt, eval_index);
+  step_body(S, sh, dsm, Hs, Hp, H0, g0, Sblk, F, Hpart, HpartT, Rt, eval_index);
   __syncthreads();
   if (tid < (int)(sizeof(DevScalars) / 8)) reinterpret_cast<long long *>(&S->sc)[tid] = reinterpret_cast<const long long *>(&sh.sc)[tid];
 }
@@ -1116,6 +1184,11 @@ int DevSolver::init(int O_) {
   if (cudaMalloc(&F, sizeof(double) * f_doubles()) != cudaSuccess) return -1;
   if (cudaMalloc(&Hpart, sizeof(double) * ((size_t)n * n + n + 8)) != cudaSuccess) return -1;
   if (cudaMemset(Hpart, 0, sizeof(double) * ((size_t)n * n + n + 8)) != cudaSuccess) return -1;
+  {
+    const size_t NBt = (n + 7) / 8, ntd = NBt * (NBt + 1) / 2 * 64;
+    if (cudaMalloc(&HpartT, sizeof(double) * ntd) != cudaSuccess || cudaMemset(HpartT, 0, sizeof(double) * ntd) != cudaSuccess) return -1;
+    if (cudaMemset(Hs, 0, sizeof(double) * n * n) != cudaSuccess) return -1;
+  }
   if (cudaMallocHost((void **)&h_st, sizeof(DevSolveState)) != cudaSuccess) return -1;
   if (cudaMemset(st, 0, sizeof(DevSolveState)) != cudaSuccess) return -1;
   if (cudaMemset(F, 0, sizeof(double) * f_doubles()) != cudaSuccess) return -1;
@@ -1127,13 +1200,13 @@ int DevSolver::init(int O_) {
 }
 
 void DevSolver::destroy() {
-  void *p[] = {st, Hs, H0, g0, Hp, F, Hpart};
+  void *p[] = {st, Hs, H0, g0, Hp, F, Hpart, HpartT};
   for (void *q : p) if (q) cudaFree(q);
   if (h_st) cudaFreeHost(h_st);
   if (aux) cudaStreamDestroy(aux);
   if (ev_fork) cudaEventDestroy(ev_fork);
   if (ev_join) cudaEventDestroy(ev_join);
-  st = nullptr; Hs = Hp = H0 = g0 = F = Hpart = nullptr; h_st = nullptr; aux = nullptr; ev_fork = ev_join = nullptr;
+  st = nullptr; Hs = Hp = H0 = g0 = F = Hpart = HpartT = nullptr; h_st = nullptr; aux = nullptr; ev_fork = ev_join = nullptr;
 }
 
 static FPtrs fptrs(const DevSolver &ds) {
@@ -1147,7 +1220,7 @@ int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *laun
   if (e == cudaSuccess) e = cudaStreamWaitEvent(ds.aux, ds.ev_fork, 0);
   if (e == cudaSuccess) {
     k_factors<<<ds.O + 1 + kFPriorCtas, kFThreads, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), eval_index);
-    k_hpart<<<64, 256, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), ds.Hpart, eval_index);
+    k_hpart<<<64, 256, 0, ds.aux>>>(ds.st, ds.Hp, fptrs(ds), ds.Hpart, ds.HpartT, eval_index);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(ds.ev_join, ds.aux);
@@ -1159,7 +1232,7 @@ int dev_solver_factors(DevSolver &ds, int eval_index, cudaStream_t st, int *laun
 int dev_solver_step(DevSolver &ds, const double *S_dev, double *Rt_dev, int eval_index, cudaStream_t st, int *launches) {
   cudaError_t e = cudaStreamWaitEvent(st, ds.ev_join, 0);
   if (e == cudaSuccess) {
-    k_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.Hs, ds.Hp, ds.H0, ds.g0, S_dev, fptrs(ds), ds.Hpart, Rt_dev, eval_index);
+    k_step<<<1, kDsThreads, ds.smem_bytes, st>>>(ds.st, ds.Hs, ds.Hp, ds.H0, ds.g0, S_dev, fptrs(ds), ds.Hpart, ds.HpartT, Rt_dev, eval_index);
     e = cudaGetLastError();
   }
   if (launches) *launches += 1;

@@ -56,7 +56,8 @@ constexpr int kFGStride = 344;     // G_i = M_i^T S_gg M_i (18 x 18) | M_i^T S_g
 
 struct DevSolver {
   DevSolveState *st = nullptr;     // device
-  double *Hs = nullptr;            // n x n row-major, LOWER triangle of the Jacobi-scaled normal matrix of the current x
+  double *Hs = nullptr;            // the Jacobi-scaled normal matrix of the current x as the step kernel's swizzled lower tiles (mu-retry / invalid-step reload)
+  double *HpartT = nullptr;        // evaluations >= 1: scaled lidar-independent share of H in the same tile layout (bulk-copied into shared memory)
                                    // (only re-read when a factorisation has to be repeated with a larger mu)
   double *Hp = nullptr;            // prior np x np
   double *H0 = nullptr, *g0 = nullptr;   // first linearisation, unscaled (parity getter)
