@@ -254,9 +254,20 @@ k_odom_round(const float4 *__restrict__ pts, const float4 *__restrict__ coef, co
   double acc[27];
 #pragma unroll
   for (int k = 0; k < 27; ++k) acc[k] = 0.0;
-  for (int i = threadIdx.x; i < n; i += kOdomRoundThreads) {
+  // four features per trip: their eight loads are issued together (the loop is latency bound: ~25 features per thread)
+#pragma unroll 1
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kOdomRoundThreads) {
+    float4 pq[4], cq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kOdomRoundThreads;
+      if (i < n) { pq[u] = __ldg(pts + i); cq[u] = __ldg(coef + i); }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+    if (i0 + u * kOdomRoundThreads >= n) break;
     float row[6], d2;
-    odom_row(tf, R, __ldg(pts + i), __ldg(coef + i), row, d2);
+    odom_row(tf, R, pq[u], cq[u], row, d2);
     int k = 0;
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
@@ -265,6 +276,7 @@ k_odom_round(const float4 *__restrict__ pts, const float4 *__restrict__ coef, co
     }
 #pragma unroll
     for (int a = 0; a < 6; ++a) acc[21 + a] += (double)(row[a] * (-d2));
+    }
   }
 #pragma unroll
   for (int k = 0; k < 27; ++k) {
@@ -454,6 +466,9 @@ struct lio_est {
   VoxelGrid vg;
   CellHash hash;
   KnnWork knn;
+  KnnWork knn2;                     // launch state of the LaserOdom chain, which runs beside the frame-batched k-NN launch
+  cudaStream_t ostream = nullptr;   // stream of that chain
+  cudaEvent_t ev_map = nullptr, ev_odom = nullptr;
   std::vector<FeatureOut> feats;  // logical frame index
   int *d_feat_counts = nullptr;   // W+1
   TransformF *d_tf = nullptr;     // W+1
@@ -604,7 +619,10 @@ extern "C" int lio_est_destroy(lio_est *e) {
   if (e->h_Rt) cudaFreeHost(e->h_Rt);
   if (e->d_Rt) cudaFree(e->d_Rt);
   if (e->h_counts) cudaFreeHost(e->h_counts);
-  e->vg.destroy(); e->hash.destroy(); e->knn.destroy(); e->asmw.destroy();
+  e->vg.destroy(); e->hash.destroy(); e->knn.destroy(); e->knn2.destroy(); e->asmw.destroy();
+  if (e->ostream) cudaStreamDestroy(e->ostream);
+  if (e->ev_map) cudaEventDestroy(e->ev_map);
+  if (e->ev_odom) cudaEventDestroy(e->ev_odom);
   delete e;
   return LIO_OK;
 }
@@ -666,6 +684,10 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   ok = ok && e->vg.init(vg_cap) == 0;
   ok = ok && e->hash.init(e->local_cap) == 0;
   ok = ok && e->knn.init(cfg->max_frame_points * (O + 1)) == 0;
+  ok = ok && e->knn2.init(cfg->max_frame_points) == 0;
+  ok = ok && cudaStreamCreateWithFlags(&e->ostream, cudaStreamNonBlocking) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&e->ev_map, cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&e->ev_odom, cudaEventDisableTiming) == cudaSuccess;
   e->feats.assign(W + 1, FeatureOut());
   long long total_feat = 0;
   for (int k = pivot + 1; k <= W && ok; ++k) {
@@ -895,6 +917,58 @@ static int build_local_map(lio_est *e) {
   e->t_build = now_s() - t0;
   const double t1 = now_s();
   EST_CUDA(cudaMemsetAsync(e->d_feat_counts, 0, sizeof(int) * (W + 1), st));
+  // CalculateLaserOdom on the newest frame: rounds after convergence are no-ops on the device (done flag), but each still costs two
+  // launches.  The chain is therefore enqueued in two batches: the first kOdomFirstBatch rounds ride with the scan's one
+  // synchronisation (it converges in 2-3 rounds); only if the flag is still clear are the remaining rounds enqueued.
+  constexpr int kOdomFirstBatch = 3;
+  const bool odom = e->cfg.imu_factor && owns_frame(e, W);
+  KnnBatch ob;
+  auto odom_rounds = [&](int from, int to, cudaStream_t q) -> int {
+    const int idx = W, slot = e->slot_of[W];
+    if (!e->cfg.keep_features) {
+      // two launches per round and no memset: the k-NN + plane fit of the newest frame, then ONE CTA that reduces the
+      // round's features to A^T A / A^T b, takes the 6 x 6 Gauss-Newton step and re-arms the k-NN launch state
+      ob.nframes = 1;
+      KnnFrame &f = ob.f[0];
+      f.surf = e->slot_ptr[slot]; f.n_dev = e->d_slot_n + slot; f.n_bound = e->cfg.max_frame_points; f.tf = e->d_tf + idx;
+      f.out_p = e->feats[idx].pts; f.out_c = e->feats[idx].coef; f.out_src = e->feats[idx].src; f.out_count = e->feats[idx].count;
+      f.append = 0; f.tile0 = 0;
+      for (int it = from; it < to; ++it) {
+        int r2 = calculate_features_batch(e->hash, ob, e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, &e->d_odom->done, e->knn2, q, &e->launches,
+                                          0, it > 0);
+        if (r2 != LIO_OK) return r2;
+        k_odom_round<<<1, kOdomRoundThreads, 0, q>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, 0.05, 0.05,
+                                                      e->knn2.status, ob.ntiles, e->knn2.ticket);
+        ++e->launches;
+      }
+    } else {
+      // keep_features: every round re-evaluates ALL kept features at the current transform (Estimator.cc:978-980), so the
+      // reduction is a pass of its own
+      const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
+      for (int it = from; it < to; ++it) {
+        int r2 = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
+                                        e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], 1,
+                                        &e->d_odom->done, e->knn2, q, &e->launches);
+        if (r2 != LIO_OK) return r2;
+        k_odom_reduce<<<nb, kOdomThreads, 0, q>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
+        k_odom_solve<<<1, 32, 0, q>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
+        e->launches += 2;
+      }
+    }
+    return LIO_OK;
+  };
+  const int odom_total = odom ? e->cfg.odom_max_iterations : 0;
+  const int odom_first = std::min(odom_total, kOdomFirstBatch);
+  if (odom) {
+    // the chain is a string of small latency-bound launches: it runs on its own stream beside the frame-batched launch below
+    // (both only read the map and its hash; the feature buffers are per frame) and joins before the read-back
+    EST_CUDA(cudaEventRecord(e->ev_map, st));
+    EST_CUDA(cudaStreamWaitEvent(e->ostream, e->ev_map, 0));
+    EST_CUDA(cudaMemsetAsync(e->d_odom, 0, sizeof(OdomState), e->ostream));
+    rc = odom_rounds(0, odom_first, e->ostream);
+    if (rc != LIO_OK) return rc;
+    EST_CUDA(cudaEventRecord(e->ev_odom, e->ostream));
+  }
   {
     // every owned frame except a LaserOdom-driven newest frame: ONE batched kNN + plane-fit launch
     KnnBatch b;
@@ -916,49 +990,27 @@ static int build_local_map(lio_est *e) {
     if (rc != LIO_OK) return rc;
     if (e->knn_timed) cudaEventRecord(e->evk1, st);
   }
-  if (e->cfg.imu_factor && owns_frame(e, W)) {
-    const int idx = W, slot = e->slot_of[W];
-    EST_CUDA(cudaMemsetAsync(e->d_odom, 0, sizeof(OdomState), st));
-    if (!e->cfg.keep_features) {
-      // two launches per round and no memset: the k-NN + plane fit of the newest frame, then ONE CTA that reduces the
-      // round's features to A^T A / A^T b, takes the 6 x 6 Gauss-Newton step and re-arms the k-NN launch state
-      KnnBatch b;
-      b.nframes = 1;
-      KnnFrame &f = b.f[0];
-      f.surf = e->slot_ptr[slot]; f.n_dev = e->d_slot_n + slot; f.n_bound = e->cfg.max_frame_points; f.tf = e->d_tf + idx;
-      f.out_p = e->feats[idx].pts; f.out_c = e->feats[idx].coef; f.out_src = e->feats[idx].src; f.out_count = e->feats[idx].count;
-      f.append = 0; f.tile0 = 0;
-      for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
-        rc = calculate_features_batch(e->hash, b, e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, &e->d_odom->done, e->knn, st, &e->launches,
-                                      0, it > 0);
-        if (rc != LIO_OK) return rc;
-        k_odom_round<<<1, kOdomRoundThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, 0.05, 0.05,
-                                                      e->knn.status, b.ntiles, e->knn.ticket);
-        ++e->launches;
-      }
-    } else {
-      // keep_features: every round re-evaluates ALL kept features at the current transform (Estimator.cc:978-980), so the
-      // reduction is a pass of its own
-      const int nb = std::max(1, std::min(e->sm_count, (e->feats[idx].cap + kOdomThreads - 1) / kOdomThreads));
-      for (int it = 0; it < e->cfg.odom_max_iterations; ++it) {
-        rc = calculate_features_dev(e->hash, e->d_map, e->slot_ptr[slot], e->d_slot_n + slot, e->cfg.max_frame_points, e->d_tf + idx,
-                                    e->cfg.min_match_sq_dis, e->cfg.min_plane_dis, e->feats[idx], 1,
-                                    &e->d_odom->done, e->knn, st, &e->launches);
-        if (rc != LIO_OK) return rc;
-        k_odom_reduce<<<nb, kOdomThreads, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count, e->d_tf + idx, e->d_odom, e->d_odom_partial);
-        k_odom_solve<<<1, 32, 0, st>>>(e->d_odom, e->d_tf + idx, 0.05, 0.05);
-        e->launches += 2;
-      }
-    }
-  }
   // one synchronisation: feature counts, map size, odom iterations
-  EST_CUDA(cudaMemcpyAsync(e->h_counts, e->d_feat_counts, sizeof(int) * (W + 1), cudaMemcpyDeviceToHost, st));
-  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 1, e->d_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
-  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 5, &e->d_odom->iter, sizeof(int), cudaMemcpyDeviceToHost, st));
-  EST_CUDA(cudaMemcpyAsync(e->h_tf + W, e->d_tf + W, sizeof(TransformF), cudaMemcpyDeviceToHost, st));
-  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 6, e->d_slot_n + e->slot_of[W], sizeof(int), cudaMemcpyDeviceToHost, st));
-  EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 7, e->vg.overflow_flag(), sizeof(int), cudaMemcpyDeviceToHost, st));
-  EST_CUDA(cudaStreamSynchronize(st));
+  auto readback = [&]() -> int {
+    EST_CUDA(cudaMemcpyAsync(e->h_counts, e->d_feat_counts, sizeof(int) * (W + 1), cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 1, e->d_counts, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 5, &e->d_odom->iter, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaMemcpyAsync(e->h_tf + W, e->d_tf + W, sizeof(TransformF), cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 6, e->d_slot_n + e->slot_of[W], sizeof(int), cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 7, e->vg.overflow_flag(), sizeof(int), cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 8, &e->d_odom->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    EST_CUDA(cudaStreamSynchronize(st));
+    return LIO_OK;
+  };
+  if (odom) EST_CUDA(cudaStreamWaitEvent(st, e->ev_odom, 0));
+  rc = readback();
+  if (rc != LIO_OK) return rc;
+  if (odom && odom_first < odom_total && !e->h_counts[W + 8]) {   // not converged yet (rare): the rest of the chain, one more synchronisation
+    rc = odom_rounds(odom_first, odom_total, st);
+    if (rc != LIO_OK) return rc;
+    rc = readback();
+    if (rc != LIO_OK) return rc;
+  }
   if (e->h_counts[W + 6] > e->cfg.max_frame_points) {   // vg_emit stopped storing at the capacity but kept counting
     lio_set_last_error(__FILE__, __LINE__, "down-sampled scan exceeds max_frame_points");
     return LIO_ERR_CAPACITY;
