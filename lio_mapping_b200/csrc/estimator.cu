@@ -512,6 +512,8 @@ struct lio_est {
   cudaEvent_t ev_gin = nullptr, ev_gout = nullptr;
   int graph_launches = 0;
   bool prior_uploaded = false;
+  bool ds_prepared = false, ds_prepared_asm = false;   // solve_dev_prepare ran for the current parameters
+  int ds_prepared_it = 0;
   cudaEvent_t evp[2 * 24] = {};
   // cached lidar reduction for the current parameter values
   bool S_valid = false;
@@ -858,7 +860,7 @@ static bool owns_frame(const lio_est *e, int idx) {  // idx: logical frame > piv
   return lio_est_frame_owner(idx - pivot, e->world) == e->rank;
 }
 
-static int build_local_map(lio_est *e) {
+static int build_local_map(lio_est *e, const std::function<int()> &before_sync = nullptr) {
   const int W = e->W, O = e->O, pivot = W - O;
   cudaStream_t st = e->stream;
   const double t0 = now_s();
@@ -1003,6 +1005,10 @@ static int build_local_map(lio_est *e) {
     return LIO_OK;
   };
   if (odom) EST_CUDA(cudaStreamWaitEvent(st, e->ev_odom, 0));
+  if (before_sync) {   // host work that only needs the window state runs here, while the GPU is busy with the launches above
+    rc = before_sync();
+    if (rc != LIO_OK) return rc;
+  }
   rc = readback();
   if (rc != LIO_OK) return rc;
   if (odom && odom_first < odom_total && !e->h_counts[W + 8]) {   // not converged yet (rare): the rest of the chain, one more synchronisation
@@ -1340,6 +1346,7 @@ static bool linearize(lio_est *e, Mat &H, Vec &g, double &cost, double *c_pim, d
 }
 
 static void prior_join(lio_est *e);
+static int solve_dev_prepare(lio_est *e, int max_it, bool assemble_only);
 static int slide_window(lio_est *e);
 static MargPrior marg_algebra(Mat A, Vec b, int O, std::vector<double> x0_pose, std::vector<double> x0_sb, const double *x0_ex);
 // ---- marginalisation (MarginalizationInfo::PreMarginalize / Marginalize, MarginalizationFactor.cc:132-311)
@@ -1503,11 +1510,16 @@ static void prior_join(lio_est *e) {
 //   scan_close  DoubleToVector, marginalisation of the oldest frame, SlideWindow                        (:2479-2568, :2040-2275, :2570-2666)
 static int scan_open_window(lio_est *e) {
   e->turn_off = true;
-  int rc = build_local_map(e);
+  e->ds_prepared = false;
+  int rc = build_local_map(e, [e]() -> int {
+    prior_join(e);  // the previous scan's marginalisation algebra ran beside the front end enqueued above
+    e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
+    vector_to_double(e);
+    // the device solver's state does not depend on the features: prepare and upload it before waiting for them
+    if (e->use_dev_solver) return solve_dev_prepare(e, e->cfg.max_num_iterations, false);
+    return LIO_OK;
+  });
   if (rc != LIO_OK) return rc;
-  prior_join(e);  // the previous scan's marginalisation algebra ran beside the front end above
-  e->ex_constant = (e->extrinsic_stage == 0 || e->cfg.opt_extrinsic == 0);
-  vector_to_double(e);
   e->window_open = true;
   return LIO_OK;
 }
@@ -1586,11 +1598,12 @@ static int scan_close_window(lio_est *e) {
 // ---- SolveOptimization with the device-resident dogleg loop --------------------------------------
 // The solve from the current para_* blocks on the device.  assemble_only: one evaluation without gates or steps, nothing of
 // the estimator's own state is touched (lio_est_assemble); the first linearisation stays readable in ds.H0 / ds.g0.
-static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
+// Everything of a device solve that does not depend on this scan's features: the solver state (parameters, prior, pre-integrations)
+// and the frame terms of the initial point, uploaded asynchronously.  process_scan calls it while the GPU is still busy with the front
+// end (before the scan's one synchronisation); solve_dev repeats it only when the parameters were replaced since.
+static int solve_dev_prepare(lio_est *e, int max_it, bool assemble_only) {
   const int O = e->O, pivot = e->W - O;
   cudaStream_t st = e->stream;
-  int rc = LIO_OK;
-  const double t0 = now_s();
   DevSolveState &S = *e->ds.h_st;
   S.sc.O = O; S.sc.n = 15 * (O + 1) + 6; S.sc.max_it = assemble_only ? 0 : max_it;
   S.sc.skip_gates = assemble_only ? 1 : 0; S.sc.pad_ = 0;
@@ -1625,6 +1638,27 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
     }
   }
   EST_CUDA(cudaMemcpyAsync(e->ds.st, &S, sizeof(DevSolveState), cudaMemcpyHostToDevice, st));
+  for (int i = 1; i <= O; ++i) {
+    double Mtmp[108];   // frame terms of the initial point; the solver writes the candidates' terms itself
+    ppp_frame_terms(e->para_pose[0].data(), e->para_pose[i].data(), e->para_ex, e->h_Rt + (i - 1) * kAsmRtStride,
+                    e->h_Rt + (i - 1) * kAsmRtStride + 9, Mtmp);
+  }
+  EST_CUDA(cudaMemcpyAsync(e->d_Rt, e->h_Rt, sizeof(double) * O * kAsmRtStride, cudaMemcpyHostToDevice, st));
+  e->ds_prepared = true; e->ds_prepared_it = max_it; e->ds_prepared_asm = assemble_only;
+  return LIO_OK;
+}
+
+static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
+  const int O = e->O, pivot = e->W - O;
+  cudaStream_t st = e->stream;
+  int rc = LIO_OK;
+  const double t0 = now_s();
+  if (!(e->ds_prepared && e->ds_prepared_it == max_it && e->ds_prepared_asm == assemble_only)) {
+    rc = solve_dev_prepare(e, max_it, assemble_only);
+    if (rc != LIO_OK) return rc;
+  }
+  e->ds_prepared = false;
+  DevSolveState &S = *e->ds.h_st;
   AsmParams ap;
   std::memset(&ap, 0, sizeof(ap));
   ap.nframes = O;
@@ -1635,11 +1669,7 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
     f.pts = fo.pts; f.coef = fo.coef;
     f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
     nfeat += f.n;
-    double Mtmp[108];   // frame terms of the initial point; the solver writes the candidates' terms itself
-    ppp_frame_terms(e->para_pose[0].data(), e->para_pose[i].data(), e->para_ex, e->h_Rt + (i - 1) * kAsmRtStride,
-                    e->h_Rt + (i - 1) * kAsmRtStride + 9, Mtmp);
   }
-  EST_CUDA(cudaMemcpyAsync(e->d_Rt, e->h_Rt, sizeof(double) * O * kAsmRtStride, cudaMemcpyHostToDevice, st));
   asm_plan(ap, e->sm_count);
   ap.skip_flag = &e->ds.st->sc.done;
   ap.stamps = &e->ds.st->dbg[12][0];   // rows 12..14 of the trace: asm_ppp entry / exit stamps per evaluation
@@ -1715,11 +1745,14 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
       for (cudaGraphNode_t nd : nodes) if (asm_is_graph_node(nd)) e->asm_nodes.push_back(nd);
       if ((int)e->asm_nodes.size() != nevals) { lio_set_last_error(__FILE__, __LINE__, "solver graph: unexpected node count"); return LIO_ERR_CUDA; }
     }
+    const double tu0 = now_s();
     for (cudaGraphNode_t nd : e->asm_nodes) {
       rc = asm_graph_update(e->sexec, nd, ap, e->d_Rt, e->asmw);
       if (rc != LIO_OK) return rc;
     }
+    e->t_lin_lidar = now_s() - tu0;   // device-solver mode: host time of re-parameterising the asm_ppp nodes
     EST_CUDA(cudaGraphLaunch(e->sexec, gs));
+    e->t_lin_host = now_s() - t0;     // device-solver mode: host time from the start of the solve to the end of the graph launch call
     e->launches += e->graph_launches;
     EST_CUDA(cudaEventRecord(e->ev_gout, gs));
     EST_CUDA(cudaStreamWaitEvent(st, e->ev_gout, 0));
@@ -1924,6 +1957,7 @@ static void load_parameters(lio_est *e, const double *pose, const double *sb, co
   }
   if (ex) std::memcpy(e->para_ex, ex, 7 * sizeof(double));
   e->S_valid = false;
+  e->ds_prepared = false;   // the uploaded solver state belongs to the previous parameter values
 }
 static void store_parameters(const lio_est *e, double *pose, double *sb, double *ex) {
   for (int k = 0; k <= e->O; ++k) {
