@@ -320,6 +320,7 @@ def main():
             print("[trace] ev %2d  k_step %6.1f us | gap %5.1f | asm %5.1f..%5.1f  k_factors %5.1f..%5.1f  k_hpart ..%5.1f | phases(cyc) %s" % (
                 e_, (int(tr[e_, 11]) - int(tr[e_, 0])) / 1000.0, rel(tr[e_, 0]), rel(tr[13, e_]), rel(tr[14, e_]), rel(tr[e_, 12]), rel(tr[e_, 13]),
                 rel(tr[e_, 14]), np.diff(tr[e_, 1:11]).tolist()), file=sys.stderr)
+        print("[trace] lidar_blocks marks (cycles from entry, eval 2): %s" % (tr[16, 1:4] - tr[16, 0]).tolist(), file=sys.stderr)
         cp = est.chol_profile
         NBp = (15 * (W + 1) + 6 + 7) // 8
         pp_ = cp[:4 * NBp].reshape(NBp, 4)

@@ -618,43 +618,70 @@ __device__ __forceinline__ double lidar_g(const GatherCtx &c, int ba, int sa) {
 
 // G_i = M_i^T S_gg M_i (18 x 18), M_i^T S_gr (18) per frame, and the blocks shared by all frames (pose_0 / extrinsic rows
 // and columns, 12 x 12 + 12) summed in frame order.  scratch: O * 108 doubles of shared memory.
-__device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const double *__restrict__ FM, double *G, double *G0, double *scratch) {
+// G_i = M_i^T S_i M_i (18 x 18 + 18 gradient terms per frame) and the block G0 shared by pose_0 and the extrinsic.  The inputs
+// (M_i: 108 doubles, S_i: 29) are staged in shared memory first and every product runs from there: the three phases used to
+// fetch their operands from global memory one dependent round trip after the other (4.8 us for 10 frames).
+// scratch: >= O * (108 + 32 + 108 + 342) doubles of shared memory (the Cholesky tiles are not in use yet).
+__device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const double *__restrict__ FM, double *G, double *G0, double *scratch, long long *marks = nullptr) {
   const int tid = threadIdx.x, T = blockDim.x;
+  if (marks && tid == 0) marks[0] = clock64();
+  double *sM = scratch, *sS = sM + O * 108, *sSM = sS + O * 32, *sG = sSM + O * 108;
+  {   // all of a thread's loads are issued before the first store (O <= 13: at most four per thread)
+    double v[4];
+    int dst[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int p = tid + k * T;
+      dst[k] = -1; v[k] = 0.0;
+      if (p < O * 140) {
+        const int i = p / 140, q = p - i * 140;
+        if (q < 108) { dst[k] = i * 108 + q; v[k] = FM[(size_t)i * kFMStride + q]; }
+        else if (q < 108 + 29) { dst[k] = O * 108 + i * 32 + (q - 108); v[k] = Sblk[i * kAsmStride + (q - 108)]; }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (dst[k] >= 0) scratch[dst[k]] = v[k];
+  }
+  __syncthreads();
+  if (marks && threadIdx.x == 0) marks[1] = clock_after(scratch[0]);
   for (int p = tid; p < O * 108; p += T) {     // SM_i = S_gg M_i (6 x 18)
     const int i = p / 108, q = p - i * 108, a = q / 18, c = q - a * 18;
-    const double *Sb = Sblk + i * kAsmStride, *M = FM + (size_t)i * kFMStride;
+    const double *Sb = sS + i * 32, *M = sM + i * 108;
     double s = 0;
 #pragma unroll
     for (int b = 0; b < 6; ++b) s += Sb[a < b ? s_idx(a, b) : s_idx(b, a)] * M[b * 18 + c];
-    scratch[p] = s;
+    sSM[p] = s;
   }
   __syncthreads();
+  if (marks && threadIdx.x == 0) marks[2] = clock_after(scratch[0]);
   for (int p = tid; p < O * 342; p += T) {
     const int i = p / 342, q = p - i * 342;
-    const double *M = FM + (size_t)i * kFMStride;
+    const double *M = sM + i * 108;
     double v = 0;
     if (q < 324) {
       const int a = q / 18, b = q - a * 18;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * scratch[i * 108 + k * 18 + b];
+      for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * sSM[i * 108 + k * 18 + b];
     } else {
       const int a = q - 324;
-      const double *Sb = Sblk + i * kAsmStride;
+      const double *Sb = sS + i * 32;
 #pragma unroll
       for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * Sb[s_idx(k, 6)];
     }
+    sG[p] = v;
     G[(size_t)i * kFGStride + q] = v;
   }
   __syncthreads();
+  if (marks && threadIdx.x == 0) marks[3] = clock_after(scratch[0]);
   for (int p = tid; p < 156; p += T) {
     double s = 0;
     if (p < 144) {
       const int ra = p / 12, rb = p - ra * 12;
       const int a = ra < 6 ? ra : ra + 6, b = rb < 6 ? rb : rb + 6;
-      for (int i = 0; i < O; ++i) s += G[(size_t)i * kFGStride + a * 18 + b];
+      for (int i = 0; i < O; ++i) s += sG[i * 342 + a * 18 + b];
     } else {
       const int ra = p - 144, a = ra < 6 ? ra : ra + 6;
-      for (int i = 0; i < O; ++i) s += G[(size_t)i * kFGStride + 324 + a];
+      for (int i = 0; i < O; ++i) s += sG[i * 342 + 324 + a];
     }
     G0[p] = s;
   }
@@ -842,7 +869,7 @@ __device__ void step_body(DevSolveState *S, StepShared &sh, double *dsm, double 
 
   if (build) {
     // ---------------- normal equations at the new current point ----------------
-    if (gc.lidar) lidar_blocks(O, Sblk, F.M, G, G0, tiles);
+    if (gc.lidar) lidar_blocks(O, Sblk, F.M, G, G0, tiles, eval_index == 2 ? &S->dbg[16][0] : nullptr);
     DS_MARK(3);
     // unscaled diagonal, gradient; Jacobi scaling is fixed at iteration zero
     // k_hpart's gather is usable when it assumed the structure that is in force now (the gates may have changed it)

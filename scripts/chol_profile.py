@@ -16,7 +16,11 @@ for _ in range(3):
     _lib.check(L.lio_dev_cholesky_solve_host(A, b, n, x, C.byref(ok), prof.ctypes.data_as(C.c_void_p), 0), "chol")
 p = prof[:4 * NB].reshape(NB, 4)
 print("n", n, "ok", ok.value, "err", np.abs(x - np.linalg.solve(A, b)).max())
-print("panel: solve own_update diag update_total(cycles)")
+# columns: [0] panel solve + barrier (chain warp's clock64, read behind the barrier), [1] %globaltimer (ns) when the chain warp starts the
+# next diagonal tile, [2] diagonal tile factor + inverse (cycles), [3] update phase incl. the wait for the workers (cycles)
+wall = np.diff(p[:NB - 1, 1])
+print("panel: solve(cyc) diag(cyc) update_total(cyc) | wall to the next panel (ns)")
 for k in range(NB):
-    print(k, p[k].tolist())
-print("sum", p.sum(0).tolist(), "backsub", int(prof[4 * NB]), "total cycles", int(p[:, 0].sum() + p[:, 3].sum() + prof[4 * NB]), "= %.1f us" % ((p[:, 0].sum() + p[:, 3].sum() + prof[4 * NB]) / 1965.0))
+    print(k, int(p[k, 0]), int(p[k, 2]), int(p[k, 3]), "|", int(wall[k]) if k < len(wall) else "-")
+cyc = int(p[:, 0].sum() + p[:, 3].sum() + prof[4 * NB])
+print("chain-warp cycles: loop", int(p[:, 0].sum() + p[:, 3].sum()), "backsub", int(prof[4 * NB]), "total", cyc, "= %.1f us at 1.965 GHz (wall by %%globaltimer: see the [k_chol_test] lines on stderr)" % (cyc / 1965.0))
