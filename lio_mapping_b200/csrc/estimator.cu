@@ -1701,7 +1701,7 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
       }
       // asm_ppp is timed on the first evaluation only: inside the captured graph every event record is a node on the critical path
       // between two k_step launches (measured: the launch behind it starts ~4 us later)
-      const bool timed = !capturing || ev == 0;
+      const bool timed = ev == 0 || (!capturing && e->world == 1);   // sharded runs: first evaluation only, like the graph
       if (timed) cudaEventRecordWithFlags(e->evp[2 * ev], q, evflag);
       r2 = asm_launch(ap, e->d_Rt, e->asmw, q, &e->launches);
       if (r2 != LIO_OK) return r2;
@@ -1770,7 +1770,7 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
     return LIO_ERR_CUDA;
   }
   const bool graph_replayed = e->sexec && e->gstream && e->world == 1 && !assemble_only && max_it == e->cfg.max_num_iterations;
-  for (int ev = 0; ev < std::min(graph_replayed ? 1 : nevals, S.sc.evaluations); ++ev) {
+  for (int ev = 0; ev < std::min((graph_replayed || e->world > 1) ? 1 : nevals, S.sc.evaluations); ++ev) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
     else (void)cudaGetLastError();   // a failed timing query must not surface as the next launch's error
