@@ -153,8 +153,9 @@ def main():
     ap.add_argument("--workload", default="hdl64", choices=["hdl64", "vlp16", "stress128"])
     ap.add_argument("--overlap-marginalization", type=int, default=1, choices=[0, 1],
                     help="0: marginalisation algebra inline (reference order); 1: on a worker thread beside the next scan's front end")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU exchange of the S blocks: fused peer-memory stores (default) or an NCCL allreduce callback")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "rows", "nccl"],
+                    help="multi-GPU: peer = per-scan exchange of the features over peer memory (default); rows = S blocks stored from the "
+                         "stage-C kernel tail at every evaluation; nccl = allreduce callback of the S blocks")
     ap.add_argument("--cpu-sample", type=int, default=4, help="scans of the cpu_baseline sample (rank 0, N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -218,15 +219,20 @@ def main():
         exchange = {"kind": "nccl allreduce (torch.distributed) of O x 32 doubles per evaluation"}
 
         def attach(e):
-            """Preferred: fused exchange over peer memory (IPC handles all-gathered once); fallback: NCCL allreduce callback."""
+            """Preferred: per-scan exchange of the features over peer memory (every rank then solves like a single GPU);
+            --exchange rows: S rows stored from the stage-C kernel tail at every evaluation; fallback: NCCL allreduce callback."""
             if args.exchange == "nccl":
                 e.set_shard(rank, world, allreduce)
                 return
             try:
-                mine = torch.from_numpy(e.exchange_handle()).to(dev)
+                feat = args.exchange != "rows"
+                mine = torch.from_numpy(e.feature_slab_handle() if feat else e.exchange_handle()).to(dev)
                 allh = [torch.zeros(64, dtype=torch.uint8, device=dev) for _ in range(world)]
                 dist.all_gather(allh, mine)
-                e.set_peers(rank, world, handles=[h.cpu().numpy() for h in allh])
+                if feat:
+                    e.set_feature_peers(rank, world, handles=[h.cpu().numpy() for h in allh])
+                else:
+                    e.set_peers(rank, world, handles=[h.cpu().numpy() for h in allh])
                 ok = torch.ones(1, device=dev)
             except Exception as exc:   # no P2P / IPC on this box
                 print(f"[bench] peer exchange unavailable on rank {rank}: {exc!r}", file=sys.stderr)
@@ -234,6 +240,9 @@ def main():
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if float(ok.item()) < 0.5:
                 e.set_shard(rank, world, allreduce)
+            elif feat:
+                exchange["kind"] = ("matching sharded by frame; once per scan every rank stores the features of its frames into every rank's feature slab "
+                                    "(P2P stores + epoch flags over CUDA-IPC peer memory), then each rank runs the complete solve like a single GPU")
             else:
                 exchange["kind"] = "fused into the stage-C kernel tail: P2P stores of the owned S blocks into every rank's buffer + epoch flags (CUDA IPC peer memory)"
         attach(est)

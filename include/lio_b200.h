@@ -394,6 +394,15 @@ int lio_est_set_shard(lio_est *est, int rank, int world, lio_allreduce_fn fn, vo
  * all ranks before the 2.5 kB result goes to the host.  No collective call, no extra pass over the data. */
 int lio_est_exchange_buffer(lio_est *est, void **dev_ptr, size_t *bytes);
 int lio_est_set_peers(lio_est *est, int world, void *const *peer_ptrs /* [world], entry [rank] ignored */);
+/* Per-scan feature exchange (preferred on one NVLink / NVSwitch node).  After lio_est_set_shard(rank, world, NULL, NULL) each rank
+ * still matches only the frames it owns, but copies their features (xyz + score, coefficients, count) into the same place of every
+ * peer's feature slab with P2P stores and publishes the scan's epoch; once all epochs have arrived every rank holds ALL frames'
+ * features and runs the complete solve exactly like a single-GPU context (one rendezvous per scan instead of one per evaluation, the
+ * solve graph stays in use).  lio_est_feature_slab returns this context's slab (all feature buffers of both scan parities, the
+ * counts and the epoch flags are ONE allocation: export it with lio_ipc_export); lio_est_set_feature_peers takes every rank's slab
+ * as mapped in this process (entry [rank] ignored).  Replaces a previous lio_est_set_peers; LIO_ERR_INVALID inside an open scan. */
+int lio_est_feature_slab(lio_est *est, void **dev_ptr, size_t *bytes);
+int lio_est_set_feature_peers(lio_est *est, int world, void *const *peer_slabs /* [world], entry [rank] ignored */);
 int lio_ipc_export(const void *dev_ptr, unsigned char handle[64]);      /* cudaIpcGetMemHandle */
 int lio_ipc_open(const unsigned char handle[64], void **dev_ptr);       /* cudaIpcOpenMemHandle, lazy peer access */
 int lio_ipc_close(void *dev_ptr);

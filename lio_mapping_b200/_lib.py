@@ -140,6 +140,8 @@ def lib():
     L.lio_est_close_scan.argtypes = [vp, vp, vp, vp]
     L.lio_est_exchange_buffer.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
     L.lio_est_set_peers.argtypes = [vp, ip, C.POINTER(vp)]
+    L.lio_est_feature_slab.argtypes = [vp, C.POINTER(vp), C.POINTER(C.c_size_t)]
+    L.lio_est_set_feature_peers.argtypes = [vp, ip, C.POINTER(vp)]
     L.lio_ipc_export.argtypes = [vp, u8p]
     L.lio_ipc_open.argtypes = [u8p, C.POINTER(vp)]
     L.lio_ipc_close.argtypes = [vp]

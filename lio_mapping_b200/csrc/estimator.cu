@@ -470,7 +470,17 @@ struct lio_est {
   cudaStream_t ostream = nullptr;   // stream of that chain
   cudaEvent_t ev_map = nullptr, ev_odom = nullptr;
   std::vector<FeatureOut> feats;  // logical frame index
-  int *d_feat_counts = nullptr;   // W+1
+  int *d_feat_counts = nullptr;   // W+1 (inside the feature slab, current parity)
+  // All feature buffers (xyz+score, coefficients, counts) live in ONE allocation with two parities, so that a sharded run can
+  // exchange the features themselves once per scan (lio_est_set_feature_peers): every rank then owns all frames' features and the
+  // whole solve runs exactly like a single-GPU solve - no rendezvous inside the 11 evaluations.
+  char *fslab = nullptr;
+  size_t fslab_bytes = 0, fpar_stride = 0, foff_cnt = 0, foff_flags = 0;
+  std::vector<size_t> foff_pts, foff_coef;
+  bool fpeers = false;
+  char *fpeer_base[kMaxPeers] = {};
+  unsigned fepoch = 0;
+  int fparity = 0;
   TransformF *d_tf = nullptr;     // W+1
   TransformF *h_tf = nullptr;     // pinned
   AsmWork asmw;
@@ -596,13 +606,53 @@ extern "C" void lio_est_default_config(lio_est_config *c) {
   c->solver_graph = 1;
 }
 
+// point the per-frame feature descriptors at one parity of the slab
+static void set_feature_parity(lio_est *e, int par) {
+  char *base = e->fslab + (size_t)par * e->fpar_stride;
+  e->d_feat_counts = reinterpret_cast<int *>(base + e->foff_cnt);
+  const int pivot = e->W - e->O;
+  for (int k = pivot + 1; k <= e->W; ++k) {
+    FeatureOut &f = e->feats[k];
+    f.pts = reinterpret_cast<float4 *>(base + e->foff_pts[k]);
+    f.coef = reinterpret_cast<float4 *>(base + e->foff_coef[k]);
+    f.count = e->d_feat_counts + k;
+  }
+  e->fparity = par;
+}
+
+// ---- per-scan feature exchange over peer memory (sharded runs) ----------------------------------------------------------
+struct FeaturePeers {
+  float4 *pts[kMaxPeers], *coef[kMaxPeers];
+  int *count[kMaxPeers];
+  int npeers, self;
+};
+// An owned frame's features go to the same place in every peer's slab (plain P2P stores over NVLink / NVSwitch).
+__global__ void __launch_bounds__(256)
+k_publish_features(const float4 *__restrict__ pts, const float4 *__restrict__ coef, const int *__restrict__ count, int cap, FeaturePeers P) {
+  const int n = min(*count, cap);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 v = pts[i], w = coef[i];
+    for (int r = 0; r < P.npeers; ++r) if (r != P.self) { P.pts[r][i] = v; P.coef[r][i] = w; }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) for (int r = 0; r < P.npeers; ++r) if (r != P.self) *P.count[r] = *count;
+}
+struct FlagPeers { unsigned *flag[kMaxPeers]; int npeers, self; };
+// after the publishing kernels of this rank have completed (stream order): the scan's epoch into every rank's flag slot
+__global__ void k_publish_flag(FlagPeers P, unsigned epoch) {
+  __threadfence_system();
+  if ((int)threadIdx.x < P.npeers) {
+    unsigned *fl = P.flag[threadIdx.x] + P.self;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(fl), "r"(epoch) : "memory");
+  }
+}
+
 extern "C" int lio_est_destroy(lio_est *e) {
   if (!e) return LIO_OK;
   if (e->mjob.running) { e->worker.wait(); e->mjob.running = false; }
   cudaSetDevice(e->device);
   for (float4 *p : e->slot_ptr) if (p) cudaFree(p);
-  for (FeatureOut &f : e->feats) { if (f.pts) cudaFree(f.pts); if (f.coef) cudaFree(f.coef); if (f.src) cudaFree(f.src); }
-  void *ptrs[] = {e->d_slot_n, e->d_own_n, e->d_scan, e->d_local, e->d_map, e->d_tmp, e->d_counts, e->d_feat_counts, e->d_tf, e->d_odom, e->d_odom_partial};
+  for (FeatureOut &f : e->feats) if (f.src) cudaFree(f.src);
+  void *ptrs[] = {e->d_slot_n, e->d_own_n, e->d_scan, e->d_local, e->d_map, e->d_tmp, e->d_counts, e->fslab, e->d_tf, e->d_odom, e->d_odom_partial};
   for (void *p : ptrs) if (p) cudaFree(p);
   for (int k = 0; k < 48; ++k) if (e->evp[k]) cudaEventDestroy(e->evp[k]);
   e->ds.destroy();
@@ -672,7 +722,6 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   ok = ok && cudaMalloc(&e->d_map, sizeof(float4) * e->local_cap) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_tmp, sizeof(float4) * e->slot_cap) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_counts, sizeof(int) * 8) == cudaSuccess;
-  ok = ok && cudaMalloc(&e->d_feat_counts, sizeof(int) * (W + 1)) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_tf, sizeof(TransformF) * (W + 1)) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_odom, sizeof(OdomState)) == cudaSuccess;
   ok = ok && cudaMalloc(&e->d_odom_partial, sizeof(double) * 32 * 1024) == cudaSuccess;
@@ -692,21 +741,28 @@ extern "C" int lio_est_create(const lio_est_config *cfg, int device, void *cuda_
   ok = ok && cudaEventCreateWithFlags(&e->ev_odom, cudaEventDisableTiming) == cudaSuccess;
   e->feats.assign(W + 1, FeatureOut());
   long long total_feat = 0;
-  for (int k = pivot + 1; k <= W && ok; ++k) {
-    int cap = cfg->max_frame_points * ((k == W && cfg->keep_features) ? cfg->odom_max_iterations : 1);
-    FeatureOut &f = e->feats[k];
-    f.cap = cap;
-    f.count = e->d_feat_counts + k;
-    ok = ok && cudaMalloc(&f.pts, sizeof(float4) * cap) == cudaSuccess;
-    ok = ok && cudaMalloc(&f.coef, sizeof(float4) * cap) == cudaSuccess;
-    ok = ok && cudaMalloc(&f.src, sizeof(int) * cap) == cudaSuccess;
-    total_feat += cap;
+  {
+    e->foff_pts.assign(W + 1, 0); e->foff_coef.assign(W + 1, 0);
+    size_t off = 0;
+    for (int k = pivot + 1; k <= W; ++k) {
+      const int cap = cfg->max_frame_points * ((k == W && cfg->keep_features) ? cfg->odom_max_iterations : 1);
+      e->feats[k].cap = cap;
+      e->foff_pts[k] = off; off += sizeof(float4) * (size_t)cap;
+      e->foff_coef[k] = off; off += sizeof(float4) * (size_t)cap;
+      total_feat += cap;
+    }
+    e->foff_cnt = off; off += ((sizeof(int) * (size_t)(W + 1) + 255) / 256) * 256;
+    e->fpar_stride = off;
+    e->foff_flags = 2 * off;
+    e->fslab_bytes = 2 * off + 256;   // epoch flags (one per source rank) + error word behind the two parities
+    ok = ok && cudaMalloc(&e->fslab, e->fslab_bytes) == cudaSuccess && cudaMemset(e->fslab, 0, e->fslab_bytes) == cudaSuccess;
+    for (int k = pivot + 1; k <= W && ok; ++k) ok = ok && cudaMalloc(&e->feats[k].src, sizeof(int) * e->feats[k].cap) == cudaSuccess;
+    if (ok) set_feature_parity(e, 0);
   }
   ok = ok && e->asmw.init((int)std::min<long long>(total_feat, 1ll << 30)) == 0;
   if (ok) {
     ok = ok && cudaMemset(e->d_slot_n, 0, sizeof(int) * (W + 1)) == cudaSuccess;
     ok = ok && cudaMemset(e->d_own_n, 0, sizeof(int) * (W + 1)) == cudaSuccess;
-    ok = ok && cudaMemset(e->d_feat_counts, 0, sizeof(int) * (W + 1)) == cudaSuccess;
     ok = ok && cudaMemset(e->d_counts, 0, sizeof(int) * 8) == cudaSuccess;
   }
   ok = ok && cudaEventCreate(&e->ev0) == cudaSuccess && cudaEventCreate(&e->ev1) == cudaSuccess;
@@ -855,10 +911,14 @@ static void double_to_vector(lio_est *e) {  // Estimator.cc:2479-2568
 
 // ---- stage B orchestration -----------------------------------------------------------------------
 extern "C" int lio_est_frame_owner(int frame_rel, int world);
+// ranks the lidar reduction of a solve is sharded over: 1 when the features themselves were exchanged (every rank holds all of them)
+static int solve_world(const lio_est *e) { return e->fpeers ? 1 : e->world; }
 static bool owns_frame(const lio_est *e, int idx) {  // idx: logical frame > pivot
   const int pivot = e->W - e->O;
   return lio_est_frame_owner(idx - pivot, e->world) == e->rank;
 }
+
+__global__ void k_xwait(const unsigned *__restrict__ flags, int npeers, unsigned epoch, int *__restrict__ err, const int *__restrict__ skip);
 
 static int build_local_map(lio_est *e, const std::function<int()> &before_sync = nullptr) {
   const int W = e->W, O = e->O, pivot = W - O;
@@ -918,7 +978,16 @@ static int build_local_map(lio_est *e, const std::function<int()> &before_sync =
   if (rc != LIO_OK) return rc;
   e->t_build = now_s() - t0;
   const double t1 = now_s();
-  EST_CUDA(cudaMemsetAsync(e->d_feat_counts, 0, sizeof(int) * (W + 1), st));
+  if (e->fpeers) {
+    // feature exchange: this scan's features go to the other parity (a rank that is one scan ahead writes into the parity nobody
+    // reads any more); only the counts of the frames this rank matches are reset - the others arrive from their owners
+    set_feature_parity(e, e->fparity ^ 1);
+    ++e->fepoch;
+    for (int idx = pivot + 1; idx <= W; ++idx)
+      if (owns_frame(e, idx)) EST_CUDA(cudaMemsetAsync(e->d_feat_counts + idx, 0, sizeof(int), st));
+  } else {
+    EST_CUDA(cudaMemsetAsync(e->d_feat_counts, 0, sizeof(int) * (W + 1), st));
+  }
   // CalculateLaserOdom on the newest frame: rounds after convergence are no-ops on the device (done flag), but each still costs two
   // launches.  The chain is therefore enqueued in two batches: the first kOdomFirstBatch rounds ride with the scan's one
   // synchronisation (it converges in 2-3 rounds); only if the flag is still clear are the remaining rounds enqueued.
@@ -960,7 +1029,7 @@ static int build_local_map(lio_est *e, const std::function<int()> &before_sync =
     return LIO_OK;
   };
   const int odom_total = odom ? e->cfg.odom_max_iterations : 0;
-  const int odom_first = std::min(odom_total, kOdomFirstBatch);
+  const int odom_first = e->fpeers ? odom_total : std::min(odom_total, kOdomFirstBatch);   // exchanged features must be final
   if (odom) {
     // the chain is a string of small latency-bound launches: it runs on its own stream beside the frame-batched launch below
     // (both only read the map and its hash; the feature buffers are per frame) and joins before the read-back
@@ -1001,10 +1070,40 @@ static int build_local_map(lio_est *e, const std::function<int()> &before_sync =
     EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 6, e->d_slot_n + e->slot_of[W], sizeof(int), cudaMemcpyDeviceToHost, st));
     EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 7, e->vg.overflow_flag(), sizeof(int), cudaMemcpyDeviceToHost, st));
     EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 8, &e->d_odom->done, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (e->fpeers) EST_CUDA(cudaMemcpyAsync(e->h_counts + W + 9, e->fslab + e->foff_flags + 128, sizeof(int), cudaMemcpyDeviceToHost, st));
     EST_CUDA(cudaStreamSynchronize(st));
     return LIO_OK;
   };
   if (odom) EST_CUDA(cudaStreamWaitEvent(st, e->ev_odom, 0));
+  if (e->fpeers) {
+    // all-gather of the features: every owned frame is copied into the same place of every peer's slab, then the scan's epoch is
+    // published in every rank's flag slot and this rank waits for the epochs of all ranks (bounded, like the S-row exchange)
+    const size_t pbase = (size_t)e->fparity * e->fpar_stride;
+    FeaturePeers fp;
+    std::memset(&fp, 0, sizeof(fp));
+    fp.npeers = e->world; fp.self = e->rank;
+    FlagPeers fl;
+    std::memset(&fl, 0, sizeof(fl));
+    fl.npeers = e->world; fl.self = e->rank;
+    for (int r = 0; r < e->world; ++r) fl.flag[r] = reinterpret_cast<unsigned *>(e->fpeer_base[r] + e->foff_flags);
+    for (int idx = pivot + 1; idx <= W; ++idx) {
+      if (!owns_frame(e, idx)) continue;
+      for (int r = 0; r < e->world; ++r) {
+        fp.pts[r] = reinterpret_cast<float4 *>(e->fpeer_base[r] + pbase + e->foff_pts[idx]);
+        fp.coef[r] = reinterpret_cast<float4 *>(e->fpeer_base[r] + pbase + e->foff_coef[idx]);
+        fp.count[r] = reinterpret_cast<int *>(e->fpeer_base[r] + pbase + e->foff_cnt) + idx;
+      }
+      const int known = e->size_surf_stack[idx];
+      const int bound = (known > 0 && idx < W) ? known : e->feats[idx].cap;
+      k_publish_features<<<std::max(1, std::min(e->sm_count * 2, (bound + 255) / 256)), 256, 0, st>>>(e->feats[idx].pts, e->feats[idx].coef, e->feats[idx].count,
+                                                                                                   e->feats[idx].cap, fp);
+      ++e->launches;
+    }
+    k_publish_flag<<<1, 32, 0, st>>>(fl, e->fepoch);
+    k_xwait<<<1, 32, 0, st>>>(reinterpret_cast<const unsigned *>(e->fslab + e->foff_flags), e->world, e->fepoch,
+                              reinterpret_cast<int *>(e->fslab + e->foff_flags + 128), nullptr);
+    e->launches += 2;
+  }
   if (before_sync) {   // host work that only needs the window state runs here, while the GPU is busy with the launches above
     rc = before_sync();
     if (rc != LIO_OK) return rc;
@@ -1016,6 +1115,11 @@ static int build_local_map(lio_est *e, const std::function<int()> &before_sync =
     if (rc != LIO_OK) return rc;
     rc = readback();
     if (rc != LIO_OK) return rc;
+  }
+  if (e->fpeers && e->h_counts[W + 9]) {
+    cudaMemsetAsync(e->fslab + e->foff_flags + 128, 0, sizeof(int), st);
+    lio_set_last_error(__FILE__, __LINE__, "feature exchange timed out (a rank did not publish its frames)");
+    return LIO_ERR_CUDA;
   }
   if (e->h_counts[W + 6] > e->cfg.max_frame_points) {   // vg_emit stopped storing at the capacity but kept counting
     lio_set_last_error(__FILE__, __LINE__, "down-sampled scan exceeds max_frame_points");
@@ -1052,7 +1156,7 @@ static int build_local_map(lio_est *e, const std::function<int()> &before_sync =
 // Waits until every rank has published `epoch` in this rank's flag array (the rows travel with the asm_ppp tails of the
 // peers as P2P stores; system-scope release / acquire).  Bounded: a peer that never arrives sets *err instead of hanging.
 __global__ void k_xwait(const unsigned *__restrict__ flags, int npeers, unsigned epoch, int *__restrict__ err,
-                        const int *__restrict__ skip = nullptr) {
+                        const int *__restrict__ skip) {
   const int p = threadIdx.x;
   if (p >= npeers) return;
   if (skip && *skip) return;   // the device solver has terminated: its asm_ppp launches publish nothing any more
@@ -1082,7 +1186,7 @@ static int eval_lidar_launch(lio_est *e, std::vector<FrameTerms> &ft) {
     AsmFrame &f = ap.f[i - 1];
     const FeatureOut &fo = e->feats[pivot + i];
     f.pts = fo.pts; f.coef = fo.coef;
-    f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
+    f.n = (e->cfg.point_distance_factor && (e->fpeers || owns_frame(e, pivot + i))) ? e->h_feat_n[pivot + i] : 0;
     std::memcpy(e->h_Rt + (i - 1) * kAsmRtStride, ft[i].R, sizeof(double) * 9);
     std::memcpy(e->h_Rt + (i - 1) * kAsmRtStride + 9, ft[i].t, sizeof(double) * 3);
   }
@@ -1091,8 +1195,8 @@ static int eval_lidar_launch(lio_est *e, std::vector<FrameTerms> &ft) {
   asm_plan(ap, e->sm_count);
   long long nfeat = 0;
   for (int k = 0; k < ap.nframes; ++k) nfeat += ap.f[k].n;
-  const bool peers = e->world > 1 && e->npeers == e->world;
-  if (e->world > 1 && !peers && !e->allreduce) {
+  const bool peers = solve_world(e) > 1 && e->npeers == e->world;
+  if (solve_world(e) > 1 && !peers && !e->allreduce) {
     lio_set_last_error(__FILE__, __LINE__, "sharded context without an exchange: call lio_est_set_peers or pass an allreduce callback");
     return LIO_ERR_INVALID;
   }
@@ -1113,10 +1217,10 @@ static int eval_lidar_launch(lio_est *e, std::vector<FrameTerms> &ft) {
   if (e->ev1) cudaEventRecord(e->ev1, e->stream);
   if (peers) {
     k_xwait<<<1, 32, 0, e->stream>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
-                                     reinterpret_cast<int *>(e->xbuf + kXErrOff));
+                                     reinterpret_cast<int *>(e->xbuf + kXErrOff), nullptr);
     ++e->launches;
     EST_CUDA(cudaMemcpyAsync(e->h_S + kMaxOpt * kAsmStride, e->xbuf + kXErrOff, sizeof(int), cudaMemcpyDeviceToHost, e->stream));
-  } else if (e->world > 1 && e->allreduce) {
+  } else if (solve_world(e) > 1 && e->allreduce) {
     rc = e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride);
     if (rc != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
   }
@@ -1667,14 +1771,14 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
     AsmFrame &f = ap.f[i - 1];
     const FeatureOut &fo = e->feats[pivot + i];
     f.pts = fo.pts; f.coef = fo.coef;
-    f.n = (e->cfg.point_distance_factor && owns_frame(e, pivot + i)) ? e->h_feat_n[pivot + i] : 0;
+    f.n = (e->cfg.point_distance_factor && (e->fpeers || owns_frame(e, pivot + i))) ? e->h_feat_n[pivot + i] : 0;
     nfeat += f.n;
   }
   asm_plan(ap, e->sm_count);
   ap.skip_flag = &e->ds.st->sc.done;
   ap.stamps = &e->ds.st->dbg[12][0];   // rows 12..14 of the trace: asm_ppp entry / exit stamps per evaluation
-  const bool peers = e->world > 1 && e->npeers == e->world;
-  if (e->world > 1 && !peers && !e->allreduce) {
+  const bool peers = solve_world(e) > 1 && e->npeers == e->world;
+  if (solve_world(e) > 1 && !peers && !e->allreduce) {
     lio_set_last_error(__FILE__, __LINE__, "sharded context without an exchange: call lio_est_set_peers or pass an allreduce callback");
     return LIO_ERR_INVALID;
   }
@@ -1701,7 +1805,7 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
       }
       // asm_ppp is timed on the first evaluation only: inside the captured graph every event record is a node on the critical path
       // between two k_step launches (measured: the launch behind it starts ~4 us later)
-      const bool timed = ev == 0 || (!capturing && e->world == 1);   // sharded runs: first evaluation only, like the graph
+      const bool timed = ev == 0 || (!capturing && solve_world(e) == 1);   // sharded runs: first evaluation only, like the graph
       if (timed) cudaEventRecordWithFlags(e->evp[2 * ev], q, evflag);
       r2 = asm_launch(ap, e->d_Rt, e->asmw, q, &e->launches);
       if (r2 != LIO_OK) return r2;
@@ -1710,7 +1814,7 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
         k_xwait<<<1, 32, 0, q>>>(reinterpret_cast<const unsigned *>(e->xbuf + kXFlagOff), e->npeers, ap.epoch,
                                  reinterpret_cast<int *>(e->xbuf + kXErrOff), &e->ds.st->sc.done);
         ++e->launches;
-      } else if (e->world > 1 && e->allreduce) {
+      } else if (solve_world(e) > 1 && e->allreduce) {
         if (e->allreduce(e->allreduce_user, e->asmw.out, O * kAsmStride) != 0) { lio_set_last_error(__FILE__, __LINE__, "allreduce callback failed"); return LIO_ERR_CUDA; }
       }
       r2 = dev_solver_step(e->ds, result, e->d_Rt, ev, q, &e->launches);
@@ -1718,7 +1822,7 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
     }
     return LIO_OK;
   };
-  if (e->gstream && e->world == 1 && !assemble_only && max_it == e->cfg.max_num_iterations) {
+  if (e->gstream && solve_world(e) == 1 && !assemble_only && max_it == e->cfg.max_num_iterations) {
     // One graph per solve: the launch sequence (and the fork / join with the factor stream) is captured the first time and
     // replayed afterwards; only the asm_ppp nodes are re-parameterised with this scan's feature counts and tile plan.
     cudaStream_t gs = e->gstream;
@@ -1769,8 +1873,8 @@ static int solve_dev(lio_est *e, int max_it, bool assemble_only) {
     lio_set_last_error(__FILE__, __LINE__, "peer exchange timed out (a rank did not publish its rows)");
     return LIO_ERR_CUDA;
   }
-  const bool graph_replayed = e->sexec && e->gstream && e->world == 1 && !assemble_only && max_it == e->cfg.max_num_iterations;
-  for (int ev = 0; ev < std::min((graph_replayed || e->world > 1) ? 1 : nevals, S.sc.evaluations); ++ev) {
+  const bool graph_replayed = e->sexec && e->gstream && solve_world(e) == 1 && !assemble_only && max_it == e->cfg.max_num_iterations;
+  for (int ev = 0; ev < std::min((graph_replayed || solve_world(e) > 1) ? 1 : nevals, S.sc.evaluations); ++ev) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, e->evp[2 * ev], e->evp[2 * ev + 1]) == cudaSuccess) { e->asm_ms_sum += ms; e->asm_launch_count += 1; e->asm_feat_sum += nfeat; }
     else (void)cudaGetLastError();   // a failed timing query must not surface as the next launch's error
@@ -2045,6 +2149,7 @@ extern "C" int lio_est_set_shard(lio_est *e, int rank, int world, lio_allreduce_
   if (!e || world < 1 || rank < 0 || rank >= world) return LIO_ERR_INVALID;
   e->rank = rank; e->world = world; e->allreduce = fn; e->allreduce_user = user;
   e->npeers = 0;
+  e->fpeers = false;
   e->worker.spin_us = world > 1 ? std::max(25.0, 400.0 / world) : 400.0;  // N processes share the host: spin less
   return LIO_OK;
 }
@@ -2063,6 +2168,25 @@ extern "C" int lio_est_set_peers(lio_est *e, int world, void *const *peer_ptrs) 
     if (!e->peer_base[r]) return LIO_ERR_INVALID;
   }
   e->npeers = world;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_feature_slab(lio_est *e, void **dev_ptr, size_t *bytes) {
+  if (!e || !dev_ptr) return LIO_ERR_INVALID;
+  *dev_ptr = e->fslab;
+  if (bytes) *bytes = e->fslab_bytes;
+  return LIO_OK;
+}
+
+extern "C" int lio_est_set_feature_peers(lio_est *e, int world, void *const *peer_slabs) {
+  if (!e || !peer_slabs || world != e->world || world < 2 || world > kMaxPeers) return LIO_ERR_INVALID;
+  if (e->window_open) { lio_set_last_error(__FILE__, __LINE__, "lio_est_set_feature_peers inside an open scan"); return LIO_ERR_INVALID; }
+  for (int r = 0; r < world; ++r) {
+    e->fpeer_base[r] = r == e->rank ? e->fslab : static_cast<char *>(peer_slabs[r]);
+    if (!e->fpeer_base[r]) return LIO_ERR_INVALID;
+  }
+  e->fpeers = true;
+  e->npeers = 0;
   return LIO_OK;
 }
 

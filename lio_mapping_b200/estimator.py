@@ -242,6 +242,34 @@ class Estimator:
                 arr[r] = p.value
         _lib.check(_lib.lib().lio_est_set_peers(self.h, world, arr), "lio_est_set_peers")
 
+    def feature_slab(self):
+        p = C.c_void_p(); n = C.c_size_t()
+        _lib.check(_lib.lib().lio_est_feature_slab(self.h, C.byref(p), C.byref(n)), "lio_est_feature_slab")
+        return p.value
+
+    def feature_slab_handle(self):
+        h = np.zeros(64, np.uint8)
+        _lib.check(_lib.lib().lio_ipc_export(C.c_void_p(self.feature_slab()), h), "lio_ipc_export")
+        return h
+
+    def set_feature_peers(self, rank, world, ptrs=None, handles=None):
+        """Sharded matching with a per-scan exchange of the features themselves (lio_est_set_feature_peers): ptrs = every rank's
+        feature slab as a device pointer valid in this process, or handles = (world, 64) uint8 IPC handles."""
+        self.set_shard(rank, world, None)
+        arr = (C.c_void_p * world)()
+        self._fpeer_open = []
+        for r in range(world):
+            if r == rank:
+                arr[r] = self.feature_slab()
+            elif ptrs is not None:
+                arr[r] = int(ptrs[r])
+            else:
+                p = C.c_void_p()
+                _lib.check(_lib.lib().lio_ipc_open(np.ascontiguousarray(handles[r], np.uint8), C.byref(p)), "lio_ipc_open")
+                self._fpeer_open.append(p.value)
+                arr[r] = p.value
+        _lib.check(_lib.lib().lio_est_set_feature_peers(self.h, world, arr), "lio_est_set_feature_peers")
+
     def kernel_profile(self, reset=False):
         o = np.zeros(8)
         _lib.check(_lib.lib().lio_est_kernel_profile(self.h, o, 1 if reset else 0), "kernel_profile")

@@ -1,6 +1,12 @@
 import os
 import sys
 
+import os
+
+# several estimator contexts of one process wait for each other inside kernels (two-rank tests on one GPU): give every stream its own
+# hardware queue so that a spinning wait kernel can never sit in front of the kernel it waits for
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

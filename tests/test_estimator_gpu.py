@@ -261,6 +261,48 @@ def test_two_rank_peer_exchange_equals_single(oracle, vlp_seq):
         assert np.abs(e.states() - x).max() <= 1e-9 * max(1.0, np.abs(x).max())
 
 
+def test_two_rank_feature_exchange_equals_single(oracle, vlp_seq):
+    """Sharded matching with the per-scan exchange of the features themselves (lio_est_set_feature_peers): each of two contexts
+    matches half of the frames, copies its features into the peer's slab and then runs the complete single-GPU solve (graph
+    included) - the window states are those of an unsharded context, bit for bit."""
+    import threading
+    import torch
+    from lio_mapping_b200 import estimator
+    W = 5
+    cfg = dict(odom_max_iterations=3, prior_factor=1)
+    ref = estimator.Estimator(window_size=W, opt_window_size=W, max_frame_points=1 << 15, max_scan_points=1 << 17, **cfg)
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    ranks = [estimator.Estimator(stream=streams[r].cuda_stream, window_size=W, opt_window_size=W, max_frame_points=1 << 15,
+                                 max_scan_points=1 << 17, **cfg) for r in range(2)]
+    mk = lambda a, g: estimator.Pim(a, g, np.zeros(3), np.zeros(3), acc_n=0.2, gyr_n=0.02)
+    for e in [ref] + ranks:
+        helpers.warm_start(e, vlp_seq, oracle, W, pose_noise=0.01, seed=1, make_pim=mk)
+    torch.cuda.synchronize()
+    slabs = [e.feature_slab() for e in ranks]
+    for r, e in enumerate(ranks):
+        e.set_feature_peers(r, 2, ptrs=slabs)
+    errs = []
+
+    def run(r):
+        try:
+            for k in range(W, 10):
+                helpers.feed_scan(ranks[r], vlp_seq, k)
+        except Exception as exc:   # pragma: no cover
+            errs.append(exc)
+    th = [threading.Thread(target=run, args=(r,)) for r in range(2)]
+    for t_ in th:
+        t_.start()
+    for k in range(W, 10):
+        helpers.feed_scan(ref, vlp_seq, k)
+    for t_ in th:
+        t_.join(timeout=300)
+    assert not errs, errs
+    x = ref.states()
+    for e in ranks:
+        assert np.array_equal(e.states(), x)
+        assert e.summary()["iterations"] == ref.summary()["iterations"]
+
+
 def test_device_solver_equals_host_solver(oracle, vlp_seq):
     """The GPU-resident dogleg loop and the host controller take the same steps."""
     from lio_mapping_b200 import estimator
