@@ -654,22 +654,38 @@ __device__ void lidar_blocks(int O, const double *__restrict__ Sblk, const doubl
   }
   __syncthreads();
   if (marks && threadIdx.x == 0) marks[2] = clock_after(scratch[0]);
-  for (int p = tid; p < O * 342; p += T) {
-    const int i = p / 342, q = p - i * 342;
-    const double *M = sM + i * 108;
-    double v = 0;
-    if (q < 324) {
-      const int a = q / 18, b = q - a * 18;
+  // G_i = M_i^T (S_gg M_i): an (18 x 6)(6 x 18) product per frame - on the fp64 tensor path (DMMA m8n8k4): 3 x 3 output tiles of
+  // 8 x 8 per frame, K = 6 padded to 8 (two k-steps), one warp per tile.  (As scalar code - 6 multiply-adds per output, every
+  // operand from shared memory - this phase was shared-memory-bandwidth bound: 4.0k cycles for 10 frames.)
+  {
+    const int w = warp_id(), l = lane_id(), fr = l >> 2, fq = l & 3;
+    for (int task = w; task < O * 9; task += kDsWarps) {
+      const int i = task / 9, t9 = task - i * 9, mt = t9 / 3, nt = t9 - mt * 3;
+      const double *M = sM + i * 108, *SM = sSM + i * 108;
+      const int m = 8 * mt + fr, nn = 8 * nt + fr;
+      double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * sSM[i * 108 + k * 18 + b];
-    } else {
-      const int a = q - 324;
-      const double *Sb = sS + i * 32;
-#pragma unroll
-      for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * Sb[s_idx(k, 6)];
+      for (int kk = 0; kk < 2; ++kk) {
+        const int k = 4 * kk + fq;
+        const double a = (k < 6 && m < 18) ? M[k * 18 + m] : 0.0;      // A[m][k] = M^T[m][k]
+        const double b = (k < 6 && nn < 18) ? SM[k * 18 + nn] : 0.0;   // B[k][n] = (S M)[k][n]
+        dmma884(d0, d1, a, b);
+      }
+      const int n0 = 8 * nt + 2 * fq;
+      if (m < 18) {
+        if (n0 < 18) { sG[i * 342 + m * 18 + n0] = d0; G[(size_t)i * kFGStride + m * 18 + n0] = d0; }
+        if (n0 + 1 < 18) { sG[i * 342 + m * 18 + n0 + 1] = d1; G[(size_t)i * kFGStride + m * 18 + n0 + 1] = d1; }
+      }
     }
-    sG[p] = v;
-    G[(size_t)i * kFGStride + q] = v;
+  }
+  for (int p = tid; p < O * 18; p += T) {   // gradient terms M_i^T S_gr
+    const int i = p / 18, a = p - i * 18;
+    const double *M = sM + i * 108, *Sb = sS + i * 32;
+    double v = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) v += M[k * 18 + a] * Sb[s_idx(k, 6)];
+    sG[i * 342 + 324 + a] = v;
+    G[(size_t)i * kFGStride + 324 + a] = v;
   }
   __syncthreads();
   if (marks && threadIdx.x == 0) marks[3] = clock_after(scratch[0]);
