@@ -61,6 +61,10 @@ class ClockSampler:
         if self.p is None:
             return out
         try:
+            for _ in range(20):          # a run shorter than the first sampling period: wait for one sample rather than report none
+                if os.path.getsize(self.path) > 0:
+                    break
+                time.sleep(0.05)
             self.p.terminate(); self.p.wait(timeout=5); self.f.close()
             sm, smax, reasons = [], [], set()
             for line in open(self.path):
@@ -75,7 +79,8 @@ class ClockSampler:
                     if val.lower().startswith("active"):
                         reasons.add(name)
             if sm:
-                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons)}
+                out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(np.max(smax)), "reasons": sorted(reasons), "samples": len(sm),
+                       "window": "warm-up + timed steps (nvidia-smi -lms 100)"}
         except Exception:
             pass
         return out
@@ -287,13 +292,15 @@ def main():
     #   warmup scans -> K device-timed scans (value) ; the e2e pass re-runs a fresh estimator on the same scans.
     k = W
     barrier()   # ranks leave the (CPU-heavy, unequal) set-up together: the device-side exchange waits are bounded
+    # nvidia-smi needs ~100 ms for its first sample and the timed region is K x 2 ms: the sampler starts with the warm-up steps
+    # (the same load) so that it is running when the timed steps begin; samples = warm-up + timed region
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         step_dev(k); k += 1
     est.kernel_profile(reset=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     profiling = os.environ.get("LIO_BENCH_PROFILE") == "1"   # ncu --profile-from-start off: capture the timed steps only
     if profiling:
         torch.cuda.cudart().cudaProfilerStart()
