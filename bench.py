@@ -409,7 +409,7 @@ def main():
                            "parallelism": "frames sharded 1..O over %d rank(s)%s" % (world, ("; exchange: " + exchange["kind"]) if world > 1 else ""),
                            "e2e_vs_device_pass_max_pos_diff_m": drift,
                            "overlap_marginalization": args.overlap_marginalization,
-                           "timing": "value: CUDA events around each scan (device-resident sweep); e2e: host perf_counter around the C-ABI calls; the bench host is shared, runs differ by about +-10 %",
+                           "timing": "value: CUDA events around each scan (device-resident sweep); e2e: host perf_counter around the C-ABI calls; the bench host is shared, runs differ by about +-10 %; host_wall keys with the device solver: t_lin_host = host time from the start of the solve to the end of the graph launch call, t_lin_lidar = re-parameterising the asm_ppp graph nodes, t_marg_wait = joining the previous scan's marginalisation algebra (overlapped with the GPU front end)",
                            "ms_per_timed_step": [round(float(v), 3) for v in ms],
                            "host_wall_ms_per_scan": {kk: 1e3 * float(np.mean(v)) for kk, v in brk.items()}},
                 "roofline": {"kernel": "asm_ppp (fused PivotPointPlane residual+Jacobian+JtJ reduction)", "bound": "hbm",

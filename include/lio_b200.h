@@ -370,11 +370,16 @@ int lio_est_last_launches(lio_est *est);
 /* Text of the last failed scan-level call on THIS context (lio_last_error() is per calling thread; a process that drives
  * several estimators from one thread reads the per-handle copy). */
 const char *lio_est_last_error(lio_est *est);
-/* Diagnostic: phase timestamps of the device-resident solver's step kernel for the evaluations of the last solve:
- * out[24][16] (row = evaluation; [0] / [11] = GPU wall clock in ns at kernel entry / exit, [1..10] = SM clock at the phase
- * boundaries entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit; [12..15] = cycles
- * reserved), followed by 4 * 28 + 4 entries: the per-panel cycle profile of evaluation 1's Cholesky in the layout of
- * lio_dev_cholesky_solve_host's prof.  cap >= 24 * 16 + 116.  Zeros when the host controller is in use. */
+/* Diagnostic: the device-side timeline of the last solve, stamped by the kernels themselves.  out[24][16]:
+ * rows 0..11 = evaluations: [0] / [11] %globaltimer (ns) at k_step entry / exit, [1..10] SM clock at its phase boundaries (entry,
+ * verdict, lidar blocks, gradient, H tiles, Cauchy scale, tiles ready, Cholesky + solve, dogleg, exit), [12] / [13] %globaltimer when
+ * the first k_factors CTA starts / the last one ends, [14] when the last k_hpart CTA ends;
+ * row 12 = launch counters of asm_ppp, row 13 / 14 = %globaltimer when its first CTA starts / its tail ends, one column per
+ * evaluation; row 16 = SM clock inside the lidar block expansion of evaluation 2 (entry, operands staged, S M, M^T (S M)).
+ * Followed by 4 * 28 + 4 entries: the per-panel profile of evaluation 1's Cholesky in the layout of
+ * lio_dev_cholesky_solve_host's prof (column 1 = %globaltimer at the start of the panel's diagonal tile), and after the back
+ * substitution cycles four %globaltimer stamps (entry, loop start, loop end, exit).  cap >= 24 * 16 + 116.  Zeros when the host
+ * controller is in use.  `LIO_BENCH_TRACE=1 python bench.py` prints it. */
 int lio_est_solver_trace(lio_est *est, long long *out, int cap);
 /* CUDA-event timing of the fused residual+Jacobian kernel accumulated since the last reset (events recorded
  * on the estimator's stream around every launch): out[0..3] = {sum ms, launches, features processed, bytes/feature};

@@ -40,10 +40,8 @@ struct DevSolveState {
   // IMU factors i -> i+1
   PimData pim[kMaxOpt];
   int pim_valid[kMaxOpt];
-  // phase timestamps of k_step per evaluation (thread 0): [0] %globaltimer at entry, [1..9] clock64 at phase boundaries
-  // (entry, verdict, lidar blocks, gradient, H gather, alpha, tiles, Cholesky, dogleg, exit), [11] %globaltimer at exit
-  // [12..15] inside the Cholesky (cycles): look-ahead diag_factor of panel 1, panel solve of panel 0, trailing update of
-  // panel 0 (incl. barrier), back substitution
+  // device-side timeline (layout documented at lio_est_solver_trace in lio_b200.h): rows 0..11 k_step phases + gap kernels per
+  // evaluation, rows 12..14 asm_ppp stamps, row 16 lidar block expansion
   long long dbg[24][16];
   long long chol_prof[4 * 28 + 4];   // per-panel cycles of the Cholesky of evaluation 1 (see lio_dev_cholesky_solve_host)
 };
